@@ -1,0 +1,341 @@
+"""ctypes binding of libhmme_b200.so + the Python mirror of the reference's TEncOpenCL surface.
+
+Reference interface mirrored (names, argument meaning, error behaviour):
+  /root/reference/source/Lib/TLibEncoder/TEncOpenCL.h:105-123
+      findDevice / compileKernelSource / createBuffers / calcMotionVectors /
+      getX / getY / getRuiCost / setLambda / setEnabled / getDeviceInfo
+The compiled drop-in for the encoder itself is the C++ class in hm-opencl_b200/host/.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+NUM_CTU_PARTS = 593
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+# every symbol include/hmme_b200.h declares (tests check header == this list == the .so's exports)
+EXPORTS = [
+    "hmme_device_count", "hmme_create", "hmme_destroy", "hmme_device_name", "hmme_last_error", "hmme_stream",
+    "hmme_set_lambda", "hmme_set_lambda_q16", "hmme_get_lambda_q16", "hmme_search_ctu",
+    "hmme_plane_alloc", "hmme_plane_free", "hmme_plane_upload_s16", "hmme_plane_upload_u8",
+    "hmme_search_frame", "hmme_search_frame_async", "hmme_fetch_results", "hmme_sync",
+    "hmme_last_kernel_ms", "hmme_kernel_launches", "hmme_measure_int_alu_peak", "hmme_partition_rect", "hmme_version",
+]
+
+
+class HmmeError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("hmme error %d: %s" % (code, msg))
+        self.code = code
+
+
+class PlaneDesc(C.Structure):
+    _fields_ = [("base", C.c_void_p), ("elemBytes", C.c_int32), ("pitch", C.c_int32), ("width", C.c_int32),
+                ("height", C.c_int32), ("marginX", C.c_int32), ("marginY", C.c_int32)]
+
+
+def lib_path():
+    return os.path.join(_HERE, "libhmme_b200.so")
+
+
+class HmmeLib:
+    """The loaded shared library.  Missing library == hard error (there is no fallback path)."""
+    _inst = None
+
+    @classmethod
+    def get(cls):
+        if cls._inst is None:
+            cls._inst = cls()
+        return cls._inst
+
+    def __init__(self):
+        path = lib_path()
+        if not os.path.exists(path):
+            raise HmmeError(-100, "CUDA extension %s is missing: run `python hm-opencl_b200/build.py` "
+                                  "(this package has no CPU fallback)" % path)
+        L = self.L = C.CDLL(path)
+        vp, i32, u32 = C.c_void_p, C.c_int, C.c_uint32
+        P = C.POINTER
+        sig = {
+            "hmme_device_count": (i32, [P(C.c_int)]),
+            "hmme_create": (i32, [P(vp), i32, i32, i32, i32]),
+            "hmme_destroy": (None, [vp]),
+            "hmme_device_name": (C.c_char_p, [vp]),
+            "hmme_last_error": (C.c_char_p, [vp]),
+            "hmme_stream": (vp, [vp]),
+            "hmme_set_lambda": (i32, [vp, C.c_double]),
+            "hmme_set_lambda_q16": (i32, [vp, u32]),
+            "hmme_get_lambda_q16": (u32, [vp]),
+            "hmme_search_ctu": (i32, [vp, vp, i32, vp, i32, i32, i32, i32, vp, vp, vp, vp]),
+            "hmme_plane_alloc": (i32, [vp, P(PlaneDesc), i32, i32, i32, i32, i32]),
+            "hmme_plane_free": (i32, [vp, P(PlaneDesc)]),
+            "hmme_plane_upload_s16": (i32, [vp, P(PlaneDesc), vp, i32]),
+            "hmme_plane_upload_u8": (i32, [vp, P(PlaneDesc), vp, i32]),
+            "hmme_search_frame": (i32, [vp, P(PlaneDesc), P(PlaneDesc), vp, i32, i32, vp, vp, vp, vp]),
+            "hmme_search_frame_async": (i32, [vp, P(PlaneDesc), P(PlaneDesc), vp, i32, i32]),
+            "hmme_fetch_results": (i32, [vp, i32, vp, vp, vp, vp]),
+            "hmme_sync": (i32, [vp]),
+            "hmme_last_kernel_ms": (i32, [vp, P(C.c_float)]),
+            "hmme_kernel_launches": (C.c_uint64, [vp]),
+            "hmme_measure_int_alu_peak": (i32, [vp, P(C.c_double), P(C.c_double), P(C.c_double)]),
+            "hmme_partition_rect": (i32, [i32, P(C.c_int), P(C.c_int), P(C.c_int), P(C.c_int)]),
+            "hmme_version": (C.c_char_p, []),
+        }
+        assert sorted(sig) == sorted(EXPORTS)
+        for name, (res, args) in sig.items():
+            fn = getattr(L, name)          # AttributeError if the .so does not export it
+            fn.restype, fn.argtypes = res, args
+
+    def partition_table(self):
+        out = np.zeros((NUM_CTU_PARTS, 4), np.int32)
+        v = [C.c_int() for _ in range(4)]
+        for p in range(NUM_CTU_PARTS):
+            assert self.L.hmme_partition_rect(p, *[C.byref(q) for q in v]) == 0
+            out[p] = [q.value for q in v]
+        return out
+
+    def device_count(self):
+        n = C.c_int(0)
+        rc = self.L.hmme_device_count(C.byref(n))
+        if rc != 0:
+            raise HmmeError(rc, self.L.hmme_last_error(None).decode())
+        return n.value
+
+
+class Plane:
+    """A device-resident luma plane (library-owned, or a view of external device memory such as a torch tensor)."""
+
+    def __init__(self, me, desc, owned):
+        self.me, self.desc, self.owned = me, desc, owned
+
+    @property
+    def nbytes(self):
+        d = self.desc
+        return d.pitch * (d.height + 2 * d.marginY) * d.elemBytes
+
+    def free(self):
+        if self.owned and self.desc.base:
+            self.me._chk(self.me.lib.L.hmme_plane_free(self.me.h, C.byref(self.desc)))
+        self.desc.base = None
+
+
+class MotionEstimator:
+    """One hmme context (one GPU, one stream)."""
+
+    def __init__(self, device=0, max_search_range=64):
+        self.lib = HmmeLib.get()
+        h = C.c_void_p()
+        rc = self.lib.L.hmme_create(C.byref(h), device, 64, 64, max_search_range)
+        if rc != 0:
+            raise HmmeError(rc, self.lib.L.hmme_last_error(None).decode())
+        self.h = h
+        self.max_search_range = max_search_range
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.L.hmme_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise HmmeError(rc, self.lib.L.hmme_last_error(self.h).decode())
+
+    # -- properties
+    @property
+    def device_name(self):
+        return self.lib.L.hmme_device_name(self.h).decode()
+
+    @property
+    def stream_ptr(self):
+        return int(self.lib.L.hmme_stream(self.h))
+
+    @property
+    def kernel_launches(self):
+        return int(self.lib.L.hmme_kernel_launches(self.h))
+
+    def set_lambda(self, lam):
+        self._chk(self.lib.L.hmme_set_lambda(self.h, float(lam)))
+
+    def set_lambda_q16(self, v):
+        self._chk(self.lib.L.hmme_set_lambda_q16(self.h, C.c_uint32(int(v))))
+
+    def get_lambda_q16(self):
+        return int(self.lib.L.hmme_get_lambda_q16(self.h))
+
+    # -- synchronous per-CTU search (TEncOpenCL::calcMotionVectors)
+    def search_ctu(self, cur, plane, ctu_x, ctu_y, origin_x, origin_y, rng, ltx, lty):
+        cur = np.ascontiguousarray(cur, np.int16)
+        assert cur.shape == (64, 64) and plane.dtype == np.int16 and plane.flags.c_contiguous
+        out = [np.zeros(NUM_CTU_PARTS, t) for t in (np.int32, np.int32, np.uint32, np.uint32)]
+        stride = plane.shape[1]
+        off = int(((origin_y + ctu_y) * stride + origin_x + ctu_x) * 2)
+        self._chk(self.lib.L.hmme_search_ctu(self.h, cur.ctypes.data, 64, plane.ctypes.data + off, stride, int(rng), int(ltx),
+                                             int(lty), *[o.ctypes.data for o in out]))
+        return tuple(out)
+
+    # -- planes
+    def alloc_plane(self, elem_bytes, width, height, margin_x, margin_y):
+        d = PlaneDesc()
+        self._chk(self.lib.L.hmme_plane_alloc(self.h, C.byref(d), elem_bytes, width, height, margin_x, margin_y))
+        return Plane(self, d, True)
+
+    def wrap_plane(self, device_ptr, elem_bytes, pitch, width, height, margin_x, margin_y):
+        """View of device memory owned by someone else (e.g. torch.Tensor.data_ptr()); must be 16-byte aligned
+        and hold pitch*(height+2*margin_y) elements plus 4 bytes of slack."""
+        d = PlaneDesc(C.c_void_p(int(device_ptr)), elem_bytes, pitch, width, height, margin_x, margin_y)
+        return Plane(self, d, False)
+
+    def upload(self, plane, host, origin_x=None, origin_y=None):
+        """host: 2-D numpy array (int16 or uint8) that includes the margins; picture sample (0,0) at
+        [origin_y, origin_x] (defaults: the plane's margins)."""
+        d = plane.desc
+        ox = d.marginX if origin_x is None else origin_x
+        oy = d.marginY if origin_y is None else origin_y
+        assert host.ndim == 2 and host.flags.c_contiguous
+        assert oy >= d.marginY and ox >= d.marginX and host.shape[0] - oy >= d.height + d.marginY and host.shape[1] - ox >= d.width + d.marginX
+        off = int(oy * host.shape[1] + ox) * host.itemsize
+        if host.dtype == np.int16:
+            self._chk(self.lib.L.hmme_plane_upload_s16(self.h, C.byref(d), host.ctypes.data + off, host.shape[1]))
+        elif host.dtype == np.uint8:
+            self._chk(self.lib.L.hmme_plane_upload_u8(self.h, C.byref(d), host.ctypes.data + off, host.shape[1]))
+        else:
+            raise TypeError("plane uploads take int16 (HM Pel) or uint8 arrays")
+
+    # -- whole-frame batch
+    @staticmethod
+    def _outs(n):
+        return [np.zeros((n, NUM_CTU_PARTS), t) for t in (np.int32, np.int32, np.uint32, np.uint32)]
+
+    def search_frame(self, cur, ref, jobs, rng):
+        jobs = np.ascontiguousarray(jobs, np.int32).reshape(-1, 4)
+        out = self._outs(jobs.shape[0])
+        self._chk(self.lib.L.hmme_search_frame(self.h, C.byref(cur.desc), C.byref(ref.desc), jobs.ctypes.data, jobs.shape[0],
+                                               int(rng), *[o.ctypes.data for o in out]))
+        return tuple(out)
+
+    def search_frame_async(self, cur, ref, jobs, rng):
+        jobs = np.ascontiguousarray(jobs, np.int32).reshape(-1, 4)
+        self._chk(self.lib.L.hmme_search_frame_async(self.h, C.byref(cur.desc), C.byref(ref.desc), jobs.ctypes.data,
+                                                     jobs.shape[0], int(rng)))
+        return jobs.shape[0]
+
+    def fetch_results(self, njobs, out=None):
+        out = out or self._outs(njobs)
+        self._chk(self.lib.L.hmme_fetch_results(self.h, njobs, *[o.ctypes.data for o in out]))
+        return tuple(out)
+
+    def sync(self):
+        self._chk(self.lib.L.hmme_sync(self.h))
+
+    def last_kernel_ms(self):
+        ms = C.c_float()
+        self._chk(self.lib.L.hmme_last_kernel_ms(self.h, C.byref(ms)))
+        return ms.value
+
+    def measure_int_alu_peak(self):
+        a, b, c = C.c_double(), C.c_double(), C.c_double()
+        self._chk(self.lib.L.hmme_measure_int_alu_peak(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return {"lane_ops_per_s": a.value, "lanes_per_clk_sm": b.value, "sm_mhz": c.value}
+
+
+class TEncOpenCL:
+    """Python mirror of the reference class (TEncOpenCL.h:105-123) with the reference's call order
+    findDevice -> compileKernelSource -> createBuffers -> setEnabled(true) (TEncTop.cpp:1129-1145).
+    Init methods return bool like the reference; there is no silent CPU fallback -- a failed init
+    leaves the object disabled and calcMotionVectors raises."""
+
+    def __init__(self):
+        self.deviceId = 0
+        self.enabled = False            # the reference leaves this uninitialised
+        self._me = None
+        self._device_ok = False
+        self._kernel_ok = False
+        self._lambda = 0.0
+        self._info = ""
+        self._x = np.zeros(NUM_CTU_PARTS, np.int32)
+        self._y = np.zeros(NUM_CTU_PARTS, np.int32)
+        self._rui = np.zeros(NUM_CTU_PARTS, np.uint32)
+        self._min = np.full(NUM_CTU_PARTS, 0xFFFFFFFF, np.uint32)
+        self.last_error = ""
+
+    def findDevice(self, device):
+        try:
+            n = HmmeLib.get().device_count()
+        except HmmeError as e:
+            self.last_error = str(e)
+            print("ERROR: %s" % e)
+            return False
+        if device < 0 or device > n - 1:    # TEncOpenCL.cpp:111-115
+            device = 0
+            print("ID device not found, use default GPU device ")
+        self.deviceId = device
+        self._device_ok = n > 0
+        return self._device_ok
+
+    def compileKernelSource(self, fileName, kernelNameCalc):
+        """Kernels are precompiled sm_100a code: the file name is accepted (it must be non-NULL, TEncTop.cpp:1131)
+        and otherwise ignored; only the 593-partition kernel exists (AMP_ENC_SPEEDUP=0)."""
+        if fileName is None or kernelNameCalc != "calcSAD_AMP":
+            self.last_error = "only calcSAD_AMP (593 partitions) is implemented"
+            return False
+        self._kernel_ok = True
+        return True
+
+    def createBuffers(self, maxCtuWidth, maxCtuHeight, searchRange):
+        if not (self._device_ok and self._kernel_ok):
+            return False
+        if maxCtuWidth != 64 or maxCtuHeight != 64:
+            self.last_error = "only 64x64 CTUs"
+            return False
+        try:
+            self._me = MotionEstimator(self.deviceId, searchRange)
+        except HmmeError as e:
+            self.last_error = str(e)
+            print("ERROR: %s" % e)
+            return False
+        self._info = self._me.device_name
+        self._me.set_lambda(self._lambda)
+        print("Using GPU device              : %s" % self._info)
+        return True
+
+    def calcMotionVectors(self, pelCtu, refPlane, ctuPosInPlane, iAreaSize, mvSrchRngLT):
+        """pelCtu: (64,64) int16; refPlane: padded int16 plane; ctuPosInPlane = (x, y) array index of the CTU's
+        top-left sample (the reference passes that pointer as pelSearch); mvSrchRngLT = (hor, ver)."""
+        if not (self.enabled and self._me):
+            raise HmmeError(-101, "TEncOpenCL is not initialised/enabled (no CPU fallback)")
+        x, y = ctuPosInPlane
+        self._x, self._y, self._rui, self._min = self._me.search_ctu(pelCtu, refPlane, x, y, 0, 0, iAreaSize,
+                                                                     mvSrchRngLT[0], mvSrchRngLT[1])
+
+    def getDeviceId(self):
+        return self.deviceId
+
+    def setDeviceId(self, i):
+        self.deviceId = i
+
+    def getDeviceInfo(self):
+        return self._info
+
+    def getRuiCost(self):
+        return self._rui
+
+    def getX(self):
+        return self._x
+
+    def getY(self):
+        return self._y
+
+    def setLambda(self, lam):
+        self._lambda = lam
+        if self._me:
+            self._me.set_lambda(lam)
+
+    def setEnabled(self, e):
+        self.enabled = bool(e)

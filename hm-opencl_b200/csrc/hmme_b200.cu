@@ -1,0 +1,497 @@
+// hmme_b200.cu -- host side of libhmme_b200.so (C ABI in include/hmme_b200.h).
+//
+// Replaces the host orchestration of /root/reference/source/Lib/TLibEncoder/TEncOpenCL.cpp:
+//   findDevice/compileKernelSource/createBuffers (:69-238)  -> hmme_create
+//   calcMotionVectors (:240-362)                             -> hmme_search_ctu (sync) / hmme_search_frame (batched)
+//   xFillSADBuffer/xResetArrays (:366-392)                   -> me_init_kernel
+// No OpenCL, no runtime compilation, no CPU fallback: every failure is an error code + message.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/hmme_b200.h"
+#include "me_common.cuh"
+#include "me_generic_kernel.cuh"
+#include "me_u8_kernel.cuh"
+
+#ifndef HMME_FAST_YB
+#define HMME_FAST_YB 3
+#endif
+
+using namespace hmme;
+
+namespace {
+
+std::mutex g_errMu;
+std::string g_createErr;
+
+struct FastGeom { int tw, th, nTx, nTy, pw, cs; size_t smemBytes; };
+
+constexpr size_t kSmemBudget = 200 * 1024;
+
+size_t fast_smem_bytes(int tw, int th, int yb, int* pwOut, int* csOut) {
+    const int rows = fast_win_rows(th, yb), pw = fast_pw(tw);
+    int cs = rows * pw;
+    cs += ((8 - cs) % 32 + 32) % 32;                       // copies 8 banks apart
+    if (pwOut) *pwOut = pw;
+    if (csOut) *csOut = cs;
+    const size_t words = 4 * (size_t)cs + 1024 + 2 * (size_t)(32 * yb) * kRecWords + ((tw + 3) & ~3) + (size_t)(((th + yb - 1) / yb) * yb) + 4;
+    return words * 4;
+}
+
+FastGeom fast_geometry(int W, int yb) {
+    FastGeom g{};
+    g.nTx = (W + 128) / 129;
+    g.tw = (W + g.nTx - 1) / g.nTx;
+    int thMax = (kMaxTileCands / g.tw) / yb * yb;
+    thMax = std::min(thMax, (W + yb - 1) / yb * yb);
+    while (thMax > yb && fast_smem_bytes(g.tw, thMax, yb, nullptr, nullptr) > kSmemBudget) thMax -= yb;
+    g.nTy = (W + thMax - 1) / thMax;
+    g.th = (((W + g.nTy - 1) / g.nTy) + yb - 1) / yb * yb;
+    g.smemBytes = fast_smem_bytes(g.tw, g.th, yb, &g.pw, &g.cs);
+    return g;
+}
+
+}  // namespace
+
+struct hmme_ctx {
+    int device = -1;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool evValid = false;
+    cudaDeviceProp prop{};
+    std::string err;
+    uint32_t lambda = 0;
+    int maxRange = 0;
+    uint64_t launches = 0;
+    // job / result buffers (grown on demand)
+    size_t jobCap = 0;
+    int4* dJobs = nullptr;
+    unsigned long long* dBest = nullptr;
+    int32_t* dRes = nullptr;      // [4][jobCap][593]: X, Y, sad, cost
+    hmme_job* hJobs = nullptr;    // pinned
+    int32_t* hRes = nullptr;      // pinned
+    // per-CTU synchronous path staging
+    size_t winElems = 0;          // (2*maxRange+64+16)^2
+    void* hWin = nullptr;         // pinned, int16-sized
+    void* dWin = nullptr;
+    void* hCurBlk = nullptr;      // pinned 64x64 int16
+    void* dCurBlk = nullptr;
+    // upload staging
+    int16_t* dStage = nullptr; size_t stageElems = 0;
+    int* dFlag = nullptr; int* hFlag = nullptr;
+};
+
+namespace {
+
+int fail(hmme_ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg;
+    else { std::lock_guard<std::mutex> l(g_errMu); g_createErr = msg; }
+    return code;
+}
+
+#define CU_TRY(c, expr)                                                                                      \
+    do {                                                                                                     \
+        cudaError_t e_ = (expr);                                                                             \
+        if (e_ != cudaSuccess)                                                                               \
+            return fail((c), HMME_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));            \
+    } while (0)
+
+int ensure_jobs(hmme_ctx* c, size_t njobs) {
+    if (njobs <= c->jobCap) return HMME_OK;
+    size_t cap = std::max<size_t>(njobs, std::max<size_t>(64, c->jobCap * 2));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    if (c->dJobs) cudaFree(c->dJobs);
+    if (c->dBest) cudaFree(c->dBest);
+    if (c->dRes) cudaFree(c->dRes);
+    if (c->hJobs) cudaFreeHost(c->hJobs);
+    if (c->hRes) cudaFreeHost(c->hRes);
+    c->dJobs = nullptr; c->dBest = nullptr; c->dRes = nullptr; c->hJobs = nullptr; c->hRes = nullptr; c->jobCap = 0;
+    CU_TRY(c, cudaMalloc(&c->dJobs, cap * sizeof(int4)));
+    CU_TRY(c, cudaMalloc(&c->dBest, cap * HMME_NPARTS * sizeof(unsigned long long)));
+    CU_TRY(c, cudaMalloc(&c->dRes, 4 * cap * HMME_NPARTS * sizeof(int32_t)));
+    CU_TRY(c, cudaMallocHost(&c->hJobs, cap * sizeof(hmme_job)));
+    CU_TRY(c, cudaMallocHost(&c->hRes, 4 * cap * HMME_NPARTS * sizeof(int32_t)));
+    c->jobCap = cap;
+    return HMME_OK;
+}
+
+size_t plane_elems(const hmme_plane* p) { return (size_t)p->pitch * (size_t)(p->height + 2 * p->marginY); }
+
+int check_plane(hmme_ctx* c, const hmme_plane* p, const char* what) {
+    if (!p || !p->base || (p->elemBytes != 1 && p->elemBytes != 2) || p->width <= 0 || p->height <= 0 || p->marginX < 0 ||
+        p->marginY < 0 || p->pitch < p->width + 2 * p->marginX)
+        return fail(c, HMME_ERR_ARG, std::string("invalid plane descriptor: ") + what);
+    if ((reinterpret_cast<uintptr_t>(p->base) & 15) != 0) return fail(c, HMME_ERR_ARG, std::string("plane base must be 16-byte aligned: ") + what);
+    return HMME_OK;
+}
+
+// Every job's 64x64 block and (2R+64)^2 window must lie inside the allocations under LINEAR addressing
+// (the reference reads pelSearchArray[j + i*iRefStride] regardless of row ends, App. B4).
+int check_jobs(hmme_ctx* c, const hmme_plane* cur, const hmme_plane* ref, const hmme_job* jobs, int njobs, int R) {
+    const long long curN = (long long)plane_elems(cur), refN = (long long)plane_elems(ref);
+    for (int j = 0; j < njobs; ++j) {
+        const hmme_job& b = jobs[j];
+        const long long c0 = (long long)(cur->marginY + b.ctuY) * cur->pitch + cur->marginX + b.ctuX;
+        const long long c1 = c0 + 63LL * cur->pitch + 63;
+        const long long r0 = (long long)(ref->marginY + b.ctuY + b.lty) * ref->pitch + ref->marginX + b.ctuX + b.ltx;
+        const long long r1 = r0 + (long long)(2 * R + 63) * ref->pitch + 2 * R + 63;
+        if (c0 < 0 || c1 >= curN || b.ctuX < -cur->marginX || b.ctuX + 64 > cur->width + cur->marginX)
+            return fail(c, HMME_ERR_BOUNDS, "job " + std::to_string(j) + ": CTU outside the current plane");
+        if (r0 < 0 || r1 >= refN)
+            return fail(c, HMME_ERR_BOUNDS, "job " + std::to_string(j) + ": search window leaves the reference allocation");
+    }
+    return HMME_OK;
+}
+
+template <typename TC, typename TR>
+void launch_generic(hmme_ctx* c, const GenericParams& gp, int njobs) {
+    me_generic_kernel<TC, TR><<<njobs * gp.nChunks, kGenThreads, 0, c->stream>>>(gp);
+}
+
+// Enqueue init -> search -> finalize for njobs jobs already present in c->dJobs.
+int enqueue_search(hmme_ctx* c, const void* curOrigin, int curElem, long long curPitch, const void* refOrigin, int refElem,
+                   long long refPitch, const void* refLo, const void* refHi, int njobs, int R) {
+    const int W = 2 * R + 1;
+    const size_t nres = (size_t)njobs * HMME_NPARTS;
+    me_init_kernel<<<(unsigned)((nres + 255) / 256), 256, 0, c->stream>>>(c->dBest, nres);
+    CU_TRY(c, cudaEventRecord(c->ev0, c->stream));
+    if (curElem == 1 && refElem == 1) {
+        const FastGeom g = fast_geometry(W, HMME_FAST_YB);
+        FastParams fp{};
+        fp.cur = static_cast<const uint8_t*>(curOrigin);
+        fp.ref = static_cast<const uint8_t*>(refOrigin);
+        fp.refLo = static_cast<const uint8_t*>(refLo);
+        fp.refHi = static_cast<const uint8_t*>(refHi);
+        fp.curPitch = curPitch; fp.refPitch = refPitch;
+        fp.jobs = c->dJobs; fp.best = c->dBest; fp.lambda = c->lambda; fp.W = W;
+        fp.tw = g.tw; fp.th = g.th; fp.nTx = g.nTx; fp.nTy = g.nTy; fp.pw = g.pw; fp.cs = g.cs;
+        CU_TRY(c, cudaFuncSetAttribute(me_u8_tile_kernel<HMME_FAST_YB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smemBytes));
+        me_u8_tile_kernel<HMME_FAST_YB><<<njobs * g.nTx * g.nTy, kFastThreads, g.smemBytes, c->stream>>>(fp);
+    } else {
+        GenericParams gp{};
+        gp.cur = curOrigin; gp.ref = refOrigin; gp.curPitch = curPitch; gp.refPitch = refPitch;
+        gp.jobs = c->dJobs; gp.best = c->dBest; gp.lambda = c->lambda; gp.W = W;
+        const int nCand = W * W;
+        int nChunks = std::max(1, std::min((nCand + 63) / 64, (4 * c->prop.multiProcessorCount + njobs - 1) / njobs));
+        gp.chunk = (nCand + nChunks - 1) / nChunks;
+        gp.chunk = (gp.chunk + kGenBatch - 1) / kGenBatch * kGenBatch;
+        gp.nChunks = (nCand + gp.chunk - 1) / gp.chunk;
+        if (curElem == 1 && refElem == 2) launch_generic<uint8_t, int16_t>(c, gp, njobs);
+        else if (curElem == 2 && refElem == 1) launch_generic<int16_t, uint8_t>(c, gp, njobs);
+        else launch_generic<int16_t, int16_t>(c, gp, njobs);
+    }
+    CU_TRY(c, cudaEventRecord(c->ev1, c->stream));
+    c->evValid = true;
+    int32_t* X = c->dRes;
+    int32_t* Y = X + c->jobCap * HMME_NPARTS;
+    uint32_t* S = reinterpret_cast<uint32_t*>(Y + c->jobCap * HMME_NPARTS);
+    uint32_t* Cst = S + c->jobCap * HMME_NPARTS;
+    me_finalize_kernel<<<(unsigned)((nres + 255) / 256), 256, 0, c->stream>>>(c->dBest, c->dJobs, njobs, W, c->lambda, X, Y, S, Cst);
+    c->launches += 3;
+    CU_TRY(c, cudaGetLastError());
+    return HMME_OK;
+}
+
+int fetch(hmme_ctx* c, int njobs, int32_t* X, int32_t* Y, uint32_t* sad, uint32_t* cost) {
+    const size_t n = (size_t)njobs * HMME_NPARTS, cap = c->jobCap * HMME_NPARTS;
+    void* outs[4] = {X, Y, sad, cost};
+    for (int k = 0; k < 4; ++k)
+        if (outs[k]) CU_TRY(c, cudaMemcpyAsync(c->hRes + k * cap, c->dRes + k * cap, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    for (int k = 0; k < 4; ++k)
+        if (outs[k]) std::memcpy(outs[k], c->hRes + k * cap, n * 4);
+    return HMME_OK;
+}
+
+const char* origin_ptr(const hmme_plane* p) {
+    return static_cast<const char*>(p->base) + ((size_t)p->marginY * p->pitch + p->marginX) * p->elemBytes;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* hmme_version(void) { return "hmme_b200 0.1 (sm_100a)"; }
+
+int hmme_device_count(int* count) {
+    if (!count) return HMME_ERR_ARG;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { *count = 0; return fail(nullptr, HMME_ERR_NO_DEVICE, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e)); }
+    *count = n;
+    return HMME_OK;
+}
+
+int hmme_create(hmme_ctx** out, int device, int maxCtuW, int maxCtuH, int maxSearchRange) {
+    if (!out) return HMME_ERR_ARG;
+    *out = nullptr;
+    if (maxCtuW != HMME_CTU_SIZE || maxCtuH != HMME_CTU_SIZE)
+        return fail(nullptr, HMME_ERR_RANGE, "only 64x64 CTUs are defined for this path (TEncSearch.cpp:3745)");
+    if (maxSearchRange < 0 || maxSearchRange > 1024) return fail(nullptr, HMME_ERR_RANGE, "search range out of [0,1024]");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(nullptr, HMME_ERR_NO_DEVICE, std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "count is 0"));
+    if (device < 0 || device >= n) return fail(nullptr, HMME_ERR_NO_DEVICE, "device index out of range");
+    hmme_ctx* c = new hmme_ctx;
+    c->device = device;
+    auto bail = [&](const std::string& m, int code) { g_createErr = m; hmme_destroy(c); return code; };
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return bail(std::string("cudaSetDevice: ") + cudaGetErrorString(e), HMME_ERR_CUDA);
+    if ((e = cudaGetDeviceProperties(&c->prop, device)) != cudaSuccess) return bail(std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e), HMME_ERR_CUDA);
+    if (c->prop.major != 10)
+        return bail(std::string("device '") + c->prop.name + "' is sm_" + std::to_string(c->prop.major) + std::to_string(c->prop.minor) +
+                    "; this library carries sm_100a code only and has no fallback", HMME_ERR_NO_DEVICE);
+    if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(std::string("cudaStreamCreate: ") + cudaGetErrorString(e), HMME_ERR_CUDA);
+    if ((e = cudaEventCreate(&c->ev0)) != cudaSuccess || (e = cudaEventCreate(&c->ev1)) != cudaSuccess) return bail(std::string("cudaEventCreate: ") + cudaGetErrorString(e), HMME_ERR_CUDA);
+    c->maxRange = maxSearchRange;
+    const size_t side = (size_t)2 * maxSearchRange + 64 + 16;
+    c->winElems = side * side;
+    if ((e = cudaMallocHost(&c->hWin, c->winElems * 2)) != cudaSuccess || (e = cudaMalloc(&c->dWin, c->winElems * 2 + 64)) != cudaSuccess ||
+        (e = cudaMallocHost(&c->hCurBlk, 4096 * 2)) != cudaSuccess || (e = cudaMalloc(&c->dCurBlk, 4096 * 2)) != cudaSuccess ||
+        (e = cudaMalloc(&c->dFlag, sizeof(int))) != cudaSuccess || (e = cudaMallocHost(&c->hFlag, sizeof(int))) != cudaSuccess)
+        return bail(std::string("buffer allocation: ") + cudaGetErrorString(e), HMME_ERR_CUDA);
+    int rc = ensure_jobs(c, 64);
+    if (rc != HMME_OK) return bail(c->err, rc);
+    *out = c;
+    return HMME_OK;
+}
+
+void hmme_destroy(hmme_ctx* c) {
+    if (!c) return;
+    if (c->device >= 0) cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    cudaFree(c->dJobs); cudaFree(c->dBest); cudaFree(c->dRes); cudaFreeHost(c->hJobs); cudaFreeHost(c->hRes);
+    cudaFreeHost(c->hWin); cudaFree(c->dWin); cudaFreeHost(c->hCurBlk); cudaFree(c->dCurBlk);
+    cudaFree(c->dStage); cudaFree(c->dFlag); cudaFreeHost(c->hFlag);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+const char* hmme_device_name(hmme_ctx* c) { return c ? c->prop.name : ""; }
+const char* hmme_last_error(hmme_ctx* c) {
+    if (c) return c->err.c_str();
+    static thread_local std::string copy;
+    std::lock_guard<std::mutex> l(g_errMu);
+    copy = g_createErr;
+    return copy.c_str();
+}
+void* hmme_stream(hmme_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+int hmme_set_lambda(hmme_ctx* c, double lambda) {
+    if (!c || !(lambda >= 0.0)) return fail(c, HMME_ERR_ARG, "lambda must be >= 0");
+    c->lambda = (uint32_t)std::floor(65536.0 * std::sqrt(lambda));   // TEncOpenCL.h:121
+    return HMME_OK;
+}
+int hmme_set_lambda_q16(hmme_ctx* c, uint32_t v) { if (!c) return HMME_ERR_ARG; c->lambda = v; return HMME_OK; }
+uint32_t hmme_get_lambda_q16(hmme_ctx* c) { return c ? c->lambda : 0; }
+
+int hmme_search_ctu(hmme_ctx* c, const int16_t* cur, int curStride, const int16_t* refAtCtu, int refStride, int range, int ltx,
+                    int lty, int32_t* X, int32_t* Y, uint32_t* sad, uint32_t* cost) {
+    if (!c) return HMME_ERR_ARG;
+    if (!cur || !refAtCtu || !X || !Y || !sad || curStride < 64) return fail(c, HMME_ERR_ARG, "hmme_search_ctu: null pointer or stride < 64");
+    if (range < 0 || range > c->maxRange) return fail(c, HMME_ERR_RANGE, "search range " + std::to_string(range) + " exceeds the context's " + std::to_string(c->maxRange));
+    CU_TRY(c, cudaSetDevice(c->device));
+    int rc = ensure_jobs(c, 1);
+    if (rc != HMME_OK) return rc;
+    const int side = 2 * range + 64;                 // TEncOpenCL.cpp:256 areaStride
+    const int wp = (side + 15) & ~15;
+    // gather block + window with the reference's linear addressing (TEncOpenCL.cpp:251,275-277) and classify the content
+    int16_t* hc = static_cast<int16_t*>(c->hCurBlk);
+    int16_t* hw = static_cast<int16_t*>(c->hWin);
+    uint32_t orAll = 0;
+    for (int r = 0; r < 64; ++r)
+        for (int q = 0; q < 64; ++q) { const int16_t v = cur[(size_t)r * curStride + q]; hc[r * 64 + q] = v; orAll |= (uint16_t)v; }
+    const int16_t* w0 = refAtCtu + (ptrdiff_t)refStride * lty + ltx;
+    for (int r = 0; r < side; ++r) {
+        const int16_t* src = w0 + (ptrdiff_t)r * refStride;
+        int16_t* dst = hw + (size_t)r * wp;
+        for (int q = 0; q < side; ++q) { dst[q] = src[q]; orAll |= (uint16_t)src[q]; }
+        for (int q = side; q < wp; ++q) dst[q] = 0;
+    }
+    const bool eight = (orAll & 0xFF00u) == 0;
+    const int elem = eight ? 1 : 2;
+    if (eight) {                                      // narrow in place on the host staging (front to back is safe)
+        uint8_t* hc8 = reinterpret_cast<uint8_t*>(hc);
+        for (int i = 0; i < 4096; ++i) hc8[i] = (uint8_t)hc[i];
+        uint8_t* hw8 = reinterpret_cast<uint8_t*>(hw);
+        for (size_t i = 0; i < (size_t)side * wp; ++i) hw8[i] = (uint8_t)hw[i];
+    }
+    CU_TRY(c, cudaMemcpyAsync(c->dCurBlk, hc, 4096 * elem, cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(c, cudaMemcpyAsync(c->dWin, hw, (size_t)side * wp * elem, cudaMemcpyHostToDevice, c->stream));
+    c->hJobs[0] = hmme_job{0, 0, ltx, lty};
+    CU_TRY(c, cudaMemcpyAsync(c->dJobs, c->hJobs, sizeof(hmme_job), cudaMemcpyHostToDevice, c->stream));
+    // virtual origin: sample (ctu + lt) is element 0 of the staged window
+    const char* refOrigin = static_cast<const char*>(c->dWin) - ((ptrdiff_t)lty * wp + ltx) * elem;
+    rc = enqueue_search(c, c->dCurBlk, elem, 64, refOrigin, elem, wp, c->dWin, static_cast<const char*>(c->dWin) + (size_t)side * wp * elem + 64, 1, range);
+    if (rc != HMME_OK) return rc;
+    return fetch(c, 1, X, Y, sad, cost);
+}
+
+int hmme_plane_alloc(hmme_ctx* c, hmme_plane* out, int elemBytes, int width, int height, int marginX, int marginY) {
+    if (!c || !out || (elemBytes != 1 && elemBytes != 2) || width <= 0 || height <= 0 || marginX < 0 || marginY < 0)
+        return fail(c, HMME_ERR_ARG, "hmme_plane_alloc: bad argument");
+    CU_TRY(c, cudaSetDevice(c->device));
+    hmme_plane p{};
+    p.elemBytes = elemBytes; p.width = width; p.height = height; p.marginX = marginX; p.marginY = marginY;
+    p.pitch = (width + 2 * marginX + 15) & ~15;       // 16-element pitch keeps every row 16-byte aligned (TMA-ready)
+    CU_TRY(c, cudaMalloc(&p.base, plane_elems(&p) * elemBytes + 64));
+    *out = p;
+    return HMME_OK;
+}
+
+int hmme_plane_free(hmme_ctx* c, hmme_plane* p) {
+    if (!c || !p) return HMME_ERR_ARG;
+    CU_TRY(c, cudaSetDevice(c->device));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    if (p->base) CU_TRY(c, cudaFree(p->base));
+    p->base = nullptr;
+    return HMME_OK;
+}
+
+int hmme_plane_upload_s16(hmme_ctx* c, const hmme_plane* p, const int16_t* hostOrigin, int hostStride) {
+    if (!c || !hostOrigin) return fail(c, HMME_ERR_ARG, "hmme_plane_upload_s16: null pointer");
+    int rc = check_plane(c, p, "upload target");
+    if (rc != HMME_OK) return rc;
+    CU_TRY(c, cudaSetDevice(c->device));
+    const int rows = p->height + 2 * p->marginY, cols = p->width + 2 * p->marginX;
+    const int16_t* src = hostOrigin - (ptrdiff_t)p->marginY * hostStride - p->marginX;
+    if (p->elemBytes == 2) {
+        CU_TRY(c, cudaMemcpy2DAsync(p->base, (size_t)p->pitch * 2, src, (size_t)hostStride * 2, (size_t)cols * 2, rows, cudaMemcpyHostToDevice, c->stream));
+        CU_TRY(c, cudaStreamSynchronize(c->stream));
+        return HMME_OK;
+    }
+    const size_t n = plane_elems(p);
+    if (c->stageElems < n) {
+        CU_TRY(c, cudaStreamSynchronize(c->stream));
+        if (c->dStage) cudaFree(c->dStage);
+        c->dStage = nullptr; c->stageElems = 0;
+        CU_TRY(c, cudaMalloc(&c->dStage, n * 2));
+        c->stageElems = n;
+    }
+    CU_TRY(c, cudaMemsetAsync(c->dStage, 0, n * 2, c->stream));      // pitch padding columns must read as in-range samples
+    CU_TRY(c, cudaMemsetAsync(c->dFlag, 0, sizeof(int), c->stream));
+    CU_TRY(c, cudaMemcpy2DAsync(c->dStage, (size_t)p->pitch * 2, src, (size_t)hostStride * 2, (size_t)cols * 2, rows, cudaMemcpyHostToDevice, c->stream));
+    me_narrow_kernel<<<(unsigned)((n / 8 + 255) / 256 + 1), 256, 0, c->stream>>>(c->dStage, static_cast<uint8_t*>(p->base), n, c->dFlag);
+    c->launches += 1;
+    CU_TRY(c, cudaMemcpyAsync(c->hFlag, c->dFlag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    if (*c->hFlag) return fail(c, HMME_ERR_CONTENT, "plane declared 8-bit holds samples outside [0,255]; allocate it with elemBytes=2");
+    return HMME_OK;
+}
+
+int hmme_plane_upload_u8(hmme_ctx* c, const hmme_plane* p, const uint8_t* hostOrigin, int hostStride) {
+    if (!c || !hostOrigin) return fail(c, HMME_ERR_ARG, "hmme_plane_upload_u8: null pointer");
+    int rc = check_plane(c, p, "upload target");
+    if (rc != HMME_OK) return rc;
+    if (p->elemBytes != 1) return fail(c, HMME_ERR_ARG, "hmme_plane_upload_u8 needs an 8-bit plane");
+    CU_TRY(c, cudaSetDevice(c->device));
+    const int rows = p->height + 2 * p->marginY, cols = p->width + 2 * p->marginX;
+    const uint8_t* src = hostOrigin - (ptrdiff_t)p->marginY * hostStride - p->marginX;
+    CU_TRY(c, cudaMemcpy2DAsync(p->base, (size_t)p->pitch, src, (size_t)hostStride, (size_t)cols, rows, cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    return HMME_OK;
+}
+
+int hmme_search_frame_async(hmme_ctx* c, const hmme_plane* cur, const hmme_plane* ref, const hmme_job* jobs, int njobs, int range) {
+    if (!c) return HMME_ERR_ARG;
+    if (!jobs || njobs <= 0) return fail(c, HMME_ERR_ARG, "hmme_search_frame: no jobs");
+    if (range < 0 || range > 1024) return fail(c, HMME_ERR_RANGE, "search range out of [0,1024]");
+    int rc = check_plane(c, cur, "current");
+    if (rc == HMME_OK) rc = check_plane(c, ref, "reference");
+    if (rc == HMME_OK) rc = check_jobs(c, cur, ref, jobs, njobs, range);
+    if (rc != HMME_OK) return rc;
+    CU_TRY(c, cudaSetDevice(c->device));
+    rc = ensure_jobs(c, (size_t)njobs);
+    if (rc != HMME_OK) return rc;
+    CU_TRY(c, cudaStreamSynchronize(c->stream));        // the pinned job staging may still be in flight from the previous call
+    std::memcpy(c->hJobs, jobs, (size_t)njobs * sizeof(hmme_job));
+    CU_TRY(c, cudaMemcpyAsync(c->dJobs, c->hJobs, (size_t)njobs * sizeof(hmme_job), cudaMemcpyHostToDevice, c->stream));
+    const char* refLo = static_cast<const char*>(ref->base);
+    return enqueue_search(c, origin_ptr(cur), cur->elemBytes, cur->pitch, origin_ptr(ref), ref->elemBytes, ref->pitch, refLo,
+                          refLo + plane_elems(ref) * ref->elemBytes, njobs, range);
+}
+
+int hmme_fetch_results(hmme_ctx* c, int njobs, int32_t* X, int32_t* Y, uint32_t* sad, uint32_t* cost) {
+    if (!c || njobs <= 0 || (size_t)njobs > c->jobCap) return fail(c, HMME_ERR_ARG, "hmme_fetch_results: bad job count");
+    CU_TRY(c, cudaSetDevice(c->device));
+    return fetch(c, njobs, X, Y, sad, cost);
+}
+
+int hmme_search_frame(hmme_ctx* c, const hmme_plane* cur, const hmme_plane* ref, const hmme_job* jobs, int njobs, int range,
+                      int32_t* X, int32_t* Y, uint32_t* sad, uint32_t* cost) {
+    if (!c) return HMME_ERR_ARG;
+    if (!X || !Y || !sad) return fail(c, HMME_ERR_ARG, "hmme_search_frame: null output");
+    int rc = hmme_search_frame_async(c, cur, ref, jobs, njobs, range);
+    if (rc != HMME_OK) return rc;
+    return fetch(c, njobs, X, Y, sad, cost);
+}
+
+int hmme_sync(hmme_ctx* c) {
+    if (!c) return HMME_ERR_ARG;
+    CU_TRY(c, cudaSetDevice(c->device));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    return HMME_OK;
+}
+
+int hmme_last_kernel_ms(hmme_ctx* c, float* ms) {
+    if (!c || !ms) return HMME_ERR_ARG;
+    if (!c->evValid) return fail(c, HMME_ERR_ARG, "no search has been enqueued yet");
+    CU_TRY(c, cudaEventSynchronize(c->ev1));
+    CU_TRY(c, cudaEventElapsedTime(ms, c->ev0, c->ev1));
+    return HMME_OK;
+}
+
+uint64_t hmme_kernel_launches(hmme_ctx* c) { return c ? c->launches : 0; }
+
+int hmme_measure_int_alu_peak(hmme_ctx* c, double* laneOpsPerSec, double* lanesPerClkPerSm, double* smMhz) {
+    if (!c) return HMME_ERR_ARG;
+    CU_TRY(c, cudaSetDevice(c->device));
+    const int sms = c->prop.multiProcessorCount, threads = 1024, iters = 4000;
+    uint32_t* dOut = nullptr; unsigned long long* dCyc = nullptr;
+    CU_TRY(c, cudaMalloc(&dOut, (size_t)sms * threads * 4));
+    CU_TRY(c, cudaMalloc(&dCyc, (size_t)sms * 8));
+    me_alu_probe_kernel<<<sms, threads, 0, c->stream>>>(dOut, dCyc, 64, 1u);          // warm-up
+    float best = 1e30f; double cycMed = 0;
+    for (int rep = 0; rep < 3; ++rep) {
+        CU_TRY(c, cudaEventRecord(c->ev0, c->stream));
+        me_alu_probe_kernel<<<sms, threads, 0, c->stream>>>(dOut, dCyc, iters, 3u + rep);
+        CU_TRY(c, cudaEventRecord(c->ev1, c->stream));
+        CU_TRY(c, cudaEventSynchronize(c->ev1));
+        float ms = 0; CU_TRY(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+        if (ms < best) {
+            best = ms;
+            std::vector<unsigned long long> cyc(sms);
+            CU_TRY(c, cudaMemcpy(cyc.data(), dCyc, (size_t)sms * 8, cudaMemcpyDeviceToHost));
+            std::sort(cyc.begin(), cyc.end());
+            cycMed = (double)cyc[sms / 2];
+        }
+    }
+    c->launches += 4; c->evValid = false;
+    cudaFree(dOut); cudaFree(dCyc);
+    const double opsPerCta = (double)threads * 8 * 32 * iters;
+    if (laneOpsPerSec) *laneOpsPerSec = opsPerCta * sms / (best * 1e-3);
+    if (lanesPerClkPerSm) *lanesPerClkPerSm = opsPerCta / cycMed;
+    if (smMhz) *smMhz = cycMed / (best * 1e-3) / 1e6;
+    return HMME_OK;
+}
+
+int hmme_partition_rect(int index, int* x, int* y, int* w, int* h) {
+    if (index < 0 || index >= HMME_NPARTS) return HMME_ERR_ARG;
+    const PartRect r = part_rect(index);
+    if (x) *x = r.x;
+    if (y) *y = r.y;
+    if (w) *w = r.w;
+    if (h) *h = r.h;
+    return HMME_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,190 @@
+// me_generic_kernel.cuh -- exact kernel for everything the packed 8-bit kernel does not take:
+// 16-bit "current" blocks (bi-prediction refinement: cur = 2*org - pred in [-255, 510],
+// /root/reference/source/Lib/TLibEncoder/TEncSearch.cpp:3702-3712, range 4), planes that are not
+// 8-bit, and the support kernels (narrowing upload, result initialisation, finalisation).
+//
+// One CTA handles one job x one contiguous chunk of candidates in scan order.  Per candidate, 256 threads
+// compute the 256 4x4 SADs (exact |a-b| on 16-bit samples like OpenCL abs_diff, sad.cl:171-186), a 17x17
+// integral image is built in shared memory, and each thread keeps the running 64-bit arg-min key of up to
+// three partitions (rectangle sums from the integral image).  Results merge through the same
+// atomicMin(best[job][593]) as the fast kernel, so both kernels share the finalize step.
+#pragma once
+#include "me_common.cuh"
+
+namespace hmme {
+
+constexpr int kGenThreads = 256;
+constexpr int kGenBatch = 4;     // candidates per shared-memory round
+
+struct GenericParams {
+    const void* cur;           // picture sample (0,0)
+    const void* ref;
+    long long curPitch, refPitch;   // elements
+    const int4* jobs;
+    unsigned long long* best;
+    uint32_t lambda;
+    int W;                     // 2R+1
+    int chunk;                 // candidates per CTA
+    int nChunks;
+};
+
+template <typename T> __device__ __forceinline__ int ld_px(const void* base, long long idx) {
+    return (int)reinterpret_cast<const T*>(base)[idx];
+}
+
+template <typename TC, typename TR>
+__global__ void __launch_bounds__(kGenThreads) me_generic_kernel(const GenericParams p) {
+    __shared__ int sCur[64 * 64];
+    __shared__ uint32_t sA[kGenBatch][16][16];
+    __shared__ uint32_t sB[kGenBatch][16][16];
+    __shared__ uint32_t sII[kGenBatch][17][17];
+    __shared__ uint32_t sMvc[kGenBatch];
+
+    const int tid = threadIdx.x;
+    const int job = blockIdx.x / p.nChunks, chunkId = blockIdx.x - job * p.nChunks;
+    const int4 jb = p.jobs[job];
+    const int nCand = p.W * p.W;
+    const int c0 = chunkId * p.chunk, c1 = min(nCand, c0 + p.chunk);
+
+    for (int idx = tid; idx < 4096; idx += kGenThreads)
+        sCur[idx] = ld_px<TC>(p.cur, (long long)(jb.y + (idx >> 6)) * p.curPitch + jb.x + (idx & 63));
+    for (int idx = tid; idx < kGenBatch * 17 * 17; idx += kGenThreads) (&sII[0][0][0])[idx] = 0;
+
+    // up to three partitions per thread: corners in 4x4 units
+    int px0[3], py0[3], px1[3], py1[3];
+    unsigned long long best[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int part = tid + k * kGenThreads;
+        const PartRect r = part_rect(part < HMME_NPARTS ? part : 0);
+        px0[k] = r.x >> 2; py0[k] = r.y >> 2; px1[k] = (r.x + r.w) >> 2; py1[k] = (r.y + r.h) >> 2;
+        best[k] = kNoWinner;
+    }
+    __syncthreads();
+
+    const int bi = tid & 15, bj = tid >> 4;
+    const long long refBase = (long long)(jb.y + jb.w) * p.refPitch + (jb.x + jb.z);   // window origin, linear
+    for (int cb = c0; cb < c1; cb += kGenBatch) {
+        // 4x4 SADs
+#pragma unroll
+        for (int n = 0; n < kGenBatch; ++n) {
+            const int c = cb + n;
+            uint32_t s = 0;
+            if (c < c1) {
+                const int y = c / p.W, x = c - y * p.W;
+                const long long o = refBase + (long long)(y + 4 * bj) * p.refPitch + x + 4 * bi;
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int d = sCur[(4 * bj + r) * 64 + 4 * bi + q] - ld_px<TR>(p.ref, o + r * p.refPitch + q);
+                        s += (uint32_t)(d < 0 ? -d : d);
+                    }
+                if (tid == 0) sMvc[n] = mv_cost(p.lambda, x + jb.z, y + jb.w);
+            }
+            sA[n][bj][bi] = s;
+        }
+        __syncthreads();
+        // row prefix
+#pragma unroll
+        for (int n = 0; n < kGenBatch; ++n) {
+            uint32_t s = 0;
+            for (int i = 0; i <= bi; ++i) s += sA[n][bj][i];
+            sB[n][bj][bi] = s;
+        }
+        __syncthreads();
+        // column prefix -> integral image (row/column 0 stay zero)
+#pragma unroll
+        for (int n = 0; n < kGenBatch; ++n) {
+            uint32_t s = 0;
+            for (int j = 0; j <= bj; ++j) s += sB[n][j][bi];
+            sII[n][bj + 1][bi + 1] = s;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int n = 0; n < kGenBatch; ++n) {
+            const int c = cb + n;
+            if (c < c1) {
+                const uint32_t mvc = sMvc[n];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const uint32_t s = sII[n][py1[k]][px1[k]] - sII[n][py0[k]][px1[k]] - sII[n][py1[k]][px0[k]] + sII[n][py0[k]][px0[k]];
+                    const unsigned long long key = ((unsigned long long)(uint32_t)(s + mvc) << 32) | (uint32_t)c;
+                    best[k] = key < best[k] ? key : best[k];
+                }
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int part = tid + k * kGenThreads;
+        if (part < HMME_NPARTS && best[k] != kNoWinner) atomicMin(p.best + (size_t)job * HMME_NPARTS + part, best[k]);
+    }
+}
+
+// best[] <- "no winner" (TEncOpenCL.cpp:366-392: minSad = UINT_MAX, X = Y = 0)
+__global__ void me_init_kernel(unsigned long long* best, size_t n) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i < n) best[i] = kNoWinner;
+}
+
+// key -> X, Y, sad (ruiCosts), cost (minSad); outputs are four planes of [njobs][593]
+__global__ void me_finalize_kernel(const unsigned long long* best, const int4* jobs, int njobs, int W, uint32_t lambda,
+                                   int32_t* X, int32_t* Y, uint32_t* sad, uint32_t* cost) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= njobs * HMME_NPARTS) return;
+    const unsigned long long key = best[i];
+    if (key == kNoWinner) { X[i] = 0; Y[i] = 0; sad[i] = 0; cost[i] = 0xFFFFFFFFu; return; }
+    const int4 jb = jobs[i / HMME_NPARTS];
+    const uint32_t c = (uint32_t)(key >> 32), g = (uint32_t)key;
+    const int y = (int)(g / (uint32_t)W), x = (int)(g - (uint32_t)y * (uint32_t)W);
+    const int mvx = x + jb.z, mvy = y + jb.w;
+    X[i] = mvx; Y[i] = mvy; cost[i] = c; sad[i] = c - mv_cost(lambda, mvx, mvy);
+}
+
+// int16 -> uint8 narrowing of a whole padded plane with a content check (the reference path is only
+// defined for 8-bit internal depth); *flag != 0 afterwards means out-of-range samples.
+__global__ void me_narrow_kernel(const int16_t* __restrict__ src, uint8_t* __restrict__ dst, size_t n, int* flag) {
+    size_t i = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) * 8;
+    if (i >= n) return;
+    bool bad = false;
+    if (i + 8 <= n && ((reinterpret_cast<uintptr_t>(src + i) & 15) == 0) && ((reinterpret_cast<uintptr_t>(dst + i) & 7) == 0)) {
+        const uint4 v = *reinterpret_cast<const uint4*>(src + i);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        uint32_t lo = 0, hi = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            bad |= (w[k] & 0xFF00FF00u) != 0;
+            const uint32_t two = (w[k] & 0xFFu) | ((w[k] >> 8) & 0xFF00u);
+            if (k < 2) lo |= two << (16 * k); else hi |= two << (16 * (k - 2));
+        }
+        *reinterpret_cast<uint2*>(dst + i) = make_uint2(lo, hi);
+    } else {
+        for (size_t k = i; k < n && k < i + 8; ++k) { const int s = src[k]; bad |= (s < 0 || s > 255); dst[k] = (uint8_t)s; }
+    }
+    if (bad) atomicOr(flag, 1);
+}
+
+// Integer-ALU issue-rate probe: a dependent-free stream of VABSDIFF4.U8.ACC (the kernel's dominant ALU
+// instruction); lanes/clk/SM from clock64, SM MHz from clock64 vs the event time.
+__global__ void __launch_bounds__(1024) me_alu_probe_kernel(uint32_t* out, unsigned long long* cyc, int iters, uint32_t seed) {
+    uint32_t a[8], b = seed * 0x9E3779B9u + threadIdx.x, c = seed ^ 0x5bd1e995u;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = threadIdx.x * 31 + k + seed;
+    const unsigned long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int s = 0; s < 32; ++s)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) asm volatile("vabsdiff4.u32.u32.u32.add %0, %1, %2, %0;" : "+r"(a[k]) : "r"(b), "r"(c));
+    }
+    const unsigned long long t1 = clock64();
+    uint32_t r = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r ^= a[k];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = r;
+    if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+}
+
+}  // namespace hmme

@@ -1,0 +1,338 @@
+// me_u8_kernel.cuh -- the hot kernel: whole-CTU integer-pel full search on 8-bit content, sm_100a.
+//
+// What it replaces: the reference's (2R+1)^2 x {calcSAD_AMP, compareSAD} launch pairs per CTU
+// (/root/reference/source/Lib/TLibEncoder/TEncOpenCL.cpp:312-333, /root/reference/cl/sad.cl:141-408).
+// Here ONE launch covers every (CTU, reference) job of a frame; nothing like tempSad touches HBM.
+//
+// Decomposition
+//   CTA (512 threads)      = one job x one candidate tile (tw x th candidates, tw*th <= 2048)
+//   warp w                 = 16x16 luma block b = w of the CTU (bx = 16*(w&3), by = 16*(w>>2))
+//   lane, per round        = one "unit": candidate column x, YB consecutive candidate rows
+// Block phase (per round, per thread): YB candidates x 64 VABSDIFF4.U8.ACC build the 16 4x4 SADs of
+// the block; every reference word fetched from shared memory serves up to YB candidates (vertical
+// reuse in registers).  The 33 partitions that live inside a 16x16 block (8x4, 4x8, 8x8, 16x8, 8x16,
+// 16x16 and the 8 AMP shapes) are built hierarchically with 37 adds and folded into 33 thread-private
+// running keys with ONE VIADDMNMX each: all sums are kept pre-shifted by 11 bits, so
+//   key = (sad << 11) + ((mvcost << 11) | candidateIndexInTile),  best = min(best, key)
+// is a single add-min and the low bits reproduce the reference's first-in-scan-order tie-break.
+// Upper phase (per round): the four 8x8 sums and the 16x16 sum of every (candidate, block) go through
+// a 20 KB shared-memory record array; 5 x (32*YB) threads (4 quadrant roles + one 64x64 role) build
+// the 65 partitions of the 32x32 and 64x64 levels the same way.
+// Tile end: warp-wide CREDUX.MIN per key, conversion to the global 64-bit key (cost<<32 | y*(2R+1)+x)
+// and one atomicMin per (warp, partition) into best[job][593]; a tiny finalize kernel decodes MVs.
+//
+// Reference window staging: four byte-shifted copies of the tile's window (copy k, word j = bytes
+// 4j+k..4j+k+3) so that 32 lanes with consecutive candidate x read 32 distinct banks with plain
+// LDS.32; copies are placed 8 banks apart.  Addressing of the source plane is linear
+// (row*pitch + col), which is exactly the reference's pelSearchArray[j + i*iRefStride] including its
+// row-wrap quirk.
+#pragma once
+#include "me_common.cuh"
+
+namespace hmme {
+
+constexpr int kFastThreads = 512;
+constexpr int kIdxBits = 11;                  // candidates per tile <= 2048
+constexpr int kMaxTileCands = 1 << kIdxBits;
+constexpr int kRecWords = 52;                 // upper-phase record: 32 (8x8 pairs, u16) + 16 (16x16<<11) + 1 (key base) + pad;
+                                              // 52 = 20 mod 32 keeps 8-lane LDS.128 phases conflict-free
+constexpr uint32_t kInvalidBlockKeyBase = 0xF0000000u;   // block sums << 11 stay below 2^27: no wrap, never wins
+constexpr uint32_t kInvalidSlot = 0xFFFFFFFFu;
+
+struct FastParams {
+    const uint8_t* cur;        // picture sample (0,0) of the current plane
+    const uint8_t* ref;        // picture sample (0,0) of the reference plane
+    const uint8_t* refLo;      // first addressable byte of the reference allocation (16B aligned)
+    const uint8_t* refHi;      // one past the last addressable byte
+    long long curPitch, refPitch;
+    const int4* jobs;          // {ctuX, ctuY, ltx, lty}
+    unsigned long long* best;  // [njobs][593]
+    uint32_t lambda;
+    int W;                     // 2R+1 candidates per axis
+    int tw, th;                // nominal tile size in candidates
+    int nTx, nTy;
+    int pw;                    // window row pitch in words
+    int cs;                    // copy stride in words (== 8 mod 32)
+};
+
+__host__ __device__ inline int fast_win_rows(int th, int yb) { return ((th + yb - 1) / yb) * yb + 63; }
+__host__ __device__ inline int fast_pw(int tw) { return ((tw - 1) >> 2) + 16; }
+
+// partition index of block-level key k (0..32) for block b
+__device__ __forceinline__ int block_part_index(int b, int k) {
+    const int bxi = b & 3, byi = b >> 2, o = byi * 4 + bxi;
+    if (k < 8)  return (4 * byi + (k >> 1)) * 8 + 2 * bxi + (k & 1);                   // 8x4
+    if (k < 16) return 128 + (2 * byi + ((k - 8) >> 2)) * 16 + 4 * bxi + ((k - 8) & 3);  // 4x8
+    if (k < 20) return 384 + (2 * byi + ((k - 16) >> 1)) * 8 + 2 * bxi + ((k - 16) & 1); // 8x8
+    if (k < 28) return 256 + (k - 20) * 16 + o;                                        // 16x4 U/D, 16x12 U/D, 4x16 L/R, 12x16 L/R
+    if (k < 30) return 448 + (2 * byi + (k - 28)) * 4 + bxi;                           // 16x8
+    if (k < 32) return 480 + byi * 8 + 2 * bxi + (k - 30);                             // 8x16
+    return 544 + o;                                                                    // 16x16
+}
+// partition index of quadrant-level key k (0..12) for quadrant q
+__device__ __forceinline__ int quad_part_index(int q, int k) {
+    const int qx = q & 1, qy = q >> 1;
+    if (k < 8)  return 512 + k * 4 + q;                   // 32x8 U/D, 32x24 U/D, 8x32 L/R, 24x32 L/R
+    if (k < 10) return 560 + (2 * qy + (k - 8)) * 2 + qx; // 32x16
+    if (k < 12) return 568 + qy * 4 + 2 * qx + (k - 10);  // 16x32
+    return 584 + q;                                       // 32x32
+}
+// partition index of CTU-level key k (0..12)
+__device__ __forceinline__ int ctu_part_index(int k) {
+    return k < 8 ? 576 + k : 588 + (k - 8);               // AMP 576..583, 64x32 588/589, 32x64 590/591, 64x64 592
+}
+
+__device__ __forceinline__ uint32_t addmin(uint32_t sum, uint32_t base, uint32_t best) {
+    return __viaddmin_u32(sum, base, best);               // one VIADDMNMX.U32: min(sum + base, best)
+}
+
+// Fold one candidate's 16 4x4 SADs (a[t][i], row-strip t, column i of the 16x16 block) into the 33 running keys
+// and hand the 8x8 / 16x16 sums to the upper levels.
+__device__ __forceinline__ void emit_block(const uint32_t (&a)[4][4], uint32_t kb, uint32_t (&best)[33],
+                                           uint32_t* rec, int b, bool writeBase, uint32_t recBase) {
+    uint32_t s[4][4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) s[t][i] = a[t][i] << kIdxBits;
+    uint32_t h[4][2], v[2][4], e[2][2], q[4], c[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        h[t][0] = s[t][0] + s[t][1];
+        h[t][1] = s[t][2] + s[t][3];
+        best[2 * t] = addmin(h[t][0], kb, best[2 * t]);
+        best[2 * t + 1] = addmin(h[t][1], kb, best[2 * t + 1]);
+        q[t] = h[t][0] + h[t][1];
+    }
+#pragma unroll
+    for (int vv = 0; vv < 2; ++vv)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            v[vv][i] = s[2 * vv][i] + s[2 * vv + 1][i];
+            best[8 + vv * 4 + i] = addmin(v[vv][i], kb, best[8 + vv * 4 + i]);
+        }
+#pragma unroll
+    for (int vv = 0; vv < 2; ++vv)
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+            e[vv][hh] = h[2 * vv][hh] + h[2 * vv + 1][hh];
+            best[16 + vv * 2 + hh] = addmin(e[vv][hh], kb, best[16 + vv * 2 + hh]);
+        }
+    const uint32_t top = q[0] + q[1], bot = q[2] + q[3];
+    best[20] = addmin(q[0], kb, best[20]);                 // 16x4  (2NxnU part 0)
+    best[21] = addmin(q[3], kb, best[21]);                 // 16x4  (2NxnD part 1)
+    best[22] = addmin(top + q[2], kb, best[22]);           // 16x12 rows 0..11
+    best[23] = addmin(q[1] + bot, kb, best[23]);           // 16x12 rows 4..15
+#pragma unroll
+    for (int i = 0; i < 4; ++i) c[i] = v[0][i] + v[1][i];
+    const uint32_t left = c[0] + c[1], right = c[2] + c[3];
+    best[24] = addmin(c[0], kb, best[24]);                 // 4x16  (nLx2N part 0)
+    best[25] = addmin(c[3], kb, best[25]);                 // 4x16  (nRx2N part 1)
+    best[26] = addmin(left + c[2], kb, best[26]);          // 12x16 cols 0..11
+    best[27] = addmin(c[1] + right, kb, best[27]);         // 12x16 cols 4..15
+    best[28] = addmin(top, kb, best[28]);                  // 16x8
+    best[29] = addmin(bot, kb, best[29]);
+    best[30] = addmin(left, kb, best[30]);                 // 8x16
+    best[31] = addmin(right, kb, best[31]);
+    const uint32_t all = top + bot;
+    best[32] = addmin(all, kb, best[32]);                  // 16x16
+    // upper-level hand-over: 8x8 sums as u16 pairs (<= 16320 each), 16x16 sum pre-shifted
+    uint2 pk;
+    pk.x = (e[0][0] >> kIdxBits) | (e[0][1] << (16 - kIdxBits));
+    pk.y = (e[1][0] >> kIdxBits) | (e[1][1] << (16 - kIdxBits));
+    *reinterpret_cast<uint2*>(rec + 2 * b) = pk;
+    rec[32 + b] = all;
+    if (writeBase) rec[48] = recBase;
+}
+
+__device__ __forceinline__ void emit_quadrant(const uint32_t* rec, int q, uint32_t (&ub)[13]) {
+    const uint32_t kb = rec[48];
+    if (kb == kInvalidSlot) return;
+    const int b0 = 8 * (q >> 1) + 2 * (q & 1);
+    const uint4 T = *reinterpret_cast<const uint4*>(rec + 2 * b0);        // blocks b0, b0+1 : {e00|e01, e10|e11} each
+    const uint4 B = *reinterpret_cast<const uint4*>(rec + 2 * (b0 + 4));  // blocks b0+4, b0+5
+    // rows of 8x8 sums across the 32-wide quadrant, still packed (each half <= 32640)
+    const uint32_t r0 = T.x + T.z, r1 = T.y + T.w, r2 = B.x + B.z, r3 = B.y + B.w;
+    const uint32_t R0 = ((r0 & 0xFFFFu) + (r0 >> 16)) << kIdxBits, R1 = ((r1 & 0xFFFFu) + (r1 >> 16)) << kIdxBits;
+    const uint32_t R2 = ((r2 & 0xFFFFu) + (r2 >> 16)) << kIdxBits, R3 = ((r3 & 0xFFFFu) + (r3 >> 16)) << kIdxBits;
+    // columns: packed sums over the four 8-row strips (each half <= 65280)
+    const uint32_t cl = T.x + T.y + B.x + B.y, cr = T.z + T.w + B.z + B.w;
+    const uint32_t C0 = (cl & 0xFFFFu) << kIdxBits, C1 = (cl >> 16) << kIdxBits;
+    const uint32_t C2 = (cr & 0xFFFFu) << kIdxBits, C3 = (cr >> 16) << kIdxBits;
+    const uint32_t top = R0 + R1, bot = R2 + R3, left = C0 + C1, right = C2 + C3;
+    ub[0] = addmin(R0, kb, ub[0]);                 // 32x8  (2NxnU part 0)
+    ub[1] = addmin(R3, kb, ub[1]);                 // 32x8  (2NxnD part 1)
+    ub[2] = addmin(top + R2, kb, ub[2]);           // 32x24 rows 0..23
+    ub[3] = addmin(R1 + bot, kb, ub[3]);           // 32x24 rows 8..31
+    ub[4] = addmin(C0, kb, ub[4]);                 // 8x32
+    ub[5] = addmin(C3, kb, ub[5]);
+    ub[6] = addmin(left + C2, kb, ub[6]);          // 24x32 cols 0..23
+    ub[7] = addmin(C1 + right, kb, ub[7]);         // 24x32 cols 8..31
+    ub[8] = addmin(top, kb, ub[8]);                // 32x16
+    ub[9] = addmin(bot, kb, ub[9]);
+    ub[10] = addmin(left, kb, ub[10]);             // 16x32
+    ub[11] = addmin(right, kb, ub[11]);
+    ub[12] = addmin(top + bot, kb, ub[12]);        // 32x32
+}
+
+__device__ __forceinline__ void emit_ctu(const uint32_t* rec, uint32_t (&ub)[13]) {
+    const uint32_t kb = rec[48];
+    if (kb == kInvalidSlot) return;
+    uint4 m[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) m[r] = *reinterpret_cast<const uint4*>(rec + 32 + 4 * r);   // 16x16 sums << 11, block row r
+    uint32_t R[4], C[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) R[r] = (m[r].x + m[r].y) + (m[r].z + m[r].w);
+    C[0] = (m[0].x + m[1].x) + (m[2].x + m[3].x);
+    C[1] = (m[0].y + m[1].y) + (m[2].y + m[3].y);
+    C[2] = (m[0].z + m[1].z) + (m[2].z + m[3].z);
+    C[3] = (m[0].w + m[1].w) + (m[2].w + m[3].w);
+    const uint32_t top = R[0] + R[1], bot = R[2] + R[3], left = C[0] + C[1], right = C[2] + C[3];
+    ub[0] = addmin(R[0], kb, ub[0]);               // 64x16 (2NxnU part 0)
+    ub[1] = addmin(R[3], kb, ub[1]);               // 64x16 (2NxnD part 1)
+    ub[2] = addmin(top + R[2], kb, ub[2]);         // 64x48 rows 0..47
+    ub[3] = addmin(R[1] + bot, kb, ub[3]);         // 64x48 rows 16..63
+    ub[4] = addmin(C[0], kb, ub[4]);               // 16x64
+    ub[5] = addmin(C[3], kb, ub[5]);
+    ub[6] = addmin(left + C[2], kb, ub[6]);        // 48x64 cols 0..47
+    ub[7] = addmin(C[1] + right, kb, ub[7]);       // 48x64 cols 16..63
+    ub[8] = addmin(top, kb, ub[8]);                // 64x32
+    ub[9] = addmin(bot, kb, ub[9]);
+    ub[10] = addmin(left, kb, ub[10]);             // 32x64
+    ub[11] = addmin(right, kb, ub[11]);
+    ub[12] = addmin(top + bot, kb, ub[12]);        // 64x64
+}
+
+// tile key -> global key, one atomicMin into best[job][part]
+__device__ __forceinline__ void publish(unsigned long long* bestJob, int part, uint32_t key, int twA, int x0, int y0, int W) {
+    if (key == 0xFFFFFFFFu) return;
+    const uint32_t cost = key >> kIdxBits, tidx = key & (kMaxTileCands - 1);
+    const uint32_t ty = tidx / (uint32_t)twA, tx = tidx - ty * (uint32_t)twA;
+    const uint32_t gidx = (uint32_t)(y0 + (int)ty) * (uint32_t)W + (uint32_t)(x0 + (int)tx);
+    atomicMin(bestJob + part, ((unsigned long long)cost << 32) | gidx);
+}
+
+template <int YB>
+__global__ void __launch_bounds__(kFastThreads, 1) me_u8_tile_kernel(const FastParams p) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    constexpr int SLOTS = 32 * YB;
+    uint32_t* sWin = smem;                                  // 4 * cs
+    uint32_t* sCur = sWin + 4 * p.cs;                       // 64 rows x 16 words
+    uint32_t* sUp = sCur + 1024;                            // 2 x SLOTS x kRecWords
+    uint32_t* sBitsX = sUp + 2 * SLOTS * kRecWords;         // tw
+    uint32_t* sBitsY = sBitsX + ((p.tw + 3) & ~3);          // roundup(th, YB)
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tilesPerJob = p.nTx * p.nTy;
+    const int job = blockIdx.x / tilesPerJob, tile = blockIdx.x - job * tilesPerJob;
+    const int tiy = tile / p.nTx, tix = tile - tiy * p.nTx;
+    const int x0 = tix * p.tw, y0 = tiy * p.th;
+    const int twA = min(p.tw, p.W - x0), thA = min(p.th, p.W - y0);
+    const int nRG = (thA + YB - 1) / YB, nUnits = twA * nRG;
+    const int4 jb = p.jobs[job];
+
+    // ---- stage the reference window: 4 byte-shifted copies, linear source addressing
+    {
+        const int rows = nRG * YB + 63, pwl = fast_pw(twA);
+        const uint8_t* wbase = p.ref + (long long)(jb.y + jb.w + y0) * p.refPitch + (jb.x + jb.z + x0);
+        const uintptr_t lo = (uintptr_t)p.refLo, hi = ((uintptr_t)p.refHi - 4) & ~(uintptr_t)3;
+        for (int idx = tid; idx < rows * pwl; idx += kFastThreads) {
+            const int row = idx / pwl, j = idx - row * pwl;
+            const uintptr_t g = (uintptr_t)(wbase + (long long)row * p.refPitch + 4 * j);
+            const uint32_t a = (uint32_t)(g & 3);
+            const uintptr_t g0 = g - a;
+            const uint32_t w0 = *reinterpret_cast<const uint32_t*>(min(max(g0, lo), hi));
+            const uint32_t w1 = *reinterpret_cast<const uint32_t*>(min(max(g0 + 4, lo), hi));
+            const uint32_t w2 = *reinterpret_cast<const uint32_t*>(min(max(g0 + 8, lo), hi));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t s = a + k;
+                const uint32_t word = s < 4 ? __funnelshift_r(w0, w1, 8 * s) : __funnelshift_r(w1, w2, 8 * (s - 4));
+                sWin[k * p.cs + row * p.pw + j] = word;
+            }
+        }
+        const uint8_t* cbase = p.cur + (long long)jb.y * p.curPitch + jb.x;
+        for (int idx = tid; idx < 1024; idx += kFastThreads) {
+            const uint8_t* c = cbase + (long long)(idx >> 4) * p.curPitch + 4 * (idx & 15);
+            sCur[idx] = (uint32_t)c[0] | ((uint32_t)c[1] << 8) | ((uint32_t)c[2] << 16) | ((uint32_t)c[3] << 24);
+        }
+        for (int x = tid; x < twA; x += kFastThreads) sBitsX[x] = mv_bits(4 * (jb.z + x0 + x));
+        for (int y = tid; y < nRG * YB; y += kFastThreads) sBitsY[y] = mv_bits(4 * (jb.w + y0 + y));
+    }
+    __syncthreads();
+
+    const int b = warp, bxw = (b & 3) * 4, by = (b >> 2) * 16;
+    uint32_t best[33], ub[13];
+#pragma unroll
+    for (int k = 0; k < 33; ++k) best[k] = 0xFFFFFFFFu;
+#pragma unroll
+    for (int k = 0; k < 13; ++k) ub[k] = 0xFFFFFFFFu;
+    const int role = tid / SLOTS, slot = tid - role * SLOTS;   // upper phase: role 0..3 quadrant, 4 CTU level, >=5 idle
+
+    const int nRounds = (nUnits + 31) >> 5;
+    for (int round = 0; round < nRounds; ++round) {
+        const int u = round * 32 + lane;
+        const bool uvalid = u < nUnits;
+        const int uu = uvalid ? u : 0;
+        const int rg = uu / twA, ux = uu - rg * twA;
+        const uint32_t* wp = sWin + (ux & 3) * p.cs + (rg * YB + by) * p.pw + (ux >> 2) + bxw;
+        const uint32_t* cp = sCur + by * 16 + bxw;
+
+        uint32_t acc[YB][4][4];
+#pragma unroll
+        for (int j = 0; j < YB; ++j)
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[j][t][i] = 0;
+        uint4 cw[YB];
+#pragma unroll
+        for (int rho = 0; rho < 16 + YB - 1; ++rho) {
+            const uint32_t r0 = wp[rho * p.pw + 0], r1 = wp[rho * p.pw + 1], r2 = wp[rho * p.pw + 2], r3 = wp[rho * p.pw + 3];
+            if (rho < 16) cw[rho % YB] = *reinterpret_cast<const uint4*>(cp + rho * 16);
+#pragma unroll
+            for (int j = 0; j < YB; ++j) {
+                const int r = rho - j;                       // row of the block this reference row meets for candidate j
+                if (r >= 0 && r < 16) {
+                    const uint4 c = cw[r % YB];
+                    acc[j][r >> 2][0] = __vsadu4(c.x, r0) + acc[j][r >> 2][0];
+                    acc[j][r >> 2][1] = __vsadu4(c.y, r1) + acc[j][r >> 2][1];
+                    acc[j][r >> 2][2] = __vsadu4(c.z, r2) + acc[j][r >> 2][2];
+                    acc[j][r >> 2][3] = __vsadu4(c.w, r3) + acc[j][r >> 2][3];
+                }
+            }
+        }
+        uint32_t* recBuf = sUp + (round & 1) * (SLOTS * kRecWords);
+        const uint32_t bitsX = sBitsX[ux];
+#pragma unroll
+        for (int j = 0; j < YB; ++j) {
+            const int y = rg * YB + j;
+            const bool valid = uvalid && y < thA;
+            const uint32_t mvc = (uint32_t)(p.lambda * (bitsX + sBitsY[y])) >> 16;
+            const uint32_t kb = (mvc << kIdxBits) | (uint32_t)(y * twA + ux);
+            emit_block(acc[j], valid ? kb : kInvalidBlockKeyBase, best, recBuf + (j * 32 + lane) * kRecWords, b, b == 0,
+                       valid ? kb : kInvalidSlot);
+        }
+        __syncthreads();
+        if (role < 4) emit_quadrant(recBuf + slot * kRecWords, role, ub);
+        else if (role == 4) emit_ctu(recBuf + slot * kRecWords, ub);
+    }
+
+    // ---- tile end: warp arg-min per key, publish
+    unsigned long long* bestJob = p.best + (size_t)job * HMME_NPARTS;
+#pragma unroll
+    for (int k = 0; k < 33; ++k) {
+        const uint32_t m = __reduce_min_sync(0xFFFFFFFFu, best[k]);
+        if (lane == (k & 31)) publish(bestJob, block_part_index(b, k), m, twA, x0, y0, p.W);
+    }
+    if (role <= 4) {                                          // warp-uniform: SLOTS is a multiple of 32
+#pragma unroll
+        for (int k = 0; k < 13; ++k) {
+            const uint32_t m = __reduce_min_sync(0xFFFFFFFFu, ub[k]);
+            if (lane == k) publish(bestJob, role < 4 ? quad_part_index(role, k) : ctu_part_index(k), m, twA, x0, y0, p.W);
+        }
+    }
+}
+
+}  // namespace hmme

@@ -1,0 +1,117 @@
+/*
+ * hmme_b200.h -- C ABI of libhmme_b200.so: whole-CTU integer-pel block-matching motion estimation
+ * for HM-OpenCL's TEncOpenCL path, hand-written CUDA for sm_100a (B200).
+ *
+ * This is the drop-in boundary.  In the reference the "FFI" is the public
+ * surface of a compiled-in C++ class, /root/reference/source/Lib/TLibEncoder/TEncOpenCL.h:105-123;
+ * the replacement class (hm-opencl_b200/host/TEncOpenCL.{h,cpp}) keeps those signatures and calls
+ * the functions below.  Each entry point names the reference interface it replaces.
+ *
+ * Conventions: every function returns 0 on success and a negative hmme_status on failure;
+ * hmme_last_error() gives the message.  There is NO CPU fallback: without a usable sm_100 device
+ * hmme_create fails.  All calls are synchronous unless the name ends in _async; a context is used
+ * from one host thread at a time (the encoder is single-threaded, SURVEY.md section 8b "Threading").
+ *
+ * Result layout: 593 entries per (CTU, reference picture) job in the order of
+ * TComDataCU::getIndexBlock (TComDataCU.cpp:4676-6461): X/Y = integer-pel MV of the winner,
+ * sad = pure SAD at the winner (TEncOpenCL::getRuiCost), cost = SAD + MV-bit cost (minSad).
+ */
+#ifndef HMME_B200_H
+#define HMME_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HMME_NUM_CTU_PARTS 593 /* TypeDef.h:263 (AMP_ENC_SPEEDUP = 0) */
+#define HMME_CTU_SIZE 64       /* TEncSearch.cpp:3745 hard-codes the 64x64 2Nx2N trigger */
+
+typedef enum {
+    HMME_OK = 0,
+    HMME_ERR_ARG = -1,        /* bad pointer / size / range */
+    HMME_ERR_NO_DEVICE = -2,  /* no CUDA device, or not compute capability 10.x */
+    HMME_ERR_CUDA = -3,       /* a CUDA runtime call failed */
+    HMME_ERR_RANGE = -4,      /* search range / CTU size beyond what the context was created for */
+    HMME_ERR_CONTENT = -5,    /* plane declared 8-bit holds samples outside [0,255] */
+    HMME_ERR_BOUNDS = -6      /* a job's window leaves the plane allocation (reference: undefined behaviour, App. B4) */
+} hmme_status;
+
+typedef struct hmme_ctx hmme_ctx;
+
+/* One search job: the CTU at picture position (ctuX, ctuY) searched over candidates
+ * (ltx + x, lty + y), x,y in 0..2R (pcMvSrchRngLT of TEncOpenCL::calcMotionVectors). */
+typedef struct { int32_t ctuX, ctuY, ltx, lty; } hmme_job;
+
+/* A luma plane resident in device memory.  `base` is the FIRST byte of the allocation (top-left of
+ * the margin); picture sample (0,0) is at base + (marginY*pitch + marginX)*elemBytes.  elemBytes is
+ * 1 (8-bit samples, the fast path) or 2 (int16, e.g. the bi-prediction "current" block 2*org-pred,
+ * TEncSearch.cpp:3702-3712).  pitch is in elements.  Rows 0..height+2*marginY-1 are addressable. */
+typedef struct {
+    void* base;
+    int32_t elemBytes, pitch, width, height, marginX, marginY;
+} hmme_plane;
+
+/* ---- discovery / lifetime: TEncOpenCL::findDevice, compileKernelSource, createBuffers (TEncOpenCL.cpp:69-238) */
+int hmme_device_count(int* count);
+int hmme_create(hmme_ctx** out, int device, int maxCtuW, int maxCtuH, int maxSearchRange);
+void hmme_destroy(hmme_ctx* ctx);
+const char* hmme_device_name(hmme_ctx* ctx);          /* TEncOpenCL::getDeviceInfo */
+const char* hmme_last_error(hmme_ctx* ctx);           /* ctx may be NULL: error of the last failed hmme_create */
+void* hmme_stream(hmme_ctx* ctx);                     /* the cudaStream_t all work of this context runs on */
+
+/* ---- lambda: TEncOpenCL::setLambda (TEncOpenCL.h:121), m_lambda = (UInt)floor(65536*sqrt(lambda)) */
+int hmme_set_lambda(hmme_ctx* ctx, double lambda);
+int hmme_set_lambda_q16(hmme_ctx* ctx, uint32_t lambdaQ16);
+uint32_t hmme_get_lambda_q16(hmme_ctx* ctx);
+
+/* ---- synchronous per-CTU search: TEncOpenCL::calcMotionVectors + getX/getY/getRuiCost
+ * (TEncOpenCL.cpp:240-362, TEncSearch.cpp:3749-3764).  Host pointers, borrowed for the call.
+ *   cur      : 64x64 int16, stride curStride
+ *   refAtCtu : pointer into the padded int16 reference plane at the CTU origin, stride refStride;
+ *              samples [lt, lt + 2R + 63] in both axes are read with LINEAR addressing (App. B4)
+ * 8-bit content in both takes the packed-SAD kernel, anything else the exact 16-bit kernel.
+ * cost may be NULL. */
+int hmme_search_ctu(hmme_ctx* ctx, const int16_t* cur, int curStride, const int16_t* refAtCtu, int refStride,
+                    int range, int ltx, int lty, int32_t* X, int32_t* Y, uint32_t* sad, uint32_t* cost);
+
+/* ---- device-resident planes (whole-frame batching; reference pictures are uploaded once per picture,
+ * the hook being where TComSlice::setRefPicList extends the borders, TComSlice.cpp:351-377) */
+int hmme_plane_alloc(hmme_ctx* ctx, hmme_plane* out, int elemBytes, int width, int height, int marginX, int marginY);
+int hmme_plane_free(hmme_ctx* ctx, hmme_plane* plane);
+/* Host int16 plane (HM's Pel) -> device plane; narrows to 8 bit on the device when plane->elemBytes == 1
+ * and fails with HMME_ERR_CONTENT if a sample does not fit.  hostOrigin points at picture sample (0,0);
+ * the margins are copied too (they must exist on the host side, as in TComPicYuv, TComPicYuv.cpp:93-94). */
+int hmme_plane_upload_s16(hmme_ctx* ctx, const hmme_plane* plane, const int16_t* hostOrigin, int hostStride);
+/* Host 8-bit plane -> device 8-bit plane (same geometry rules). */
+int hmme_plane_upload_u8(hmme_ctx* ctx, const hmme_plane* plane, const uint8_t* hostOrigin, int hostStride);
+
+/* ---- whole-frame batch: njobs independent calcMotionVectors calls in one launch sequence.
+ * jobs, X, Y, sad, cost are HOST arrays ([njobs] and [njobs][593]); cost may be NULL.
+ * Enqueues H2D(jobs) -> kernels -> D2H(results) on the context stream and waits. */
+int hmme_search_frame(hmme_ctx* ctx, const hmme_plane* cur, const hmme_plane* ref, const hmme_job* jobs, int njobs,
+                      int range, int32_t* X, int32_t* Y, uint32_t* sad, uint32_t* cost);
+/* Same, but only enqueues the kernels (jobs already copied by this call, results left in the context's
+ * device result buffer): the kernel-only leg of bench.py.  Pair with hmme_fetch_results. */
+int hmme_search_frame_async(hmme_ctx* ctx, const hmme_plane* cur, const hmme_plane* ref, const hmme_job* jobs,
+                            int njobs, int range);
+int hmme_fetch_results(hmme_ctx* ctx, int njobs, int32_t* X, int32_t* Y, uint32_t* sad, uint32_t* cost);
+int hmme_sync(hmme_ctx* ctx);
+
+/* ---- measurement hooks (bench.py / profiles): CUDA-event time of the dominant kernel of the most recent
+ * search call on this context's stream, kernel launches issued so far, and the integer-ALU issue-rate
+ * micro-benchmark that fixes the roofline denominator. */
+int hmme_last_kernel_ms(hmme_ctx* ctx, float* searchKernelMs);
+uint64_t hmme_kernel_launches(hmme_ctx* ctx);
+int hmme_measure_int_alu_peak(hmme_ctx* ctx, double* laneOpsPerSec, double* lanesPerClkPerSm, double* smMhz);
+
+/* ---- the 593-entry layout, for callers that want it without linking HM (index -> x, y, w, h) */
+int hmme_partition_rect(int index, int* x, int* y, int* w, int* h);
+const char* hmme_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HMME_B200_H */

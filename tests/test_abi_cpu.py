@@ -1,0 +1,78 @@
+"""CPU-side checks of the product's boundary: the C-ABI library loads without a GPU, exports exactly what
+include/hmme_b200.h declares, and its host-only entry points (layout table) agree with getIndexBlock.
+No compute call is made here."""
+import json
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as ge
+    ge.build()
+    from _pkg import hm
+    return hm.HmmeLib.get()
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "hmme_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(hmme_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_exports_match_header(lib):
+    from _pkg import hm
+    from importlib import import_module
+    api = import_module("hm_opencl_b200.api")
+    declared = header_symbols()
+    assert declared == sorted(api.EXPORTS)
+    nm = subprocess.run(["nm", "-D", "--defined-only", hm.lib_path()], stdout=subprocess.PIPE, text=True, check=True).stdout
+    exported = sorted(set(re.findall(r" T (hmme_[a-z0-9_]+)", nm)))
+    assert exported == declared
+
+
+def test_library_carries_sm100a_code_only(lib):
+    from _pkg import hm
+    out = subprocess.run(["cuobjdump", "-lelf", hm.lib_path()], stdout=subprocess.PIPE, text=True).stdout
+    assert "sm_100a" in out and not re.search(r"sm_(?!100a)\d+", out)
+
+
+def test_product_layout_matches_getindexblock(lib):
+    from hevc_geom import decode_key, pu_rect
+    cases = json.load(open(os.path.join(ROOT, "tests/golden/getindexblock_593.json")))["cases"]
+    tab = lib.partition_table()
+    for key, idx in cases:
+        assert tuple(tab[idx]) == pu_rect(*decode_key(key)), (key, idx)
+
+
+def test_product_and_oracle_layout_agree(lib, oracle):
+    assert np.array_equal(lib.partition_table(), oracle.partition_table())
+
+
+def test_no_gpu_is_a_loud_error(lib):
+    import torch
+    from _pkg import hm
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(hm.HmmeError):
+        hm.MotionEstimator(0, 64)
+    t = hm.TEncOpenCL()
+    assert t.findDevice(0) is False
+
+
+def test_product_never_touches_the_oracle():
+    """The oracle is test infrastructure: no file of the product may import, link or name it."""
+    pkg = os.path.join(ROOT, "hm-opencl_b200")
+    for d, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                txt = open(os.path.join(d, f), errors="ignore").read()
+                assert "pyoracle" not in txt and "hmme_oracle" not in txt and "oracle/" not in txt.replace("never imported here", "").replace("The oracle under oracle/", ""), f

@@ -1,0 +1,218 @@
+"""GPU parity tests (run by the driver with -m gpu on a B200): the CUDA path, called through the C ABI
+(libhmme_b200.so via ctypes), against the CPU oracle and the reference-derived golden vectors.
+Bar: bit-exact X, Y, sad (ruiCosts) and cost (minSad) -- integer work."""
+import os
+
+import numpy as np
+import pytest
+
+from _pkg import hm
+from synth import frame_jobs, luma_frames, pad_plane
+
+pytestmark = pytest.mark.gpu
+NAMES = ("X", "Y", "sad", "cost")
+
+
+@pytest.fixture(scope="module")
+def me():
+    m = hm.MotionEstimator(0, 128)
+    yield m
+    m.close()
+
+
+def assert_same(got, want, ctx=""):
+    for g, w, n in zip(got, want, NAMES):
+        if not np.array_equal(g, w):
+            bad = np.argwhere(np.asarray(g) != np.asarray(w))
+            raise AssertionError(f"{ctx}: {n} differs at {bad[:8].tolist()} got {np.asarray(g)[tuple(bad[0])]} want {np.asarray(w)[tuple(bad[0])]} ({len(bad)} mismatches)")
+
+
+def test_golden_vectors_through_c_abi(me, golden):
+    """Every reference-derived fixture (8-bit, 16-bit bi-pred cur, ties, wrap-around lambda ...) via hmme_search_ctu."""
+    for name in [str(n) for n in golden["names"]]:
+        m, R, ltx, lty, lam = (int(v) for v in golden[name + ".meta"])
+        me.set_lambda_q16(lam)
+        got = me.search_ctu(golden[name + ".cur"], golden[name + ".plane"], 0, 0, m, m, R, ltx, lty)
+        assert_same(got, [golden[f"{name}.{k}"] for k in NAMES], name)
+
+
+@pytest.mark.parametrize("R", [1, 4, 7, 16, 32])
+def test_frame_batch_vs_oracle(me, oracle, R):
+    W, H = 256, 128
+    f = luma_frames(W, H, 2, seed=100 + R)
+    M = R + 16
+    cur, ref = pad_plane(f[1], M, M), pad_plane(f[0], M, M)
+    jobs = frame_jobs(W, H, R)
+    jobs[1::2, 2] += 5      # off-centre windows on every other CTU
+    jobs[1::2, 3] -= 3
+    lam = 460000
+    me.set_lambda_q16(lam)
+    pc, pr = me.alloc_plane(1, W, H, M, M), me.alloc_plane(1, W, H, M, M)
+    me.upload(pc, cur); me.upload(pr, ref)
+    got = me.search_frame(pc, pr, jobs, R)
+    want = oracle.search_frame(cur, (M, M), ref, (M, M), jobs, R, lam, nthreads=8)
+    assert_same(got, want, f"R={R}")
+    pc.free(); pr.free()
+
+
+@pytest.mark.parametrize("R,lam", [(64, 460000), (64, 0), (128, 1000000)])
+def test_headline_ranges_vs_oracle(me, oracle, R, lam):
+    """+-64 (BASELINE config 2) and +-128 (config 4) on a few CTUs: multi-tile merge, 9 and 2x43 tiles per job."""
+    W, H = 128, 64
+    f = luma_frames(W, H, 2, seed=7 + R)
+    M = R + 8
+    cur, ref = pad_plane(f[1], M, M), pad_plane(f[0], M, M)
+    jobs = frame_jobs(W, H, R)
+    me.set_lambda_q16(lam)
+    pc, pr = me.alloc_plane(1, W, H, M, M), me.alloc_plane(1, W, H, M, M)
+    me.upload(pc, cur); me.upload(pr, ref)
+    got = me.search_frame(pc, pr, jobs, R)
+    want = oracle.search_frame(cur, (M, M), ref, (M, M), jobs, R, lam, nthreads=8)
+    assert_same(got, want, f"R={R}")
+    pc.free(); pr.free()
+
+
+def test_all_ties_tiebreak_across_tiles(me, oracle):
+    """Constant planes: every candidate has SAD 0; with lambda = 0 the first candidate in scan order (LT) must win
+    in every partition even though 9 tiles race through atomicMin; with lambda > 0 the cheapest MV wins."""
+    R, W, H = 64, 64, 64
+    M = R + 8
+    cur = np.full((H + 2 * M, W + 2 * M), 93, np.int16)
+    ref = cur.copy()
+    pc, pr = me.alloc_plane(1, W, H, M, M), me.alloc_plane(1, W, H, M, M)
+    me.upload(pc, cur); me.upload(pr, ref)
+    jobs = np.array([[0, 0, -R, -R]], np.int32)
+    for lam in (0, 460000):
+        me.set_lambda_q16(lam)
+        got = me.search_frame(pc, pr, jobs, R)
+        want = oracle.search_frame(cur, (M, M), ref, (M, M), jobs, R, lam)
+        assert_same(got, want, f"ties lam={lam}")
+        exp = -R if lam == 0 else 0
+        assert (got[0] == exp).all() and (got[1] == exp).all()
+    pc.free(); pr.free()
+
+
+def test_extreme_contrast_64(me, oracle):
+    """cur = 0, ref = 255 everywhere: 4x4 SAD = 4080, 64x64 SAD = 1044480 (largest value the packed keys must hold),
+    together with the largest lambda that keeps mvcost at 16 bits."""
+    R, W, H = 16, 64, 64
+    M = R + 8
+    cur = np.zeros((H + 2 * M, W + 2 * M), np.int16)
+    ref = np.full_like(cur, 255)
+    ref[M + 70, M + 3] = 254
+    pc, pr = me.alloc_plane(1, W, H, M, M), me.alloc_plane(1, W, H, M, M)
+    me.upload(pc, cur); me.upload(pr, ref)
+    jobs = np.array([[0, 0, -R, -R]], np.int32)
+    for lam in (0, 0xFFFFFFFF, 0x7FFF0000):
+        me.set_lambda_q16(lam)
+        got = me.search_frame(pc, pr, jobs, R)
+        want = oracle.search_frame(cur, (M, M), ref, (M, M), jobs, R, lam)
+        assert_same(got, want, f"contrast lam={lam:#x}")
+    pc.free(); pr.free()
+
+
+@pytest.mark.parametrize("ce,re_", [(2, 1), (1, 2), (2, 2)])
+def test_16bit_planes_generic_kernel(me, oracle, ce, re_):
+    """Bi-prediction style input: cur = 2*org - pred (signed 16 bit), R = 4 (bipredSearchRange), and 16-bit reference planes."""
+    R, W, H = 4, 128, 64
+    g = np.random.default_rng(3)
+    M = R + 8
+    shape = (H + 2 * M, W + 2 * M)
+    cur = (g.integers(-255, 511, size=shape) if ce == 2 else g.integers(0, 256, size=shape)).astype(np.int16)
+    ref = (g.integers(-300, 700, size=shape) if re_ == 2 else g.integers(0, 256, size=shape)).astype(np.int16)
+    pc, pr = me.alloc_plane(ce, W, H, M, M), me.alloc_plane(re_, W, H, M, M)
+    me.upload(pc, cur); me.upload(pr, ref)
+    jobs = frame_jobs(W, H, R)
+    me.set_lambda_q16(460000)
+    got = me.search_frame(pc, pr, jobs, R)
+    want = oracle.search_frame(cur, (M, M), ref, (M, M), jobs, R, 460000)
+    assert_same(got, want, f"elem {ce},{re_}")
+    pc.free(); pr.free()
+
+
+def test_row_wrap_linear_addressing(me, oracle):
+    """A window pushed past the right margin reads on into the next row of the padded plane:
+    the CUDA path must reproduce the reference's linear addressing."""
+    R, W, H = 8, 128, 128
+    f = luma_frames(W, H, 2, seed=5)
+    M = 16
+    cur, ref = pad_plane(f[1], M, M), pad_plane(f[0], M, M)
+    pc, pr = me.alloc_plane(1, W, H, M, M), me.alloc_plane(1, W, H, M, M)
+    assert pr.desc.pitch == ref.shape[1]       # 128 + 32 = 160 is already a multiple of 16: same linear layout as the host plane
+    me.upload(pc, cur); me.upload(pr, ref)
+    jobs = np.array([[64, 0, 10, -4], [64, 64, 12, -20]], np.int32)   # x: 64+10+2*8+63 = 153 > 128+16
+    me.set_lambda_q16(262144)
+    got = me.search_frame(pc, pr, jobs, R)
+    want = oracle.search_frame(cur, (M, M), ref, (M, M), jobs, R, 262144)
+    assert_same(got, want, "row wrap")
+    pc.free(); pr.free()
+
+
+def test_errors_are_loud(me):
+    W, H, M = 64, 64, 8
+    pc, pr = me.alloc_plane(1, W, H, M, M), me.alloc_plane(1, W, H, M, M)
+    ok = np.zeros((H + 2 * M, W + 2 * M), np.int16)
+    me.upload(pc, ok); me.upload(pr, ok)
+    with pytest.raises(hm.HmmeError) as e:
+        me.search_frame(pc, pr, np.array([[0, 0, -16, -16]], np.int32), 16)     # window leaves the allocation
+    assert e.value.code == -6
+    bad = ok.copy(); bad[3, 3] = 300
+    with pytest.raises(hm.HmmeError) as e:
+        me.upload(pr, bad)                                                       # not 8-bit content
+    assert e.value.code == -5
+    with pytest.raises(hm.HmmeError) as e:
+        me.search_ctu(ok[:64, :64], ok, 0, 0, M, M, 4096, 0, 0)                  # beyond createBuffers' range
+    assert e.value.code == -4
+    with pytest.raises(hm.HmmeError):
+        hm.MotionEstimator(0, 64).__class__(999, 64)                             # no such device
+    pc.free(); pr.free()
+
+
+def test_python_mirror_of_reference_class(oracle, golden):
+    """Same call order as TEncTop::xInitOpenCL + TEncSearch::xMotionEstimation."""
+    t = hm.TEncOpenCL()
+    assert t.findDevice(0)
+    assert not t.compileKernelSource("cl/sad.cl", "calcSAD")       # 425-entry kernel is not part of the path
+    assert t.compileKernelSource("cl/sad.cl", "calcSAD_AMP")
+    assert t.createBuffers(64, 64, 64)
+    with pytest.raises(hm.HmmeError):
+        t.calcMotionVectors(np.zeros((64, 64), np.int16), np.zeros((200, 200), np.int16), (70, 70), 4, (-4, -4))
+    t.setEnabled(True)
+    t.setLambda(49.3)
+    name = "shifted_offcentre_R8"
+    m, R, ltx, lty, _ = (int(v) for v in golden[name + ".meta"])
+    t.calcMotionVectors(golden[name + ".cur"], golden[name + ".plane"], (m, m), R, (ltx, lty))
+    lam = oracle.lambda_q16(49.3)
+    want = oracle.search_ctu(golden[name + ".cur"], golden[name + ".plane"], 0, 0, m, m, R, ltx, lty, lam)
+    assert np.array_equal(t.getX(), want[0]) and np.array_equal(t.getY(), want[1]) and np.array_equal(t.getRuiCost(), want[2])
+
+
+def test_full_1080p_pm64_properties_and_samples(me, oracle):
+    """BASELINE config 2 at full size: 480 CTUs x 16641 candidates.  Size-independent properties on every job
+    (global pan recovered by the 64x64 partition, cost = sad + mvcost(winner), winners inside the window) and a
+    bit-exact comparison with the oracle on 6 sampled CTUs."""
+    W, H, R = 1920, 1080, 64
+    f = luma_frames(W, H, 2)
+    M = 80 + 64
+    cur, ref = pad_plane(f[1], M, M), pad_plane(f[0], M, M)
+    pc, pr = me.alloc_plane(1, W, H, M, M), me.alloc_plane(1, W, H, M, M)
+    me.upload(pc, cur); me.upload(pr, ref)
+    jobs = frame_jobs(W, H, R)
+    assert len(jobs) == 480
+    lam = 460000
+    me.set_lambda_q16(lam)
+    X, Y, S, Cst = me.search_frame(pc, pr, jobs, R)
+    assert (X >= -R).all() and (X <= R).all() and (Y >= -R).all() and (Y <= R).all()
+    bits = np.vectorize(lambda v: oracle.mv_bits(4 * int(v)))
+    mvc = ((lam * (bits(X) + bits(Y)).astype(np.uint64)) & 0xFFFFFFFF) >> 16
+    assert np.array_equal(Cst.astype(np.uint64), S.astype(np.uint64) + mvc)
+    # frame 1 is frame 0 panned by (+3,+2): away from the moving square the 64x64 block matches at MV (3,2) with SAD 0
+    hit = (X[:, 592] == 3) & (Y[:, 592] == 2) & (S[:, 592] == 0)
+    assert hit.sum() >= 450      # all CTUs except those under the moving square or whose match leaves the picture
+    # hierarchy consistency where winners coincide: the 64x64 SAD is the sum of the four 32x32 SADs
+    same = hit & np.all(X[:, 584:588] == 3, 1) & np.all(Y[:, 584:588] == 2, 1)
+    assert same.sum() >= 400 and (S[same, 584:588].sum(1) == S[same, 592]).all()
+    pick = [0, 29, 137, 200, 333, 479]
+    want = oracle.search_frame(cur, (M, M), ref, (M, M), jobs[pick], R, lam, nthreads=8)
+    assert_same([a[pick] for a in (X, Y, S, Cst)], want, "1080p sample")
+    pc.free(); pr.free()
