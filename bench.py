@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""bench.py -- whole-CTU integer-pel motion estimation throughput on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload 1080p64|4k128|...] [--impl reference]
+
+A step = the integer ME of ONE frame against ONE reference picture: every full 64x64 CTU of the frame,
+(2R+1)^2 candidates each, 593 partitions per candidate (config[1] of BASELINE.json at N=1: 1920x1080,
++-64 -> 480 jobs x 16641 candidates).  With N > 1 (torchrun, one rank per GPU) the frame is split into
+contiguous CTU-row bands (strong scaling); the reference picture is uploaded by rank 0
+and NCCL-broadcast, each rank uploads and searches only its band.
+
+Output: ONE JSON line on rank 0 (contract in the task statement): `value` = block-SAD evaluations/s with
+inputs resident in HBM (CUDA events on the library's stream, L2 flushed between steps), `e2e` = the same
+metric through the public C-ABI calls with pinned HOST buffers (H2D of both int16 planes + jobs, D2H of the
+four result arrays inside the timed region), `roofline` = algorithmic integer lane-ops/s of the dominant
+kernel against the ALU issue rate measured live, `cpu_baseline` = the CPU oracle port on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+from synth import band_rows, frame_jobs, luma_frames, pad_plane  # noqa: E402
+
+WORKLOADS = {                      # name: (W, H, R)   -- BASELINE.json configs
+    "1080p64": (1920, 1080, 64),   # config[1] (and the metric's "1080p frames/s (+-64)")
+    "4k128": (3840, 2160, 128),    # config[3]
+    "1080p32": (1920, 1080, 32),
+    "1080p16": (1920, 1080, 16),
+    "416x240_64": (416, 240, 64),  # config[0] geometry
+}
+NPARTS = 593
+INT_OPS_PER_CAND = 2803            # 1024 packed SADs + 593 adds + 593 cost adds + 593 min
+PX_PER_CAND = 4096
+LAMBDA_Q16 = 460000                # QP ~32 (SURVEY.md section 8d synthetic inputs)
+
+
+def workload_geometry(name):
+    W, H, R = WORKLOADS[name]
+    margin = max(80, R + 16)       # HM pads by 80 (TComPicYuv.cpp:93-94); larger ranges need more for in-bounds windows
+    return W, H, R, margin
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.05)
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=6)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "samples": len(sm),
+                "power_w_max": max(float(r[2]) for r in self.rows), "reasons": reasons}
+
+
+def cpu_oracle_throughput(W, H, R, margin, njobs_sample, threads):
+    """Times the CPU oracle port (oracle/hmme_oracle.c, hierarchical variant) on a bounded sample of the workload's jobs."""
+    from oracle.pyoracle import Oracle
+    f = luma_frames(W, H, 2)
+    cur, ref = pad_plane(f[1], margin, margin), pad_plane(f[0], margin, margin)
+    jobs = frame_jobs(W, H, R)
+    pick = np.linspace(0, len(jobs) - 1, num=min(njobs_sample, len(jobs))).astype(int)
+    o = Oracle()
+    t0 = time.perf_counter()
+    o.search_frame(cur, (margin, margin), ref, (margin, margin), jobs[pick], R, LAMBDA_Q16, nthreads=threads)
+    dt = time.perf_counter() - t0
+    cands = len(pick) * (2 * R + 1) ** 2
+    return cands * NPARTS / dt, dt, len(pick)
+
+
+def run_reference(args, rank):
+    """--impl reference: the CPU implementation of the path on the host cores (the oracle port of the reference's
+    calcMotionVectors semantics; the reference's OpenCL kernels themselves only run here in lock-step emulation,
+    oracle/_ref, which is a checker, not a timing baseline)."""
+    if rank != 0:
+        return
+    W, H, R, margin = workload_geometry(args.workload)
+    threads = os.cpu_count() or 1
+    per_step = max(threads, 32)
+    vals = []
+    for s in range(args.warmup + args.steps):
+        v, dt, n = cpu_oracle_throughput(W, H, R, margin, per_step, threads)
+        if s >= args.warmup:
+            vals.append((v, dt))
+    value = float(np.mean([v for v, _ in vals]))
+    ms = float(np.mean([dt for _, dt in vals])) * 1e3
+    frames_s = value / (NPARTS * (2 * R + 1) ** 2 * (W // 64) * (H // 64))
+    sample = "%d of %d CTU jobs per step, all %d host threads" % (per_step, (W // 64) * (H // 64), threads)
+    print(json.dumps({
+        "impl": "reference", "metric": "me_block_sad_evaluations_per_s", "value": value, "unit": "block-SAD evaluations/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "frames_per_s": frames_s,
+        "config": {"workload": "%s: %dx%d luma, 64x64 CTU, integer-pel full search +-%d, 1 reference picture" % (args.workload, W, H, R),
+                   "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "block-SAD evaluations/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "block-SAD evaluations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="1080p64", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from _pkg import hm
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    W, H, R, margin = workload_geometry(args.workload)
+    ncx, ncy = W // 64, H // 64
+    r0, r1 = band_rows(ncy, world, rank)
+    jobs = frame_jobs(W, H, R, rows=(r0, r1))
+    njobs = len(jobs)
+    cands_per_job = (2 * R + 1) ** 2
+    total_jobs = ncx * ncy
+
+    me = hm.MotionEstimator(local_rank, R)
+    me.set_lambda_q16(LAMBDA_Q16)
+    ext = torch.cuda.ExternalStream(me.stream_ptr, device=dev)
+
+    # device planes live in torch tensors (so NCCL can broadcast them); the library works on views
+    pitch = (W + 2 * margin + 15) // 16 * 16
+    rows = H + 2 * margin
+    t_cur = torch.zeros(rows * pitch + 64, dtype=torch.uint8, device=dev)
+    t_ref = torch.zeros(rows * pitch + 64, dtype=torch.uint8, device=dev)
+    p_cur = me.wrap_plane(t_cur.data_ptr(), 1, pitch, W, H, margin, margin)
+    p_ref = me.wrap_plane(t_ref.data_ptr(), 1, pitch, W, H, margin, margin)
+    # this rank's band of the current frame as its own upload target (rows [64*r0, 64*r1), no vertical margin)
+    band_h = 64 * (r1 - r0)
+    p_cur_band = me.wrap_plane(t_cur.data_ptr() + (margin + 64 * r0) * pitch, 1, pitch, W, band_h, margin, 0) if band_h else None
+
+    # pinned host frames in HM's sample type (Pel = int16), synthetic content
+    f = luma_frames(W, H, 2)
+    h_cur = torch.from_numpy(pad_plane(f[1], margin, margin)).pin_memory()
+    h_ref = torch.from_numpy(pad_plane(f[0], margin, margin)).pin_memory()
+    n_cur, n_ref = h_cur.numpy(), h_ref.numpy()
+    n_cur_band = n_cur[margin + 64 * r0: margin + 64 * r1] if band_h else None
+
+    def upload_inputs():
+        """The per-step host->device leg of the public API: reference picture (rank 0, then NCCL broadcast), band of the
+        current frame (every rank)."""
+        if rank == 0:
+            me.upload(p_ref, n_ref)
+        if world > 1:
+            with torch.cuda.stream(ext):
+                dist.broadcast(t_ref, src=0)
+        if band_h:
+            me.upload(p_cur_band, n_cur_band, origin_x=margin, origin_y=0)
+
+    upload_inputs()
+    me.sync()
+    torch.cuda.synchronize()
+    peak = me.measure_int_alu_peak()
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        if njobs:
+            me.search_frame_async(p_cur, p_ref, jobs, R)
+
+    # ------------------------------------------------------------------ value: inputs resident in HBM
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    launches0 = me.kernel_launches
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kernel_ms = []
+    barrier()
+    wall0 = time.perf_counter()
+    with torch.cuda.stream(ext):
+        for s in range(args.steps):
+            flush.zero_()                                              # L2 flush between timed iterations
+            ev[s][0].record(ext)
+            step_resident()
+            ev[s][1].record(ext)
+            if njobs:
+                kernel_ms.append(me.last_kernel_ms())                  # CUDA events around the dominant kernel, same stream
+    barrier()
+    wall1 = time.perf_counter()
+    launches = me.kernel_launches - launches0
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    kern_ms = torch.tensor([float(np.mean(kernel_ms)) if kernel_ms else 0.0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(kern_ms, op=dist.ReduceOp.MAX)
+    total_ms, kern_ms = float(total_ms.item()), float(kern_ms.item())
+    clocks = sampler.summary() if sampler else None
+
+    # ------------------------------------------------------------------ e2e: host buffers through the public API
+    outs = me._outs(max(njobs, 1))
+    for _ in range(2):
+        upload_inputs()
+        if njobs:
+            me.search_frame_async(p_cur, p_ref, jobs, R)
+            me.fetch_results(njobs, outs)
+    barrier()
+    e0 = time.perf_counter()
+    for s in range(args.steps):
+        upload_inputs()
+        if njobs:
+            me.search_frame_async(p_cur, p_ref, jobs, R)
+            me.fetch_results(njobs, outs)
+        if world > 1:
+            me.sync()
+    barrier()
+    e1 = time.perf_counter()
+    e2e_ms = torch.tensor([(e1 - e0) * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_ms = float(e2e_ms.item())
+    h2d = (n_ref.nbytes if rank == 0 else 0) + (n_cur_band.nbytes if band_h else 0) + jobs.nbytes
+    d2h = 4 * njobs * NPARTS * 4
+    io = torch.tensor([h2d, d2h], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(io, op=dist.ReduceOp.SUM)
+
+    if rank == 0:
+        total_cands = total_jobs * cands_per_job
+        ms_per_step = total_ms / args.steps
+        value = total_cands * NPARTS / (ms_per_step * 1e-3)
+        e2e_value = total_cands * NPARTS / (e2e_ms / args.steps * 1e-3)
+        # dominant kernel roofline: algorithmic integer lane-ops of THIS rank's launch / its CUDA-event duration
+        cands_rank = njobs * cands_per_job
+        achieved = cands_rank * INT_OPS_PER_CAND / (kern_ms * 1e-3) if kern_ms > 0 else 0.0
+        alg_bytes = (W + 2 * margin) * (H + 2 * margin) + W * H + total_jobs * NPARTS * 16
+        out = {
+            "metric": "me_block_sad_evaluations_per_s", "value": value, "unit": "block-SAD evaluations/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "frames_per_s": 1e3 / ms_per_step,
+            "ctu_candidates_per_s": total_cands / (ms_per_step * 1e-3),
+            "config": {"workload": "%s: %dx%d luma, 64x64 CTU, integer-pel full search +-%d, 1 reference picture, %d CTU jobs x %d candidates x 593 partitions"
+                                   % (args.workload, W, H, R, total_jobs, cands_per_job),
+                       "sharding": "CTU-row bands over %d GPU(s), reference plane NCCL-broadcast from rank 0" % world,
+                       "lambda_q16": LAMBDA_Q16, "l2": "256 MiB flush buffer written between timed steps",
+                       "timer": "CUDA events on the library stream per step, max over ranks"},
+            "clocks": clocks,
+            "gpu_launches": int(launches),
+            "wall_ms_timed_region": (wall1 - wall0) * 1e3,
+            "e2e": {"value": e2e_value, "unit": "block-SAD evaluations/s", "h2d_bytes_per_step": int(io[0].item()),
+                    "d2h_bytes_per_step": int(io[1].item()), "frames_per_s": 1e3 / (e2e_ms / args.steps),
+                    "ms_per_step": e2e_ms / args.steps,
+                    "timer": "host wall clock around K x {upload int16 planes from pinned memory, broadcast, search, fetch results}, max over ranks"},
+            "roofline": {"bound": "int_alu", "kernel": "me_u8_tile_kernel", "achieved": achieved / 1e12, "peak": peak["lane_ops_per_s"] / 1e12,
+                         "unit": "T int-lane-op/s", "frac": achieved / peak["lane_ops_per_s"] if peak["lane_ops_per_s"] else None,
+                         "traffic": None,
+                         "ops_per_ctu_candidate": INT_OPS_PER_CAND, "kernel_ms": kern_ms,
+                         "pixel_abs_diffs_per_s": cands_rank * PX_PER_CAND / (kern_ms * 1e-3) if kern_ms > 0 else 0.0,
+                         "peak_source": "measured live: VABSDIFF4.U8.ACC issue rate, %.1f lanes/clk/SM x %d SMs at %.0f MHz"
+                                        % (peak["lanes_per_clk_sm"], torch.cuda.get_device_properties(dev).multi_processor_count, peak["sm_mhz"]),
+                         "hbm": {"algorithmic_bytes_per_step": alg_bytes, "achieved_gbs": alg_bytes / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else 0.0,
+                                 "peak_gbs": _measured_hbm()}},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            v, dt, n = cpu_oracle_throughput(W, H, R, margin, max(8 * threads, 64), threads)
+            out["cpu_baseline"] = {"value": v, "unit": "block-SAD evaluations/s", "cores": threads, "kind": "port",
+                                   "sample": "%d of %d CTU jobs of the same frame, %.1f s wall on %d threads (oracle/hmme_oracle.c)" % (n, total_jobs, dt, threads)}
+        print(json.dumps(out))
+    me.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _measured_hbm():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        return 6650.0   # fallback stated in B200_PROFILING.md
+
+
+if __name__ == "__main__":
+    main()

@@ -412,9 +412,9 @@ int hmme_search_frame_async(hmme_ctx* c, const hmme_plane* cur, const hmme_plane
     CU_TRY(c, cudaSetDevice(c->device));
     rc = ensure_jobs(c, (size_t)njobs);
     if (rc != HMME_OK) return rc;
-    CU_TRY(c, cudaStreamSynchronize(c->stream));        // the pinned job staging may still be in flight from the previous call
-    std::memcpy(c->hJobs, jobs, (size_t)njobs * sizeof(hmme_job));
-    CU_TRY(c, cudaMemcpyAsync(c->dJobs, c->hJobs, (size_t)njobs * sizeof(hmme_job), cudaMemcpyHostToDevice, c->stream));
+    // straight from the caller's (pageable) array: the runtime stages it before returning, and stream order protects dJobs,
+    // so consecutive frames can be enqueued without a host synchronisation in between
+    CU_TRY(c, cudaMemcpyAsync(c->dJobs, jobs, (size_t)njobs * sizeof(hmme_job), cudaMemcpyHostToDevice, c->stream));
     const char* refLo = static_cast<const char*>(ref->base);
     return enqueue_search(c, origin_ptr(cur), cur->elemBytes, cur->pitch, origin_ptr(ref), ref->elemBytes, ref->pitch, refLo,
                           refLo + plane_elems(ref) * ref->elemBytes, njobs, range);
