@@ -31,30 +31,26 @@ namespace {
 std::mutex g_errMu;
 std::string g_createErr;
 
-struct FastGeom { int tw, th, nTx, nTy, pw, cs; size_t smemBytes; };
+struct FastGeom { int tw, th, nTx, nTy; size_t smemBytes; };
 
 constexpr size_t kSmemBudget = 200 * 1024;
 
-size_t fast_smem_bytes(int tw, int th, int yb, int* pwOut, int* csOut) {
-    const int rows = fast_win_rows(th, yb), pw = fast_pw(tw);
-    int cs = rows * pw;
-    cs += ((8 - cs) % 32 + 32) % 32;                       // copies 8 banks apart
-    if (pwOut) *pwOut = pw;
-    if (csOut) *csOut = cs;
-    const size_t words = 4 * (size_t)cs + 1024 + 2 * (size_t)(32 * yb) * kRecWords + ((tw + 3) & ~3) + (size_t)(((th + yb - 1) / yb) * yb) + 4;
+size_t fast_smem_bytes(int tw, int th, int yb) {
+    const size_t words = (size_t)fast_win_rows(th, yb) * kWinPitch + 1024 + 2 * (size_t)(32 * yb) * kRecWords + ((tw + 3) & ~3) +
+                         (size_t)(((th + yb - 1) / yb) * yb) + 4;
     return words * 4;
 }
 
 FastGeom fast_geometry(int W, int yb) {
     FastGeom g{};
-    g.nTx = (W + 128) / 129;
+    g.nTx = (W + kMaxTileW - 1) / kMaxTileW;
     g.tw = (W + g.nTx - 1) / g.nTx;
     int thMax = (kMaxTileCands / g.tw) / yb * yb;
     thMax = std::min(thMax, (W + yb - 1) / yb * yb);
-    while (thMax > yb && fast_smem_bytes(g.tw, thMax, yb, nullptr, nullptr) > kSmemBudget) thMax -= yb;
+    while (thMax > yb && fast_smem_bytes(g.tw, thMax, yb) > kSmemBudget) thMax -= yb;
     g.nTy = (W + thMax - 1) / thMax;
     g.th = (((W + g.nTy - 1) / g.nTy) + yb - 1) / yb * yb;
-    g.smemBytes = fast_smem_bytes(g.tw, g.th, yb, &g.pw, &g.cs);
+    g.smemBytes = fast_smem_bytes(g.tw, g.th, yb);
     return g;
 }
 
@@ -171,7 +167,7 @@ int enqueue_search(hmme_ctx* c, const void* curOrigin, int curElem, long long cu
         fp.refHi = static_cast<const uint8_t*>(refHi);
         fp.curPitch = curPitch; fp.refPitch = refPitch;
         fp.jobs = c->dJobs; fp.best = c->dBest; fp.lambda = c->lambda; fp.W = W;
-        fp.tw = g.tw; fp.th = g.th; fp.nTx = g.nTx; fp.nTy = g.nTy; fp.pw = g.pw; fp.cs = g.cs;
+        fp.tw = g.tw; fp.th = g.th; fp.nTx = g.nTx; fp.nTy = g.nTy;
         CU_TRY(c, cudaFuncSetAttribute(me_u8_tile_kernel<HMME_FAST_YB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smemBytes));
         me_u8_tile_kernel<HMME_FAST_YB><<<njobs * g.nTx * g.nTy, kFastThreads, g.smemBytes, c->stream>>>(fp);
     } else {

@@ -21,11 +21,12 @@
 // Tile end: warp-wide CREDUX.MIN per key, conversion to the global 64-bit key (cost<<32 | y*(2R+1)+x)
 // and one atomicMin per (warp, partition) into best[job][593]; a tiny finalize kernel decodes MVs.
 //
-// Reference window staging: four byte-shifted copies of the tile's window (copy k, word j = bytes
-// 4j+k..4j+k+3) so that 32 lanes with consecutive candidate x read 32 distinct banks with plain
-// LDS.32; copies are placed 8 banks apart.  Addressing of the source plane is linear
-// (row*pitch + col), which is exactly the reference's pelSearchArray[j + i*iRefStride] including its
-// row-wrap quirk.
+// Reference window staging: the tile's window is kept in shared memory as SLIDING WORDS -- entry x of a row is the
+// 32-bit word made of bytes x..x+3 -- so lane l (candidate column x0+l) reads entry x+4i with a plain LDS.32 and 32
+// lanes with consecutive candidate x always hit 32 distinct banks, whatever the alignment of x.  The row pitch is a
+// compile-time 192 words, which turns every address in the unrolled inner loop into an immediate offset.
+// Addressing of the source plane is linear (row*pitch + col), which is exactly the reference's
+// pelSearchArray[j + i*iRefStride] including its row-wrap quirk.
 #pragma once
 #include "me_common.cuh"
 
@@ -34,8 +35,10 @@ namespace hmme {
 constexpr int kFastThreads = 512;
 constexpr int kIdxBits = 11;                  // candidates per tile <= 2048
 constexpr int kMaxTileCands = 1 << kIdxBits;
-constexpr int kRecWords = 52;                 // upper-phase record: 32 (8x8 pairs, u16) + 16 (16x16<<11) + 1 (key base) + pad;
-                                              // 52 = 20 mod 32 keeps 8-lane LDS.128 phases conflict-free
+constexpr int kWinPitch = 192;                // sliding-word entries per window row: (tw-1) + 4*15 + 1 <= 189 for tw <= 129
+constexpr int kMaxTileW = 129;
+constexpr int kRecWords = 49;                 // upper-phase words per candidate slot: 32 (8x8 pairs, u16) + 16 (16x16<<11) + 1 (key base),
+                                              // stored slot-minor ([word][slot]) so that every access is lane-contiguous
 constexpr uint32_t kInvalidBlockKeyBase = 0xF0000000u;   // block sums << 11 stay below 2^27: no wrap, never wins
 constexpr uint32_t kInvalidSlot = 0xFFFFFFFFu;
 
@@ -51,12 +54,17 @@ struct FastParams {
     int W;                     // 2R+1 candidates per axis
     int tw, th;                // nominal tile size in candidates
     int nTx, nTy;
-    int pw;                    // window row pitch in words
-    int cs;                    // copy stride in words (== 8 mod 32)
 };
 
 __host__ __device__ inline int fast_win_rows(int th, int yb) { return ((th + yb - 1) / yb) * yb + 63; }
-__host__ __device__ inline int fast_pw(int tw) { return ((tw - 1) >> 2) + 16; }
+
+// one VABSDIFF4.U8.ACC: acc += sum of |a.b[k] - b.b[k]| over the four bytes.  Written as PTX so that the accumulate operand
+// stays chained (the compiler otherwise splits it into VABSDIFF4(...,RZ) + an extra add per packed SAD).
+__device__ __forceinline__ uint32_t sad4_acc(uint32_t a, uint32_t b, uint32_t acc) {
+    uint32_t d;
+    asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(acc));
+    return d;
+}
 
 // partition index of block-level key k (0..32) for block b
 __device__ __forceinline__ int block_part_index(int b, int k) {
@@ -89,7 +97,7 @@ __device__ __forceinline__ uint32_t addmin(uint32_t sum, uint32_t base, uint32_t
 // Fold one candidate's 16 4x4 SADs (a[t][i], row-strip t, column i of the 16x16 block) into the 33 running keys
 // and hand the 8x8 / 16x16 sums to the upper levels.
 __device__ __forceinline__ void emit_block(const uint32_t (&a)[4][4], uint32_t kb, uint32_t (&best)[33],
-                                           uint32_t* rec, int b, bool writeBase, uint32_t recBase) {
+                                           uint32_t* rec, int b, bool writeBase, uint32_t recBase, int slots) {
     uint32_t s[4][4];
 #pragma unroll
     for (int t = 0; t < 4; ++t)
@@ -137,20 +145,20 @@ __device__ __forceinline__ void emit_block(const uint32_t (&a)[4][4], uint32_t k
     const uint32_t all = top + bot;
     best[32] = addmin(all, kb, best[32]);                  // 16x16
     // upper-level hand-over: 8x8 sums as u16 pairs (<= 16320 each), 16x16 sum pre-shifted
-    uint2 pk;
-    pk.x = (e[0][0] >> kIdxBits) | (e[0][1] << (16 - kIdxBits));
-    pk.y = (e[1][0] >> kIdxBits) | (e[1][1] << (16 - kIdxBits));
-    *reinterpret_cast<uint2*>(rec + 2 * b) = pk;
-    rec[32 + b] = all;
-    if (writeBase) rec[48] = recBase;
+    // (rec already points at this candidate's slot; word w of the record lives at rec[w * slots])
+    rec[(2 * b) * slots] = (e[0][0] >> kIdxBits) | (e[0][1] << (16 - kIdxBits));
+    rec[(2 * b + 1) * slots] = (e[1][0] >> kIdxBits) | (e[1][1] << (16 - kIdxBits));
+    rec[(32 + b) * slots] = all;
+    if (writeBase) rec[48 * slots] = recBase;
 }
 
-__device__ __forceinline__ void emit_quadrant(const uint32_t* rec, int q, uint32_t (&ub)[13]) {
-    const uint32_t kb = rec[48];
+__device__ __forceinline__ void emit_quadrant(const uint32_t* rec, int q, uint32_t (&ub)[13], int slots) {
+    const uint32_t kb = rec[48 * slots];
     if (kb == kInvalidSlot) return;
     const int b0 = 8 * (q >> 1) + 2 * (q & 1);
-    const uint4 T = *reinterpret_cast<const uint4*>(rec + 2 * b0);        // blocks b0, b0+1 : {e00|e01, e10|e11} each
-    const uint4 B = *reinterpret_cast<const uint4*>(rec + 2 * (b0 + 4));  // blocks b0+4, b0+5
+    uint4 T, B;                                                             // blocks b0, b0+1 / b0+4, b0+5 : {e00|e01, e10|e11} each
+    T.x = rec[(2 * b0) * slots]; T.y = rec[(2 * b0 + 1) * slots]; T.z = rec[(2 * b0 + 2) * slots]; T.w = rec[(2 * b0 + 3) * slots];
+    B.x = rec[(2 * b0 + 8) * slots]; B.y = rec[(2 * b0 + 9) * slots]; B.z = rec[(2 * b0 + 10) * slots]; B.w = rec[(2 * b0 + 11) * slots];
     // rows of 8x8 sums across the 32-wide quadrant, still packed (each half <= 32640)
     const uint32_t r0 = T.x + T.z, r1 = T.y + T.w, r2 = B.x + B.z, r3 = B.y + B.w;
     const uint32_t R0 = ((r0 & 0xFFFFu) + (r0 >> 16)) << kIdxBits, R1 = ((r1 & 0xFFFFu) + (r1 >> 16)) << kIdxBits;
@@ -175,12 +183,15 @@ __device__ __forceinline__ void emit_quadrant(const uint32_t* rec, int q, uint32
     ub[12] = addmin(top + bot, kb, ub[12]);        // 32x32
 }
 
-__device__ __forceinline__ void emit_ctu(const uint32_t* rec, uint32_t (&ub)[13]) {
-    const uint32_t kb = rec[48];
+__device__ __forceinline__ void emit_ctu(const uint32_t* rec, uint32_t (&ub)[13], int slots) {
+    const uint32_t kb = rec[48 * slots];
     if (kb == kInvalidSlot) return;
     uint4 m[4];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) m[r] = *reinterpret_cast<const uint4*>(rec + 32 + 4 * r);   // 16x16 sums << 11, block row r
+    for (int r = 0; r < 4; ++r) {                                           // 16x16 sums << 11, block row r
+        m[r].x = rec[(32 + 4 * r) * slots]; m[r].y = rec[(33 + 4 * r) * slots];
+        m[r].z = rec[(34 + 4 * r) * slots]; m[r].w = rec[(35 + 4 * r) * slots];
+    }
     uint32_t R[4], C[4];
 #pragma unroll
     for (int r = 0; r < 4; ++r) R[r] = (m[r].x + m[r].y) + (m[r].z + m[r].w);
@@ -217,9 +228,10 @@ template <int YB>
 __global__ void __launch_bounds__(kFastThreads, 1) me_u8_tile_kernel(const FastParams p) {
     extern __shared__ __align__(16) uint32_t smem[];
     constexpr int SLOTS = 32 * YB;
-    uint32_t* sWin = smem;                                  // 4 * cs
-    uint32_t* sCur = sWin + 4 * p.cs;                       // 64 rows x 16 words
-    uint32_t* sUp = sCur + 1024;                            // 2 x SLOTS x kRecWords
+    const int winRows = fast_win_rows(p.th, YB);
+    uint32_t* sWin = smem;                                  // winRows x kWinPitch sliding words
+    uint32_t* sCur = sWin + winRows * kWinPitch;            // 64 rows x 16 words
+    uint32_t* sUp = sCur + 1024;                            // 2 x kRecWords x SLOTS
     uint32_t* sBitsX = sUp + 2 * SLOTS * kRecWords;         // tw
     uint32_t* sBitsY = sBitsX + ((p.tw + 3) & ~3);          // roundup(th, YB)
 
@@ -232,24 +244,27 @@ __global__ void __launch_bounds__(kFastThreads, 1) me_u8_tile_kernel(const FastP
     const int nRG = (thA + YB - 1) / YB, nUnits = twA * nRG;
     const int4 jb = p.jobs[job];
 
-    // ---- stage the reference window: 4 byte-shifted copies, linear source addressing
+    // ---- stage the reference window as sliding words (linear source addressing), the CTU, and the MV-bit tables
     {
-        const int rows = nRG * YB + 63, pwl = fast_pw(twA);
+        const int rows = nRG * YB + 63, nPos = twA + 60;      // entries 0 .. (twA-1) + 4*15
         const uint8_t* wbase = p.ref + (long long)(jb.y + jb.w + y0) * p.refPitch + (jb.x + jb.z + x0);
         const uintptr_t lo = (uintptr_t)p.refLo, hi = ((uintptr_t)p.refHi - 4) & ~(uintptr_t)3;
-        for (int idx = tid; idx < rows * pwl; idx += kFastThreads) {
-            const int row = idx / pwl, j = idx - row * pwl;
-            const uintptr_t g = (uintptr_t)(wbase + (long long)row * p.refPitch + 4 * j);
-            const uint32_t a = (uint32_t)(g & 3);
+        const int wordsPerRow = (nPos + 3 + 3) / 4 + 1;       // aligned words that cover bytes [-3, nPos+3) of the row
+        for (int row = warp; row < rows; row += kFastThreads / 32) {
+            const uintptr_t g = (uintptr_t)(wbase + (long long)row * p.refPitch);
+            const int a = (int)(g & 3);
             const uintptr_t g0 = g - a;
-            const uint32_t w0 = *reinterpret_cast<const uint32_t*>(min(max(g0, lo), hi));
-            const uint32_t w1 = *reinterpret_cast<const uint32_t*>(min(max(g0 + 4, lo), hi));
-            const uint32_t w2 = *reinterpret_cast<const uint32_t*>(min(max(g0 + 8, lo), hi));
+            uint32_t* dst = sWin + row * kWinPitch;
+            for (int j0 = 0; j0 < wordsPerRow; j0 += 32) {       // warp-uniform trip count: the shuffle needs all lanes
+                const int j = j0 + lane;
+                const uint32_t w0 = *reinterpret_cast<const uint32_t*>(min(max(g0 + 4 * (uintptr_t)j, lo), hi));
+                uint32_t w1 = __shfl_down_sync(0xFFFFFFFFu, w0, 1);
+                if (lane == 31) w1 = *reinterpret_cast<const uint32_t*>(min(max(g0 + 4 * (uintptr_t)j + 4, lo), hi));
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const uint32_t s = a + k;
-                const uint32_t word = s < 4 ? __funnelshift_r(w0, w1, 8 * s) : __funnelshift_r(w1, w2, 8 * (s - 4));
-                sWin[k * p.cs + row * p.pw + j] = word;
+                for (int k = 0; k < 4; ++k) {                 // aligned bytes 4j+k.. are window bytes x = 4j + k - a ..
+                    const int x = 4 * j + k - a;
+                    if (x >= 0 && x < nPos) dst[x] = __funnelshift_r(w0, w1, 8 * k);
+                }
             }
         }
         const uint8_t* cbase = p.cur + (long long)jb.y * p.curPitch + jb.x;
@@ -262,13 +277,14 @@ __global__ void __launch_bounds__(kFastThreads, 1) me_u8_tile_kernel(const FastP
     }
     __syncthreads();
 
-    const int b = warp, bxw = (b & 3) * 4, by = (b >> 2) * 16;
+    const int b = warp, bx = (b & 3) * 16, by = (b >> 2) * 16;
     uint32_t best[33], ub[13];
 #pragma unroll
     for (int k = 0; k < 33; ++k) best[k] = 0xFFFFFFFFu;
 #pragma unroll
     for (int k = 0; k < 13; ++k) ub[k] = 0xFFFFFFFFu;
     const int role = tid / SLOTS, slot = tid - role * SLOTS;   // upper phase: role 0..3 quadrant, 4 CTU level, >=5 idle
+    const uint32_t* cp = sCur + by * 16 + (bx >> 2);
 
     const int nRounds = (nUnits + 31) >> 5;
     for (int round = 0; round < nRounds; ++round) {
@@ -276,8 +292,7 @@ __global__ void __launch_bounds__(kFastThreads, 1) me_u8_tile_kernel(const FastP
         const bool uvalid = u < nUnits;
         const int uu = uvalid ? u : 0;
         const int rg = uu / twA, ux = uu - rg * twA;
-        const uint32_t* wp = sWin + (ux & 3) * p.cs + (rg * YB + by) * p.pw + (ux >> 2) + bxw;
-        const uint32_t* cp = sCur + by * 16 + bxw;
+        const uint32_t* wp = sWin + (rg * YB + by) * kWinPitch + ux + bx;
 
         uint32_t acc[YB][4][4];
 #pragma unroll
@@ -289,17 +304,17 @@ __global__ void __launch_bounds__(kFastThreads, 1) me_u8_tile_kernel(const FastP
         uint4 cw[YB];
 #pragma unroll
         for (int rho = 0; rho < 16 + YB - 1; ++rho) {
-            const uint32_t r0 = wp[rho * p.pw + 0], r1 = wp[rho * p.pw + 1], r2 = wp[rho * p.pw + 2], r3 = wp[rho * p.pw + 3];
+            const uint32_t r0 = wp[rho * kWinPitch + 0], r1 = wp[rho * kWinPitch + 4], r2 = wp[rho * kWinPitch + 8], r3 = wp[rho * kWinPitch + 12];
             if (rho < 16) cw[rho % YB] = *reinterpret_cast<const uint4*>(cp + rho * 16);
 #pragma unroll
             for (int j = 0; j < YB; ++j) {
                 const int r = rho - j;                       // row of the block this reference row meets for candidate j
                 if (r >= 0 && r < 16) {
                     const uint4 c = cw[r % YB];
-                    acc[j][r >> 2][0] = __vsadu4(c.x, r0) + acc[j][r >> 2][0];
-                    acc[j][r >> 2][1] = __vsadu4(c.y, r1) + acc[j][r >> 2][1];
-                    acc[j][r >> 2][2] = __vsadu4(c.z, r2) + acc[j][r >> 2][2];
-                    acc[j][r >> 2][3] = __vsadu4(c.w, r3) + acc[j][r >> 2][3];
+                    acc[j][r >> 2][0] = sad4_acc(c.x, r0, acc[j][r >> 2][0]);
+                    acc[j][r >> 2][1] = sad4_acc(c.y, r1, acc[j][r >> 2][1]);
+                    acc[j][r >> 2][2] = sad4_acc(c.z, r2, acc[j][r >> 2][2]);
+                    acc[j][r >> 2][3] = sad4_acc(c.w, r3, acc[j][r >> 2][3]);
                 }
             }
         }
@@ -311,12 +326,12 @@ __global__ void __launch_bounds__(kFastThreads, 1) me_u8_tile_kernel(const FastP
             const bool valid = uvalid && y < thA;
             const uint32_t mvc = (uint32_t)(p.lambda * (bitsX + sBitsY[y])) >> 16;
             const uint32_t kb = (mvc << kIdxBits) | (uint32_t)(y * twA + ux);
-            emit_block(acc[j], valid ? kb : kInvalidBlockKeyBase, best, recBuf + (j * 32 + lane) * kRecWords, b, b == 0,
-                       valid ? kb : kInvalidSlot);
+            emit_block(acc[j], valid ? kb : kInvalidBlockKeyBase, best, recBuf + j * 32 + lane, b, b == 0,
+                       valid ? kb : kInvalidSlot, SLOTS);
         }
         __syncthreads();
-        if (role < 4) emit_quadrant(recBuf + slot * kRecWords, role, ub);
-        else if (role == 4) emit_ctu(recBuf + slot * kRecWords, ub);
+        if (role < 4) emit_quadrant(recBuf + slot, role, ub, SLOTS);
+        else if (role == 4) emit_ctu(recBuf + slot, ub, SLOTS);
     }
 
     // ---- tile end: warp arg-min per key, publish
