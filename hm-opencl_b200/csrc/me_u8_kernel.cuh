@@ -94,62 +94,80 @@ __device__ __forceinline__ uint32_t addmin(uint32_t sum, uint32_t base, uint32_t
     return __viaddmin_u32(sum, base, best);               // one VIADDMNMX.U32: min(sum + base, best)
 }
 
-// Fold one candidate's 16 4x4 SADs (a[t][i], row-strip t, column i of the 16x16 block) into the 33 running keys
-// and hand the 8x8 / 16x16 sums to the upper levels.
-__device__ __forceinline__ void emit_block(const uint32_t (&a)[4][4], uint32_t kb, uint32_t (&best)[33],
+// Per-candidate state carried across the row loop: sums are folded strip by strip (4 rows at a time) as soon as a strip
+// of 4x4 SADs completes, so that the shift/add work (FMA pipe) and the add-min updates interleave with the packed SADs
+// (ALU pipe) of the candidates that are still being accumulated, instead of forming a separate FMA-bound phase.
+struct BlockState {
+    uint32_t sp[4];     // shifted 4x4 sums of the previous even strip
+    uint32_t hp[2];     // its two 8x4 sums
+    uint32_t q0, q1, q2;  // 16x4 strip sums
+    uint32_t v0[4];     // 4x8 sums of strips 0+1
+    uint32_t e0[2];     // 8x8 sums of the top half
+    uint32_t top;       // 16x8 top
+};
+
+// Strip T (rows 4T..4T+3 of the 16x16 block) of one candidate is complete: a[i] = its four 4x4 SADs.
+template <int T>
+__device__ __forceinline__ void emit_strip(const uint32_t (&a)[4], BlockState& st, uint32_t kb, uint32_t (&best)[33],
                                            uint32_t* rec, int b, bool writeBase, uint32_t recBase, int slots) {
-    uint32_t s[4][4];
+    uint32_t s[4];
 #pragma unroll
-    for (int t = 0; t < 4; ++t)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) s[t][i] = a[t][i] << kIdxBits;
-    uint32_t h[4][2], v[2][4], e[2][2], q[4], c[4];
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-        h[t][0] = s[t][0] + s[t][1];
-        h[t][1] = s[t][2] + s[t][3];
-        best[2 * t] = addmin(h[t][0], kb, best[2 * t]);
-        best[2 * t + 1] = addmin(h[t][1], kb, best[2 * t + 1]);
-        q[t] = h[t][0] + h[t][1];
+    for (int i = 0; i < 4; ++i) s[i] = a[i] << kIdxBits;
+    const uint32_t h0 = s[0] + s[1], h1 = s[2] + s[3], q = h0 + h1;
+    best[2 * T] = addmin(h0, kb, best[2 * T]);                     // 8x4
+    best[2 * T + 1] = addmin(h1, kb, best[2 * T + 1]);
+    if constexpr (T == 0) {
+        best[20] = addmin(q, kb, best[20]);                        // 16x4  (2NxnU part 0)
+        st.q0 = q;
     }
+    if constexpr (T == 0 || T == 2) {
 #pragma unroll
-    for (int vv = 0; vv < 2; ++vv)
+        for (int i = 0; i < 4; ++i) st.sp[i] = s[i];
+        st.hp[0] = h0; st.hp[1] = h1;
+    }
+    if constexpr (T == 1) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            v[vv][i] = s[2 * vv][i] + s[2 * vv + 1][i];
-            best[8 + vv * 4 + i] = addmin(v[vv][i], kb, best[8 + vv * 4 + i]);
-        }
+        for (int i = 0; i < 4; ++i) { st.v0[i] = st.sp[i] + s[i]; best[8 + i] = addmin(st.v0[i], kb, best[8 + i]); }   // 4x8
+        st.e0[0] = st.hp[0] + h0; st.e0[1] = st.hp[1] + h1;
+        best[16] = addmin(st.e0[0], kb, best[16]);                 // 8x8
+        best[17] = addmin(st.e0[1], kb, best[17]);
+        st.q1 = q;
+        st.top = st.q0 + q;
+        best[28] = addmin(st.top, kb, best[28]);                   // 16x8 top
+    }
+    if constexpr (T == 2) {
+        st.q2 = q;
+        best[22] = addmin(st.top + q, kb, best[22]);               // 16x12 rows 0..11
+    }
+    if constexpr (T == 3) {
+        uint32_t v1[4], c[4];
 #pragma unroll
-    for (int vv = 0; vv < 2; ++vv)
+        for (int i = 0; i < 4; ++i) { v1[i] = st.sp[i] + s[i]; best[12 + i] = addmin(v1[i], kb, best[12 + i]); }     // 4x8
+        const uint32_t e10 = st.hp[0] + h0, e11 = st.hp[1] + h1;
+        best[18] = addmin(e10, kb, best[18]);                      // 8x8
+        best[19] = addmin(e11, kb, best[19]);
+        const uint32_t bot = st.q2 + q;
+        best[21] = addmin(q, kb, best[21]);                        // 16x4  (2NxnD part 1)
+        best[29] = addmin(bot, kb, best[29]);                      // 16x8 bottom
+        best[23] = addmin(st.q1 + bot, kb, best[23]);              // 16x12 rows 4..15
 #pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-            e[vv][hh] = h[2 * vv][hh] + h[2 * vv + 1][hh];
-            best[16 + vv * 2 + hh] = addmin(e[vv][hh], kb, best[16 + vv * 2 + hh]);
-        }
-    const uint32_t top = q[0] + q[1], bot = q[2] + q[3];
-    best[20] = addmin(q[0], kb, best[20]);                 // 16x4  (2NxnU part 0)
-    best[21] = addmin(q[3], kb, best[21]);                 // 16x4  (2NxnD part 1)
-    best[22] = addmin(top + q[2], kb, best[22]);           // 16x12 rows 0..11
-    best[23] = addmin(q[1] + bot, kb, best[23]);           // 16x12 rows 4..15
-#pragma unroll
-    for (int i = 0; i < 4; ++i) c[i] = v[0][i] + v[1][i];
-    const uint32_t left = c[0] + c[1], right = c[2] + c[3];
-    best[24] = addmin(c[0], kb, best[24]);                 // 4x16  (nLx2N part 0)
-    best[25] = addmin(c[3], kb, best[25]);                 // 4x16  (nRx2N part 1)
-    best[26] = addmin(left + c[2], kb, best[26]);          // 12x16 cols 0..11
-    best[27] = addmin(c[1] + right, kb, best[27]);         // 12x16 cols 4..15
-    best[28] = addmin(top, kb, best[28]);                  // 16x8
-    best[29] = addmin(bot, kb, best[29]);
-    best[30] = addmin(left, kb, best[30]);                 // 8x16
-    best[31] = addmin(right, kb, best[31]);
-    const uint32_t all = top + bot;
-    best[32] = addmin(all, kb, best[32]);                  // 16x16
-    // upper-level hand-over: 8x8 sums as u16 pairs (<= 16320 each), 16x16 sum pre-shifted
-    // (rec already points at this candidate's slot; word w of the record lives at rec[w * slots])
-    rec[(2 * b) * slots] = (e[0][0] >> kIdxBits) | (e[0][1] << (16 - kIdxBits));
-    rec[(2 * b + 1) * slots] = (e[1][0] >> kIdxBits) | (e[1][1] << (16 - kIdxBits));
-    rec[(32 + b) * slots] = all;
-    if (writeBase) rec[48 * slots] = recBase;
+        for (int i = 0; i < 4; ++i) c[i] = st.v0[i] + v1[i];
+        const uint32_t left = c[0] + c[1], right = c[2] + c[3];
+        best[24] = addmin(c[0], kb, best[24]);                     // 4x16  (nLx2N part 0)
+        best[25] = addmin(c[3], kb, best[25]);                     // 4x16  (nRx2N part 1)
+        best[26] = addmin(left + c[2], kb, best[26]);              // 12x16 cols 0..11
+        best[27] = addmin(c[1] + right, kb, best[27]);             // 12x16 cols 4..15
+        best[30] = addmin(left, kb, best[30]);                     // 8x16
+        best[31] = addmin(right, kb, best[31]);
+        const uint32_t all = st.top + bot;
+        best[32] = addmin(all, kb, best[32]);                      // 16x16
+        // upper-level hand-over: 8x8 sums as u16 pairs (<= 16320 each), 16x16 sum pre-shifted.
+        // (rec already points at this candidate's slot; word w of the record lives at rec[w * slots])
+        rec[(2 * b) * slots] = (st.e0[0] >> kIdxBits) | (st.e0[1] << (16 - kIdxBits));
+        rec[(2 * b + 1) * slots] = (e10 >> kIdxBits) | (e11 << (16 - kIdxBits));
+        rec[(32 + b) * slots] = all;
+        if (writeBase) rec[48 * slots] = recBase;
+    }
 }
 
 __device__ __forceinline__ void emit_quadrant(const uint32_t* rec, int q, uint32_t (&ub)[13], int slots) {
@@ -224,6 +242,61 @@ __device__ __forceinline__ void publish(unsigned long long* bestJob, int part, u
     atomicMin(bestJob + part, ((unsigned long long)cost << 32) | gidx);
 }
 
+// One round of one warp: lane = unit (candidate column ux, rows rg*YB .. rg*YB+YB-1), block (bx, by).
+// CHECKED = false is the steady state (all lanes and rows valid); CHECKED = true handles the ragged last rounds.
+template <int YB, bool CHECKED>
+__device__ __forceinline__ void round_body(const uint32_t* sWin, const uint32_t* cp, const uint32_t* sBitsX, const uint32_t* sBitsY,
+                                           uint32_t* recBuf, uint32_t (&best)[33], int rg, int ux, int by, int bx, int b, int lane,
+                                           int twA, int thA, int nRG, uint32_t lambda) {
+    constexpr int SLOTS = 32 * YB;
+    const bool uvalid = !CHECKED || rg < nRG;
+    const int rgc = (CHECKED && !uvalid) ? 0 : rg, uxc = (CHECKED && !uvalid) ? 0 : ux;
+    const uint32_t* wp = sWin + (rgc * YB + by) * kWinPitch + uxc + bx;
+    uint32_t kb[YB], kbRec[YB];
+    const uint32_t bitsX = sBitsX[uxc];
+#pragma unroll
+    for (int j = 0; j < YB; ++j) {
+        const int y = rgc * YB + j;
+        const uint32_t mvc = (uint32_t)(lambda * (bitsX + sBitsY[y])) >> 16;
+        const uint32_t k = (mvc << kIdxBits) | (uint32_t)(y * twA + uxc);
+        const bool valid = !CHECKED || (uvalid && y < thA);
+        kb[j] = valid ? k : kInvalidBlockKeyBase;
+        kbRec[j] = valid ? k : kInvalidSlot;
+    }
+    uint32_t acc[YB][4];
+    BlockState st[YB];
+#pragma unroll
+    for (int j = 0; j < YB; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[j][i] = 0;
+    uint4 cw[YB];
+#pragma unroll
+    for (int rho = 0; rho < 16 + YB - 1; ++rho) {
+        const uint32_t r0 = wp[rho * kWinPitch + 0], r1 = wp[rho * kWinPitch + 4], r2 = wp[rho * kWinPitch + 8], r3 = wp[rho * kWinPitch + 12];
+        if (rho < 16) cw[rho % YB] = *reinterpret_cast<const uint4*>(cp + rho * 16);
+#pragma unroll
+        for (int j = 0; j < YB; ++j) {
+            const int r = rho - j;                           // row of the block this reference row meets for candidate j
+            if (r >= 0 && r < 16) {
+                const uint4 c = cw[r % YB];
+                acc[j][0] = sad4_acc(c.x, r0, acc[j][0]);
+                acc[j][1] = sad4_acc(c.y, r1, acc[j][1]);
+                acc[j][2] = sad4_acc(c.z, r2, acc[j][2]);
+                acc[j][3] = sad4_acc(c.w, r3, acc[j][3]);
+                if ((r & 3) == 3) {
+                    uint32_t* rec = recBuf + j * 32 + lane;
+                    if (r == 3) emit_strip<0>(acc[j], st[j], kb[j], best, rec, b, b == 0, kbRec[j], SLOTS);
+                    if (r == 7) emit_strip<1>(acc[j], st[j], kb[j], best, rec, b, b == 0, kbRec[j], SLOTS);
+                    if (r == 11) emit_strip<2>(acc[j], st[j], kb[j], best, rec, b, b == 0, kbRec[j], SLOTS);
+                    if (r == 15) emit_strip<3>(acc[j], st[j], kb[j], best, rec, b, b == 0, kbRec[j], SLOTS);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) acc[j][i] = 0;
+                }
+            }
+        }
+    }
+}
+
 template <int YB>
 __global__ void __launch_bounds__(kFastThreads, 1) me_u8_tile_kernel(const FastParams p) {
     extern __shared__ __align__(16) uint32_t smem[];
@@ -287,48 +360,16 @@ __global__ void __launch_bounds__(kFastThreads, 1) me_u8_tile_kernel(const FastP
     const uint32_t* cp = sCur + by * 16 + (bx >> 2);
 
     const int nRounds = (nUnits + 31) >> 5;
+    const int nFull = (twA * (thA / YB)) >> 5;              // rounds in which every lane and every candidate row is valid
+    int rg = lane / twA, ux = lane - rg * twA;              // this lane's unit of round 0, advanced incrementally
     for (int round = 0; round < nRounds; ++round) {
-        const int u = round * 32 + lane;
-        const bool uvalid = u < nUnits;
-        const int uu = uvalid ? u : 0;
-        const int rg = uu / twA, ux = uu - rg * twA;
-        const uint32_t* wp = sWin + (rg * YB + by) * kWinPitch + ux + bx;
-
-        uint32_t acc[YB][4][4];
-#pragma unroll
-        for (int j = 0; j < YB; ++j)
-#pragma unroll
-            for (int t = 0; t < 4; ++t)
-#pragma unroll
-                for (int i = 0; i < 4; ++i) acc[j][t][i] = 0;
-        uint4 cw[YB];
-#pragma unroll
-        for (int rho = 0; rho < 16 + YB - 1; ++rho) {
-            const uint32_t r0 = wp[rho * kWinPitch + 0], r1 = wp[rho * kWinPitch + 4], r2 = wp[rho * kWinPitch + 8], r3 = wp[rho * kWinPitch + 12];
-            if (rho < 16) cw[rho % YB] = *reinterpret_cast<const uint4*>(cp + rho * 16);
-#pragma unroll
-            for (int j = 0; j < YB; ++j) {
-                const int r = rho - j;                       // row of the block this reference row meets for candidate j
-                if (r >= 0 && r < 16) {
-                    const uint4 c = cw[r % YB];
-                    acc[j][r >> 2][0] = sad4_acc(c.x, r0, acc[j][r >> 2][0]);
-                    acc[j][r >> 2][1] = sad4_acc(c.y, r1, acc[j][r >> 2][1]);
-                    acc[j][r >> 2][2] = sad4_acc(c.z, r2, acc[j][r >> 2][2]);
-                    acc[j][r >> 2][3] = sad4_acc(c.w, r3, acc[j][r >> 2][3]);
-                }
-            }
-        }
         uint32_t* recBuf = sUp + (round & 1) * (SLOTS * kRecWords);
-        const uint32_t bitsX = sBitsX[ux];
-#pragma unroll
-        for (int j = 0; j < YB; ++j) {
-            const int y = rg * YB + j;
-            const bool valid = uvalid && y < thA;
-            const uint32_t mvc = (uint32_t)(p.lambda * (bitsX + sBitsY[y])) >> 16;
-            const uint32_t kb = (mvc << kIdxBits) | (uint32_t)(y * twA + ux);
-            emit_block(acc[j], valid ? kb : kInvalidBlockKeyBase, best, recBuf + j * 32 + lane, b, b == 0,
-                       valid ? kb : kInvalidSlot, SLOTS);
-        }
+        if (round < nFull)
+            round_body<YB, false>(sWin, cp, sBitsX, sBitsY, recBuf, best, rg, ux, by, bx, b, lane, twA, thA, nRG, p.lambda);
+        else
+            round_body<YB, true>(sWin, cp, sBitsX, sBitsY, recBuf, best, rg, ux, by, bx, b, lane, twA, thA, nRG, p.lambda);
+        ux += 32;
+        while (ux >= twA) { ux -= twA; ++rg; }
         __syncthreads();
         if (role < 4) emit_quadrant(recBuf + slot, role, ub, SLOTS);
         else if (role == 4) emit_ctu(recBuf + slot, ub, SLOTS);
