@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -36,7 +37,7 @@ struct FastGeom { int tw, th, nTx, nTy; size_t smemBytes; };
 constexpr size_t kSmemBudget = 200 * 1024;
 
 size_t fast_smem_bytes(int tw, int th, int yb) {
-    const size_t words = (size_t)fast_win_rows(th, yb) * kWinPitch + 1024 + 2 * (size_t)(32 * yb) * kRecWords + ((tw + 3) & ~3) +
+    const size_t words = (size_t)fast_win_rows(th, yb) * kWinPitch + 1024 + kRing * (size_t)(32 * yb) * kRecWords + ((tw + 3) & ~3) +
                          (size_t)(((th + yb - 1) / yb) * yb) + 4;
     return words * 4;
 }
@@ -66,6 +67,8 @@ struct hmme_ctx {
     uint32_t lambda = 0;
     int maxRange = 0;
     uint64_t launches = 0;
+    int stagger = 1300;          // cycles of start skew between the two warp groups of the packed kernel (HMME_STAGGER env overrides)
+    int fastYb = HMME_FAST_YB;   // candidate rows per thread in the packed kernel (HMME_FAST_YB env overrides: 2 or 3; 5*32*YB upper-level tasks must fit 512 threads)
     // job / result buffers (grown on demand)
     size_t jobCap = 0;
     int4* dJobs = nullptr;
@@ -159,7 +162,8 @@ int enqueue_search(hmme_ctx* c, const void* curOrigin, int curElem, long long cu
     me_init_kernel<<<(unsigned)((nres + 255) / 256), 256, 0, c->stream>>>(c->dBest, nres);
     CU_TRY(c, cudaEventRecord(c->ev0, c->stream));
     if (curElem == 1 && refElem == 1) {
-        const FastGeom g = fast_geometry(W, HMME_FAST_YB);
+        const int yb = c->fastYb;
+        const FastGeom g = fast_geometry(W, yb);
         FastParams fp{};
         fp.cur = static_cast<const uint8_t*>(curOrigin);
         fp.ref = static_cast<const uint8_t*>(refOrigin);
@@ -167,9 +171,16 @@ int enqueue_search(hmme_ctx* c, const void* curOrigin, int curElem, long long cu
         fp.refHi = static_cast<const uint8_t*>(refHi);
         fp.curPitch = curPitch; fp.refPitch = refPitch;
         fp.jobs = c->dJobs; fp.best = c->dBest; fp.lambda = c->lambda; fp.W = W;
-        fp.tw = g.tw; fp.th = g.th; fp.nTx = g.nTx; fp.nTy = g.nTy;
-        CU_TRY(c, cudaFuncSetAttribute(me_u8_tile_kernel<HMME_FAST_YB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smemBytes));
-        me_u8_tile_kernel<HMME_FAST_YB><<<njobs * g.nTx * g.nTy, kFastThreads, g.smemBytes, c->stream>>>(fp);
+        fp.tw = g.tw; fp.th = g.th; fp.nTx = g.nTx; fp.nTy = g.nTy; fp.stagger = c->stagger;
+        const unsigned grid = (unsigned)(njobs * g.nTx * g.nTy);
+        auto launch = [&](auto kernel) -> cudaError_t {
+            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smemBytes);
+            if (e != cudaSuccess) return e;
+            kernel<<<grid, kFastThreads, g.smemBytes, c->stream>>>(fp);
+            return cudaSuccess;
+        };
+        if (yb == 2) CU_TRY(c, launch(me_u8_tile_kernel<2>));
+        else CU_TRY(c, launch(me_u8_tile_kernel<3>));
     } else {
         GenericParams gp{};
         gp.cur = curOrigin; gp.ref = refOrigin; gp.curPitch = curPitch; gp.refPitch = refPitch;
@@ -247,6 +258,8 @@ int hmme_create(hmme_ctx** out, int device, int maxCtuW, int maxCtuH, int maxSea
     if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(std::string("cudaStreamCreate: ") + cudaGetErrorString(e), HMME_ERR_CUDA);
     if ((e = cudaEventCreate(&c->ev0)) != cudaSuccess || (e = cudaEventCreate(&c->ev1)) != cudaSuccess) return bail(std::string("cudaEventCreate: ") + cudaGetErrorString(e), HMME_ERR_CUDA);
     c->maxRange = maxSearchRange;
+    if (const char* e = std::getenv("HMME_STAGGER")) c->stagger = std::max(0, std::atoi(e));
+    if (const char* e = std::getenv("HMME_FAST_YB")) { const int v = std::atoi(e); if (v >= 2 && v <= 3) c->fastYb = v; }
     const size_t side = (size_t)2 * maxSearchRange + 64 + 16;
     c->winElems = side * side;
     if ((e = cudaMallocHost(&c->hWin, c->winElems * 2)) != cudaSuccess || (e = cudaMalloc(&c->dWin, c->winElems * 2 + 64)) != cudaSuccess ||

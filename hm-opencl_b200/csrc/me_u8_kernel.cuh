@@ -41,6 +41,7 @@ constexpr int kRecWords = 49;                 // upper-phase words per candidate
                                               // stored slot-minor ([word][slot]) so that every access is lane-contiguous
 constexpr uint32_t kInvalidBlockKeyBase = 0xF0000000u;   // block sums << 11 stay below 2^27: no wrap, never wins
 constexpr uint32_t kInvalidSlot = 0xFFFFFFFFu;
+constexpr int kRing = 4;                      // record buffers: upper phase lags the block phase by one round, ring >= 2*lag + 2
 
 struct FastParams {
     const uint8_t* cur;        // picture sample (0,0) of the current plane
@@ -54,6 +55,7 @@ struct FastParams {
     int W;                     // 2R+1 candidates per axis
     int tw, th;                // nominal tile size in candidates
     int nTx, nTy;
+    int stagger;               // SM cycles by which warps 8..15 start their first round late (0 = off), see the kernel
 };
 
 __host__ __device__ inline int fast_win_rows(int th, int yb) { return ((th + yb - 1) / yb) * yb + 63; }
@@ -64,6 +66,21 @@ __device__ __forceinline__ uint32_t sad4_acc(uint32_t a, uint32_t b, uint32_t ac
     uint32_t d;
     asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(acc));
     return d;
+}
+
+// ---- mbarrier (shared::cta) helpers: the record ring between the block phase (producers: all 16 warps) and the upper phase
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("{ .reg .b64 st; mbarrier.arrive.shared::cta.b64 st, [%0]; }" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{ .reg .pred p;\n"
+        "W_%=: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@!p bra W_%=;\n}" ::"r"(a), "r"(parity) : "memory");
 }
 
 // partition index of block-level key k (0..32) for block b
@@ -90,6 +107,19 @@ __device__ __forceinline__ int ctu_part_index(int k) {
     return k < 8 ? 576 + k : 588 + (k - 8);               // AMP 576..583, 64x32 588/589, 32x64 590/591, 64x64 592
 }
 
+// a + b on the FMA pipe (IMAD a*1+b).  The ALU pipe is the kernel's bottleneck (packed SADs + add-mins live there), so the
+// hierarchy's plain additions are kept off it; written as PTX because the compiler otherwise folds them into 3-input ALU adds.
+__device__ __forceinline__ uint32_t fadd(uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, 1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+// (a << 11) + b, likewise one IMAD
+__device__ __forceinline__ uint32_t fshladd(uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, 2048, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
 __device__ __forceinline__ uint32_t addmin(uint32_t sum, uint32_t base, uint32_t best) {
     return __viaddmin_u32(sum, base, best);               // one VIADDMNMX.U32: min(sum + base, best)
 }
@@ -111,9 +141,9 @@ template <int T>
 __device__ __forceinline__ void emit_strip(const uint32_t (&a)[4], BlockState& st, uint32_t kb, uint32_t (&best)[33],
                                            uint32_t* rec, int b, bool writeBase, uint32_t recBase, int slots) {
     uint32_t s[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) s[i] = a[i] << kIdxBits;
-    const uint32_t h0 = s[0] + s[1], h1 = s[2] + s[3], q = h0 + h1;
+    s[1] = a[1] << kIdxBits; s[3] = a[3] << kIdxBits;
+    const uint32_t h0 = fshladd(a[0], s[1]), h1 = fshladd(a[2], s[3]), q = fadd(h0, h1);
+    s[0] = a[0] << kIdxBits; s[2] = a[2] << kIdxBits;
     best[2 * T] = addmin(h0, kb, best[2 * T]);                     // 8x4
     best[2 * T + 1] = addmin(h1, kb, best[2 * T + 1]);
     if constexpr (T == 0) {
@@ -127,39 +157,39 @@ __device__ __forceinline__ void emit_strip(const uint32_t (&a)[4], BlockState& s
     }
     if constexpr (T == 1) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { st.v0[i] = st.sp[i] + s[i]; best[8 + i] = addmin(st.v0[i], kb, best[8 + i]); }   // 4x8
-        st.e0[0] = st.hp[0] + h0; st.e0[1] = st.hp[1] + h1;
+        for (int i = 0; i < 4; ++i) { st.v0[i] = fadd(st.sp[i], s[i]); best[8 + i] = addmin(st.v0[i], kb, best[8 + i]); }   // 4x8
+        st.e0[0] = fadd(st.hp[0], h0); st.e0[1] = fadd(st.hp[1], h1);
         best[16] = addmin(st.e0[0], kb, best[16]);                 // 8x8
         best[17] = addmin(st.e0[1], kb, best[17]);
         st.q1 = q;
-        st.top = st.q0 + q;
+        st.top = fadd(st.q0, q);
         best[28] = addmin(st.top, kb, best[28]);                   // 16x8 top
     }
     if constexpr (T == 2) {
         st.q2 = q;
-        best[22] = addmin(st.top + q, kb, best[22]);               // 16x12 rows 0..11
+        best[22] = addmin(fadd(st.top, q), kb, best[22]);               // 16x12 rows 0..11
     }
     if constexpr (T == 3) {
         uint32_t v1[4], c[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { v1[i] = st.sp[i] + s[i]; best[12 + i] = addmin(v1[i], kb, best[12 + i]); }     // 4x8
-        const uint32_t e10 = st.hp[0] + h0, e11 = st.hp[1] + h1;
+        for (int i = 0; i < 4; ++i) { v1[i] = fadd(st.sp[i], s[i]); best[12 + i] = addmin(v1[i], kb, best[12 + i]); }     // 4x8
+        const uint32_t e10 = fadd(st.hp[0], h0), e11 = fadd(st.hp[1], h1);
         best[18] = addmin(e10, kb, best[18]);                      // 8x8
         best[19] = addmin(e11, kb, best[19]);
-        const uint32_t bot = st.q2 + q;
+        const uint32_t bot = fadd(st.q2, q);
         best[21] = addmin(q, kb, best[21]);                        // 16x4  (2NxnD part 1)
         best[29] = addmin(bot, kb, best[29]);                      // 16x8 bottom
-        best[23] = addmin(st.q1 + bot, kb, best[23]);              // 16x12 rows 4..15
+        best[23] = addmin(fadd(st.q1, bot), kb, best[23]);              // 16x12 rows 4..15
 #pragma unroll
-        for (int i = 0; i < 4; ++i) c[i] = st.v0[i] + v1[i];
-        const uint32_t left = c[0] + c[1], right = c[2] + c[3];
+        for (int i = 0; i < 4; ++i) c[i] = fadd(st.v0[i], v1[i]);
+        const uint32_t left = fadd(c[0], c[1]), right = fadd(c[2], c[3]);
         best[24] = addmin(c[0], kb, best[24]);                     // 4x16  (nLx2N part 0)
         best[25] = addmin(c[3], kb, best[25]);                     // 4x16  (nRx2N part 1)
-        best[26] = addmin(left + c[2], kb, best[26]);              // 12x16 cols 0..11
-        best[27] = addmin(c[1] + right, kb, best[27]);             // 12x16 cols 4..15
+        best[26] = addmin(fadd(left, c[2]), kb, best[26]);              // 12x16 cols 0..11
+        best[27] = addmin(fadd(c[1], right), kb, best[27]);             // 12x16 cols 4..15
         best[30] = addmin(left, kb, best[30]);                     // 8x16
         best[31] = addmin(right, kb, best[31]);
-        const uint32_t all = st.top + bot;
+        const uint32_t all = fadd(st.top, bot);
         best[32] = addmin(all, kb, best[32]);                      // 16x16
         // upper-level hand-over: 8x8 sums as u16 pairs (<= 16320 each), 16x16 sum pre-shifted.
         // (rec already points at this candidate's slot; word w of the record lives at rec[w * slots])
@@ -304,8 +334,8 @@ __global__ void __launch_bounds__(kFastThreads, 1) me_u8_tile_kernel(const FastP
     const int winRows = fast_win_rows(p.th, YB);
     uint32_t* sWin = smem;                                  // winRows x kWinPitch sliding words
     uint32_t* sCur = sWin + winRows * kWinPitch;            // 64 rows x 16 words
-    uint32_t* sUp = sCur + 1024;                            // 2 x kRecWords x SLOTS
-    uint32_t* sBitsX = sUp + 2 * SLOTS * kRecWords;         // tw
+    uint32_t* sUp = sCur + 1024;                            // kRing x kRecWords x SLOTS
+    uint32_t* sBitsX = sUp + kRing * SLOTS * kRecWords;     // tw
     uint32_t* sBitsY = sBitsX + ((p.tw + 3) & ~3);          // roundup(th, YB)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -316,6 +346,11 @@ __global__ void __launch_bounds__(kFastThreads, 1) me_u8_tile_kernel(const FastP
     const int twA = min(p.tw, p.W - x0), thA = min(p.th, p.W - y0);
     const int nRG = (thA + YB - 1) / YB, nUnits = twA * nRG;
     const int4 jb = p.jobs[job];
+    __shared__ uint64_t fullBar[kRing];
+    if (tid == 0) {
+#pragma unroll
+        for (int k = 0; k < kRing; ++k) mbar_init(&fullBar[k], kFastThreads / 32);
+    }
 
     // ---- stage the reference window as sliding words (linear source addressing), the CTU, and the MV-bit tables
     {
@@ -362,32 +397,54 @@ __global__ void __launch_bounds__(kFastThreads, 1) me_u8_tile_kernel(const FastP
     const int nRounds = (nUnits + 31) >> 5;
     const int nFull = (twA * (thA / YB)) >> 5;              // rounds in which every lane and every candidate row is valid
     int rg = lane / twA, ux = lane - rg * twA;              // this lane's unit of round 0, advanced incrementally
-    for (int round = 0; round < nRounds; ++round) {
-        uint32_t* recBuf = sUp + (round & 1) * (SLOTS * kRecWords);
-        if (round < nFull)
-            round_body<YB, false>(sWin, cp, sBitsX, sBitsY, recBuf, best, rg, ux, by, bx, b, lane, twA, thA, nRG, p.lambda);
-        else
-            round_body<YB, true>(sWin, cp, sBitsX, sBitsY, recBuf, best, rg, ux, by, bx, b, lane, twA, thA, nRG, p.lambda);
-        ux += 32;
-        while (ux >= twA) { ux -= twA; ++rg; }
-        __syncthreads();
-        if (role < 4) emit_quadrant(recBuf + slot, role, ub, SLOTS);
-        else if (role == 4) emit_ctu(recBuf + slot, ub, SLOTS);
+    // Warps are NOT barrier-locked per round: records travel through a ring of kRing buffers guarded by mbarriers, and the
+    // upper phase of round k runs after the block phase of round k+1, by which time every producer has long arrived.  That
+    // lets the two warps of each scheduler that start `stagger` cycles late stay half a round out of phase, so the
+    // SAD-heavy (ALU pipe) and sum-heavy (FMA pipe) stretches of different warps overlap.
+    if (p.stagger > 0 && (warp & 8)) {
+        const long long t0 = clock64();
+        while (clock64() - t0 < p.stagger) {}
+    }
+    for (int round = 0; round <= nRounds; ++round) {
+        if (round < nRounds) {
+            uint32_t* recBuf = sUp + (round & (kRing - 1)) * (SLOTS * kRecWords);
+            if (round < nFull)
+                round_body<YB, false>(sWin, cp, sBitsX, sBitsY, recBuf, best, rg, ux, by, bx, b, lane, twA, thA, nRG, p.lambda);
+            else
+                round_body<YB, true>(sWin, cp, sBitsX, sBitsY, recBuf, best, rg, ux, by, bx, b, lane, twA, thA, nRG, p.lambda);
+            ux += 32;
+            while (ux >= twA) { ux -= twA; ++rg; }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&fullBar[round & (kRing - 1)]);
+        }
+        if (round >= 1) {
+            const int k = round - 1;
+            mbar_wait(&fullBar[k & (kRing - 1)], (uint32_t)(k / kRing) & 1u);
+            const uint32_t* recBuf = sUp + (k & (kRing - 1)) * (SLOTS * kRecWords);
+            if (role < 4) emit_quadrant(recBuf + slot, role, ub, SLOTS);
+            else if (role == 4) emit_ctu(recBuf + slot, ub, SLOTS);
+        }
     }
 
-    // ---- tile end: warp arg-min per key, publish
+    // ---- tile end: warp arg-min per key (CREDUX.MIN), lane k keeps key k, then all lanes publish in parallel
     unsigned long long* bestJob = p.best + (size_t)job * HMME_NPARTS;
+    uint32_t mine = 0xFFFFFFFFu, last = 0xFFFFFFFFu;
 #pragma unroll
     for (int k = 0; k < 33; ++k) {
         const uint32_t m = __reduce_min_sync(0xFFFFFFFFu, best[k]);
-        if (lane == (k & 31)) publish(bestJob, block_part_index(b, k), m, twA, x0, y0, p.W);
+        if (k < 32) mine = (lane == k) ? m : mine;
+        else last = m;
     }
+    publish(bestJob, block_part_index(b, lane), mine, twA, x0, y0, p.W);
+    if (lane == 0) publish(bestJob, block_part_index(b, 32), last, twA, x0, y0, p.W);
     if (role <= 4) {                                          // warp-uniform: SLOTS is a multiple of 32
+        mine = 0xFFFFFFFFu;
 #pragma unroll
         for (int k = 0; k < 13; ++k) {
             const uint32_t m = __reduce_min_sync(0xFFFFFFFFu, ub[k]);
-            if (lane == k) publish(bestJob, role < 4 ? quad_part_index(role, k) : ctu_part_index(k), m, twA, x0, y0, p.W);
+            mine = (lane == k) ? m : mine;
         }
+        if (lane < 13) publish(bestJob, role < 4 ? quad_part_index(role, lane) : ctu_part_index(lane), mine, twA, x0, y0, p.W);
     }
 }
 
