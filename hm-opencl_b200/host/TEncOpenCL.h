@@ -1,0 +1,93 @@
+/*
+ * TEncOpenCL.h -- drop-in replacement of HM-OpenCL's GPU motion-estimation host class.
+ *
+ * Same class name and public surface as /root/reference/source/Lib/TLibEncoder/TEncOpenCL.h:105-123, so that
+ * TEncTop (TEncTop.h:82, TEncTop.cpp:1116-1162), TEncSearch (TEncSearch.cpp:3743-3771) and TEncSlice
+ * (TEncSlice.cpp:125,150,799,893) compile and behave unchanged.  Everything behind it is new: no OpenCL, the
+ * work goes through the C ABI of libhmme_b200.so (include/hmme_b200.h) to hand-written sm_100a CUDA kernels.
+ *
+ * Deliberately NOT reproduced from the reference: uninitialised members, use of mapped
+ * pointers after unmap, dangling alloca'd device lists, clFinish(NULL) in the destructor, and the silent CPU
+ * fallback -- a failed initialisation returns false with a message and leaves the object disabled; calling
+ * calcMotionVectors on a disabled object aborts with a message instead of computing on the CPU.
+ *
+ * Build inside HM: replace TLibEncoder/TEncOpenCL.{h,cpp} by this pair, add -I<repo>/include, link
+ * -L<repo>/hm-opencl_b200 -lhmme_b200 instead of -lOpenCL.
+ * Build standalone (tests): -DHMME_STANDALONE supplies the handful of HM typedefs this header needs.
+ */
+#ifndef TENCOPENCL_H
+#define TENCOPENCL_H
+
+#ifdef HMME_STANDALONE
+#include <stdint.h>
+typedef void Void;
+typedef bool Bool;
+typedef char Char;
+typedef short Short;
+typedef int Int;
+typedef unsigned int UInt;
+typedef double Double;
+typedef Short Pel;               // TypeDef.h:706
+typedef UInt Distortion;         // TypeDef.h:717
+#define NUM_CTU_PARTS 593        // TypeDef.h:263
+class TComMv {                   // TComMv.h:54-55: a pair of Short
+    Short m_iHor, m_iVer;
+public:
+    TComMv() : m_iHor(0), m_iVer(0) {}
+    TComMv(Short h, Short v) : m_iHor(h), m_iVer(v) {}
+    Short getHor() const { return m_iHor; }
+    Short getVer() const { return m_iVer; }
+};
+#else
+#include "TLibCommon/TypeDef.h"
+#include "TLibCommon/TComMv.h"
+#endif
+
+#include <string>
+
+struct hmme_ctx;
+
+class TEncOpenCL {
+protected:
+    hmme_ctx*    m_ctx;                         ///< CUDA context of libhmme_b200 (NULL until createBuffers succeeds)
+    Bool         deviceFound;                   ///< findDevice succeeded
+    Bool         compileKernel;                 ///< compileKernelSource accepted the request
+    Int          deviceId;                      ///< CUDA device ordinal (option OpenCLDevice)
+    Bool         enabled;
+    std::string  info;                          ///< device name (getDeviceInfo)
+    Int          searchRange;                   ///< range createBuffers was sized for
+    Double       m_lambdaDouble;                ///< last value given to setLambda (applied once the context exists)
+    UInt         m_lambda;                      ///< (UInt)floor(65536*sqrt(lambda)), TEncOpenCL.h:121 of the reference
+
+    Int          Xarray[NUM_CTU_PARTS];         ///< integer-pel MV x of the best candidate per partition
+    Int          Yarray[NUM_CTU_PARTS];
+    Distortion   minSad[NUM_CTU_PARTS];         ///< SAD + MV-bit cost of the winner
+    Distortion   ruiCosts[NUM_CTU_PARTS];       ///< pure SAD of the winner
+
+public:
+    TEncOpenCL();
+    virtual         ~TEncOpenCL();
+    Bool            compileKernelSource(const Char* fileName, const Char* kernelNameCalc);
+    Bool            findDevice(Int device);
+    Bool            findDevices(Int device) { return findDevice(device); }   ///< the reference README's spelling
+    Bool            createBuffers(UInt i_maxCtuWidth, UInt i_maxCtuHeight, Int i_searchRange);
+    Void            calcMotionVectors(Pel* pelCtu, Pel* pelSearch, Int i_iRefStride, Int i_iCtuStride, Int i_areaSize, TComMv* pcMvSrchRngLT);
+
+    //======== getters and setters ================
+    Int             getDeviceId         ()              { return deviceId; }
+    Void            setDeviceId         ( Int i )       { deviceId = i; }
+    const Char*     getDeviceInfo       ()              { return info.c_str(); }
+    Distortion*     getRuiCost          ()              { return ruiCosts; }
+    Int*            getX                ()              { return Xarray; }
+    Int*            getY                ()              { return Yarray; }
+    Void            setLambda           (Double lambda);
+    Void            setEnabled          (Bool e)        { enabled = e; }
+    Bool            isEnabled           () const        { return enabled; }
+    const Char*     getLastError        () const;
+
+private:
+    TEncOpenCL(const TEncOpenCL&);              // owns a device context: not copyable
+    TEncOpenCL& operator=(const TEncOpenCL&);
+};
+
+#endif /* TENCOPENCL_H */

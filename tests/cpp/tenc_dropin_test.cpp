@@ -1,0 +1,59 @@
+// tenc_dropin_test.cpp -- exercises the C++ drop-in class (hm-opencl_b200/host/TEncOpenCL) exactly the way HM does
+// (TEncTop::xInitOpenCL call order, TEncSearch::xMotionEstimation per-CTU call + getters) and checks every output
+// against the CPU oracle.  Test code: it may link the oracle.  Built and run by tests/test_gpu_dropin_cpp.py.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "TEncOpenCL.h"
+#include "hmme_oracle.h"
+
+static unsigned lcg(unsigned& s) { s = s * 1664525u + 1013904223u; return s >> 8; }
+
+int main() {
+    TEncOpenCL me;                                                       // TEncTop.h:82: a by-value member, constructed in every run
+    if (!me.findDevice(0)) { printf("FAIL findDevice\n"); return 1; }
+    if (me.compileKernelSource(NULL, "calcSAD_AMP")) { printf("FAIL NULL kernel file accepted\n"); return 1; }
+    if (!me.compileKernelSource("cl/sad.cl", "calcSAD_AMP")) { printf("FAIL compileKernelSource\n"); return 1; }
+    if (!me.createBuffers(64, 64, 64)) { printf("FAIL createBuffers: %s\n", me.getLastError()); return 1; }
+    me.setEnabled(true);
+    printf("device: %s\n", me.getDeviceInfo());
+
+    const int W = 256, H = 192, M = 80, S = W + 2 * M;                   // padded plane like TComPicYuv (margin 80)
+    std::vector<Pel> ref((size_t)S * (H + 2 * M)), cur((size_t)S * (H + 2 * M));
+    unsigned seed = 12345;
+    for (size_t i = 0; i < ref.size(); ++i) ref[i] = (Pel)(lcg(seed) & 255);
+    for (int y = 0; y < H + 2 * M; ++y)
+        for (int x = 0; x < S; ++x) {
+            const int sy = y + 2 < H + 2 * M ? y + 2 : y, sx = x + 3 < S ? x + 3 : x;
+            cur[(size_t)y * S + x] = (Pel)((ref[(size_t)sy * S + sx] + (int)(lcg(seed) % 5) - 2) & 255);
+        }
+    int bad = 0, calls = 0;
+    const double lambdas[3] = {49.3, 4.0, 1200.0};
+    const int ranges[3] = {64, 16, 4};
+    for (int t = 0; t < 3; ++t) {
+        me.setLambda(lambdas[t]);                                        // TEncSlice::setUpLambda
+        const int R = ranges[t];
+        for (int cy = 0; cy + 64 <= H; cy += 64)
+            for (int cx = 0; cx + 64 <= W; cx += 64) {
+                Pel blk[64 * 64];
+                for (int r = 0; r < 64; ++r) memcpy(blk + 64 * r, &cur[(size_t)(M + cy + r) * S + M + cx], 64 * sizeof(Pel));
+                if (t == 2)                                              // bi-pred style 16-bit block 2*org - pred
+                    for (int i = 0; i < 4096; ++i) blk[i] = (Pel)(2 * blk[i] - (Pel)(lcg(seed) & 255));
+                TComMv lt((Short)(-R + (cx ? 3 : 0)), (Short)(-R - (cy ? 2 : 0)));
+                Pel* refAtCtu = &ref[(size_t)(M + cy) * S + M + cx];
+                me.calcMotionVectors(blk, refAtCtu, S, 64, R, &lt);
+                int32_t X[593], Y[593]; uint32_t sad[593], cost[593];
+                hmme_oracle_search_ctu(blk, 64, refAtCtu, S, R, lt.getHor(), lt.getVer(), hmme_oracle_lambda_q16(lambdas[t]), X, Y, sad, cost);
+                ++calls;
+                for (int p = 0; p < 593; ++p)
+                    if (me.getX()[p] != X[p] || me.getY()[p] != Y[p] || me.getRuiCost()[p] != sad[p]) {
+                        if (bad++ < 5) printf("MISMATCH R=%d ctu(%d,%d) part %d: got (%d,%d,%u) want (%d,%d,%u)\n", R, cx, cy, p, me.getX()[p], me.getY()[p],
+                                              me.getRuiCost()[p], X[p], Y[p], sad[p]);
+                    }
+            }
+    }
+    printf("%s: %d calcMotionVectors calls, %d mismatches\n", bad ? "FAIL" : "PASS", calls, bad);
+    return bad ? 1 : 0;
+}
