@@ -32,10 +32,3 @@ def frame_jobs(W, H, R, pred=(0, 0), rows=None):
     nx, ny = W // 64, H // 64
     r0, r1 = rows if rows is not None else (0, ny)
     return np.array([[cx * 64, cy * 64, pred[0] - R, pred[1] - R] for cy in range(r0, r1) for cx in range(nx)], np.int32).reshape(-1, 4)
-
-
-def band_rows(n_rows, world, rank):
-    """Contiguous CTU-row band of `rank`: sizes differ by at most one row."""
-    base, extra = divmod(n_rows, world)
-    r0 = rank * base + min(rank, extra)
-    return r0, r0 + base + (1 if rank < extra else 0)

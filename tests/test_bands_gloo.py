@@ -1,0 +1,70 @@
+"""N > 1 host logic on the CPU: two gloo ranks shard a frame into CTU-row bands (hm.band_jobs), rank 0 broadcasts the
+reference plane, each rank searches its band (with the oracle standing in for the device here -- there is no GPU in this
+container) and the gathered result must equal the single-rank result.  Mirrors what bench.py does over NCCL."""
+import os
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, out_dir):
+    import sys
+    sys.path.insert(0, ROOT)
+    from _pkg import hm
+    from oracle.pyoracle import Oracle
+    from synth import luma_frames, pad_plane
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    W, H, R, M, lam = 256, 320, 5, 24, 460000          # 4 x 5 CTUs: bands of 3 and 2 rows
+    f = luma_frames(W, H, 2, seed=9)
+    cur = pad_plane(f[1], M, M)
+    ref = torch.from_numpy(pad_plane(f[0], M, M)) if rank == 0 else torch.zeros((H + 2 * M, W + 2 * M), dtype=torch.int16)
+    dist.broadcast(ref.view(torch.uint8), src=0)        # reference-picture distribution (bytes, like the u8 plane over NCCL)
+    jobs, (r0, r1) = hm.band_jobs(W, H, R, world, rank)
+    assert len(jobs) == (r1 - r0) * (W // 64)
+    y0, y1 = hm.band_reference_rows(r0, r1, R, -R, -R)
+    assert y0 >= -M and y1 <= H + M                     # the halo stays inside the padded plane
+    res = Oracle().search_frame(cur, (M, M), ref.numpy(), (M, M), jobs, R, lam)
+    np.savez(os.path.join(out_dir, "rank%d.npz" % rank), X=res[0], Y=res[1], S=res[2], C=res[3], r=np.array([r0, r1]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_band_sharding_matches_single_rank(tmp_path, oracle):
+    import sys
+    sys.path.insert(0, ROOT)
+    from _pkg import hm
+    from synth import frame_jobs, luma_frames, pad_plane
+    world = 2
+    mp.spawn(_worker, args=(world, 29500 + os.getpid() % 2000, str(tmp_path)), nprocs=world, join=True)
+    parts = []
+    rows = []
+    for r in range(world):
+        z = np.load(tmp_path / ("rank%d.npz" % r))
+        parts.append((z["X"], z["Y"], z["S"], z["C"]))
+        rows.append(tuple(z["r"]))
+    assert rows == [(0, 3), (3, 5)]
+    got = hm.merge_bands(parts)
+    W, H, R, M, lam = 256, 320, 5, 24, 460000
+    f = luma_frames(W, H, 2, seed=9)
+    want = oracle.search_frame(pad_plane(f[1], M, M), (M, M), pad_plane(f[0], M, M), (M, M), frame_jobs(W, H, R), R, lam, nthreads=4)
+    for g, w in zip(got, want):
+        assert np.array_equal(g, w)
+
+
+def test_band_rows_cover_exactly():
+    import sys
+    sys.path.insert(0, ROOT)
+    from _pkg import hm
+    for n in (1, 16, 17, 33):
+        for world in (1, 2, 4, 8):
+            bands = [hm.band_rows(n, world, r) for r in range(world)]
+            assert bands[0][0] == 0 and bands[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(bands, bands[1:]))
+            sizes = [b - a for a, b in bands]
+            assert max(sizes) - min(sizes) <= 1
