@@ -25,8 +25,8 @@ def band_jobs(width, height, search_range, world, rank, pred=(0, 0)):
 
 def band_reference_rows(r0, r1, search_range, lty_min, lty_max):
     """Picture rows [y0, y1) of the reference plane a band reads: its own rows plus the halo of the search window
-    (band +- (R + |pred|)).  Only needed when a rank uploads the band instead of receiving the whole plane."""
-    return 64 * r0 + lty_min, 64 * r1 - 1 + lty_max + 2 * search_range + 63 + 1
+    (a CTU at row y reads rows [y + lty, y + lty + 2R + 63]).  Only needed when a rank uploads the band instead of receiving the whole plane."""
+    return 64 * r0 + lty_min, 64 * (r1 - 1) + lty_max + 2 * search_range + 63 + 1
 
 
 def merge_bands(parts):
