@@ -75,7 +75,6 @@ struct hmme_ctx {
     unsigned long long* dBest = nullptr;
     int32_t* dRes = nullptr;      // [4][jobCap][593]: X, Y, sad, cost
     hmme_job* hJobs = nullptr;    // pinned
-    int32_t* hRes = nullptr;      // pinned
     // per-CTU synchronous path staging
     size_t winElems = 0;          // (2*maxRange+64+16)^2
     void* hWin = nullptr;         // pinned, int16-sized
@@ -110,13 +109,11 @@ int ensure_jobs(hmme_ctx* c, size_t njobs) {
     if (c->dBest) cudaFree(c->dBest);
     if (c->dRes) cudaFree(c->dRes);
     if (c->hJobs) cudaFreeHost(c->hJobs);
-    if (c->hRes) cudaFreeHost(c->hRes);
-    c->dJobs = nullptr; c->dBest = nullptr; c->dRes = nullptr; c->hJobs = nullptr; c->hRes = nullptr; c->jobCap = 0;
+    c->dJobs = nullptr; c->dBest = nullptr; c->dRes = nullptr; c->hJobs = nullptr; c->jobCap = 0;
     CU_TRY(c, cudaMalloc(&c->dJobs, cap * sizeof(int4)));
     CU_TRY(c, cudaMalloc(&c->dBest, cap * HMME_NPARTS * sizeof(unsigned long long)));
     CU_TRY(c, cudaMalloc(&c->dRes, 4 * cap * HMME_NPARTS * sizeof(int32_t)));
     CU_TRY(c, cudaMallocHost(&c->hJobs, cap * sizeof(hmme_job)));
-    CU_TRY(c, cudaMallocHost(&c->hRes, 4 * cap * HMME_NPARTS * sizeof(int32_t)));
     c->jobCap = cap;
     return HMME_OK;
 }
@@ -207,14 +204,20 @@ int enqueue_search(hmme_ctx* c, const void* curOrigin, int curElem, long long cu
 }
 
 int fetch(hmme_ctx* c, int njobs, int32_t* X, int32_t* Y, uint32_t* sad, uint32_t* cost) {
+    // straight into the caller's arrays: a true DMA when they are page-locked (bench.py, the drop-in class), a driver-staged
+    // copy otherwise -- either way no extra host-side memcpy
     const size_t n = (size_t)njobs * HMME_NPARTS, cap = c->jobCap * HMME_NPARTS;
     void* outs[4] = {X, Y, sad, cost};
     for (int k = 0; k < 4; ++k)
-        if (outs[k]) CU_TRY(c, cudaMemcpyAsync(c->hRes + k * cap, c->dRes + k * cap, n * 4, cudaMemcpyDeviceToHost, c->stream));
+        if (outs[k]) CU_TRY(c, cudaMemcpyAsync(outs[k], c->dRes + k * cap, n * 4, cudaMemcpyDeviceToHost, c->stream));
     CU_TRY(c, cudaStreamSynchronize(c->stream));
-    for (int k = 0; k < 4; ++k)
-        if (outs[k]) std::memcpy(outs[k], c->hRes + k * cap, n * 4);
     return HMME_OK;
+}
+
+// host rows -> device rows; one linear copy when both sides have the same pitch
+cudaError_t copy_rows_h2d(void* dst, size_t dpitch, const void* src, size_t spitch, size_t rowBytes, size_t rows, cudaStream_t s) {
+    if (dpitch == spitch) return cudaMemcpyAsync(dst, src, spitch * (rows - 1) + rowBytes, cudaMemcpyHostToDevice, s);
+    return cudaMemcpy2DAsync(dst, dpitch, src, spitch, rowBytes, rows, cudaMemcpyHostToDevice, s);
 }
 
 const char* origin_ptr(const hmme_plane* p) {
@@ -276,7 +279,7 @@ void hmme_destroy(hmme_ctx* c) {
     if (!c) return;
     if (c->device >= 0) cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    cudaFree(c->dJobs); cudaFree(c->dBest); cudaFree(c->dRes); cudaFreeHost(c->hJobs); cudaFreeHost(c->hRes);
+    cudaFree(c->dJobs); cudaFree(c->dBest); cudaFree(c->dRes); cudaFreeHost(c->hJobs);
     cudaFreeHost(c->hWin); cudaFree(c->dWin); cudaFreeHost(c->hCurBlk); cudaFree(c->dCurBlk);
     cudaFree(c->dStage); cudaFree(c->dFlag); cudaFreeHost(c->hFlag);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -374,7 +377,7 @@ int hmme_plane_upload_s16(hmme_ctx* c, const hmme_plane* p, const int16_t* hostO
     const int rows = p->height + 2 * p->marginY, cols = p->width + 2 * p->marginX;
     const int16_t* src = hostOrigin - (ptrdiff_t)p->marginY * hostStride - p->marginX;
     if (p->elemBytes == 2) {
-        CU_TRY(c, cudaMemcpy2DAsync(p->base, (size_t)p->pitch * 2, src, (size_t)hostStride * 2, (size_t)cols * 2, rows, cudaMemcpyHostToDevice, c->stream));
+        CU_TRY(c, copy_rows_h2d(p->base, (size_t)p->pitch * 2, src, (size_t)hostStride * 2, (size_t)cols * 2, rows, c->stream));
         CU_TRY(c, cudaStreamSynchronize(c->stream));
         return HMME_OK;
     }
@@ -386,9 +389,9 @@ int hmme_plane_upload_s16(hmme_ctx* c, const hmme_plane* p, const int16_t* hostO
         CU_TRY(c, cudaMalloc(&c->dStage, n * 2));
         c->stageElems = n;
     }
-    CU_TRY(c, cudaMemsetAsync(c->dStage, 0, n * 2, c->stream));      // pitch padding columns must read as in-range samples
+    if (p->pitch != cols) CU_TRY(c, cudaMemsetAsync(c->dStage, 0, n * 2, c->stream));   // pitch padding columns must read as in-range samples
     CU_TRY(c, cudaMemsetAsync(c->dFlag, 0, sizeof(int), c->stream));
-    CU_TRY(c, cudaMemcpy2DAsync(c->dStage, (size_t)p->pitch * 2, src, (size_t)hostStride * 2, (size_t)cols * 2, rows, cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(c, copy_rows_h2d(c->dStage, (size_t)p->pitch * 2, src, (size_t)hostStride * 2, (size_t)cols * 2, rows, c->stream));
     me_narrow_kernel<<<(unsigned)((n / 8 + 255) / 256 + 1), 256, 0, c->stream>>>(c->dStage, static_cast<uint8_t*>(p->base), n, c->dFlag);
     c->launches += 1;
     CU_TRY(c, cudaMemcpyAsync(c->hFlag, c->dFlag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -405,7 +408,7 @@ int hmme_plane_upload_u8(hmme_ctx* c, const hmme_plane* p, const uint8_t* hostOr
     CU_TRY(c, cudaSetDevice(c->device));
     const int rows = p->height + 2 * p->marginY, cols = p->width + 2 * p->marginX;
     const uint8_t* src = hostOrigin - (ptrdiff_t)p->marginY * hostStride - p->marginX;
-    CU_TRY(c, cudaMemcpy2DAsync(p->base, (size_t)p->pitch, src, (size_t)hostStride, (size_t)cols, rows, cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(c, copy_rows_h2d(p->base, (size_t)p->pitch, src, (size_t)hostStride, (size_t)cols, rows, c->stream));
     CU_TRY(c, cudaStreamSynchronize(c->stream));
     return HMME_OK;
 }
