@@ -188,7 +188,7 @@ class MotionEstimator:
 
     def wrap_plane(self, device_ptr, elem_bytes, pitch, width, height, margin_x, margin_y):
         """View of device memory owned by someone else (e.g. torch.Tensor.data_ptr()); must be 16-byte aligned
-        and hold pitch*(height+2*margin_y) elements plus 4 bytes of slack."""
+        and hold pitch*(height+2*margin_y) elements plus 64 bytes of slack (16-byte granular TMA row copies)."""
         d = PlaneDesc(C.c_void_p(int(device_ptr)), elem_bytes, pitch, width, height, margin_x, margin_y)
         return Plane(self, d, False)
 

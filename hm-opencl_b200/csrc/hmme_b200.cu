@@ -428,8 +428,10 @@ int hmme_search_frame_async(hmme_ctx* c, const hmme_plane* cur, const hmme_plane
     // so consecutive frames can be enqueued without a host synchronisation in between
     CU_TRY(c, cudaMemcpyAsync(c->dJobs, jobs, (size_t)njobs * sizeof(hmme_job), cudaMemcpyHostToDevice, c->stream));
     const char* refLo = static_cast<const char*>(ref->base);
+    // planes carry 64 bytes of slack after the last row (hmme_plane_alloc adds it; required of external memory): the
+    // 16-byte granular TMA row copies may run a few bytes past the window's last sample
     return enqueue_search(c, origin_ptr(cur), cur->elemBytes, cur->pitch, origin_ptr(ref), ref->elemBytes, ref->pitch, refLo,
-                          refLo + plane_elems(ref) * ref->elemBytes, njobs, range);
+                          refLo + plane_elems(ref) * ref->elemBytes + 64, njobs, range);
 }
 
 int hmme_fetch_results(hmme_ctx* c, int njobs, int32_t* X, int32_t* Y, uint32_t* sad, uint32_t* cost) {

@@ -37,6 +37,7 @@ constexpr int kIdxBits = 11;                  // candidates per tile <= 2048
 constexpr int kMaxTileCands = 1 << kIdxBits;
 constexpr int kWinPitch = 192;                // sliding-word entries per window row: (tw-1) + 4*15 + 1 <= 189 for tw <= 129
 constexpr int kMaxTileW = 129;
+constexpr int kDensePitch = 224;              // bytes per row of the TMA landing buffer: 15 (alignment) + 129 + 63 + 3, rounded up to 16
 constexpr int kRecWords = 49;                 // upper-phase words per candidate slot: 32 (8x8 pairs, u16) + 16 (16x16<<11) + 1 (key base),
                                               // stored slot-minor ([word][slot]) so that every access is lane-contiguous
 constexpr uint32_t kInvalidBlockKeyBase = 0xF0000000u;   // block sums << 11 stay below 2^27: no wrap, never wins
@@ -81,6 +82,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "{ .reg .pred p;\n"
         "W_%=: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
         "@!p bra W_%=;\n}" ::"r"(a), "r"(parity) : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+// TMA bulk copy global -> shared (cp.async.bulk, SASS UBLKCP): 16-byte aligned source/destination, size a multiple of 16;
+// completion is signalled as transaction bytes on the mbarrier.
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     (uint32_t)__cvta_generic_to_shared(dst)),
+                 "l"(src), "r"(bytes), "r"((uint32_t)__cvta_generic_to_shared(bar))
+                 : "memory");
 }
 
 // partition index of block-level key k (0..32) for block b
@@ -347,41 +360,58 @@ __global__ void __launch_bounds__(kFastThreads, 1) me_u8_tile_kernel(const FastP
     const int nRG = (thA + YB - 1) / YB, nUnits = twA * nRG;
     const int4 jb = p.jobs[job];
     __shared__ uint64_t fullBar[kRing];
+    __shared__ uint64_t winBar;
     if (tid == 0) {
 #pragma unroll
         for (int k = 0; k < kRing; ++k) mbar_init(&fullBar[k], kFastThreads / 32);
     }
 
-    // ---- stage the reference window as sliding words (linear source addressing), the CTU, and the MV-bit tables
+    // ---- stage the reference window, the CTU and the MV-bit tables.
+    // TMA bulk copies (one per window row, 16-byte aligned superset of the row's bytes; linear source addressing, so the
+    // reference's row-wrap behaviour is kept) land in a dense buffer that aliases the not-yet-used record ring; the CTU rows
+    // go the same way when they are 16-byte aligned.  All threads then expand the dense rows into sliding words.
     {
         const int rows = nRG * YB + 63, nPos = twA + 60;      // entries 0 .. (twA-1) + 4*15
         const uint8_t* wbase = p.ref + (long long)(jb.y + jb.w + y0) * p.refPitch + (jb.x + jb.z + x0);
-        const uintptr_t lo = (uintptr_t)p.refLo, hi = ((uintptr_t)p.refHi - 4) & ~(uintptr_t)3;
-        const int wordsPerRow = (nPos + 3 + 3) / 4 + 1;       // aligned words that cover bytes [-3, nPos+3) of the row
-        for (int row = warp; row < rows; row += kFastThreads / 32) {
-            const uintptr_t g = (uintptr_t)(wbase + (long long)row * p.refPitch);
-            const int a = (int)(g & 3);
-            const uintptr_t g0 = g - a;
-            uint32_t* dst = sWin + row * kWinPitch;
-            for (int j0 = 0; j0 < wordsPerRow; j0 += 32) {       // warp-uniform trip count: the shuffle needs all lanes
-                const int j = j0 + lane;
-                const uint32_t w0 = *reinterpret_cast<const uint32_t*>(min(max(g0 + 4 * (uintptr_t)j, lo), hi));
-                uint32_t w1 = __shfl_down_sync(0xFFFFFFFFu, w0, 1);
-                if (lane == 31) w1 = *reinterpret_cast<const uint32_t*>(min(max(g0 + 4 * (uintptr_t)j + 4, lo), hi));
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {                 // aligned bytes 4j+k.. are window bytes x = 4j + k - a ..
-                    const int x = 4 * j + k - a;
-                    if (x >= 0 && x < nPos) dst[x] = __funnelshift_r(w0, w1, 8 * k);
-                }
-            }
-        }
         const uint8_t* cbase = p.cur + (long long)jb.y * p.curPitch + jb.x;
-        for (int idx = tid; idx < 1024; idx += kFastThreads) {
-            const uint8_t* c = cbase + (long long)(idx >> 4) * p.curPitch + 4 * (idx & 15);
-            sCur[idx] = (uint32_t)c[0] | ((uint32_t)c[1] << 8) | ((uint32_t)c[2] << 16) | ((uint32_t)c[3] << 24);
+        const bool curTma = (((uintptr_t)cbase | (uintptr_t)p.curPitch) & 15) == 0;
+        uint8_t* dense = reinterpret_cast<uint8_t*>(sUp);
+        if (tid == 0) {
+            mbar_init(&winBar, (uint32_t)(rows + (curTma ? 64 : 0)));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (tid < rows) {
+            const uintptr_t g = (uintptr_t)(wbase + (long long)tid * p.refPitch);
+            const uintptr_t g0 = g & ~(uintptr_t)15;
+            uint32_t bytes = (uint32_t)(((g - g0) + (uintptr_t)(nPos + 3) + 15) & ~(uintptr_t)15);
+            const uintptr_t room = ((uintptr_t)p.refHi - g0) & ~(uintptr_t)15;          // never read past the allocation (+slack)
+            bytes = (uint32_t)min((uintptr_t)bytes, room);
+            mbar_arrive_expect_tx(&winBar, bytes);
+            tma_bulk_g2s(dense + tid * kDensePitch, reinterpret_cast<const void*>(g0), bytes, &winBar);
+        } else if (curTma && tid >= kFastThreads - 64) {
+            const int r = tid - (kFastThreads - 64);
+            mbar_arrive_expect_tx(&winBar, 64);
+            tma_bulk_g2s(sCur + r * 16, cbase + (long long)r * p.curPitch, 64, &winBar);
+        }
+        if (!curTma) {
+            for (int idx = tid; idx < 1024; idx += kFastThreads) {
+                const uint8_t* c = cbase + (long long)(idx >> 4) * p.curPitch + 4 * (idx & 15);
+                sCur[idx] = (uint32_t)c[0] | ((uint32_t)c[1] << 8) | ((uint32_t)c[2] << 16) | ((uint32_t)c[3] << 24);
+            }
         }
         for (int x = tid; x < twA; x += kFastThreads) sBitsX[x] = mv_bits(4 * (jb.z + x0 + x));
         for (int y = tid; y < nRG * YB; y += kFastThreads) sBitsY[y] = mv_bits(4 * (jb.w + y0 + y));
+        mbar_wait(&winBar, 0);
+        for (int row = warp; row < rows; row += kFastThreads / 32) {
+            const uint32_t off = (uint32_t)((uintptr_t)(wbase + (long long)row * p.refPitch) & 15);
+            const uint32_t* d = reinterpret_cast<const uint32_t*>(dense + row * kDensePitch);
+            uint32_t* dst = sWin + row * kWinPitch;
+            for (int x = lane; x < nPos; x += 32) {           // lane-contiguous stores, 4-lane broadcast loads: conflict-free
+                const uint32_t q = off + (uint32_t)x;
+                dst[x] = __funnelshift_r(d[q >> 2], d[(q >> 2) + 1], 8 * (q & 3));
+            }
+        }
     }
     __syncthreads();
 

@@ -48,7 +48,9 @@ typedef struct { int32_t ctuX, ctuY, ltx, lty; } hmme_job;
 /* A luma plane resident in device memory.  `base` is the FIRST byte of the allocation (top-left of
  * the margin); picture sample (0,0) is at base + (marginY*pitch + marginX)*elemBytes.  elemBytes is
  * 1 (8-bit samples, the fast path) or 2 (int16, e.g. the bi-prediction "current" block 2*org-pred,
- * TEncSearch.cpp:3702-3712).  pitch is in elements.  Rows 0..height+2*marginY-1 are addressable. */
+ * TEncSearch.cpp:3702-3712).  pitch is in elements.  Rows 0..height+2*marginY-1 are addressable; base is 16-byte
+ * aligned and the allocation extends 64 bytes past the last row (hmme_plane_alloc does both; memory wrapped from elsewhere,
+ * e.g. a torch tensor, must too: the kernels fetch window rows with 16-byte granular TMA bulk copies). */
 typedef struct {
     void* base;
     int32_t elemBytes, pitch, width, height, marginX, marginY;
