@@ -176,7 +176,7 @@ def run_reference(args, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="1080p64", choices=sorted(WORKLOADS))
@@ -349,7 +349,7 @@ def main():
                     "timer": "host wall clock around K x {upload int16 planes from pinned memory, broadcast, search, fetch results}, max over ranks"},
             "roofline": {"bound": "int_alu", "kernel": "me_u8_tile_kernel", "achieved": achieved / 1e12, "peak": peak["lane_ops_per_s"] / 1e12,
                          "unit": "T int-lane-op/s", "frac": achieved / peak["lane_ops_per_s"] if peak["lane_ops_per_s"] else None,
-                         "traffic": None,
+                         "traffic": _ncu_traffic(args.workload) if world == 1 else None,
                          "ops_per_ctu_candidate": INT_OPS_PER_CAND, "kernel_ms": kern_ms,
                          "pixel_abs_diffs_per_s": cands_rank * PX_PER_CAND / (kern_ms * 1e-3) if kern_ms > 0 else 0.0,
                          "peak_source": "measured live: VABSDIFF4.U8.ACC issue rate, %.1f lanes/clk/SM x %d SMs at %.0f MHz"
@@ -367,6 +367,15 @@ def main():
     me.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def _ncu_traffic(workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the committed ncu capture."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        return t["traffic_bytes_per_launch"] if t["workload"].startswith(workload) else None
+    except Exception:
+        return None
 
 
 def _measured_hbm():

@@ -216,3 +216,29 @@ def test_full_1080p_pm64_properties_and_samples(me, oracle):
     want = oracle.search_frame(cur, (M, M), ref, (M, M), jobs[pick], R, lam, nthreads=8)
     assert_same([a[pick] for a in (X, Y, S, Cst)], want, "1080p sample")
     pc.free(); pr.free()
+
+
+def test_full_4k_pm128_properties_and_samples(me, oracle):
+    """BASELINE config 4 geometry at full size on one GPU: 3840x2160, +-128, 1980 CTUs x 66049 candidates (2 x 43 tiles per
+    job).  Properties on every job + bit-exact comparison with the oracle on 4 sampled CTUs."""
+    W, H, R = 3840, 2160, 128
+    f = luma_frames(W, H, 2, seed=77)
+    M = R + 16
+    cur, ref = pad_plane(f[1], M, M), pad_plane(f[0], M, M)
+    pc, pr = me.alloc_plane(1, W, H, M, M), me.alloc_plane(1, W, H, M, M)
+    me.upload(pc, cur); me.upload(pr, ref)
+    jobs = frame_jobs(W, H, R)
+    assert len(jobs) == 1980
+    lam = 1000000
+    me.set_lambda_q16(lam)
+    X, Y, S, Cst = me.search_frame(pc, pr, jobs, R)
+    assert (X >= -R).all() and (X <= R).all() and (Y >= -R).all() and (Y <= R).all()
+    bits = np.vectorize(lambda v: oracle.mv_bits(4 * int(v)))
+    mvc = ((lam * (bits(X) + bits(Y)).astype(np.uint64)) & 0xFFFFFFFF) >> 16
+    assert np.array_equal(Cst.astype(np.uint64), S.astype(np.uint64) + mvc)
+    hit = (X[:, 592] == 3) & (Y[:, 592] == 2) & (S[:, 592] == 0)
+    assert hit.sum() >= 1900
+    pick = [0, 59, 1000, 1979]
+    want = oracle.search_frame(cur, (M, M), ref, (M, M), jobs[pick], R, lam, nthreads=8)
+    assert_same([a[pick] for a in (X, Y, S, Cst)], want, "4K sample")
+    pc.free(); pr.free()
