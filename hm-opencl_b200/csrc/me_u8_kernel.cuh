@@ -138,10 +138,11 @@ __device__ __forceinline__ uint32_t addmin(uint32_t sum, uint32_t base, uint32_t
 }
 
 // Per-candidate state carried across the row loop: sums are folded strip by strip (4 rows at a time) as soon as a strip
-// of 4x4 SADs completes, so that the shift/add work (FMA pipe) and the add-min updates interleave with the packed SADs
-// (ALU pipe) of the candidates that are still being accumulated, instead of forming a separate FMA-bound phase.
+// of 4x4 SADs completes, so that the add/key work (FMA pipe) and the min updates interleave with the packed SADs (ALU
+// pipe) of the candidates that are still being accumulated, instead of forming a separate FMA-bound phase.
+// All sums are plain (unshifted) SADs; a key is formed by one IMAD: key = sum * 2^11 + ((mvcost << 11) | idxInTile).
 struct BlockState {
-    uint32_t sp[4];     // shifted 4x4 sums of the previous even strip
+    uint32_t sp[4];     // 4x4 sums of the previous even strip
     uint32_t hp[2];     // its two 8x4 sums
     uint32_t q0, q1, q2;  // 16x4 strip sums
     uint32_t v0[4];     // 4x8 sums of strips 0+1
@@ -149,69 +150,114 @@ struct BlockState {
     uint32_t top;       // 16x8 top
 };
 
-// Strip T (rows 4T..4T+3 of the 16x16 block) of one candidate is complete: a[i] = its four 4x4 SADs.
-template <int T>
-__device__ __forceinline__ void emit_strip(const uint32_t (&a)[4], BlockState& st, uint32_t kb, uint32_t (&best)[33],
-                                           uint32_t* rec, int b, bool writeBase, uint32_t recBase, int slots) {
-    uint32_t s[4];
-    s[1] = a[1] << kIdxBits; s[3] = a[3] << kIdxBits;
-    const uint32_t h0 = fshladd(a[0], s[1]), h1 = fshladd(a[2], s[3]), q = fadd(h0, h1);
-    s[0] = a[0] << kIdxBits; s[2] = a[2] << kIdxBits;
-    best[2 * T] = addmin(h0, kb, best[2 * T]);                     // 8x4
-    best[2 * T + 1] = addmin(h1, kb, best[2 * T + 1]);
+// best = min(best, key(sum[c], kb[c]) for the NC candidates handled together).  Two candidates cost ONE ALU instruction
+// (VIMNMX3) plus two IMADs on the FMA pipe, instead of two ALU add-mins: the ALU pipe is the kernel's bottleneck.
+template <int NC>
+__device__ __forceinline__ void upd(uint32_t& best, const uint32_t (&sum)[NC], const uint32_t (&kb)[NC]) {
+    if constexpr (NC == 1) best = min(best, fshladd(sum[0], kb[0]));
+    else best = min(min(best, fshladd(sum[0], kb[0])), fshladd(sum[1], kb[1]));
+}
+
+// Strip T (rows 4T..4T+3 of the 16x16 block) of NC candidates is complete: a[c][i] = the four 4x4 SADs of candidate c.
+// rec[c] points at candidate c's slot of the upper-level record (word w lives at rec[c][w * slots]).
+template <int T, int NC>
+__device__ __forceinline__ void emit_strip(const uint32_t (&a)[NC][4], BlockState (&st)[NC], const uint32_t (&kb)[NC], uint32_t (&best)[33],
+                                           uint32_t* const (&rec)[NC], int b, bool writeBase, const uint32_t (&recBase)[NC], int slots) {
+    uint32_t h0[NC], h1[NC], q[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) { h0[c] = fadd(a[c][0], a[c][1]); h1[c] = fadd(a[c][2], a[c][3]); q[c] = fadd(h0[c], h1[c]); }
+    upd<NC>(best[2 * T], h0, kb);                                  // 8x4
+    upd<NC>(best[2 * T + 1], h1, kb);
     if constexpr (T == 0) {
-        best[20] = addmin(q, kb, best[20]);                        // 16x4  (2NxnU part 0)
-        st.q0 = q;
+        upd<NC>(best[20], q, kb);                                  // 16x4  (2NxnU part 0)
+#pragma unroll
+        for (int c = 0; c < NC; ++c) st[c].q0 = q[c];
     }
     if constexpr (T == 0 || T == 2) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) st.sp[i] = s[i];
-        st.hp[0] = h0; st.hp[1] = h1;
+        for (int c = 0; c < NC; ++c) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) st[c].sp[i] = a[c][i];
+            st[c].hp[0] = h0[c]; st[c].hp[1] = h1[c];
+        }
     }
     if constexpr (T == 1) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { st.v0[i] = fadd(st.sp[i], s[i]); best[8 + i] = addmin(st.v0[i], kb, best[8 + i]); }   // 4x8
-        st.e0[0] = fadd(st.hp[0], h0); st.e0[1] = fadd(st.hp[1], h1);
-        best[16] = addmin(st.e0[0], kb, best[16]);                 // 8x8
-        best[17] = addmin(st.e0[1], kb, best[17]);
-        st.q1 = q;
-        st.top = fadd(st.q0, q);
-        best[28] = addmin(st.top, kb, best[28]);                   // 16x8 top
+        for (int i = 0; i < 4; ++i) {
+            uint32_t v[NC];
+#pragma unroll
+            for (int c = 0; c < NC; ++c) v[c] = st[c].v0[i] = fadd(st[c].sp[i], a[c][i]);
+            upd<NC>(best[8 + i], v, kb);                           // 4x8
+        }
+        uint32_t e0[NC], e1[NC], top[NC];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            e0[c] = st[c].e0[0] = fadd(st[c].hp[0], h0[c]);
+            e1[c] = st[c].e0[1] = fadd(st[c].hp[1], h1[c]);
+            st[c].q1 = q[c];
+            top[c] = st[c].top = fadd(st[c].q0, q[c]);
+        }
+        upd<NC>(best[16], e0, kb);                                 // 8x8
+        upd<NC>(best[17], e1, kb);
+        upd<NC>(best[28], top, kb);                                // 16x8 top
     }
     if constexpr (T == 2) {
-        st.q2 = q;
-        best[22] = addmin(fadd(st.top, q), kb, best[22]);               // 16x12 rows 0..11
+        uint32_t t12[NC];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) { st[c].q2 = q[c]; t12[c] = fadd(st[c].top, q[c]); }
+        upd<NC>(best[22], t12, kb);                                // 16x12 rows 0..11
     }
     if constexpr (T == 3) {
-        uint32_t v1[4], c[4];
+        uint32_t cs[4][NC];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { v1[i] = fadd(st.sp[i], s[i]); best[12 + i] = addmin(v1[i], kb, best[12 + i]); }     // 4x8
-        const uint32_t e10 = fadd(st.hp[0], h0), e11 = fadd(st.hp[1], h1);
-        best[18] = addmin(e10, kb, best[18]);                      // 8x8
-        best[19] = addmin(e11, kb, best[19]);
-        const uint32_t bot = fadd(st.q2, q);
-        best[21] = addmin(q, kb, best[21]);                        // 16x4  (2NxnD part 1)
-        best[29] = addmin(bot, kb, best[29]);                      // 16x8 bottom
-        best[23] = addmin(fadd(st.q1, bot), kb, best[23]);              // 16x12 rows 4..15
+        for (int i = 0; i < 4; ++i) {
+            uint32_t v[NC];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) c[i] = fadd(st.v0[i], v1[i]);
-        const uint32_t left = fadd(c[0], c[1]), right = fadd(c[2], c[3]);
-        best[24] = addmin(c[0], kb, best[24]);                     // 4x16  (nLx2N part 0)
-        best[25] = addmin(c[3], kb, best[25]);                     // 4x16  (nRx2N part 1)
-        best[26] = addmin(fadd(left, c[2]), kb, best[26]);              // 12x16 cols 0..11
-        best[27] = addmin(fadd(c[1], right), kb, best[27]);             // 12x16 cols 4..15
-        best[30] = addmin(left, kb, best[30]);                     // 8x16
-        best[31] = addmin(right, kb, best[31]);
-        const uint32_t all = fadd(st.top, bot);
-        best[32] = addmin(all, kb, best[32]);                      // 16x16
-        // upper-level hand-over: 8x8 sums as u16 pairs (<= 16320 each), 16x16 sum pre-shifted.
-        // (rec already points at this candidate's slot; word w of the record lives at rec[w * slots])
-        rec[(2 * b) * slots] = (st.e0[0] >> kIdxBits) | (st.e0[1] << (16 - kIdxBits));
-        rec[(2 * b + 1) * slots] = (e10 >> kIdxBits) | (e11 << (16 - kIdxBits));
-        rec[(32 + b) * slots] = all;
-        if (writeBase) rec[48 * slots] = recBase;
+            for (int c = 0; c < NC; ++c) { v[c] = fadd(st[c].sp[i], a[c][i]); cs[i][c] = fadd(st[c].v0[i], v[c]); }
+            upd<NC>(best[12 + i], v, kb);                          // 4x8
+        }
+        uint32_t e10[NC], e11[NC], bot[NC], b12[NC], left[NC], right[NC], l12[NC], r12[NC], all[NC];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            e10[c] = fadd(st[c].hp[0], h0[c]); e11[c] = fadd(st[c].hp[1], h1[c]);
+            bot[c] = fadd(st[c].q2, q[c]); b12[c] = fadd(st[c].q1, bot[c]);
+            left[c] = fadd(cs[0][c], cs[1][c]); right[c] = fadd(cs[2][c], cs[3][c]);
+            l12[c] = fadd(left[c], cs[2][c]); r12[c] = fadd(cs[1][c], right[c]);
+            all[c] = fadd(st[c].top, bot[c]);
+        }
+        upd<NC>(best[18], e10, kb);                                // 8x8
+        upd<NC>(best[19], e11, kb);
+        upd<NC>(best[21], q, kb);                                  // 16x4  (2NxnD part 1)
+        upd<NC>(best[29], bot, kb);                                // 16x8 bottom
+        upd<NC>(best[23], b12, kb);                                // 16x12 rows 4..15
+        upd<NC>(best[24], cs[0], kb);                              // 4x16  (nLx2N part 0)
+        upd<NC>(best[25], cs[3], kb);                              // 4x16  (nRx2N part 1)
+        upd<NC>(best[26], l12, kb);                                // 12x16 cols 0..11
+        upd<NC>(best[27], r12, kb);                                // 12x16 cols 4..15
+        upd<NC>(best[30], left, kb);                               // 8x16
+        upd<NC>(best[31], right, kb);
+        upd<NC>(best[32], all, kb);                                // 16x16
+        // upper-level hand-over: 8x8 sums as u16 pairs (<= 16320 each), 16x16 sum (<= 65280)
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            uint32_t pk0, pk1;
+            asm("mad.lo.u32 %0, %1, 65536, %2;" : "=r"(pk0) : "r"(st[c].e0[1]), "r"(st[c].e0[0]));
+            asm("mad.lo.u32 %0, %1, 65536, %2;" : "=r"(pk1) : "r"(e11[c]), "r"(e10[c]));
+            rec[c][(2 * b) * slots] = pk0;
+            rec[c][(2 * b + 1) * slots] = pk1;
+            rec[c][(32 + b) * slots] = all[c];
+            if (writeBase) rec[c][48 * slots] = recBase[c];
+        }
     }
 }
+
+// low + high half of a packed u16 pair (each sum <= 65535): (r * 0x10001) >> 16, one IMAD + one shift
+__device__ __forceinline__ uint32_t lohi(uint32_t r) {
+    uint32_t t;
+    asm("mad.lo.u32 %0, %1, 65537, 0;" : "=r"(t) : "r"(r));
+    return t >> 16;
+}
+__device__ __forceinline__ void upd1(uint32_t& best, uint32_t sum, uint32_t kb) { best = min(best, fshladd(sum, kb)); }
 
 __device__ __forceinline__ void emit_quadrant(const uint32_t* rec, int q, uint32_t (&ub)[13], int slots) {
     const uint32_t kb = rec[48 * slots];
@@ -220,28 +266,25 @@ __device__ __forceinline__ void emit_quadrant(const uint32_t* rec, int q, uint32
     uint4 T, B;                                                             // blocks b0, b0+1 / b0+4, b0+5 : {e00|e01, e10|e11} each
     T.x = rec[(2 * b0) * slots]; T.y = rec[(2 * b0 + 1) * slots]; T.z = rec[(2 * b0 + 2) * slots]; T.w = rec[(2 * b0 + 3) * slots];
     B.x = rec[(2 * b0 + 8) * slots]; B.y = rec[(2 * b0 + 9) * slots]; B.z = rec[(2 * b0 + 10) * slots]; B.w = rec[(2 * b0 + 11) * slots];
-    // rows of 8x8 sums across the 32-wide quadrant, still packed (each half <= 32640)
-    const uint32_t r0 = T.x + T.z, r1 = T.y + T.w, r2 = B.x + B.z, r3 = B.y + B.w;
-    const uint32_t R0 = ((r0 & 0xFFFFu) + (r0 >> 16)) << kIdxBits, R1 = ((r1 & 0xFFFFu) + (r1 >> 16)) << kIdxBits;
-    const uint32_t R2 = ((r2 & 0xFFFFu) + (r2 >> 16)) << kIdxBits, R3 = ((r3 & 0xFFFFu) + (r3 >> 16)) << kIdxBits;
+    // rows of 8x8 sums across the 32-wide quadrant, still packed (each half <= 32640), then low + high
+    const uint32_t R0 = lohi(fadd(T.x, T.z)), R1 = lohi(fadd(T.y, T.w)), R2 = lohi(fadd(B.x, B.z)), R3 = lohi(fadd(B.y, B.w));
     // columns: packed sums over the four 8-row strips (each half <= 65280)
-    const uint32_t cl = T.x + T.y + B.x + B.y, cr = T.z + T.w + B.z + B.w;
-    const uint32_t C0 = (cl & 0xFFFFu) << kIdxBits, C1 = (cl >> 16) << kIdxBits;
-    const uint32_t C2 = (cr & 0xFFFFu) << kIdxBits, C3 = (cr >> 16) << kIdxBits;
-    const uint32_t top = R0 + R1, bot = R2 + R3, left = C0 + C1, right = C2 + C3;
-    ub[0] = addmin(R0, kb, ub[0]);                 // 32x8  (2NxnU part 0)
-    ub[1] = addmin(R3, kb, ub[1]);                 // 32x8  (2NxnD part 1)
-    ub[2] = addmin(top + R2, kb, ub[2]);           // 32x24 rows 0..23
-    ub[3] = addmin(R1 + bot, kb, ub[3]);           // 32x24 rows 8..31
-    ub[4] = addmin(C0, kb, ub[4]);                 // 8x32
-    ub[5] = addmin(C3, kb, ub[5]);
-    ub[6] = addmin(left + C2, kb, ub[6]);          // 24x32 cols 0..23
-    ub[7] = addmin(C1 + right, kb, ub[7]);         // 24x32 cols 8..31
-    ub[8] = addmin(top, kb, ub[8]);                // 32x16
-    ub[9] = addmin(bot, kb, ub[9]);
-    ub[10] = addmin(left, kb, ub[10]);             // 16x32
-    ub[11] = addmin(right, kb, ub[11]);
-    ub[12] = addmin(top + bot, kb, ub[12]);        // 32x32
+    const uint32_t cl = fadd(fadd(T.x, T.y), fadd(B.x, B.y)), cr = fadd(fadd(T.z, T.w), fadd(B.z, B.w));
+    const uint32_t C0 = cl & 0xFFFFu, C1 = cl >> 16, C2 = cr & 0xFFFFu, C3 = cr >> 16;
+    const uint32_t top = fadd(R0, R1), bot = fadd(R2, R3), left = fadd(C0, C1), right = fadd(C2, C3);
+    upd1(ub[0], R0, kb);                           // 32x8  (2NxnU part 0)
+    upd1(ub[1], R3, kb);                           // 32x8  (2NxnD part 1)
+    upd1(ub[2], fadd(top, R2), kb);                // 32x24 rows 0..23
+    upd1(ub[3], fadd(R1, bot), kb);                // 32x24 rows 8..31
+    upd1(ub[4], C0, kb);                           // 8x32
+    upd1(ub[5], C3, kb);
+    upd1(ub[6], fadd(left, C2), kb);               // 24x32 cols 0..23
+    upd1(ub[7], fadd(C1, right), kb);              // 24x32 cols 8..31
+    upd1(ub[8], top, kb);                          // 32x16
+    upd1(ub[9], bot, kb);
+    upd1(ub[10], left, kb);                        // 16x32
+    upd1(ub[11], right, kb);
+    upd1(ub[12], fadd(top, bot), kb);              // 32x32
 }
 
 __device__ __forceinline__ void emit_ctu(const uint32_t* rec, uint32_t (&ub)[13], int slots) {
@@ -249,31 +292,31 @@ __device__ __forceinline__ void emit_ctu(const uint32_t* rec, uint32_t (&ub)[13]
     if (kb == kInvalidSlot) return;
     uint4 m[4];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {                                           // 16x16 sums << 11, block row r
+    for (int r = 0; r < 4; ++r) {                                           // 16x16 sums, block row r
         m[r].x = rec[(32 + 4 * r) * slots]; m[r].y = rec[(33 + 4 * r) * slots];
         m[r].z = rec[(34 + 4 * r) * slots]; m[r].w = rec[(35 + 4 * r) * slots];
     }
     uint32_t R[4], C[4];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) R[r] = (m[r].x + m[r].y) + (m[r].z + m[r].w);
-    C[0] = (m[0].x + m[1].x) + (m[2].x + m[3].x);
-    C[1] = (m[0].y + m[1].y) + (m[2].y + m[3].y);
-    C[2] = (m[0].z + m[1].z) + (m[2].z + m[3].z);
-    C[3] = (m[0].w + m[1].w) + (m[2].w + m[3].w);
-    const uint32_t top = R[0] + R[1], bot = R[2] + R[3], left = C[0] + C[1], right = C[2] + C[3];
-    ub[0] = addmin(R[0], kb, ub[0]);               // 64x16 (2NxnU part 0)
-    ub[1] = addmin(R[3], kb, ub[1]);               // 64x16 (2NxnD part 1)
-    ub[2] = addmin(top + R[2], kb, ub[2]);         // 64x48 rows 0..47
-    ub[3] = addmin(R[1] + bot, kb, ub[3]);         // 64x48 rows 16..63
-    ub[4] = addmin(C[0], kb, ub[4]);               // 16x64
-    ub[5] = addmin(C[3], kb, ub[5]);
-    ub[6] = addmin(left + C[2], kb, ub[6]);        // 48x64 cols 0..47
-    ub[7] = addmin(C[1] + right, kb, ub[7]);       // 48x64 cols 16..63
-    ub[8] = addmin(top, kb, ub[8]);                // 64x32
-    ub[9] = addmin(bot, kb, ub[9]);
-    ub[10] = addmin(left, kb, ub[10]);             // 32x64
-    ub[11] = addmin(right, kb, ub[11]);
-    ub[12] = addmin(top + bot, kb, ub[12]);        // 64x64
+    for (int r = 0; r < 4; ++r) R[r] = fadd(fadd(m[r].x, m[r].y), fadd(m[r].z, m[r].w));
+    C[0] = fadd(fadd(m[0].x, m[1].x), fadd(m[2].x, m[3].x));
+    C[1] = fadd(fadd(m[0].y, m[1].y), fadd(m[2].y, m[3].y));
+    C[2] = fadd(fadd(m[0].z, m[1].z), fadd(m[2].z, m[3].z));
+    C[3] = fadd(fadd(m[0].w, m[1].w), fadd(m[2].w, m[3].w));
+    const uint32_t top = fadd(R[0], R[1]), bot = fadd(R[2], R[3]), left = fadd(C[0], C[1]), right = fadd(C[2], C[3]);
+    upd1(ub[0], R[0], kb);                         // 64x16 (2NxnU part 0)
+    upd1(ub[1], R[3], kb);                         // 64x16 (2NxnD part 1)
+    upd1(ub[2], fadd(top, R[2]), kb);              // 64x48 rows 0..47
+    upd1(ub[3], fadd(R[1], bot), kb);              // 64x48 rows 16..63
+    upd1(ub[4], C[0], kb);                         // 16x64
+    upd1(ub[5], C[3], kb);
+    upd1(ub[6], fadd(left, C[2]), kb);             // 48x64 cols 0..47
+    upd1(ub[7], fadd(C[1], right), kb);            // 48x64 cols 16..63
+    upd1(ub[8], top, kb);                          // 64x32
+    upd1(ub[9], bot, kb);
+    upd1(ub[10], left, kb);                        // 32x64
+    upd1(ub[11], right, kb);
+    upd1(ub[12], fadd(top, bot), kb);              // 64x64
 }
 
 // tile key -> global key, one atomicMin into best[job][part]
@@ -306,8 +349,13 @@ __device__ __forceinline__ void round_body(const uint32_t* sWin, const uint32_t*
         kb[j] = valid ? k : kInvalidBlockKeyBase;
         kbRec[j] = valid ? k : kInvalidSlot;
     }
-    uint32_t acc[YB][4];
-    BlockState st[YB];
+    // Candidates 0 and 1 are folded together (their strips complete one reference row apart), the odd one out alone.
+    uint32_t acc[YB][4], held[4];
+    BlockState stP[2], stS[1];
+    const uint32_t kbP[2] = {kb[0], kb[1]}, kbRecP[2] = {kbRec[0], kbRec[1]};
+    uint32_t* const recP[2] = {recBuf + lane, recBuf + 32 + lane};
+    const uint32_t kbS[1] = {kb[YB - 1]}, kbRecS[1] = {kbRec[YB - 1]};
+    uint32_t* const recS[1] = {recBuf + (YB - 1) * 32 + lane};
 #pragma unroll
     for (int j = 0; j < YB; ++j)
 #pragma unroll
@@ -327,11 +375,22 @@ __device__ __forceinline__ void round_body(const uint32_t* sWin, const uint32_t*
                 acc[j][2] = sad4_acc(c.z, r2, acc[j][2]);
                 acc[j][3] = sad4_acc(c.w, r3, acc[j][3]);
                 if ((r & 3) == 3) {
-                    uint32_t* rec = recBuf + j * 32 + lane;
-                    if (r == 3) emit_strip<0>(acc[j], st[j], kb[j], best, rec, b, b == 0, kbRec[j], SLOTS);
-                    if (r == 7) emit_strip<1>(acc[j], st[j], kb[j], best, rec, b, b == 0, kbRec[j], SLOTS);
-                    if (r == 11) emit_strip<2>(acc[j], st[j], kb[j], best, rec, b, b == 0, kbRec[j], SLOTS);
-                    if (r == 15) emit_strip<3>(acc[j], st[j], kb[j], best, rec, b, b == 0, kbRec[j], SLOTS);
+                    if (j == 0) {                            // hold candidate 0's strip until candidate 1's arrives with the next row
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) held[i] = acc[0][i];
+                    } else if (j == 1) {
+                        const uint32_t a2[2][4] = {{held[0], held[1], held[2], held[3]}, {acc[1][0], acc[1][1], acc[1][2], acc[1][3]}};
+                        if (r == 3) emit_strip<0, 2>(a2, stP, kbP, best, recP, b, b == 0, kbRecP, SLOTS);
+                        if (r == 7) emit_strip<1, 2>(a2, stP, kbP, best, recP, b, b == 0, kbRecP, SLOTS);
+                        if (r == 11) emit_strip<2, 2>(a2, stP, kbP, best, recP, b, b == 0, kbRecP, SLOTS);
+                        if (r == 15) emit_strip<3, 2>(a2, stP, kbP, best, recP, b, b == 0, kbRecP, SLOTS);
+                    } else {
+                        const uint32_t a1[1][4] = {{acc[j][0], acc[j][1], acc[j][2], acc[j][3]}};
+                        if (r == 3) emit_strip<0, 1>(a1, stS, kbS, best, recS, b, b == 0, kbRecS, SLOTS);
+                        if (r == 7) emit_strip<1, 1>(a1, stS, kbS, best, recS, b, b == 0, kbRecS, SLOTS);
+                        if (r == 11) emit_strip<2, 1>(a1, stS, kbS, best, recS, b, b == 0, kbRecS, SLOTS);
+                        if (r == 15) emit_strip<3, 1>(a1, stS, kbS, best, recS, b, b == 0, kbRecS, SLOTS);
+                    }
 #pragma unroll
                     for (int i = 0; i < 4; ++i) acc[j][i] = 0;
                 }
