@@ -20,6 +20,7 @@ EXPORTS = [
     "hmme_set_lambda", "hmme_set_lambda_q16", "hmme_get_lambda_q16", "hmme_search_ctu",
     "hmme_plane_alloc", "hmme_plane_free", "hmme_plane_upload_s16", "hmme_plane_upload_u8",
     "hmme_search_frame", "hmme_search_frame_async", "hmme_fetch_results", "hmme_sync",
+    "hmme_plane_upload_s16_async", "hmme_fetch_results_async",
     "hmme_last_kernel_ms", "hmme_kernel_launches", "hmme_measure_int_alu_peak", "hmme_partition_rect", "hmme_version",
 ]
 
@@ -75,6 +76,8 @@ class HmmeLib:
             "hmme_search_frame": (i32, [vp, P(PlaneDesc), P(PlaneDesc), vp, i32, i32, vp, vp, vp, vp]),
             "hmme_search_frame_async": (i32, [vp, P(PlaneDesc), P(PlaneDesc), vp, i32, i32]),
             "hmme_fetch_results": (i32, [vp, i32, vp, vp, vp, vp]),
+            "hmme_fetch_results_async": (i32, [vp, i32, vp, vp, vp, vp]),
+            "hmme_plane_upload_s16_async": (i32, [vp, P(PlaneDesc), vp, i32]),
             "hmme_sync": (i32, [vp]),
             "hmme_last_kernel_ms": (i32, [vp, P(C.c_float)]),
             "hmme_kernel_launches": (C.c_uint64, [vp]),
@@ -192,7 +195,7 @@ class MotionEstimator:
         d = PlaneDesc(C.c_void_p(int(device_ptr)), elem_bytes, pitch, width, height, margin_x, margin_y)
         return Plane(self, d, False)
 
-    def upload(self, plane, host, origin_x=None, origin_y=None):
+    def upload(self, plane, host, origin_x=None, origin_y=None, asynchronous=False):
         """host: 2-D numpy array (int16 or uint8) that includes the margins; picture sample (0,0) at
         [origin_y, origin_x] (defaults: the plane's margins)."""
         d = plane.desc
@@ -202,7 +205,8 @@ class MotionEstimator:
         assert oy >= d.marginY and ox >= d.marginX and host.shape[0] - oy >= d.height + d.marginY and host.shape[1] - ox >= d.width + d.marginX
         off = int(oy * host.shape[1] + ox) * host.itemsize
         if host.dtype == np.int16:
-            self._chk(self.lib.L.hmme_plane_upload_s16(self.h, C.byref(d), host.ctypes.data + off, host.shape[1]))
+            fn = self.lib.L.hmme_plane_upload_s16_async if asynchronous else self.lib.L.hmme_plane_upload_s16
+            self._chk(fn(self.h, C.byref(d), host.ctypes.data + off, host.shape[1]))
         elif host.dtype == np.uint8:
             self._chk(self.lib.L.hmme_plane_upload_u8(self.h, C.byref(d), host.ctypes.data + off, host.shape[1]))
         else:
@@ -226,9 +230,10 @@ class MotionEstimator:
                                                      jobs.shape[0], int(rng)))
         return jobs.shape[0]
 
-    def fetch_results(self, njobs, out=None):
+    def fetch_results(self, njobs, out=None, asynchronous=False):
         out = out or self._outs(njobs)
-        self._chk(self.lib.L.hmme_fetch_results(self.h, njobs, *[o.ctypes.data for o in out]))
+        fn = self.lib.L.hmme_fetch_results_async if asynchronous else self.lib.L.hmme_fetch_results
+        self._chk(fn(self.h, njobs, *[o.ctypes.data for o in out]))
         return tuple(out)
 
     def sync(self):

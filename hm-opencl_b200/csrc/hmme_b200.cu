@@ -59,7 +59,10 @@ FastGeom fast_geometry(int W, int yb) {
 
 struct hmme_ctx {
     int device = -1;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;      // compute: init / search / finalize / result copies
+    cudaStream_t ioStream[2] = {nullptr, nullptr};   // high priority, one per staging buffer: a frame's two plane uploads copy back to back
+                                                      // instead of the second copy queueing behind the first plane's narrowing kernel
+    cudaEvent_t evUpload[2] = {nullptr, nullptr}, evSearch = nullptr;   // io -> compute and compute -> io ordering
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool evValid = false;
     cudaDeviceProp prop{};
@@ -82,8 +85,10 @@ struct hmme_ctx {
     void* hCurBlk = nullptr;      // pinned 64x64 int16
     void* dCurBlk = nullptr;
     // upload staging
-    int16_t* dStage = nullptr; size_t stageElems = 0;
+    int16_t* dStage[2] = {nullptr, nullptr}; size_t stageElems[2] = {0, 0}; int stageNext = 0;   // two staging buffers: a frame's reference
+                                                                                                  // and current plane copy back to back
     int* dFlag = nullptr; int* hFlag = nullptr;
+    bool contentCheckPending = false;   // an _async 8-bit upload has not had its range flag read back yet
 };
 
 namespace {
@@ -200,18 +205,38 @@ int enqueue_search(hmme_ctx* c, const void* curOrigin, int curElem, long long cu
     me_finalize_kernel<<<(unsigned)((nres + 255) / 256), 256, 0, c->stream>>>(c->dBest, c->dJobs, njobs, W, c->lambda, X, Y, S, Cst);
     c->launches += 3;
     CU_TRY(c, cudaGetLastError());
+    CU_TRY(c, cudaEventRecord(c->evSearch, c->stream));
     return HMME_OK;
 }
 
-int fetch(hmme_ctx* c, int njobs, int32_t* X, int32_t* Y, uint32_t* sad, uint32_t* cost) {
-    // straight into the caller's arrays: a true DMA when they are page-locked (bench.py, the drop-in class), a driver-staged
-    // copy otherwise -- either way no extra host-side memcpy
+// stream sync + deferred content check of asynchronous 8-bit uploads
+int sync_ctx(hmme_ctx* c) {
+    CU_TRY(c, cudaStreamSynchronize(c->ioStream[0]));
+    CU_TRY(c, cudaStreamSynchronize(c->ioStream[1]));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    if (c->contentCheckPending) {
+        c->contentCheckPending = false;
+        CU_TRY(c, cudaMemcpy(c->hFlag, c->dFlag, sizeof(int), cudaMemcpyDeviceToHost));
+        if (*c->hFlag) {
+            CU_TRY(c, cudaMemset(c->dFlag, 0, sizeof(int)));
+            return fail(c, HMME_ERR_CONTENT, "plane declared 8-bit holds samples outside [0,255]; allocate it with elemBytes=2");
+        }
+    }
+    return HMME_OK;
+}
+
+int fetch_async(hmme_ctx* c, int njobs, int32_t* X, int32_t* Y, uint32_t* sad, uint32_t* cost) {
+    // straight into the caller's arrays: a true DMA when they are page-locked (bench.py), a driver-staged copy otherwise
     const size_t n = (size_t)njobs * HMME_NPARTS, cap = c->jobCap * HMME_NPARTS;
     void* outs[4] = {X, Y, sad, cost};
     for (int k = 0; k < 4; ++k)
         if (outs[k]) CU_TRY(c, cudaMemcpyAsync(outs[k], c->dRes + k * cap, n * 4, cudaMemcpyDeviceToHost, c->stream));
-    CU_TRY(c, cudaStreamSynchronize(c->stream));
     return HMME_OK;
+}
+
+int fetch(hmme_ctx* c, int njobs, int32_t* X, int32_t* Y, uint32_t* sad, uint32_t* cost) {
+    const int rc = fetch_async(c, njobs, X, Y, sad, cost);
+    return rc != HMME_OK ? rc : sync_ctx(c);
 }
 
 // host rows -> device rows; one linear copy when both sides have the same pitch
@@ -258,8 +283,17 @@ int hmme_create(hmme_ctx** out, int device, int maxCtuW, int maxCtuH, int maxSea
     if (c->prop.major != 10)
         return bail(std::string("device '") + c->prop.name + "' is sm_" + std::to_string(c->prop.major) + std::to_string(c->prop.minor) +
                     "; this library carries sm_100a code only and has no fallback", HMME_ERR_NO_DEVICE);
-    if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(std::string("cudaStreamCreate: ") + cudaGetErrorString(e), HMME_ERR_CUDA);
-    if ((e = cudaEventCreate(&c->ev0)) != cudaSuccess || (e = cudaEventCreate(&c->ev1)) != cudaSuccess) return bail(std::string("cudaEventCreate: ") + cudaGetErrorString(e), HMME_ERR_CUDA);
+    int prLo = 0, prHi = 0;
+    cudaDeviceGetStreamPriorityRange(&prLo, &prHi);
+    if ((e = cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prLo)) != cudaSuccess ||
+        (e = cudaStreamCreateWithPriority(&c->ioStream[0], cudaStreamNonBlocking, prHi)) != cudaSuccess ||
+        (e = cudaStreamCreateWithPriority(&c->ioStream[1], cudaStreamNonBlocking, prHi)) != cudaSuccess)
+        return bail(std::string("cudaStreamCreate: ") + cudaGetErrorString(e), HMME_ERR_CUDA);
+    if ((e = cudaEventCreate(&c->ev0)) != cudaSuccess || (e = cudaEventCreate(&c->ev1)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&c->evUpload[0], cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&c->evUpload[1], cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&c->evSearch, cudaEventDisableTiming)) != cudaSuccess)
+        return bail(std::string("cudaEventCreate: ") + cudaGetErrorString(e), HMME_ERR_CUDA);
     c->maxRange = maxSearchRange;
     if (const char* e = std::getenv("HMME_STAGGER")) c->stagger = std::max(0, std::atoi(e));
     if (const char* e = std::getenv("HMME_FAST_YB")) { const int v = std::atoi(e); if (v >= 2 && v <= 3) c->fastYb = v; }
@@ -269,6 +303,7 @@ int hmme_create(hmme_ctx** out, int device, int maxCtuW, int maxCtuH, int maxSea
         (e = cudaMallocHost(&c->hCurBlk, 4096 * 2)) != cudaSuccess || (e = cudaMalloc(&c->dCurBlk, 4096 * 2)) != cudaSuccess ||
         (e = cudaMalloc(&c->dFlag, sizeof(int))) != cudaSuccess || (e = cudaMallocHost(&c->hFlag, sizeof(int))) != cudaSuccess)
         return bail(std::string("buffer allocation: ") + cudaGetErrorString(e), HMME_ERR_CUDA);
+    if ((e = cudaMemset(c->dFlag, 0, sizeof(int))) != cudaSuccess) return bail(std::string("cudaMemset: ") + cudaGetErrorString(e), HMME_ERR_CUDA);
     int rc = ensure_jobs(c, 64);
     if (rc != HMME_OK) return bail(c->err, rc);
     *out = c;
@@ -281,7 +316,12 @@ void hmme_destroy(hmme_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->dJobs); cudaFree(c->dBest); cudaFree(c->dRes); cudaFreeHost(c->hJobs);
     cudaFreeHost(c->hWin); cudaFree(c->dWin); cudaFreeHost(c->hCurBlk); cudaFree(c->dCurBlk);
-    cudaFree(c->dStage); cudaFree(c->dFlag); cudaFreeHost(c->hFlag);
+    cudaFree(c->dStage[0]); cudaFree(c->dStage[1]); cudaFree(c->dFlag); cudaFreeHost(c->hFlag);
+    for (int k = 0; k < 2; ++k) {
+        if (c->evUpload[k]) cudaEventDestroy(c->evUpload[k]);
+        if (c->ioStream[k]) { cudaStreamSynchronize(c->ioStream[k]); cudaStreamDestroy(c->ioStream[k]); }
+    }
+    if (c->evSearch) cudaEventDestroy(c->evSearch);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -369,7 +409,7 @@ int hmme_plane_free(hmme_ctx* c, hmme_plane* p) {
     return HMME_OK;
 }
 
-int hmme_plane_upload_s16(hmme_ctx* c, const hmme_plane* p, const int16_t* hostOrigin, int hostStride) {
+int hmme_plane_upload_s16_async(hmme_ctx* c, const hmme_plane* p, const int16_t* hostOrigin, int hostStride) {
     if (!c || !hostOrigin) return fail(c, HMME_ERR_ARG, "hmme_plane_upload_s16: null pointer");
     int rc = check_plane(c, p, "upload target");
     if (rc != HMME_OK) return rc;
@@ -378,26 +418,37 @@ int hmme_plane_upload_s16(hmme_ctx* c, const hmme_plane* p, const int16_t* hostO
     const int16_t* src = hostOrigin - (ptrdiff_t)p->marginY * hostStride - p->marginX;
     if (p->elemBytes == 2) {
         CU_TRY(c, copy_rows_h2d(p->base, (size_t)p->pitch * 2, src, (size_t)hostStride * 2, (size_t)cols * 2, rows, c->stream));
-        CU_TRY(c, cudaStreamSynchronize(c->stream));
         return HMME_OK;
     }
     const size_t n = plane_elems(p);
-    if (c->stageElems < n) {
-        CU_TRY(c, cudaStreamSynchronize(c->stream));
-        if (c->dStage) cudaFree(c->dStage);
-        c->dStage = nullptr; c->stageElems = 0;
-        CU_TRY(c, cudaMalloc(&c->dStage, n * 2));
-        c->stageElems = n;
+    const int sb = c->stageNext;
+    c->stageNext ^= 1;
+    cudaStream_t io = c->ioStream[sb];
+    if (c->stageElems[sb] < n) {
+        CU_TRY(c, cudaStreamSynchronize(io));
+        if (c->dStage[sb]) cudaFree(c->dStage[sb]);
+        c->dStage[sb] = nullptr; c->stageElems[sb] = 0;
+        CU_TRY(c, cudaMalloc(&c->dStage[sb], n * 2));
+        c->stageElems[sb] = n;
     }
-    if (p->pitch != cols) CU_TRY(c, cudaMemsetAsync(c->dStage, 0, n * 2, c->stream));   // pitch padding columns must read as in-range samples
-    CU_TRY(c, cudaMemsetAsync(c->dFlag, 0, sizeof(int), c->stream));
-    CU_TRY(c, copy_rows_h2d(c->dStage, (size_t)p->pitch * 2, src, (size_t)hostStride * 2, (size_t)cols * 2, rows, c->stream));
-    me_narrow_kernel<<<(unsigned)((n / 8 + 255) / 256 + 1), 256, 0, c->stream>>>(c->dStage, static_cast<uint8_t*>(p->base), n, c->dFlag);
+    // Uploads run on high-priority io streams (one per staging buffer): the copies of a frame's two planes start at once and
+    // the tiny narrowing kernels are scheduled as soon as an SM frees a slot, even while another context's search kernel
+    // fills the device.  Searches already enqueued on this context may still read the plane: wait for them first; the
+    // next search waits for this upload.
+    CU_TRY(c, cudaStreamWaitEvent(io, c->evSearch, 0));
+    if (p->pitch != cols) CU_TRY(c, cudaMemsetAsync(c->dStage[sb], 0, n * 2, io));   // pitch padding columns must read as in-range samples
+    CU_TRY(c, copy_rows_h2d(c->dStage[sb], (size_t)p->pitch * 2, src, (size_t)hostStride * 2, (size_t)cols * 2, rows, io));
+    me_narrow_kernel<<<(unsigned)((n / 8 + 255) / 256 + 1), 256, 0, io>>>(c->dStage[sb], static_cast<uint8_t*>(p->base), n, c->dFlag);
     c->launches += 1;
-    CU_TRY(c, cudaMemcpyAsync(c->hFlag, c->dFlag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    CU_TRY(c, cudaStreamSynchronize(c->stream));
-    if (*c->hFlag) return fail(c, HMME_ERR_CONTENT, "plane declared 8-bit holds samples outside [0,255]; allocate it with elemBytes=2");
+    CU_TRY(c, cudaEventRecord(c->evUpload[sb], io));
+    CU_TRY(c, cudaStreamWaitEvent(c->stream, c->evUpload[sb], 0));
+    c->contentCheckPending = true;                      // sticky device flag, read back at the next synchronising call
     return HMME_OK;
+}
+
+int hmme_plane_upload_s16(hmme_ctx* c, const hmme_plane* p, const int16_t* hostOrigin, int hostStride) {
+    const int rc = hmme_plane_upload_s16_async(c, p, hostOrigin, hostStride);
+    return rc != HMME_OK ? rc : sync_ctx(c);
 }
 
 int hmme_plane_upload_u8(hmme_ctx* c, const hmme_plane* p, const uint8_t* hostOrigin, int hostStride) {
@@ -449,11 +500,16 @@ int hmme_search_frame(hmme_ctx* c, const hmme_plane* cur, const hmme_plane* ref,
     return fetch(c, njobs, X, Y, sad, cost);
 }
 
+int hmme_fetch_results_async(hmme_ctx* c, int njobs, int32_t* X, int32_t* Y, uint32_t* sad, uint32_t* cost) {
+    if (!c || njobs <= 0 || (size_t)njobs > c->jobCap) return fail(c, HMME_ERR_ARG, "hmme_fetch_results: bad job count");
+    CU_TRY(c, cudaSetDevice(c->device));
+    return fetch_async(c, njobs, X, Y, sad, cost);
+}
+
 int hmme_sync(hmme_ctx* c) {
     if (!c) return HMME_ERR_ARG;
     CU_TRY(c, cudaSetDevice(c->device));
-    CU_TRY(c, cudaStreamSynchronize(c->stream));
-    return HMME_OK;
+    return sync_ctx(c);
 }
 
 int hmme_last_kernel_ms(hmme_ctx* c, float* ms) {

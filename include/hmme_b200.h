@@ -100,6 +100,11 @@ int hmme_search_frame(hmme_ctx* ctx, const hmme_plane* cur, const hmme_plane* re
 int hmme_search_frame_async(hmme_ctx* ctx, const hmme_plane* cur, const hmme_plane* ref, const hmme_job* jobs,
                             int njobs, int range);
 int hmme_fetch_results(hmme_ctx* ctx, int njobs, int32_t* X, int32_t* Y, uint32_t* sad, uint32_t* cost);
+/* Fully asynchronous legs for pipelining frames over two contexts (copies of one context overlap the kernels of the
+ * other): enqueue only; host buffers must stay valid (and should be page-locked) until hmme_sync returns.  The 8-bit
+ * content check of an asynchronous upload is reported by the next hmme_sync / synchronous call (HMME_ERR_CONTENT). */
+int hmme_plane_upload_s16_async(hmme_ctx* ctx, const hmme_plane* plane, const int16_t* hostOrigin, int hostStride);
+int hmme_fetch_results_async(hmme_ctx* ctx, int njobs, int32_t* X, int32_t* Y, uint32_t* sad, uint32_t* cost);
 int hmme_sync(hmme_ctx* ctx);
 
 /* ---- measurement hooks (bench.py / profiles): CUDA-event time of the dominant kernel of the most recent
