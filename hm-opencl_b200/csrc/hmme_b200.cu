@@ -37,7 +37,7 @@ struct FastGeom { int tw, th, nTx, nTy; size_t smemBytes; };
 constexpr size_t kSmemBudget = 200 * 1024;
 
 size_t fast_smem_bytes(int tw, int th, int yb) {
-    const size_t words = (size_t)fast_win_rows(th, yb) * kWinPitch + 1024 + kRing * (size_t)(32 * yb) * kRecWords + ((tw + 3) & ~3) +
+    const size_t words = (((size_t)fast_win_rows(th, yb) * kWinPitch + 3) & ~(size_t)3) + 1024 + kRing * (size_t)(32 * yb) * kRecWords + ((tw + 3) & ~3) +
                          (size_t)(((th + yb - 1) / yb) * yb) + 4;
     return words * 4;
 }

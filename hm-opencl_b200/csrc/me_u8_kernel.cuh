@@ -24,7 +24,7 @@
 // Reference window staging: the tile's window is kept in shared memory as SLIDING WORDS -- entry x of a row is the
 // 32-bit word made of bytes x..x+3 -- so lane l (candidate column x0+l) reads entry x+4i with a plain LDS.32 and 32
 // lanes with consecutive candidate x always hit 32 distinct banks, whatever the alignment of x.  The row pitch is a
-// compile-time 192 words, which turns every address in the unrolled inner loop into an immediate offset.
+// compile-time constant, which turns every address in the unrolled inner loop into an immediate offset.
 // Addressing of the source plane is linear (row*pitch + col), which is exactly the reference's
 // pelSearchArray[j + i*iRefStride] including its row-wrap quirk.
 #pragma once
@@ -35,7 +35,9 @@ namespace hmme {
 constexpr int kFastThreads = 512;
 constexpr int kIdxBits = 11;                  // candidates per tile <= 2048
 constexpr int kMaxTileCands = 1 << kIdxBits;
-constexpr int kWinPitch = 192;                // sliding-word entries per window row: (tw-1) + 4*15 + 1 <= 189 for tw <= 129
+constexpr int kWinPitch = 203;                // sliding-word entries per window row: (tw-1) + 4*15 + 1 <= 189 for tw <= 129, padded so that
+                                              // YB * pitch == 129 (mod 32): a warp whose 32 units straddle two row groups of a 129-wide
+                                              // tile (+-64) still reads 32 distinct banks
 constexpr int kMaxTileW = 129;
 constexpr int kDensePitch = 224;              // bytes per row of the TMA landing buffer: 15 (alignment) + 129 + 63 + 3, rounded up to 16
 constexpr int kRecWords = 49;                 // upper-phase words per candidate slot: 32 (8x8 pairs, u16) + 16 (16x16<<11) + 1 (key base),
@@ -405,7 +407,7 @@ __global__ void __launch_bounds__(kFastThreads, 1) me_u8_tile_kernel(const FastP
     constexpr int SLOTS = 32 * YB;
     const int winRows = fast_win_rows(p.th, YB);
     uint32_t* sWin = smem;                                  // winRows x kWinPitch sliding words
-    uint32_t* sCur = sWin + winRows * kWinPitch;            // 64 rows x 16 words
+    uint32_t* sCur = sWin + ((winRows * kWinPitch + 3) & ~3); // 64 rows x 16 words, 16-byte aligned (LDS.128, TMA destination)
     uint32_t* sUp = sCur + 1024;                            // kRing x kRecWords x SLOTS
     uint32_t* sBitsX = sUp + kRing * SLOTS * kRecWords;     // tw
     uint32_t* sBitsY = sBitsX + ((p.tw + 3) & ~3);          // roundup(th, YB)
