@@ -13,7 +13,8 @@ Output: ONE JSON line on rank 0 (contract in the task statement): `value` = bloc
 inputs resident in HBM (CUDA events on the library's stream, L2 flushed between steps), `e2e` = the same
 metric through the public C-ABI calls with pinned HOST buffers (H2D of both int16 planes + jobs, D2H of the
 four result arrays inside the timed region), `roofline` = algorithmic integer lane-ops/s of the dominant
-kernel against the ALU issue rate measured live, `cpu_baseline` = the CPU oracle port on the host cores.
+kernel against the ALU issue rate measured live, `cpu_baseline` = the reference's own CPU full-search ME
+(oracle/_ref/TAppEncoder_cpume, one single-threaded process per core), `cpu_port` = the CPU oracle port.
 """
 import argparse
 import json
