@@ -554,6 +554,10 @@ int hmme_measure_int_alu_peak(hmme_ctx* c, double* laneOpsPerSec, double* lanesP
     return HMME_OK;
 }
 
+int hmme_index_block(int partSize, int depth, int partIdx, int absZIdxInCtu, int cuWidth, int cuHeight) {
+    return index_block(partSize, depth, partIdx, absZIdxInCtu, cuWidth, cuHeight);
+}
+
 int hmme_partition_rect(int index, int* x, int* y, int* w, int* h) {
     if (index < 0 || index >= HMME_NPARTS) return HMME_ERR_ARG;
     const PartRect r = part_rect(index);

@@ -78,6 +78,39 @@ __host__ __device__ inline PartRect part_rect(int p) {
     return r;
 }
 
+// Closed form of TComDataCU::getIndexBlock (TComDataCU.cpp:3379-6464, 593-entry variant): (PartSize, depth, partIdx,
+// z-order index of the CU in 4x4 units, CU width, CU height) -> partition index, or -1 for every combination the
+// reference's 1786-line switch does not list.  PartSize: 0 2Nx2N, 1 2NxN, 2 Nx2N, 4 2NxnU, 5 2NxnD, 6 nLx2N, 7 nRx2N.
+__host__ __device__ inline int index_block(int partSize, int depth, int partIdx, int zIdx, int cuW, int cuH) {
+    if (depth < 0 || depth > 3 || partIdx < 0 || partIdx > 1 || zIdx < 0 || zIdx > 255) return -1;
+    const int S = 64 >> depth;
+    if (cuW != S || cuH != S) return -1;
+    if (partSize < 0 || partSize > 7 || partSize == 3) return -1;           // NxN is never searched (TEncCu.cpp:500)
+    if (partSize == 0 && partIdx != 0) return -1;
+    if (partSize >= 4 && depth == 3) return -1;                             // no AMP for 8x8 CUs
+    const int unitsPerCu = (S / 4) * (S / 4);
+    if (zIdx % unitsPerCu) return -1;                                       // CU origin must be aligned to its size
+    int x4 = 0, y4 = 0;                                                     // de-interleave the z-order index
+    for (int b = 0; b < 4; ++b) { x4 |= ((zIdx >> (2 * b)) & 1) << b; y4 |= ((zIdx >> (2 * b + 1)) & 1) << b; }
+    const int cx = 4 * x4, cy = 4 * y4, N = S / 2, q = S / 4;
+    int x = cx, y = cy, w = S, h = S;
+    switch (partSize) {
+        case 1: h = N; y += partIdx * N; break;
+        case 2: w = N; x += partIdx * N; break;
+        case 4: h = partIdx ? S - q : q; y += partIdx ? q : 0; break;
+        case 5: h = partIdx ? q : S - q; y += partIdx ? S - q : 0; break;
+        case 6: w = partIdx ? S - q : q; x += partIdx ? q : 0; break;
+        case 7: w = partIdx ? q : S - q; x += partIdx ? S - q : 0; break;
+        default: break;
+    }
+    // locate (x, y, w, h) in the layout: each (w, h) pair belongs to at most two groups, told apart by the offset in the CU
+    for (int p = 0; p < HMME_NPARTS; ++p) {
+        const PartRect r = part_rect(p);
+        if (r.x == x && r.y == y && r.w == w && r.h == h) return p;
+    }
+    return -1;
+}
+
 // bits(v) = 2*floor(log2 t) + 1 with t = (v <= 0) ? -2v+1 : 2v   (sad.cl:377-396)
 __host__ __device__ inline uint32_t mv_bits(int v) {
     uint32_t t = (v <= 0) ? (uint32_t)(-2 * v) + 1u : (uint32_t)(2 * v);

@@ -11,17 +11,19 @@
 // Block phase (per round, per thread): YB candidates x 64 VABSDIFF4.U8.ACC build the 16 4x4 SADs of
 // the block; every reference word fetched from shared memory serves up to YB candidates (vertical
 // reuse in registers).  The 33 partitions that live inside a 16x16 block (8x4, 4x8, 8x8, 16x8, 8x16,
-// 16x16 and the 8 AMP shapes) are built hierarchically with 37 adds and folded into 33 thread-private
-// running keys with ONE VIADDMNMX each: all sums are kept pre-shifted by 11 bits, so
-//   key = (sad << 11) + ((mvcost << 11) | candidateIndexInTile),  best = min(best, key)
-// is a single add-min and the low bits reproduce the reference's first-in-scan-order tie-break.
-// Upper phase (per round): the four 8x8 sums and the 16x16 sum of every (candidate, block) go through
-// a 20 KB shared-memory record array; 5 x (32*YB) threads (4 quadrant roles + one 64x64 role) build
-// the 65 partitions of the 32x32 and 64x64 levels the same way.
+// 16x16 and the 8 AMP shapes) are built hierarchically, strip by strip as the SADs complete, with 37
+// additions and one key formation per partition on the FMA pipe (IMAD):
+//   key = sad * 2^11 + ((mvcost << 11) | candidateIndexInTile)
+// and folded into 33 thread-private running keys on the ALU pipe -- one VIMNMX3 for two candidates at
+// a time.  The low bits of the key reproduce the reference's first-in-scan-order tie-break.
+// Upper phase (per round, lagging one round behind): the four 8x8 sums and the 16x16 sum of every
+// (candidate, block) go through a shared-memory record ring guarded by mbarriers; 5 x (32*YB) threads
+// (4 quadrant roles + one 64x64 role) build the 65 partitions of the 32x32 and 64x64 levels.
 // Tile end: warp-wide CREDUX.MIN per key, conversion to the global 64-bit key (cost<<32 | y*(2R+1)+x)
 // and one atomicMin per (warp, partition) into best[job][593]; a tiny finalize kernel decodes MVs.
 //
-// Reference window staging: the tile's window is kept in shared memory as SLIDING WORDS -- entry x of a row is the
+// Reference window staging: rows arrive by TMA bulk copies (cp.async.bulk + mbarrier) and are expanded in shared memory
+// into SLIDING WORDS -- entry x of a row is the
 // 32-bit word made of bytes x..x+3 -- so lane l (candidate column x0+l) reads entry x+4i with a plain LDS.32 and 32
 // lanes with consecutive candidate x always hit 32 distinct banks, whatever the alignment of x.  The row pitch is a
 // compile-time constant, which turns every address in the unrolled inner loop into an immediate offset.
@@ -135,10 +137,6 @@ __device__ __forceinline__ uint32_t fshladd(uint32_t a, uint32_t b) {
     asm("mad.lo.u32 %0, %1, 2048, %2;" : "=r"(d) : "r"(a), "r"(b));
     return d;
 }
-__device__ __forceinline__ uint32_t addmin(uint32_t sum, uint32_t base, uint32_t best) {
-    return __viaddmin_u32(sum, base, best);               // one VIADDMNMX.U32: min(sum + base, best)
-}
-
 // Per-candidate state carried across the row loop: sums are folded strip by strip (4 rows at a time) as soon as a strip
 // of 4x4 SADs completes, so that the add/key work (FMA pipe) and the min updates interleave with the packed SADs (ALU
 // pipe) of the candidates that are still being accumulated, instead of forming a separate FMA-bound phase.

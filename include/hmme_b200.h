@@ -116,6 +116,9 @@ int hmme_measure_int_alu_peak(hmme_ctx* ctx, double* laneOpsPerSec, double* lane
 
 /* ---- the 593-entry layout, for callers that want it without linking HM (index -> x, y, w, h) */
 int hmme_partition_rect(int index, int* x, int* y, int* w, int* h);
+/* Closed form of TComDataCU::getIndexBlock (TComDataCU.cpp:3379-6464): PartSize enum value, CU depth, PU index, z-order
+ * index of the CU in 4x4 units, CU width/height -> index 0..592, or -1 exactly where the reference's switch has no case. */
+int hmme_index_block(int partSize, int depth, int partIdx, int absZIdxInCtu, int cuWidth, int cuHeight);
 const char* hmme_version(void);
 
 #ifdef __cplusplus

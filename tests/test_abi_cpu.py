@@ -53,6 +53,28 @@ def test_product_layout_matches_getindexblock(lib):
         assert tuple(tab[idx]) == pu_rect(*decode_key(key)), (key, idx)
 
 
+def test_closed_form_index_block_equals_the_reference_switch(lib):
+    """hmme_index_block must return the reference's index for all 593 listed keys and -1 for every other key the
+    switch does not list (checked exhaustively over the whole key space the encoder can form)."""
+    from hevc_geom import decode_key
+    cases = dict((k, v) for k, v in json.load(open(os.path.join(ROOT, "tests/golden/getindexblock_593.json")))["cases"])
+    for key, idx in cases.items():
+        w, h, z, ps, depth, part = decode_key(key)
+        assert lib.index_block(ps, depth, part, z, w, h) == idx, key
+    hits = 0
+    for depth in range(4):
+        S = 64 >> depth
+        for ps in range(8):
+            for part in range(2):
+                for z in range(256):
+                    key = S + 100 * (S + 100 * (z + 1000 * (ps + 10 * depth + 100 * part)))
+                    got = lib.index_block(ps, depth, part, z, S, S)
+                    assert got == cases.get(key, -1), (depth, ps, part, z)
+                    hits += got >= 0
+    assert hits == 593
+    assert lib.index_block(0, 0, 0, 0, 32, 64) == -1 and lib.index_block(0, 4, 0, 0, 4, 4) == -1
+
+
 def test_product_and_oracle_layout_agree(lib, oracle):
     assert np.array_equal(lib.partition_table(), oracle.partition_table())
 

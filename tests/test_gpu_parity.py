@@ -242,3 +242,32 @@ def test_full_4k_pm128_properties_and_samples(me, oracle):
     want = oracle.search_frame(cur, (M, M), ref, (M, M), jobs[pick], R, lam, nthreads=8)
     assert_same([a[pick] for a in (X, Y, S, Cst)], want, "4K sample")
     pc.free(); pr.free()
+
+
+@pytest.mark.parametrize("R", [0, 2, 3])
+def test_tiny_ranges_and_u8_host_upload(me, oracle, R):
+    """Degenerate windows (R = 0: one candidate; a tile narrower than a warp) and the 8-bit host upload entry point."""
+    W, H = 192, 64
+    f = luma_frames(W, H, 2, seed=31 + R)
+    M = R + 8
+    cur16, ref16 = pad_plane(f[1], M, M), pad_plane(f[0], M, M)
+    pc, pr = me.alloc_plane(1, W, H, M, M), me.alloc_plane(1, W, H, M, M)
+    me.upload(pc, pad_plane(f[1], M, M, np.uint8)); me.upload(pr, pad_plane(f[0], M, M, np.uint8))
+    jobs = frame_jobs(W, H, R, pred=(1, -2))
+    me.set_lambda_q16(262144)
+    got = me.search_frame(pc, pr, jobs, R)
+    want = oracle.search_frame(cur16, (M, M), ref16, (M, M), jobs, R, 262144)
+    assert_same(got, want, f"R={R}")
+    pc.free(); pr.free()
+
+
+def test_async_upload_reports_bad_content_at_sync(me):
+    W, H, M = 64, 64, 8
+    p = me.alloc_plane(1, W, H, M, M)
+    bad = np.zeros((H + 2 * M, W + 2 * M), np.int16); bad[5, 5] = -1
+    me.upload(p, bad, asynchronous=True)           # enqueue only
+    with pytest.raises(hm.HmmeError) as e:
+        me.sync()                                  # the deferred 8-bit content check fires here
+    assert e.value.code == -5
+    me.upload(p, np.zeros_like(bad))               # the context stays usable
+    p.free()
