@@ -49,36 +49,49 @@ def workload_geometry(name):
     return W, H, R, margin
 
 
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe): one long-running
+    `nvidia-smi -lms` process, started before the region and stopped after it; samples outside [t0, t1] are dropped."""
+    Q = "timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
-        super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], threading.Event()
+        self.rows, self.t = [], []
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
 
-    def run(self):
-        while not self.stop_flag.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
-                                     stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
-            except Exception:
-                pass
-            self.stop_flag.wait(0.05)
+    def _read(self):
+        if not self.proc:
+            return
+        for line in self.proc.stdout:
+            c = [x.strip() for x in line.split(",")]
+            if len(c) >= 8:
+                self.rows.append(c[1:])
+                self.t.append(time.perf_counter())
+
+    def start(self):
+        time.sleep(0.15)                       # let the first samples arrive before the region starts
+        self.t0 = time.perf_counter()
 
     def summary(self):
-        self.stop_flag.set()
-        self.join(timeout=6)
-        if not self.rows:
+        t1 = time.perf_counter()
+        time.sleep(0.05)
+        if self.proc:
+            self.proc.terminate()
+        self.thread.join(timeout=3)
+        rows = [r for r, t in zip(self.rows, self.t) if self.t0 <= t <= t1 + 0.03] or self.rows[-3:]
+        if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        sm = sorted(float(r[0]) for r in self.rows)
+        sm = sorted(float(r[0]) for r in rows)
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "samples": len(sm),
-                "power_w_max": max(float(r[2]) for r in self.rows), "reasons": reasons}
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][1]), "samples": len(sm),
+                "power_w_max": max(float(r[2]) for r in rows), "reasons": reasons}
 
 
 def cpu_oracle_throughput(W, H, R, margin, njobs_sample, threads):
@@ -177,7 +190,7 @@ def run_reference(args, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="1080p64", choices=sorted(WORKLOADS))

@@ -23,6 +23,8 @@ def build(ref=True):
     subprocess.check_call(["make", "-s", "-C", HERE, "all"])
     if ref and os.path.isdir("/root/reference/cl"):
         subprocess.check_call(["make", "-s", "-C", HERE, "ref"])
+        # reference-encoder variants (bitstream-parity goldens, B200 drop-in build, CPU-ME baseline); incremental
+        subprocess.check_call(["make", "-s", "-C", HERE, "encoders"], stdout=subprocess.DEVNULL)
 
 
 class Oracle:
