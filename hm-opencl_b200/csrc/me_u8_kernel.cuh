@@ -46,7 +46,8 @@ constexpr int kRecWords = 49;                 // upper-phase words per candidate
                                               // stored slot-minor ([word][slot]) so that every access is lane-contiguous
 constexpr uint32_t kInvalidBlockKeyBase = 0xF0000000u;   // block sums << 11 stay below 2^27: no wrap, never wins
 constexpr uint32_t kInvalidSlot = 0xFFFFFFFFu;
-constexpr int kRing = 4;                      // record buffers: upper phase lags the block phase by one round, ring >= 2*lag + 2
+constexpr int kLag = 1;                       // the upper phase of round k runs after the block phase of round k + kLag
+constexpr int kRing = 2 * kLag + 2;           // record buffers: a slot may be rewritten only after every warp consumed it (ring >= 2*lag + 2)
 
 struct FastParams {
     const uint8_t* cur;        // picture sample (0,0) of the current plane
@@ -487,16 +488,18 @@ __global__ void __launch_bounds__(kFastThreads, 1) me_u8_tile_kernel(const FastP
     const int nFull = (twA * (thA / YB)) >> 5;              // rounds in which every lane and every candidate row is valid
     int rg = lane / twA, ux = lane - rg * twA;              // this lane's unit of round 0, advanced incrementally
     // Warps are NOT barrier-locked per round: records travel through a ring of kRing buffers guarded by mbarriers, and the
-    // upper phase of round k runs after the block phase of round k+1, by which time every producer has long arrived.  That
+    // upper phase of round k runs after the block phase of round k+kLag, by which time every producer has long arrived.  That
     // lets the two warps of each scheduler that start `stagger` cycles late stay half a round out of phase, so the
     // SAD-heavy (ALU pipe) and sum-heavy (FMA pipe) stretches of different warps overlap.
     if (p.stagger > 0 && (warp & 8)) {
         const long long t0 = clock64();
         while (clock64() - t0 < p.stagger) {}
     }
-    for (int round = 0; round <= nRounds; ++round) {
+    int wSlot = 0, rSlot = 0;
+    uint32_t rPhase = 0;
+    for (int round = 0; round < nRounds + kLag; ++round) {
         if (round < nRounds) {
-            uint32_t* recBuf = sUp + (round & (kRing - 1)) * (SLOTS * kRecWords);
+            uint32_t* recBuf = sUp + wSlot * (SLOTS * kRecWords);
             if (round < nFull)
                 round_body<YB, false>(sWin, cp, sBitsX, sBitsY, recBuf, best, rg, ux, by, bx, b, lane, twA, thA, nRG, p.lambda);
             else
@@ -504,14 +507,15 @@ __global__ void __launch_bounds__(kFastThreads, 1) me_u8_tile_kernel(const FastP
             ux += 32;
             while (ux >= twA) { ux -= twA; ++rg; }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&fullBar[round & (kRing - 1)]);
+            if (lane == 0) mbar_arrive(&fullBar[wSlot]);
+            wSlot = (wSlot + 1 == kRing) ? 0 : wSlot + 1;
         }
-        if (round >= 1) {
-            const int k = round - 1;
-            mbar_wait(&fullBar[k & (kRing - 1)], (uint32_t)(k / kRing) & 1u);
-            const uint32_t* recBuf = sUp + (k & (kRing - 1)) * (SLOTS * kRecWords);
+        if (round >= kLag) {
+            mbar_wait(&fullBar[rSlot], rPhase);
+            const uint32_t* recBuf = sUp + rSlot * (SLOTS * kRecWords);
             if (role < 4) emit_quadrant(recBuf + slot, role, ub, SLOTS);
             else if (role == 4) emit_ctu(recBuf + slot, ub, SLOTS);
+            if (++rSlot == kRing) { rSlot = 0; rPhase ^= 1u; }
         }
     }
 
