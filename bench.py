@@ -113,7 +113,7 @@ CPUME_BIN = os.path.join(ROOT, "oracle", "_ref", "TAppEncoder_cpume")
 CPUME_CFG = os.path.join(ROOT, "oracle", "_ref", "cfg", "encoder_lowdelay_P_main.cfg")
 
 
-def reference_cpu_me(R, clip, procs):
+def reference_cpu_me(R, clip, procs, fast_search=0):
     """The reference's OWN CPU integer ME (--OpenCL=0 --FastSearch=0: TEncSearch::xPatternSearch + TComRdCost::xGetSAD*,
     TEncSearch.cpp:3774-3791,3835-3897) timed inside the reference encoder built from source with the counters of
     BASELINE.md section 3 (oracle/patch_cpume.py): `procs` independent single-threaded encoder processes (HM has no threads)
@@ -129,7 +129,7 @@ def reference_cpu_me(R, clip, procs):
                 fh.write(y.tobytes())
                 fh.write(np.full((H // 2) * (W // 2) * 2, 128, np.uint8).tobytes())
         cmds = [[CPUME_BIN, "-c", CPUME_CFG, "-i", yuv, "-wdt", str(W), "-hgt", str(H), "-fr", "30", "-f", "2", "-q", "32",
-                 "-b", os.path.join(d, "o%d.hevc" % i), "-o", "", "--OpenCL=0", "--FastSearch=0", "--SearchRange=%d" % R] for i in range(procs)]
+                 "-b", os.path.join(d, "o%d.hevc" % i), "-o", "", "--OpenCL=0", "--FastSearch=%d" % fast_search, "--SearchRange=%d" % R] for i in range(procs)]
         t0 = time.perf_counter()
         ps = [subprocess.Popen(c, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for c in cmds]
         outs = [p.communicate()[0] for p in ps]
@@ -394,6 +394,11 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"], _ = cpu_baseline_entry(R, 30.0)
+            if os.path.exists(CPUME_BIN):       # the reference's default (fast) integer search, for context: TZ evaluates ~600x fewer candidates
+                v, me_s, calls, wall = reference_cpu_me(R, (416, 240), 1, fast_search=1)
+                out["cpu_tz"] = {"value": v, "unit": "block-SAD evaluations/s", "cores": 1, "kind": "reference",
+                                 "sample": "same encoder, --FastSearch=1 (xTZSearch): %d DistFunc calls in %.3f s of integer ME for the P frame of a "
+                                           "416x240 clip (18 full CTUs) on one core" % (calls, me_s)}
             threads = os.cpu_count() or 1
             v, dt, n = cpu_oracle_throughput(W, H, R, margin, max(8 * threads, 64), threads)
             out["cpu_port"] = {"value": v, "unit": "block-SAD evaluations/s", "cores": threads, "kind": "port",

@@ -3,7 +3,7 @@
 // Replaces the host orchestration of /root/reference/source/Lib/TLibEncoder/TEncOpenCL.cpp:
 //   findDevice/compileKernelSource/createBuffers (:69-238)  -> hmme_create
 //   calcMotionVectors (:240-362)                             -> hmme_search_ctu (sync) / hmme_search_frame (batched)
-//   xFillSADBuffer/xResetArrays (:366-392)                   -> me_init_kernel
+//   xFillSADBuffer/xResetArrays (:366-392)                   -> arg-min scratch kept in its reset state by the kernels
 // No OpenCL, no runtime compilation, no CPU fallback: every failure is an error code + message.
 #include <algorithm>
 #include <cmath>
@@ -62,7 +62,7 @@ struct hmme_ctx {
     cudaStream_t stream = nullptr;      // compute: init / search / finalize / result copies
     cudaStream_t ioStream[2] = {nullptr, nullptr};   // high priority, one per staging buffer: a frame's two plane uploads copy back to back
                                                       // instead of the second copy queueing behind the first plane's narrowing kernel
-    cudaEvent_t evUpload[2] = {nullptr, nullptr}, evSearch = nullptr;   // io -> compute and compute -> io ordering
+    cudaEvent_t evUpload[2] = {nullptr, nullptr}, evSearch = nullptr, evFinal = nullptr;   // io -> compute and compute -> io ordering
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool evValid = false;
     cudaDeviceProp prop{};
@@ -75,7 +75,7 @@ struct hmme_ctx {
     // job / result buffers (grown on demand)
     size_t jobCap = 0;
     int4* dJobs = nullptr;
-    unsigned long long* dBest = nullptr;
+    unsigned long long* dBest = nullptr;   // arg-min scratch, kept all "no winner" between searches
     int32_t* dRes = nullptr;      // [4][jobCap][593]: X, Y, sad, cost
     hmme_job* hJobs = nullptr;    // pinned
     // per-CTU synchronous path staging
@@ -117,6 +117,7 @@ int ensure_jobs(hmme_ctx* c, size_t njobs) {
     c->dJobs = nullptr; c->dBest = nullptr; c->dRes = nullptr; c->hJobs = nullptr; c->jobCap = 0;
     CU_TRY(c, cudaMalloc(&c->dJobs, cap * sizeof(int4)));
     CU_TRY(c, cudaMalloc(&c->dBest, cap * HMME_NPARTS * sizeof(unsigned long long)));
+    me_init_kernel<<<(unsigned)((cap * HMME_NPARTS + 255) / 256), 256, 0, c->stream>>>(c->dBest, cap * HMME_NPARTS);
     CU_TRY(c, cudaMalloc(&c->dRes, 4 * cap * HMME_NPARTS * sizeof(int32_t)));
     CU_TRY(c, cudaMallocHost(&c->hJobs, cap * sizeof(hmme_job)));
     c->jobCap = cap;
@@ -156,12 +157,16 @@ void launch_generic(hmme_ctx* c, const GenericParams& gp, int njobs) {
     me_generic_kernel<TC, TR><<<njobs * gp.nChunks, kGenThreads, 0, c->stream>>>(gp);
 }
 
-// Enqueue init -> search -> finalize for njobs jobs already present in c->dJobs.
+// Enqueue search -> finalize for njobs jobs already present in c->dJobs.  The arg-min scratch is in its reset state before and
+// after (me_init_kernel once per allocation, me_finalize_kernel restores it).
 int enqueue_search(hmme_ctx* c, const void* curOrigin, int curElem, long long curPitch, const void* refOrigin, int refElem,
                    long long refPitch, const void* refLo, const void* refHi, int njobs, int R) {
     const int W = 2 * R + 1;
     const size_t nres = (size_t)njobs * HMME_NPARTS;
-    me_init_kernel<<<(unsigned)((nres + 255) / 256), 256, 0, c->stream>>>(c->dBest, nres);
+    int32_t* X = c->dRes;
+    int32_t* Y = X + c->jobCap * HMME_NPARTS;
+    uint32_t* S = reinterpret_cast<uint32_t*>(Y + c->jobCap * HMME_NPARTS);
+    uint32_t* Cst = S + c->jobCap * HMME_NPARTS;
     CU_TRY(c, cudaEventRecord(c->ev0, c->stream));
     if (curElem == 1 && refElem == 1) {
         const int yb = c->fastYb;
@@ -198,12 +203,14 @@ int enqueue_search(hmme_ctx* c, const void* curOrigin, int curElem, long long cu
     }
     CU_TRY(c, cudaEventRecord(c->ev1, c->stream));
     c->evValid = true;
-    int32_t* X = c->dRes;
-    int32_t* Y = X + c->jobCap * HMME_NPARTS;
-    uint32_t* S = reinterpret_cast<uint32_t*>(Y + c->jobCap * HMME_NPARTS);
-    uint32_t* Cst = S + c->jobCap * HMME_NPARTS;
-    me_finalize_kernel<<<(unsigned)((nres + 255) / 256), 256, 0, c->stream>>>(c->dBest, c->dJobs, njobs, W, c->lambda, X, Y, S, Cst);
-    c->launches += 3;
+    // Finalisation (keys -> X, Y, sad, cost; keys handed back in their reset state) runs on a high-priority stream: a tiny
+    // kernel on the compute stream would queue behind every pending CTA of another context's search, delaying the result
+    // copy -- and with it the host -- by a whole search.
+    CU_TRY(c, cudaStreamWaitEvent(c->ioStream[0], c->ev1, 0));
+    me_finalize_kernel<<<(unsigned)((nres + 255) / 256), 256, 0, c->ioStream[0]>>>(c->dBest, c->dJobs, njobs, W, c->lambda, X, Y, S, Cst);
+    CU_TRY(c, cudaEventRecord(c->evFinal, c->ioStream[0]));
+    CU_TRY(c, cudaStreamWaitEvent(c->stream, c->evFinal, 0));
+    c->launches += 2;
     CU_TRY(c, cudaGetLastError());
     CU_TRY(c, cudaEventRecord(c->evSearch, c->stream));
     return HMME_OK;
@@ -292,7 +299,8 @@ int hmme_create(hmme_ctx** out, int device, int maxCtuW, int maxCtuH, int maxSea
     if ((e = cudaEventCreate(&c->ev0)) != cudaSuccess || (e = cudaEventCreate(&c->ev1)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&c->evUpload[0], cudaEventDisableTiming)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&c->evUpload[1], cudaEventDisableTiming)) != cudaSuccess ||
-        (e = cudaEventCreateWithFlags(&c->evSearch, cudaEventDisableTiming)) != cudaSuccess)
+        (e = cudaEventCreateWithFlags(&c->evSearch, cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&c->evFinal, cudaEventDisableTiming)) != cudaSuccess)
         return bail(std::string("cudaEventCreate: ") + cudaGetErrorString(e), HMME_ERR_CUDA);
     c->maxRange = maxSearchRange;
     if (const char* e = std::getenv("HMME_STAGGER")) c->stagger = std::max(0, std::atoi(e));
@@ -322,6 +330,7 @@ void hmme_destroy(hmme_ctx* c) {
         if (c->ioStream[k]) { cudaStreamSynchronize(c->ioStream[k]); cudaStreamDestroy(c->ioStream[k]); }
     }
     if (c->evSearch) cudaEventDestroy(c->evSearch);
+    if (c->evFinal) cudaEventDestroy(c->evFinal);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->stream) cudaStreamDestroy(c->stream);

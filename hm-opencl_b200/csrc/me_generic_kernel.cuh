@@ -123,24 +123,33 @@ __global__ void __launch_bounds__(kGenThreads) me_generic_kernel(const GenericPa
     }
 }
 
-// best[] <- "no winner" (TEncOpenCL.cpp:366-392: minSad = UINT_MAX, X = Y = 0)
+// best[] <- "no winner" (TEncOpenCL.cpp:366-392: minSad = UINT_MAX, X = Y = 0); run once per allocation, the searches
+// restore this state themselves when they read their results out
 __global__ void me_init_kernel(unsigned long long* best, size_t n) {
     const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i < n) best[i] = kNoWinner;
 }
 
-// key -> X, Y, sad (ruiCosts), cost (minSad); outputs are four planes of [njobs][593]
-__global__ void me_finalize_kernel(const unsigned long long* best, const int4* jobs, int njobs, int W, uint32_t lambda,
+// key -> X, Y, sad (ruiCosts), cost (minSad) for result slot i of a job with search-range origin (ltx, lty)
+__device__ __forceinline__ void decode_key(unsigned long long key, int ltx, int lty, int W, uint32_t lambda, int i,
+                                           int32_t* X, int32_t* Y, uint32_t* sad, uint32_t* cost) {
+    if (key == kNoWinner) { X[i] = 0; Y[i] = 0; sad[i] = 0; cost[i] = 0xFFFFFFFFu; return; }
+    const uint32_t c = (uint32_t)(key >> 32), g = (uint32_t)key;
+    const int y = (int)(g / (uint32_t)W), x = (int)(g - (uint32_t)y * (uint32_t)W);
+    const int mvx = x + ltx, mvy = y + lty;
+    X[i] = mvx; Y[i] = mvy; cost[i] = c; sad[i] = c - mv_cost(lambda, mvx, mvy);
+}
+
+// Finalisation pass of the generic path; outputs are four planes of [njobs][593].  Every key is handed back as "no winner"
+// (the state me_init_kernel set up once), so the arg-min scratch is always ready for the next search.
+__global__ void me_finalize_kernel(unsigned long long* best, const int4* jobs, int njobs, int W, uint32_t lambda,
                                    int32_t* X, int32_t* Y, uint32_t* sad, uint32_t* cost) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= njobs * HMME_NPARTS) return;
     const unsigned long long key = best[i];
-    if (key == kNoWinner) { X[i] = 0; Y[i] = 0; sad[i] = 0; cost[i] = 0xFFFFFFFFu; return; }
+    best[i] = kNoWinner;
     const int4 jb = jobs[i / HMME_NPARTS];
-    const uint32_t c = (uint32_t)(key >> 32), g = (uint32_t)key;
-    const int y = (int)(g / (uint32_t)W), x = (int)(g - (uint32_t)y * (uint32_t)W);
-    const int mvx = x + jb.z, mvy = y + jb.w;
-    X[i] = mvx; Y[i] = mvy; cost[i] = c; sad[i] = c - mv_cost(lambda, mvx, mvy);
+    decode_key(key, jb.z, jb.w, W, lambda, i, X, Y, sad, cost);
 }
 
 // int16 -> uint8 narrowing of a whole padded plane with a content check (the reference path is only

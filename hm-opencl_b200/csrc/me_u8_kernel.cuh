@@ -56,7 +56,7 @@ struct FastParams {
     const uint8_t* refHi;      // one past the last addressable byte
     long long curPitch, refPitch;
     const int4* jobs;          // {ctuX, ctuY, ltx, lty}
-    unsigned long long* best;  // [njobs][593]
+    unsigned long long* best;  // [njobs][593] arg-min keys, all "no winner" between searches
     uint32_t lambda;
     int W;                     // 2R+1 candidates per axis
     int tw, th;                // nominal tile size in candidates
