@@ -51,6 +51,21 @@ def md5(path):
     return hashlib.md5(open(path, "rb").read()).hexdigest()
 
 
+def decode_check(bitstream, recon, workdir):
+    """Reference decoder (oracle/_ref/TAppDecoder_ref): every picture's decoded-picture-hash SEI must verify "(OK)" and the
+    decoder output must equal the encoder's reconstruction.  Returns the number of pictures checked, or None if the
+    decoder was not built."""
+    dec = os.path.join(REFDIR, "TAppDecoder_ref")
+    if not os.path.exists(dec):
+        return None
+    out = os.path.join(workdir, "dec.yuv")
+    r = subprocess.run([dec, "-b", bitstream, "-o", out], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout[-2000:]
+    assert "***ERROR***" not in r.stdout, r.stdout[-2000:]
+    assert md5(out) == md5(recon), "decoder output differs from the encoder reconstruction"
+    return r.stdout.count("(OK)")
+
+
 def run_case(binary, name, kernel_path, workdir):
     W, H, F, cfg, extra = CASES[name]
     yuv, bit, rec = (os.path.join(workdir, name + e) for e in (".yuv", ".hevc", "_rec.yuv"))
@@ -60,6 +75,7 @@ def run_case(binary, name, kernel_path, workdir):
     if r.returncode != 0:
         raise RuntimeError("encoder failed:\n" + r.stdout[-3000:])
     return {"bitstream_md5": md5(bit), "bitstream_bytes": os.path.getsize(bit), "recon_md5": md5(rec), "yuv_md5": md5(yuv),
+            "decoded_ok": decode_check(bit, rec, workdir), "frames": F,
             "seconds": round(time.time() - t0, 1), "poc_lines": [l.strip()[:120] for l in r.stdout.splitlines() if l.startswith("POC")]}
 
 

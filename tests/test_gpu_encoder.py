@@ -28,4 +28,6 @@ def test_bitstream_identical_to_reference_gpu_me(name):
     assert got["bitstream_bytes"] == gold["bitstream_bytes"]
     assert got["bitstream_md5"] == gold["bitstream_md5"]
     assert got["recon_md5"] == gold["recon_md5"]
+    if got["decoded_ok"] is not None:          # reference decoder: hash SEI verified for every picture, output == recon
+        assert got["decoded_ok"] == got["frames"]
     print(name, "GPU-ME encode %.1f s vs reference emulation %.1f s" % (got["seconds"], gold["seconds"]))
