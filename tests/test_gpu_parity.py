@@ -271,3 +271,39 @@ def test_async_upload_reports_bad_content_at_sync(me):
     assert e.value.code == -5
     me.upload(p, np.zeros_like(bad))               # the context stays usable
     p.free()
+
+
+def test_randomised_differential_vs_oracle(me, oracle):
+    """Seeded fuzz: random ranges (every residue of the tile/round/row-group arithmetic), window offsets, lambdas, content
+    classes and plane margins (so the CTU and the window start at arbitrary byte alignments)."""
+    g = np.random.default_rng(2026)
+    for it in range(36):
+        R = int(g.integers(0, 45))
+        W, H = 64 * int(g.integers(1, 4)), 64 * int(g.integers(1, 3))
+        M = R + int(g.integers(6, 23))
+        kind = it % 4
+        shape = (H + 2 * M, W + 2 * M)
+        if kind == 0:
+            ref = g.integers(0, 256, size=shape)
+        elif kind == 1:                                      # smooth: many near-ties
+            ref = (np.add.outer(np.arange(shape[0]) // 3, np.arange(shape[1]) // 5) % 256)
+        elif kind == 2:                                      # blocky constant regions: exact ties across tiles
+            ref = np.kron(g.integers(0, 256, size=(shape[0] // 16 + 1, shape[1] // 16 + 1)), np.ones((16, 16), int))[:shape[0], :shape[1]]
+        else:                                                # binary extremes
+            ref = g.integers(0, 2, size=shape) * 255
+        ref = ref.astype(np.int16)
+        dy, dx = int(g.integers(-3, 4)), int(g.integers(-3, 4))
+        cur = np.roll(ref, (dy, dx), (0, 1)).copy()
+        cur = np.clip(cur + g.integers(-2, 3, size=shape), 0, 255).astype(np.int16)
+        jobs = frame_jobs(W, H, R)
+        room = M - R                                         # keep every window inside the allocation
+        jobs[:, 2] += g.integers(-room + 1, room, size=len(jobs))
+        jobs[:, 3] += g.integers(-room + 1, room, size=len(jobs))
+        lam = int(g.choice([0, 1, 65536, 262144, 460000, 4500000, 0x7FFFFFFF]))
+        me.set_lambda_q16(lam)
+        pc, pr = me.alloc_plane(1, W, H, M, M), me.alloc_plane(1, W, H, M, M)
+        me.upload(pc, cur); me.upload(pr, ref)
+        got = me.search_frame(pc, pr, jobs, R)
+        want = oracle.search_frame(cur, (M, M), ref, (M, M), jobs, R, lam, nthreads=8)
+        assert_same(got, want, f"fuzz it={it} R={R} {W}x{H} M={M} kind={kind} lam={lam}")
+        pc.free(); pr.free()
