@@ -370,7 +370,7 @@ def main():
             "ctu_candidates_per_s": total_cands / (ms_per_step * 1e-3),
             "config": {"workload": "%s: %dx%d luma, 64x64 CTU, integer-pel full search +-%d, 1 reference picture, %d CTU jobs x %d candidates x 593 partitions"
                                    % (args.workload, W, H, R, total_jobs, cands_per_job),
-                       "sharding": "CTU-row bands over %d GPU(s), reference plane NCCL-broadcast from rank 0" % world,
+                       "sharding": "CTU-row bands (cut at CTU granularity) over %d GPU(s), reference plane NCCL-broadcast from rank 0" % world,
                        "lambda_q16": LAMBDA_Q16, "l2": "256 MiB flush buffer written between timed steps",
                        "timer": "CUDA events on the library stream per step, max over ranks"},
             "clocks": clocks,

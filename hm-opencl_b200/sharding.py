@@ -1,7 +1,7 @@
 """CTU-row band sharding of a frame over the GPUs of one box.
 
 The path has no data-path exchange step: every (CTU, reference) job is independent once the reference plane is on the
-device, so ranks take contiguous bands of CTU rows, rank 0's reference upload is NCCL-broadcast, and results come back
+device, so ranks take contiguous bands of CTU rows (cut at CTU granularity), rank 0's reference upload is NCCL-broadcast, and results come back
 per rank.  (The reference itself has no multi-device code at all: one queue on one device, TEncOpenCL.cpp:185.)
 """
 import numpy as np
@@ -14,13 +14,24 @@ def band_rows(n_ctu_rows, world, rank):
     return r0, r0 + base + (1 if rank < extra else 0)
 
 
+def band_ctus(n_ctus, world, rank):
+    """Contiguous raster range [c0, c1) of CTUs for `rank`: a CTU-row band whose first and last row may be partial, so
+    that every rank gets the same number of jobs (+-1) even when the row count does not divide (4K: 33 rows over 8 GPUs
+    would otherwise leave one rank with 5 rows against 4)."""
+    base, extra = divmod(n_ctus, world)
+    c0 = rank * base + min(rank, extra)
+    return c0, c0 + base + (1 if rank < extra else 0)
+
+
 def band_jobs(width, height, search_range, world, rank, pred=(0, 0)):
     """Jobs {ctuX, ctuY, ltx, lty} of this rank's band: one per FULL 64x64 CTU (partial boundary CTUs never run the
-    depth-0 search, TEncCu.cpp:424-425), raster order, window centred on `pred`."""
+    depth-0 search, TEncCu.cpp:424-425), raster order, window centred on `pred`.  Returns (jobs, (r0, r1)) with
+    [r0, r1) the CTU rows the band touches (the rows of the current frame this rank has to upload)."""
     nx, ny = width // 64, height // 64
-    r0, r1 = band_rows(ny, world, rank)
-    jobs = [[cx * 64, cy * 64, pred[0] - search_range, pred[1] - search_range] for cy in range(r0, r1) for cx in range(nx)]
-    return np.asarray(jobs, np.int32).reshape(-1, 4), (r0, r1)
+    c0, c1 = band_ctus(nx * ny, world, rank)
+    jobs = [[(c % nx) * 64, (c // nx) * 64, pred[0] - search_range, pred[1] - search_range] for c in range(c0, c1)]
+    rows = (c0 // nx, (c1 - 1) // nx + 1) if c1 > c0 else (0, 0)
+    return np.asarray(jobs, np.int32).reshape(-1, 4), rows
 
 
 def band_reference_rows(r0, r1, search_range, lty_min, lty_max):

@@ -26,7 +26,8 @@ def _worker(rank, world, port, out_dir):
     ref = torch.from_numpy(pad_plane(f[0], M, M)) if rank == 0 else torch.zeros((H + 2 * M, W + 2 * M), dtype=torch.int16)
     dist.broadcast(ref.view(torch.uint8), src=0)        # reference-picture distribution (bytes, like the u8 plane over NCCL)
     jobs, (r0, r1) = hm.band_jobs(W, H, R, world, rank)
-    assert len(jobs) == (r1 - r0) * (W // 64)
+    c0, c1 = hm.band_ctus((W // 64) * (H // 64), world, rank)
+    assert len(jobs) == c1 - c0 and (r0, r1) == (c0 // (W // 64), (c1 - 1) // (W // 64) + 1)
     y0, y1 = hm.band_reference_rows(r0, r1, R, -R, -R)
     assert y0 >= -M and y1 <= H + M                     # the halo stays inside the padded plane
     res = Oracle().search_frame(cur, (M, M), ref.numpy(), (M, M), jobs, R, lam)
@@ -48,13 +49,27 @@ def test_two_rank_band_sharding_matches_single_rank(tmp_path, oracle):
         z = np.load(tmp_path / ("rank%d.npz" % r))
         parts.append((z["X"], z["Y"], z["S"], z["C"]))
         rows.append(tuple(z["r"]))
-    assert rows == [(0, 3), (3, 5)]
+    assert rows == [(0, 3), (2, 5)]          # 20 CTUs -> 10 + 10: the middle row is shared
     got = hm.merge_bands(parts)
     W, H, R, M, lam = 256, 320, 5, 24, 460000
     f = luma_frames(W, H, 2, seed=9)
     want = oracle.search_frame(pad_plane(f[1], M, M), (M, M), pad_plane(f[0], M, M), (M, M), frame_jobs(W, H, R), R, lam, nthreads=4)
     for g, w in zip(got, want):
         assert np.array_equal(g, w)
+
+
+def test_band_ctus_cover_exactly_and_balance():
+    import sys
+    sys.path.insert(0, ROOT)
+    from _pkg import hm
+    for n in (1, 480, 1980, 18):
+        for world in (1, 2, 4, 8):
+            bands = [hm.band_ctus(n, world, r) for r in range(world)]
+            assert bands[0][0] == 0 and bands[-1][1] == n and all(a[1] == b[0] for a, b in zip(bands, bands[1:]))
+            sizes = [b - a for a, b in bands]
+            assert max(sizes) - min(sizes) <= 1
+    jobs, rows = hm.band_jobs(3840, 2160, 128, 8, 0)
+    assert len(jobs) == 248 and rows == (0, 5)
 
 
 def test_band_rows_cover_exactly():
