@@ -195,6 +195,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="1080p64", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--virtual-world", type=int, default=0, help="experiments: on ONE GPU, run only the band rank 0 would get in a world of this size")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -218,10 +219,10 @@ def main():
 
     W, H, R, margin = workload_geometry(args.workload)
     ncx, ncy = W // 64, H // 64
-    jobs, (r0, r1) = hm.band_jobs(W, H, R, world, rank)
+    jobs, (r0, r1) = hm.band_jobs(W, H, R, args.virtual_world or world, rank)
     njobs = len(jobs)
     cands_per_job = (2 * R + 1) ** 2
-    total_jobs = ncx * ncy
+    total_jobs = len(jobs) if args.virtual_world else ncx * ncy
 
     # pinned host frames in HM's sample type (Pel = int16), synthetic content
     f = luma_frames(W, H, 2)

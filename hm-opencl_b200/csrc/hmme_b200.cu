@@ -42,15 +42,28 @@ size_t fast_smem_bytes(int tw, int th, int yb) {
     return words * 4;
 }
 
-FastGeom fast_geometry(int W, int yb) {
+// Tile geometry of the packed kernel for a (2R+1)^2 window and njobs jobs on `sms` SMs (1 CTA per SM).
+// x: tiles of at most 129 columns.  y: k row groups (YB rows each) per tile, k <= what the 11-bit in-tile index and the
+// shared-memory budget allow.  Among the admissible k the one with the smallest predicted makespan wins:
+//   waves(k) * (rounds(k) + c),  waves = ceil(CTAs / sms),  rounds = ceil(tw * k / 32),  c ~ 4 rounds of per-tile overhead
+// (staging + publish, measured on B200).  With few jobs per GPU (8-GPU bands) a smaller k fills the last wave better.
+FastGeom fast_geometry(int W, int yb, int njobs, int sms, int forceRG) {
     FastGeom g{};
     g.nTx = (W + kMaxTileW - 1) / kMaxTileW;
     g.tw = (W + g.nTx - 1) / g.nTx;
-    int thMax = (kMaxTileCands / g.tw) / yb * yb;
-    thMax = std::min(thMax, (W + yb - 1) / yb * yb);
-    while (thMax > yb && fast_smem_bytes(g.tw, thMax, yb) > kSmemBudget) thMax -= yb;
-    g.nTy = (W + thMax - 1) / thMax;
-    g.th = (((W + g.nTy - 1) / g.nTy) + yb - 1) / yb * yb;
+    const int nRGjob = (W + yb - 1) / yb;
+    int maxRG = std::max(1, std::min(kMaxTileCands / (g.tw * yb), nRGjob));
+    while (maxRG > 1 && fast_smem_bytes(g.tw, maxRG * yb, yb) > kSmemBudget) --maxRG;
+    int bestK = maxRG;
+    double bestCost = 1e300;
+    for (int k = maxRG; k >= 1; --k) {
+        const long long ctas = (long long)njobs * g.nTx * ((nRGjob + k - 1) / k);
+        const double cost = (double)((ctas + sms - 1) / sms) * ((g.tw * k + 31) / 32 + 4.0);
+        if (cost < bestCost * 0.995) { bestCost = cost; bestK = k; }      // prefer the larger tile unless clearly worse
+    }
+    if (forceRG >= 1 && forceRG <= maxRG) bestK = forceRG;
+    g.th = bestK * yb;
+    g.nTy = (nRGjob + bestK - 1) / bestK;
     g.smemBytes = fast_smem_bytes(g.tw, g.th, yb);
     return g;
 }
@@ -71,6 +84,7 @@ struct hmme_ctx {
     int maxRange = 0;
     uint64_t launches = 0;
     int stagger = 1300;          // cycles of start skew between the two warp groups of the packed kernel (HMME_STAGGER env overrides)
+    int forceRG = 0;             // HMME_FAST_RG env: force the number of row groups per tile (experiments)
     int fastYb = HMME_FAST_YB;   // candidate rows per thread in the packed kernel (HMME_FAST_YB env overrides: 2 or 3; 5*32*YB upper-level tasks must fit 512 threads)
     // job / result buffers (grown on demand)
     size_t jobCap = 0;
@@ -170,7 +184,7 @@ int enqueue_search(hmme_ctx* c, const void* curOrigin, int curElem, long long cu
     CU_TRY(c, cudaEventRecord(c->ev0, c->stream));
     if (curElem == 1 && refElem == 1) {
         const int yb = c->fastYb;
-        const FastGeom g = fast_geometry(W, yb);
+        const FastGeom g = fast_geometry(W, yb, njobs, c->prop.multiProcessorCount, c->forceRG);
         FastParams fp{};
         fp.cur = static_cast<const uint8_t*>(curOrigin);
         fp.ref = static_cast<const uint8_t*>(refOrigin);
@@ -303,6 +317,7 @@ int hmme_create(hmme_ctx** out, int device, int maxCtuW, int maxCtuH, int maxSea
         (e = cudaEventCreateWithFlags(&c->evFinal, cudaEventDisableTiming)) != cudaSuccess)
         return bail(std::string("cudaEventCreate: ") + cudaGetErrorString(e), HMME_ERR_CUDA);
     c->maxRange = maxSearchRange;
+    if (const char* e = std::getenv("HMME_FAST_RG")) c->forceRG = std::atoi(e);
     if (const char* e = std::getenv("HMME_STAGGER")) c->stagger = std::max(0, std::atoi(e));
     if (const char* e = std::getenv("HMME_FAST_YB")) { const int v = std::atoi(e); if (v >= 2 && v <= 3) c->fastYb = v; }
     const size_t side = (size_t)2 * maxSearchRange + 64 + 16;
