@@ -148,7 +148,7 @@ def cpu_baseline_entry(R, budget_s, all_cores=True):
     """cpu_baseline object: the reference's CPU ME when oracle/_ref holds its build, else the oracle port."""
     threads = os.cpu_count() or 1
     if os.path.exists(CPUME_BIN) and os.path.exists(CPUME_CFG):
-        clip = (416, 240) if budget_s >= 30 else (192, 128) if budget_s >= 10 else (128, 64)
+        clip = (416, 240) if budget_s >= 30 else (192, 128) if budget_s >= 10 else (128, 64) if budget_s >= 4 else (64, 64)
         procs = threads if all_cores else 1
         v, me_s, calls, wall = reference_cpu_me(R, clip, procs)
         return {"value": v, "unit": "block-SAD evaluations/s", "cores": procs, "kind": "reference",
@@ -190,14 +190,19 @@ def run_reference(args, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=None, help="default: 200 (b200 arm), 3 (reference arm)")
+    ap.add_argument("--warmup", type=int, default=None, help="default: 3 (b200 arm), 1 (reference arm)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="1080p64", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--virtual-world", type=int, default=0, help="experiments: on ONE GPU, run only the band rank 0 would get in a world of this size")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":          # each step is seconds of single-threaded CPU encoders: keep the default run short
+        args.steps = 3 if args.steps is None else args.steps
+        args.warmup = 1 if args.warmup is None else args.warmup
+    else:
+        args.steps = 200 if args.steps is None else args.steps
+        args.warmup = max(3 if args.warmup is None else args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
