@@ -72,9 +72,10 @@ FastGeom fast_geometry(int W, int yb, int njobs, int sms, int forceRG) {
 
 struct hmme_ctx {
     int device = -1;
-    cudaStream_t stream = nullptr;      // compute: init / search / finalize / result copies
+    cudaStream_t stream = nullptr;      // compute: search kernels and result copies
     cudaStream_t ioStream[2] = {nullptr, nullptr};   // high priority, one per staging buffer: a frame's two plane uploads copy back to back
-                                                      // instead of the second copy queueing behind the first plane's narrowing kernel
+                                                      // instead of the second copy queueing behind the first plane's narrowing kernel;
+                                                      // ioStream[0] also runs the finalize kernel
     cudaEvent_t evUpload[2] = {nullptr, nullptr}, evSearch = nullptr, evFinal = nullptr;   // io -> compute and compute -> io ordering
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool evValid = false;
@@ -123,7 +124,7 @@ int fail(hmme_ctx* c, int code, const std::string& msg) {
 int ensure_jobs(hmme_ctx* c, size_t njobs) {
     if (njobs <= c->jobCap) return HMME_OK;
     size_t cap = std::max<size_t>(njobs, std::max<size_t>(64, c->jobCap * 2));
-    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    for (cudaStream_t s : {c->ioStream[0], c->ioStream[1], c->stream}) CU_TRY(c, cudaStreamSynchronize(s));
     if (c->dJobs) cudaFree(c->dJobs);
     if (c->dBest) cudaFree(c->dBest);
     if (c->dRes) cudaFree(c->dRes);
