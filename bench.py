@@ -196,6 +196,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="1080p64", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-dist", default="broadcast", choices=["allgather", "broadcast"],
+                    help="N > 1: how the reference plane reaches every GPU: rank 0 uploads all of it and NCCL broadcasts (default), or each "
+                         "rank uploads 1/N of it and NCCL all-gathers (faster when steps are serial, no gain once frames are pipelined)")
     ap.add_argument("--virtual-world", type=int, default=0, help="experiments: on ONE GPU, run only the band rank 0 would get in a world of this size")
     args = ap.parse_args()
     if args.impl == "reference":          # each step is seconds of single-threaded CPU encoders: keep the default run short
@@ -239,6 +242,8 @@ def main():
     n_cur_band = n_cur[margin + 64 * r0: margin + 64 * r1] if band_h else None
     pitch = (W + 2 * margin + 15) // 16 * 16
     rows = H + 2 * margin
+    slice_rows = -(-rows // world)                      # reference rows each rank uploads when the plane is all-gathered
+    s0, s1 = min(rank * slice_rows, rows), min((rank + 1) * slice_rows, rows)
 
     class Pipe:
         """One library context with its own stream, device planes (torch tensors, so NCCL can broadcast them; the library
@@ -249,22 +254,32 @@ def main():
             self.me.set_lambda_q16(LAMBDA_Q16)
             self.ext = torch.cuda.ExternalStream(self.me.stream_ptr, device=dev)
             self.t_cur = torch.zeros(rows * pitch + 64, dtype=torch.uint8, device=dev)
-            self.t_ref = torch.zeros(rows * pitch + 64, dtype=torch.uint8, device=dev)
+            self.t_ref = torch.zeros(slice_rows * world * pitch + 64, dtype=torch.uint8, device=dev)
             self.p_cur = self.me.wrap_plane(self.t_cur.data_ptr(), 1, pitch, W, H, margin, margin)
             self.p_ref = self.me.wrap_plane(self.t_ref.data_ptr(), 1, pitch, W, H, margin, margin)
             # this rank's band of the current frame as its own upload target (rows [64*r0, 64*r1), no vertical margin)
             self.p_cur_band = self.me.wrap_plane(self.t_cur.data_ptr() + (margin + 64 * r0) * pitch, 1, pitch, W, band_h, margin, 0) if band_h else None
+            # this rank's horizontal slice of the (padded) reference plane as its own upload target
+            self.p_ref_slice = self.me.wrap_plane(self.t_ref.data_ptr() + s0 * pitch, 1, pitch, W, s1 - s0, margin, 0) if s1 > s0 else None
             self.outs = [torch.zeros((max(njobs, 1), NPARTS), dtype=torch.int32).pin_memory().numpy().view(t)
                          for t in (np.int32, np.int32, np.uint32, np.uint32)]
 
         def upload_inputs(self, asynchronous=False):
             """The per-step host->device leg of the public API: reference picture (rank 0, then NCCL broadcast over NVLink),
             band of the current frame (every rank)."""
-            if rank == 0:
-                self.me.upload(self.p_ref, n_ref, asynchronous=asynchronous)
-            if world > 1:
+            if world > 1 and args.ref_dist == "allgather":
+                # every rank pushes 1/N of the reference over its own PCIe link, then NCCL all-gathers the 8-bit slices in place
+                if self.p_ref_slice is not None:
+                    self.me.upload(self.p_ref_slice, n_ref[s0:s1], origin_x=margin, origin_y=0, asynchronous=asynchronous)
                 with torch.cuda.stream(self.ext):
-                    dist.broadcast(self.t_ref, src=0)
+                    full = self.t_ref[:slice_rows * world * pitch]
+                    dist.all_gather_into_tensor(full, full[rank * slice_rows * pitch:(rank + 1) * slice_rows * pitch])
+            else:
+                if rank == 0:
+                    self.me.upload(self.p_ref, n_ref, asynchronous=asynchronous)
+                if world > 1:
+                    with torch.cuda.stream(self.ext):
+                        dist.broadcast(self.t_ref, src=0)
             if band_h:
                 self.me.upload(self.p_cur_band, n_cur_band, origin_x=margin, origin_y=0, asynchronous=asynchronous)
 
@@ -384,7 +399,8 @@ def main():
     if world > 1:
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_ms, serial_ms = float(e2e_ms[0].item()), float(e2e_ms[1].item())
-    h2d = (n_ref.nbytes if rank == 0 else 0) + (n_cur_band.nbytes if band_h else 0) + jobs.nbytes
+    ref_bytes = n_ref[s0:s1].nbytes if (world > 1 and args.ref_dist == "allgather") else (n_ref.nbytes if rank == 0 else 0)
+    h2d = ref_bytes + (n_cur_band.nbytes if band_h else 0) + jobs.nbytes
     d2h = 4 * njobs * NPARTS * 4
     io = torch.tensor([h2d, d2h], dtype=torch.float64, device=dev)
     if world > 1:
@@ -407,7 +423,7 @@ def main():
             "ctu_candidates_per_s": total_cands / (ms_per_step * 1e-3),
             "config": {"workload": "%s: %dx%d luma, 64x64 CTU, integer-pel full search +-%d, 1 reference picture, %d CTU jobs x %d candidates x 593 partitions"
                                    % (args.workload, W, H, R, total_jobs, cands_per_job),
-                       "sharding": "CTU-row bands (cut at CTU granularity) over %d GPU(s), reference plane NCCL-broadcast from rank 0" % world,
+                       "sharding": "CTU-row bands (cut at CTU granularity) over %d GPU(s); reference plane: %s" % (world, "single GPU" if world == 1 else ("each rank uploads 1/N, NCCL all-gather over NVLink" if args.ref_dist == "allgather" else "rank 0 uploads, NCCL broadcast over NVLink")),
                        "lambda_q16": LAMBDA_Q16,
                        "l2": "inputs larger than L2: %d resident (current, reference) plane pairs at distinct addresses (%.0f MiB), cycled step by step" % (nsets, 2 * nsets * plane_stride / 2**20),
                        "timer": "CUDA events around the whole K-step region, frames alternating over two library contexts/streams, max over ranks; "
