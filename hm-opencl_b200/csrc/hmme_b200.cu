@@ -44,9 +44,11 @@ size_t fast_smem_bytes(int tw, int th, int yb) {
 
 // Tile geometry of the packed kernel for a (2R+1)^2 window and njobs jobs on `sms` SMs (1 CTA per SM).
 // x: tiles of at most 129 columns.  y: k row groups (YB rows each) per tile, k <= what the 11-bit in-tile index and the
-// shared-memory budget allow.  Among the admissible k the one with the smallest predicted makespan wins:
+// shared-memory budget allow.  The largest k has the least per-tile overhead and is used whenever it still yields at
+// least one full wave of CTAs (partially filled last waves are covered by the next frame's CTAs when frames are
+// pipelined over two streams).  For smaller launches -- the per-CTU call of the encoder is ONE job -- the k with the
+// smallest predicted makespan wins, which spreads a single job over up to 43 SMs:
 //   waves(k) * (rounds(k) + c),  waves = ceil(CTAs / sms),  rounds = ceil(tw * k / 32),  c ~ 4 rounds of per-tile overhead
-// (staging + publish, measured on B200).  With few jobs per GPU (8-GPU bands) a smaller k fills the last wave better.
 FastGeom fast_geometry(int W, int yb, int njobs, int sms, int forceRG) {
     FastGeom g{};
     g.nTx = (W + kMaxTileW - 1) / kMaxTileW;
@@ -56,7 +58,8 @@ FastGeom fast_geometry(int W, int yb, int njobs, int sms, int forceRG) {
     while (maxRG > 1 && fast_smem_bytes(g.tw, maxRG * yb, yb) > kSmemBudget) --maxRG;
     int bestK = maxRG;
     double bestCost = 1e300;
-    for (int k = maxRG; k >= 1; --k) {
+    const bool fullWave = (long long)njobs * g.nTx * ((nRGjob + maxRG - 1) / maxRG) >= sms;
+    for (int k = maxRG; k >= 1 && !fullWave; --k) {
         const long long ctas = (long long)njobs * g.nTx * ((nRGjob + k - 1) / k);
         const double cost = (double)((ctas + sms - 1) / sms) * ((g.tw * k + 31) / 32 + 4.0);
         if (cost < bestCost * 0.995) { bestCost = cost; bestK = k; }      // prefer the larger tile unless clearly worse
