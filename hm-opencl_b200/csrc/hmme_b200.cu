@@ -89,7 +89,6 @@ struct hmme_ctx {
     uint64_t launches = 0;
     int stagger = 1300;          // cycles of start skew between the two warp groups of the packed kernel (HMME_STAGGER env overrides)
     int forceRG = 0;             // HMME_FAST_RG env: force the number of row groups per tile (experiments)
-    int fastYb = HMME_FAST_YB;   // candidate rows per thread in the packed kernel (HMME_FAST_YB env overrides: 2 or 3; 5*32*YB upper-level tasks must fit 512 threads)
     // job / result buffers (grown on demand)
     size_t jobCap = 0;
     int4* dJobs = nullptr;
@@ -187,7 +186,7 @@ int enqueue_search(hmme_ctx* c, const void* curOrigin, int curElem, long long cu
     uint32_t* Cst = S + c->jobCap * HMME_NPARTS;
     CU_TRY(c, cudaEventRecord(c->ev0, c->stream));
     if (curElem == 1 && refElem == 1) {
-        const int yb = c->fastYb;
+        constexpr int yb = HMME_FAST_YB;             // candidate rows per thread (3: measured best; 2 is 17 % slower, 4 does not fit)
         const FastGeom g = fast_geometry(W, yb, njobs, c->prop.multiProcessorCount, c->forceRG);
         FastParams fp{};
         fp.cur = static_cast<const uint8_t*>(curOrigin);
@@ -204,8 +203,7 @@ int enqueue_search(hmme_ctx* c, const void* curOrigin, int curElem, long long cu
             kernel<<<grid, kFastThreads, g.smemBytes, c->stream>>>(fp);
             return cudaSuccess;
         };
-        if (yb == 2) CU_TRY(c, launch(me_u8_tile_kernel<2>));
-        else CU_TRY(c, launch(me_u8_tile_kernel<3>));
+        CU_TRY(c, launch(me_u8_tile_kernel<HMME_FAST_YB>));
     } else {
         GenericParams gp{};
         gp.cur = curOrigin; gp.ref = refOrigin; gp.curPitch = curPitch; gp.refPitch = refPitch;
@@ -323,7 +321,6 @@ int hmme_create(hmme_ctx** out, int device, int maxCtuW, int maxCtuH, int maxSea
     c->maxRange = maxSearchRange;
     if (const char* e = std::getenv("HMME_FAST_RG")) c->forceRG = std::atoi(e);
     if (const char* e = std::getenv("HMME_STAGGER")) c->stagger = std::max(0, std::atoi(e));
-    if (const char* e = std::getenv("HMME_FAST_YB")) { const int v = std::atoi(e); if (v >= 2 && v <= 3) c->fastYb = v; }
     const size_t side = (size_t)2 * maxSearchRange + 64 + 16;
     c->winElems = side * side;
     if ((e = cudaMallocHost(&c->hWin, c->winElems * 2)) != cudaSuccess || (e = cudaMalloc(&c->dWin, c->winElems * 2 + 64)) != cudaSuccess ||
