@@ -276,8 +276,8 @@ def test_async_upload_reports_bad_content_at_sync(me):
 def test_randomised_differential_vs_oracle(me, oracle):
     """Seeded fuzz: random ranges (every residue of the tile/round/row-group arithmetic), window offsets, lambdas, content
     classes and plane margins (so the CTU and the window start at arbitrary byte alignments)."""
-    g = np.random.default_rng(2026)
-    for it in range(36):
+    g = np.random.default_rng(int(os.environ.get("HMME_FUZZ_SEED", "2026")))
+    for it in range(int(os.environ.get("HMME_FUZZ_ITERS", "120"))):       # soak: HMME_FUZZ_ITERS=400 HMME_FUZZ_SEED=n
         R = int(g.integers(0, 45))
         W, H = 64 * int(g.integers(1, 4)), 64 * int(g.integers(1, 3))
         M = R + int(g.integers(6, 23))
