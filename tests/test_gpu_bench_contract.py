@@ -1,0 +1,30 @@
+"""Runs bench.py (short) on the GPU and checks the JSON line against the contract the driver reads."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_bench_line_on_gpu():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "12", "--warmup", "3", "--no-cpu-baseline"],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    d = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert d["metric"] == "me_block_sad_evaluations_per_s" and d["unit"] == "block-SAD evaluations/s" and d["n_gpus"] == 1
+    assert d["steps"] == 12 and d["warmup"] == 3 and d["higher_is_better"] is True and d["vs_baseline"] is None
+    assert d["dtype"] == "u8" and d["data"] == "synthetic" and "workload" in d["config"] and "model" not in d["config"]
+    assert abs(d["value"] - 480 * 16641 * 593 / (d["ms_per_step"] * 1e-3)) / d["value"] < 1e-6
+    assert d["gpu_launches"] == 2 * 12                              # search + finalize per step, all of them this library's kernels
+    e = d["e2e"]
+    assert e["value"] > 0 and e["h2d_bytes_per_step"] > 9_000_000 and e["d2h_bytes_per_step"] == 480 * 593 * 16
+    rf = d["roofline"]
+    assert rf["bound"] == "int_alu" and 0.3 < rf["frac"] < 1.5 and rf["peak"] > 10 and rf["achieved"] > 5 and rf["traffic"]
+    assert abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9
+    c = d["clocks"]
+    assert c["sm_mhz"] and c["sm_max_mhz"] and not set(c["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    assert 0.5 < d["ms_per_step"] < 5.0                             # 1080p +-64 on one B200: ~1.3 ms
