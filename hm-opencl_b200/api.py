@@ -21,7 +21,7 @@ EXPORTS = [
     "hmme_plane_alloc", "hmme_plane_free", "hmme_plane_upload_s16", "hmme_plane_upload_u8",
     "hmme_search_frame", "hmme_search_frame_async", "hmme_fetch_results", "hmme_sync",
     "hmme_plane_upload_s16_async", "hmme_fetch_results_async",
-    "hmme_last_kernel_ms", "hmme_kernel_launches", "hmme_measure_int_alu_peak", "hmme_partition_rect", "hmme_index_block", "hmme_version",
+    "hmme_last_kernel_ms", "hmme_kernel_launches", "hmme_measure_int_alu_peak", "hmme_partition_rect", "hmme_index_block", "hmme_search_window", "hmme_version",
 ]
 
 
@@ -84,6 +84,7 @@ class HmmeLib:
             "hmme_measure_int_alu_peak": (i32, [vp, P(C.c_double), P(C.c_double), P(C.c_double)]),
             "hmme_partition_rect": (i32, [i32, P(C.c_int), P(C.c_int), P(C.c_int), P(C.c_int)]),
             "hmme_index_block": (i32, [i32] * 6),
+            "hmme_search_window": (i32, [i32] * 7 + [P(C.c_int)] * 4),
             "hmme_version": (C.c_char_p, []),
         }
         assert sorted(sig) == sorted(EXPORTS)
@@ -101,6 +102,11 @@ class HmmeLib:
 
     def index_block(self, part_size, depth, part_idx, z_idx, cu_w, cu_h):
         return int(self.L.hmme_index_block(part_size, depth, part_idx, z_idx, cu_w, cu_h))
+
+    def search_window(self, pred_hor_qpel, pred_ver_qpel, rng, cu_x, cu_y, pic_w, pic_h):
+        v = [C.c_int() for _ in range(4)]
+        assert self.L.hmme_search_window(pred_hor_qpel, pred_ver_qpel, rng, cu_x, cu_y, pic_w, pic_h, *[C.byref(q) for q in v]) == 0
+        return tuple(q.value for q in v)      # ltx, lty, rbx, rby
 
     def device_count(self):
         n = C.c_int(0)

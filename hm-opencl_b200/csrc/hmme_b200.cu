@@ -579,6 +579,16 @@ int hmme_measure_int_alu_peak(hmme_ctx* c, double* laneOpsPerSec, double* lanesP
     return HMME_OK;
 }
 
+int hmme_search_window(int predHorQpel, int predVerQpel, int range, int cuX, int cuY, int picWidth, int picHeight, int* ltx, int* lty,
+                       int* rbx, int* rby) {
+    if (!ltx || !lty || range < 0) return HMME_ERR_ARG;
+    int rx = 0, ry = 0;
+    search_window(predHorQpel, predVerQpel, range, cuX, cuY, picWidth, picHeight, HMME_CTU_SIZE, HMME_CTU_SIZE, ltx, lty, &rx, &ry);
+    if (rbx) *rbx = rx;
+    if (rby) *rby = ry;
+    return HMME_OK;
+}
+
 int hmme_index_block(int partSize, int depth, int partIdx, int absZIdxInCtu, int cuWidth, int cuHeight) {
     return index_block(partSize, depth, partIdx, absZIdxInCtu, cuWidth, cuHeight);
 }

@@ -111,6 +111,26 @@ __host__ __device__ inline int index_block(int partSize, int depth, int partIdx,
     return -1;
 }
 
+// Search-window placement of TEncSearch::xSetSearchRange (TEncSearch.cpp:3814-3830) with TComDataCU::clipMv
+// (TComDataCU.cpp:2907-2920): the quarter-pel MV the window is centred on (the AMVP predictor, or the current MV for the
+// bi-prediction refinement) is clipped to the picture + 8 samples (+ one CTU on the low side), +-range is applied in
+// quarter-pel units, both corners are clipped again and brought to integer-pel with an arithmetic shift.
+// The GPU path then searches [lt, lt + 2*range] in both axes and ignores rb.
+__host__ __device__ inline void search_window(int predHorQpel, int predVerQpel, int range, int cuX, int cuY, int picW, int picH,
+                                              int maxCuW, int maxCuH, int* ltx, int* lty, int* rbx, int* rby) {
+    const int sh = 2, off = 8;
+    const int horMax = (picW + off - cuX - 1) * 4, horMin = (-maxCuW - off - cuX + 1) * 4;
+    const int verMax = (picH + off - cuY - 1) * 4, verMin = (-maxCuH - off - cuY + 1) * 4;
+    auto clipH = [&](int v) { return v < horMin ? horMin : (v > horMax ? horMax : v); };
+    auto clipV = [&](int v) { return v < verMin ? verMin : (v > verMax ? verMax : v); };
+    auto s16 = [](int v) { return (int)(short)v; };                      // TComMv stores Short (TComMv.h:54-55)
+    const int ph = clipH(s16(predHorQpel)), pv = clipV(s16(predVerQpel));
+    *ltx = clipH(s16(ph - (range << sh))) >> sh;
+    *lty = clipV(s16(pv - (range << sh))) >> sh;
+    *rbx = clipH(s16(ph + (range << sh))) >> sh;
+    *rby = clipV(s16(pv + (range << sh))) >> sh;
+}
+
 // bits(v) = 2*floor(log2 t) + 1 with t = (v <= 0) ? -2v+1 : 2v   (sad.cl:377-396)
 __host__ __device__ inline uint32_t mv_bits(int v) {
     uint32_t t = (v <= 0) ? (uint32_t)(-2 * v) + 1u : (uint32_t)(2 * v);

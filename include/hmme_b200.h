@@ -116,6 +116,11 @@ int hmme_measure_int_alu_peak(hmme_ctx* ctx, double* laneOpsPerSec, double* lane
 
 /* ---- the 593-entry layout, for callers that want it without linking HM (index -> x, y, w, h) */
 int hmme_partition_rect(int index, int* x, int* y, int* w, int* h);
+/* Search-window placement: TEncSearch::xSetSearchRange (TEncSearch.cpp:3814-3830) + TComDataCU::clipMv (TComDataCU.cpp:2907-2920)
+ * for a 64x64 CTU at (cuX, cuY): quarter-pel centre MV -> integer-pel left/top (what calcMotionVectors receives as
+ * pcMvSrchRngLT, i.e. a job's ltx/lty) and right/bottom (unused by the GPU path, may be NULL). */
+int hmme_search_window(int predHorQpel, int predVerQpel, int range, int cuX, int cuY, int picWidth, int picHeight,
+                       int* ltx, int* lty, int* rbx, int* rby);
 /* Closed form of TComDataCU::getIndexBlock (TComDataCU.cpp:3379-6464): PartSize enum value, CU depth, PU index, z-order
  * index of the CU in 4x4 units, CU width/height -> index 0..592, or -1 exactly where the reference's switch has no case. */
 int hmme_index_block(int partSize, int depth, int partIdx, int absZIdxInCtu, int cuWidth, int cuHeight);

@@ -33,4 +33,10 @@ once('          xPatternSearchFast  ( pcCU, pcPatternKey, piRefY, iRefStride, &c
 n = s.count("m_cDistParam.DistFunc( &m_cDistParam )")
 assert n == 5, n
 s = s.replace("m_cDistParam.DistFunc( &m_cDistParam )", "(g_hmmeDistCalls += g_hmmeInMe, m_cDistParam.DistFunc( &m_cDistParam ))")
+# optional log of every search-window placement handed to the GPU path (golden for hmme_search_window_lt)
+once('            m_ppcOpenCLME->calcMotionVectors(piCtu, piRefY, iRefStride, iCtuStride, iSrchRng ,&cMvSrchRngLT);',
+     '            if (getenv("HMME_LOG_LT")) { const TComMv& pm_ = bBi ? rcMv : cMvPred; printf("HMME_LT %d %d %d %d %d %d %d %d %d %d %d\\n", (int)pm_.getHor(), (int)pm_.getVer(), iSrchRng, '
+     '(int)pcCU->getCUPelX(), (int)pcCU->getCUPelY(), (int)pcCU->getSlice()->getSPS()->getPicWidthInLumaSamples(), (int)pcCU->getSlice()->getSPS()->getPicHeightInLumaSamples(), '
+     '(int)cMvSrchRngLT.getHor(), (int)cMvSrchRngLT.getVer(), (int)cMvSrchRngRB.getHor(), (int)cMvSrchRngRB.getVer()); }\n'
+     '            m_ppcOpenCLME->calcMotionVectors(piCtu, piRefY, iRefStride, iCtuStride, iSrchRng ,&cMvSrchRngLT);')
 open(path, "w").write(s)

@@ -75,6 +75,21 @@ def test_closed_form_index_block_equals_the_reference_switch(lib):
     assert lib.index_block(0, 0, 0, 0, 32, 64) == -1 and lib.index_block(0, 4, 0, 0, 4, 4) == -1
 
 
+def test_search_window_matches_the_reference_encoder(lib):
+    """hmme_search_window against every window placement the reference encoder itself computed (xSetSearchRange + clipMv,
+    logged by the instrumented build; oracle/gen_window_golden.py): uni- and bi-prediction calls, ranges 4/8/64/96,
+    clipping at all four picture borders."""
+    g = json.load(open(os.path.join(ROOT, "tests/golden/search_window_lt.json")))
+    rows = g["rows"]
+    assert len(rows) > 100
+    ranges, clipped = set(), 0
+    for ph, pv, R, cx, cy, W, H, ltx, lty, rbx, rby in rows:
+        assert lib.search_window(ph, pv, R, cx, cy, W, H) == (ltx, lty, rbx, rby), (ph, pv, R, cx, cy)
+        ranges.add(R)
+        clipped += (rbx - ltx != 2 * R) or (rby - lty != 2 * R)
+    assert {4, 8, 64, 96} <= ranges and clipped > 10
+
+
 def test_product_and_oracle_layout_agree(lib, oracle):
     assert np.array_equal(lib.partition_table(), oracle.partition_table())
 
