@@ -32,7 +32,7 @@ def main():
             write_yuv(yuv, W, H, F)
             env = dict(os.environ, HMME_LOG_LT="1")
             r = subprocess.run([binary, "-c", os.path.join(REFDIR, "cfg", cfg), "-i", yuv, "-wdt", str(W), "-hgt", str(H), "-fr", "30", "-f", str(F),
-                                "-q", "32", "-b", os.path.join(d, "o.hevc"), "--OpenCL=1", "--KernelOpenCL=/root/reference/cl/sad.cl",
+                                "-q", "32", "-b", os.path.join(d, "o.hevc"), "-o", os.path.join(d, "rec.yuv"), "--OpenCL=1", "--KernelOpenCL=/root/reference/cl/sad.cl",
                                 "--SearchRange=%d" % R], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env)
             assert r.returncode == 0, r.stdout[-2000:]
             for line in r.stdout.splitlines():
