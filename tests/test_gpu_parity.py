@@ -307,3 +307,32 @@ def test_randomised_differential_vs_oracle(me, oracle):
         want = oracle.search_frame(cur, (M, M), ref, (M, M), jobs, R, lam, nthreads=8)
         assert_same(got, want, f"fuzz it={it} R={R} {W}x{H} M={M} kind={kind} lam={lam}")
         pc.free(); pr.free()
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_virtual_bands_equal_whole_frame(me, world):
+    """band-sharded results must be identical to the single-GPU result.  The same sharding
+    code the ranks use (hm.band_jobs / merge_bands) is exercised here with `world` virtual bands on one GPU, each band
+    seeing only its own rows of the current frame (the rest of its plane is poisoned)."""
+    W, H, R = 448, 320, 12                               # 7 x 5 CTUs: bands cut mid-row
+    f = luma_frames(W, H, 2, seed=world)
+    M = R + 16
+    cur, ref = pad_plane(f[1], M, M), pad_plane(f[0], M, M)
+    me.set_lambda_q16(460000)
+    pr, pc = me.alloc_plane(1, W, H, M, M), me.alloc_plane(1, W, H, M, M)
+    me.upload(pr, ref); me.upload(pc, cur)
+    whole = me.search_frame(pc, pr, frame_jobs(W, H, R), R)
+    parts = []
+    for rank in range(world):
+        jobs, (r0, r1) = hm.band_jobs(W, H, R, world, rank)
+        if len(jobs) == 0:
+            parts.append(tuple(np.zeros((0, 593), a.dtype) for a in whole))
+            continue
+        band = np.full_like(cur, 255)                    # this rank only uploads rows [64*r0, 64*r1) of the current frame
+        band[M + 64 * r0:M + 64 * r1] = cur[M + 64 * r0:M + 64 * r1]
+        pb = me.alloc_plane(1, W, H, M, M)
+        me.upload(pb, band)
+        parts.append(me.search_frame(pb, pr, jobs, R))
+        pb.free()
+    assert_same(hm.merge_bands(parts), whole, f"world={world}")
+    pc.free(); pr.free()
