@@ -74,6 +74,20 @@ int hmme_oracle_search_frame(const int16_t* curOrigin, int curStride,
                              int nthreads,
                              int32_t* X, int32_t* Y, uint32_t* sad, uint32_t* cost);
 
+/*
+ * Fractional-pel refinement after the integer search (hmme_frac_oracle.c has the citations):
+ * TEncSearch::xPatternSearchFracDIF for a list of prediction units.  Planes are int16 with origin = picture sample (0,0)
+ * (cur may hold the 16-bit bi-prediction target 2*org - pred, ref has 8-bit content); each PU gives its rectangle, the
+ * integer-pel MV found by the search and the quarter-pel predictor the bit cost is relative to.  lambda is
+ * TComRdCost::m_uiCost (= m_uiLambdaMotionSAD = floor(65536*sqrt(lambda))); useHad = HadamardME && !lossless.
+ * Outputs per PU: mvq = final quarter-pel MV, half / qter = the two stage winners (each -1..1), cost = ruiCost as
+ * xPatternSearchFracDIF returns it, dist = cost minus the MV cost of the winner.
+ */
+typedef struct { int32_t x, y, w, h, mvx, mvy, predx, predy; } hmme_oracle_pu;
+int hmme_oracle_refine_frac(const int16_t* curOrigin, int curStride, const int16_t* refOrigin, int refStride,
+                            const hmme_oracle_pu* pus, int npus, uint32_t lambda, int useHad,
+                            int32_t* mvq, int32_t* half, int32_t* qter, uint32_t* cost, uint32_t* dist);
+
 #ifdef __cplusplus
 }
 #endif

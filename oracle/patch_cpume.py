@@ -39,4 +39,35 @@ once('            m_ppcOpenCLME->calcMotionVectors(piCtu, piRefY, iRefStride, iC
      '(int)pcCU->getCUPelX(), (int)pcCU->getCUPelY(), (int)pcCU->getSlice()->getSPS()->getPicWidthInLumaSamples(), (int)pcCU->getSlice()->getSPS()->getPicHeightInLumaSamples(), '
      '(int)cMvSrchRngLT.getHor(), (int)cMvSrchRngLT.getVer(), (int)cMvSrchRngRB.getHor(), (int)cMvSrchRngRB.getVer()); }\n'
      '            m_ppcOpenCLME->calcMotionVectors(piCtu, piRefY, iRefStride, iCtuStride, iSrchRng ,&cMvSrchRngLT);')
+# optional binary log of fractional-pel refinements (golden records for the frac oracle): inputs as the
+# function sees them (current block, reference patch with the 8-tap apron, integer MV, predictor, lambda) and its outputs
+once('#include "TEncSearch.h"', '#include "TEncSearch.h"\n#include <map>')
+once("""  ruiCost = xPatternRefinement( pcPatternKey, baseRefMv, 1, rcMvQter, !bIsLosslessCoded );
+}""", """  ruiCost = xPatternRefinement( pcPatternKey, baseRefMv, 1, rcMvQter, !bIsLosslessCoded );
+  if (const char* logName_ = getenv("HMME_LOG_FRAC"))
+  {
+    static FILE* f_ = fopen(logName_, "wb");
+    static std::map<int, int> seen_;
+    static const int cap_ = getenv("HMME_LOG_FRAC_CAP") ? atoi(getenv("HMME_LOG_FRAC_CAP")) : 8;
+    static const int stride_ = getenv("HMME_LOG_FRAC_STRIDE") ? atoi(getenv("HMME_LOG_FRAC_STRIDE")) : 29;
+    const int w_ = pcPatternKey->getROIYWidth(), h_ = pcPatternKey->getROIYHeight();
+    const int n_ = seen_[(w_ * 100 + h_) * 2 + (biPred ? 1 : 0)]++;
+    if (f_ && n_ % stride_ == 0 && n_ / stride_ < cap_)
+    {
+      const int hdr_[16] = { 0x46524143, w_, h_, biPred ? 1 : 0, (m_pcEncCfg->getUseHADME() && !bIsLosslessCoded) ? 1 : 0,
+                             pcMvInt->getHor(), pcMvInt->getVer(), m_pcRdCost->m_mvPredictor.getHor(), m_pcRdCost->m_mvPredictor.getVer(),
+                             (int)m_pcRdCost->m_uiCost, rcMvHalf.getHor(), rcMvHalf.getVer(), rcMvQter.getHor(), rcMvQter.getVer(), (int)ruiCost, 0 };
+      fwrite(hdr_, sizeof(int), 16, f_);
+      for (int r_ = 0; r_ < h_; ++r_) fwrite(pcPatternKey->getROIY() + r_ * pcPatternKey->getPatternLStride(), sizeof(Pel), w_, f_);
+      for (int r_ = -4; r_ < h_ + 4; ++r_) fwrite(piRefY + iOffset + r_ * iRefStride - 4, sizeof(Pel), w_ + 8, f_);
+      fflush(f_);
+    }
+  }
+}""")
 open(path, "w").write(s)
+# the log reads the predictor and lambda straight from TComRdCost: open its first private section in the scratch copy
+import os
+rd = os.path.join(os.path.dirname(path), "..", "TLibCommon", "TComRdCost.h")
+t = open(rd).read()
+assert t.count("private:\n  // for distortion") == 1
+open(rd, "w").write(t.replace("private:\n  // for distortion", "public:\n  // for distortion"))
