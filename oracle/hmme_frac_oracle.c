@@ -99,7 +99,7 @@ static const int kQter[9][2] = {{0, 0}, {0, -1}, {0, 1}, {-1, -1}, {1, -1}, {-1,
 
 int hmme_oracle_refine_frac(const int16_t* curOrigin, int curStride, const int16_t* refOrigin, int refStride,
                             const hmme_oracle_pu* pus, int npus, uint32_t lambda, int useHad,
-                            int32_t* mvq, int32_t* half, int32_t* qter, uint32_t* cost, uint32_t* dist) {
+                            int32_t* mvq, int32_t* half, int32_t* qter, uint32_t* cost, uint32_t* dist, uint32_t* cand) {
     for (int n = 0; n < npus; ++n) {
         const hmme_oracle_pu* P = &pus[n];
         if (P->w <= 0 || P->h <= 0 || P->w > 64 || P->h > 64 || (P->w & 3) || (P->h & 3)) return -1;
@@ -112,6 +112,7 @@ int hmme_oracle_refine_frac(const int16_t* curOrigin, int curStride, const int16
             predict(ref0, refStride, 2 * kHalf[i][0], 2 * kHalf[i][1], P->w, P->h, pred);
             const uint32_t mvc = mv_cost(lambda, 2 * P->mvx + kHalf[i][0], 2 * P->mvy + kHalf[i][1], 1, P->predx, P->predy);
             const uint32_t c = distortion(cur, curStride, pred, P->w, P->h, useHad) + mvc;
+            if (cand) cand[18 * n + i] = c;
             if (c < best) { best = c; bi = i; }
         }
         const int hx = kHalf[bi][0], hy = kHalf[bi][1];
@@ -122,6 +123,7 @@ int hmme_oracle_refine_frac(const int16_t* curOrigin, int curStride, const int16
             predict(ref0, refStride, dx, dy, P->w, P->h, pred);
             const uint32_t mvc = mv_cost(lambda, 4 * P->mvx + dx, 4 * P->mvy + dy, 0, P->predx, P->predy);
             const uint32_t c = distortion(cur, curStride, pred, P->w, P->h, useHad) + mvc;
+            if (cand) cand[18 * n + 9 + i] = c;
             if (c < best) { best = c; bq = i; bestMvc = mvc; }
         }
         half[2 * n] = hx; half[2 * n + 1] = hy;

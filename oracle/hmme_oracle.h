@@ -86,7 +86,8 @@ int hmme_oracle_search_frame(const int16_t* curOrigin, int curStride,
 typedef struct { int32_t x, y, w, h, mvx, mvy, predx, predy; } hmme_oracle_pu;
 int hmme_oracle_refine_frac(const int16_t* curOrigin, int curStride, const int16_t* refOrigin, int refStride,
                             const hmme_oracle_pu* pus, int npus, uint32_t lambda, int useHad,
-                            int32_t* mvq, int32_t* half, int32_t* qter, uint32_t* cost, uint32_t* dist);
+                            int32_t* mvq, int32_t* half, int32_t* qter, uint32_t* cost, uint32_t* dist,
+                            uint32_t* cand /* optional [npus][18]: cost of each half- then quarter-pel candidate */);
 
 #ifdef __cplusplus
 }

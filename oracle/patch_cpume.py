@@ -41,7 +41,19 @@ once('            m_ppcOpenCLME->calcMotionVectors(piCtu, piRefY, iRefStride, iC
      '            m_ppcOpenCLME->calcMotionVectors(piCtu, piRefY, iRefStride, iCtuStride, iSrchRng ,&cMvSrchRngLT);')
 # optional binary log of fractional-pel refinements (golden records for the frac oracle): inputs as the
 # function sees them (current block, reference patch with the 8-tap apron, integer MV, predictor, lambda) and its outputs
-once('#include "TEncSearch.h"', '#include "TEncSearch.h"\n#include <map>')
+once('#include "TEncSearch.h"', '#include "TEncSearch.h"\n#include <map>\nstatic unsigned g_hmmeFracCosts[18];')
+once("""    uiDist += m_pcRdCost->getCost( cMvTest.getHor(), cMvTest.getVer() );
+
+    if ( uiDist < uiDistBest )
+    {
+      uiDistBest  = uiDist;
+      uiDirecBest = i;""", """    uiDist += m_pcRdCost->getCost( cMvTest.getHor(), cMvTest.getVer() );
+    g_hmmeFracCosts[i + (iFrac == 2 ? 0 : 9)] = (unsigned)uiDist;
+
+    if ( uiDist < uiDistBest )
+    {
+      uiDistBest  = uiDist;
+      uiDirecBest = i;""")
 once("""  ruiCost = xPatternRefinement( pcPatternKey, baseRefMv, 1, rcMvQter, !bIsLosslessCoded );
 }""", """  ruiCost = xPatternRefinement( pcPatternKey, baseRefMv, 1, rcMvQter, !bIsLosslessCoded );
   if (const char* logName_ = getenv("HMME_LOG_FRAC"))
@@ -58,6 +70,7 @@ once("""  ruiCost = xPatternRefinement( pcPatternKey, baseRefMv, 1, rcMvQter, !b
                              pcMvInt->getHor(), pcMvInt->getVer(), m_pcRdCost->m_mvPredictor.getHor(), m_pcRdCost->m_mvPredictor.getVer(),
                              (int)m_pcRdCost->m_uiCost, rcMvHalf.getHor(), rcMvHalf.getVer(), rcMvQter.getHor(), rcMvQter.getVer(), (int)ruiCost, 0 };
       fwrite(hdr_, sizeof(int), 16, f_);
+      fwrite(g_hmmeFracCosts, sizeof(unsigned), 18, f_);
       for (int r_ = 0; r_ < h_; ++r_) fwrite(pcPatternKey->getROIY() + r_ * pcPatternKey->getPatternLStride(), sizeof(Pel), w_, f_);
       for (int r_ = -4; r_ < h_ + 4; ++r_) fwrite(piRefY + iOffset + r_ * iRefStride - 4, sizeof(Pel), w_ + 8, f_);
       fflush(f_);

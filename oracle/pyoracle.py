@@ -45,7 +45,7 @@ class Oracle:
                                                C.c_uint32, C.c_int] + [C.c_void_p] * 4
         L.hmme_oracle_refine_frac.restype = C.c_int
         L.hmme_oracle_refine_frac.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_uint32,
-                                              C.c_int] + [C.c_void_p] * 5
+                                              C.c_int] + [C.c_void_p] * 6
 
     def partition_table(self):
         out = np.zeros((NUM_PARTS, 4), np.int32)
@@ -95,19 +95,19 @@ class Oracle:
     def refine_frac(self, cur_plane, cur_origin, ref_plane, ref_origin, pus, lam, use_had=True):
         """Fractional-pel refinement (xPatternSearchFracDIF) of a PU list.  Planes int16 2-D, *_origin = (ox, oy) of
         picture sample (0,0); pus (n,8) int32 rows {x, y, w, h, mvx, mvy (integer pel), predx, predy (quarter pel)}.
-        Returns dict of mvq (n,2), half (n,2), qter (n,2), cost (n,), dist (n,)."""
+        Returns dict of mvq (n,2), half (n,2), qter (n,2), cost (n,), dist (n,), cand (n,18) = cost of every candidate."""
         pus = np.ascontiguousarray(pus, np.int32).reshape(-1, 8)
         n = pus.shape[0]
         assert cur_plane.dtype == np.int16 and ref_plane.dtype == np.int16
         assert cur_plane.flags.c_contiguous and ref_plane.flags.c_contiguous
         out = dict(mvq=np.zeros((n, 2), np.int32), half=np.zeros((n, 2), np.int32), qter=np.zeros((n, 2), np.int32),
-                   cost=np.zeros(n, np.uint32), dist=np.zeros(n, np.uint32))
+                   cost=np.zeros(n, np.uint32), dist=np.zeros(n, np.uint32), cand=np.zeros((n, 18), np.uint32))
         cs, rs = cur_plane.shape[1], ref_plane.shape[1]
         co = int((cur_origin[1] * cs + cur_origin[0]) * 2)
         ro = int((ref_origin[1] * rs + ref_origin[0]) * 2)
         rc = self.lib.hmme_oracle_refine_frac(cur_plane.ctypes.data + co, cs, ref_plane.ctypes.data + ro, rs, pus.ctypes.data, n,
                                               C.c_uint32(lam), int(bool(use_had)), out["mvq"].ctypes.data, out["half"].ctypes.data,
-                                              out["qter"].ctypes.data, out["cost"].ctypes.data, out["dist"].ctypes.data)
+                                              out["qter"].ctypes.data, out["cost"].ctypes.data, out["dist"].ctypes.data, out["cand"].ctypes.data)
         assert rc == 0
         return out
 
