@@ -21,6 +21,7 @@ EXPORTS = [
     "hmme_plane_alloc", "hmme_plane_free", "hmme_plane_upload_s16", "hmme_plane_upload_u8",
     "hmme_search_frame", "hmme_search_frame_async", "hmme_fetch_results", "hmme_sync",
     "hmme_plane_upload_s16_async", "hmme_fetch_results_async",
+    "hmme_refine_frac", "hmme_refine_frame", "hmme_refine_frame_async", "hmme_fetch_frac_async", "hmme_last_frac_ms",
     "hmme_last_kernel_ms", "hmme_kernel_launches", "hmme_measure_int_alu_peak", "hmme_partition_rect", "hmme_index_block", "hmme_search_window", "hmme_version",
 ]
 
@@ -79,6 +80,11 @@ class HmmeLib:
             "hmme_fetch_results_async": (i32, [vp, i32, vp, vp, vp, vp]),
             "hmme_plane_upload_s16_async": (i32, [vp, P(PlaneDesc), vp, i32]),
             "hmme_sync": (i32, [vp]),
+            "hmme_refine_frac": (i32, [vp, P(PlaneDesc), P(PlaneDesc), vp, i32, i32, vp, vp]),
+            "hmme_refine_frame": (i32, [vp, P(PlaneDesc), P(PlaneDesc), i32, vp, i32, vp]),
+            "hmme_refine_frame_async": (i32, [vp, P(PlaneDesc), P(PlaneDesc), i32, vp, i32]),
+            "hmme_fetch_frac_async": (i32, [vp, i32, vp]),
+            "hmme_last_frac_ms": (i32, [vp, P(C.c_float)]),
             "hmme_last_kernel_ms": (i32, [vp, P(C.c_float)]),
             "hmme_kernel_launches": (C.c_uint64, [vp]),
             "hmme_measure_int_alu_peak": (i32, [vp, P(C.c_double), P(C.c_double), P(C.c_double)]),
@@ -248,6 +254,41 @@ class MotionEstimator:
 
     def sync(self):
         self._chk(self.lib.L.hmme_sync(self.h))
+
+    # -- fractional-pel refinement (TEncSearch::xPatternSearchFracDIF, TEncSearch.cpp:4294-4331)
+    FRAC_DTYPE = np.dtype([("mvx", np.int32), ("mvy", np.int32), ("cost", np.uint32), ("dist", np.uint32)])
+
+    def refine_frac(self, cur, ref, pus, use_had=True, want_candidates=False):
+        """pus: (n, 8) int32 rows {x, y, w, h, mvx, mvy (integer pel), predx, predy (quarter pel)}.  Returns a structured
+        array (mvx, mvy quarter-pel; cost; dist) and, on request, the (n, 18) candidate costs in the reference's table order."""
+        pus = np.ascontiguousarray(pus, np.int32).reshape(-1, 8)
+        n = pus.shape[0]
+        res = np.zeros(n, self.FRAC_DTYPE)
+        cand = np.zeros((n, 18), np.uint32) if want_candidates else None
+        self._chk(self.lib.L.hmme_refine_frac(self.h, C.byref(cur.desc), C.byref(ref.desc), pus.ctypes.data, n, int(bool(use_had)),
+                                              res.ctypes.data, cand.ctypes.data if want_candidates else None))
+        return (res, cand) if want_candidates else res
+
+    def refine_frame(self, cur, ref, njobs, preds=None, use_had=True, asynchronous=False, out=None):
+        """All 593 partitions of every job of the preceding search_frame[_async] on this context, from its integer winners
+        (which stay on the device).  preds: None or (njobs, 2) quarter-pel predictors.  Returns (njobs, 593) structured."""
+        if preds is not None:
+            preds = np.ascontiguousarray(preds, np.int32).reshape(njobs, 2)
+        pp = preds.ctypes.data if preds is not None else None
+        if asynchronous:
+            self._keep = preds                                  # the copy is enqueued from this array: keep it alive until sync()
+            self._chk(self.lib.L.hmme_refine_frame_async(self.h, C.byref(cur.desc), C.byref(ref.desc), int(njobs), pp, int(bool(use_had))))
+            if out is not None:
+                self._chk(self.lib.L.hmme_fetch_frac_async(self.h, int(njobs), out.ctypes.data))
+            return out
+        res = out if out is not None else np.zeros((njobs, NUM_CTU_PARTS), self.FRAC_DTYPE)
+        self._chk(self.lib.L.hmme_refine_frame(self.h, C.byref(cur.desc), C.byref(ref.desc), int(njobs), pp, int(bool(use_had)), res.ctypes.data))
+        return res
+
+    def last_frac_ms(self):
+        ms = C.c_float()
+        self._chk(self.lib.L.hmme_last_frac_ms(self.h, C.byref(ms)))
+        return ms.value
 
     def last_kernel_ms(self):
         ms = C.c_float()

@@ -4,6 +4,8 @@
 //   findDevice/compileKernelSource/createBuffers (:69-238)  -> hmme_create
 //   calcMotionVectors (:240-362)                             -> hmme_search_ctu (sync) / hmme_search_frame (batched)
 //   xFillSADBuffer/xResetArrays (:366-392)                   -> arg-min scratch kept in its reset state by the kernels
+// and, one step further along the encoder's path,
+//   TEncSearch::xPatternSearchFracDIF (TEncSearch.cpp:4294-4331) -> hmme_refine_frac (PU list) / hmme_refine_frame (all partitions)
 // No OpenCL, no runtime compilation, no CPU fallback: every failure is an error code + message.
 #include <algorithm>
 #include <cmath>
@@ -18,6 +20,7 @@
 
 #include "../../include/hmme_b200.h"
 #include "me_common.cuh"
+#include "me_frac_kernel.cuh"
 #include "me_generic_kernel.cuh"
 #include "me_u8_kernel.cuh"
 
@@ -106,6 +109,13 @@ struct hmme_ctx {
                                                                                                   // and current plane copy back to back
     int* dFlag = nullptr; int* hFlag = nullptr;
     bool contentCheckPending = false;   // an _async 8-bit upload has not had its range flag read back yet
+    // fractional-pel refinement (grown on demand)
+    size_t puCap = 0;
+    FracPu* dPus = nullptr; int* dSlots = nullptr; int4* dFrac = nullptr; uint32_t* dCand = nullptr;
+    int* dOrder = nullptr;        // 593 partition indices, large to small
+    int2* dPreds = nullptr; size_t predCap = 0;
+    cudaEvent_t evF0 = nullptr, evF1 = nullptr; bool evFracValid = false;
+    int lastSearchJobs = 0;       // job count of the most recent frame search (its winners feed hmme_refine_frame)
 };
 
 namespace {
@@ -166,6 +176,76 @@ int check_jobs(hmme_ctx* c, const hmme_plane* cur, const hmme_plane* ref, const 
         if (r0 < 0 || r1 >= refN)
             return fail(c, HMME_ERR_BOUNDS, "job " + std::to_string(j) + ": search window leaves the reference allocation");
     }
+    return HMME_OK;
+}
+
+const char* origin_ptr(const hmme_plane* p) {
+    return static_cast<const char*>(p->base) + ((size_t)p->marginY * p->pitch + p->marginX) * p->elemBytes;
+}
+
+int ensure_pus(hmme_ctx* c, size_t npus) {
+    if (!c->evF0) { CU_TRY(c, cudaEventCreate(&c->evF0)); CU_TRY(c, cudaEventCreate(&c->evF1)); }
+    if (!c->dOrder) {
+        // partitions by area, large to small (stable), so that consecutive PUs of the whole-frame list cost about the same
+        std::vector<int> order(HMME_NPARTS);
+        for (int i = 0; i < HMME_NPARTS; ++i) order[i] = i;
+        std::stable_sort(order.begin(), order.end(), [](int a, int b) { const PartRect ra = part_rect(a), rb = part_rect(b); return ra.w * ra.h > rb.w * rb.h; });
+        CU_TRY(c, cudaMalloc(&c->dOrder, HMME_NPARTS * sizeof(int)));
+        CU_TRY(c, cudaMemcpy(c->dOrder, order.data(), HMME_NPARTS * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    if (npus <= c->puCap) return HMME_OK;
+    const size_t cap = std::max<size_t>(npus, std::max<size_t>(1024, c->puCap * 2));
+    for (cudaStream_t s : {c->ioStream[0], c->ioStream[1], c->stream}) CU_TRY(c, cudaStreamSynchronize(s));
+    cudaFree(c->dPus); cudaFree(c->dSlots); cudaFree(c->dFrac); cudaFree(c->dCand);
+    c->dPus = nullptr; c->dSlots = nullptr; c->dFrac = nullptr; c->dCand = nullptr; c->puCap = 0;
+    CU_TRY(c, cudaMalloc(&c->dPus, cap * sizeof(FracPu)));
+    CU_TRY(c, cudaMalloc(&c->dSlots, cap * sizeof(int)));
+    CU_TRY(c, cudaMalloc(&c->dFrac, cap * sizeof(int4)));
+    c->puCap = cap;
+    return HMME_OK;
+}
+
+// the 8-tap filters read 4 samples around the MV-displaced PU; the kernel fetches whole 16x16 patches per 8x8 tile
+int check_pus(hmme_ctx* c, const hmme_plane* cur, const hmme_plane* ref, const hmme_pu* pus, int npus) {
+    for (int n = 0; n < npus; ++n) {
+        const hmme_pu& u = pus[n];
+        if (u.w <= 0 || u.h <= 0 || u.w > 64 || u.h > 64 || (u.w & 3) || (u.h & 3))
+            return fail(c, HMME_ERR_ARG, "PU " + std::to_string(n) + ": width/height must be multiples of 4 in [4,64]");
+        if (u.x < -cur->marginX || u.y < -cur->marginY || u.x + u.w > cur->width + cur->marginX || u.y + u.h > cur->height + cur->marginY)
+            return fail(c, HMME_ERR_BOUNDS, "PU " + std::to_string(n) + ": outside the current plane");
+        const int w8 = (u.w + 7) & ~7, h8 = (u.h + 7) & ~7;
+        if (u.x + u.mvx - 4 < -ref->marginX || u.y + u.mvy - 4 < -ref->marginY || u.x + u.mvx + w8 + 4 > ref->width + ref->marginX ||
+            u.y + u.mvy + h8 + 4 > ref->height + ref->marginY)
+            return fail(c, HMME_ERR_BOUNDS, "PU " + std::to_string(n) + ": interpolation apron leaves the reference plane (needs 4 samples + tile padding)");
+    }
+    return HMME_OK;
+}
+
+int enqueue_frac(hmme_ctx* c, const hmme_plane* cur, const hmme_plane* ref, int npus, bool slots, int useHad, bool wantCand) {
+    if (wantCand && !c->dCand) CU_TRY(c, cudaMalloc(&c->dCand, c->puCap * 18 * sizeof(uint32_t)));
+    FracParams fp{};
+    fp.cur = origin_ptr(cur); fp.ref = reinterpret_cast<const uint8_t*>(origin_ptr(ref));
+    fp.curPitch = cur->pitch; fp.refPitch = ref->pitch; fp.curBytes = cur->elemBytes;
+    fp.pus = c->dPus; fp.slots = slots ? c->dSlots : nullptr; fp.npus = npus;
+    fp.lambda = c->lambda; fp.useHad = useHad ? 1 : 0;
+    fp.out = c->dFrac; fp.cand = wantCand ? c->dCand : nullptr;
+    // enough warps to fill the machine several times over; each takes PUs round-robin
+    const int ctas = std::max(1, std::min((npus + kFracWarps - 1) / kFracWarps, c->prop.multiProcessorCount * 16));
+    CU_TRY(c, cudaEventRecord(c->evF0, c->stream));
+    me_frac_kernel<<<ctas, kFracThreads, 0, c->stream>>>(fp);
+    CU_TRY(c, cudaEventRecord(c->evF1, c->stream));
+    c->evFracValid = true;
+    c->launches += 1;
+    CU_TRY(c, cudaGetLastError());
+    return HMME_OK;
+}
+
+int check_frac_planes(hmme_ctx* c, const hmme_plane* cur, const hmme_plane* ref) {
+    int rc = check_plane(c, cur, "current");
+    if (rc == HMME_OK) rc = check_plane(c, ref, "reference");
+    if (rc != HMME_OK) return rc;
+    if (ref->elemBytes != 1)
+        return fail(c, HMME_ERR_ARG, "fractional refinement needs an 8-bit reference plane (the path is defined for 8-bit video only)");
     return HMME_OK;
 }
 
@@ -268,10 +348,6 @@ cudaError_t copy_rows_h2d(void* dst, size_t dpitch, const void* src, size_t spit
     return cudaMemcpy2DAsync(dst, dpitch, src, spitch, rowBytes, rows, cudaMemcpyHostToDevice, s);
 }
 
-const char* origin_ptr(const hmme_plane* p) {
-    return static_cast<const char*>(p->base) + ((size_t)p->marginY * p->pitch + p->marginX) * p->elemBytes;
-}
-
 }  // namespace
 
 extern "C" {
@@ -341,6 +417,9 @@ void hmme_destroy(hmme_ctx* c) {
     cudaFree(c->dJobs); cudaFree(c->dBest); cudaFree(c->dRes); cudaFreeHost(c->hJobs);
     cudaFreeHost(c->hWin); cudaFree(c->dWin); cudaFreeHost(c->hCurBlk); cudaFree(c->dCurBlk);
     cudaFree(c->dStage[0]); cudaFree(c->dStage[1]); cudaFree(c->dFlag); cudaFreeHost(c->hFlag);
+    cudaFree(c->dPus); cudaFree(c->dSlots); cudaFree(c->dFrac); cudaFree(c->dCand); cudaFree(c->dOrder); cudaFree(c->dPreds);
+    if (c->evF0) cudaEventDestroy(c->evF0);
+    if (c->evF1) cudaEventDestroy(c->evF1);
     for (int k = 0; k < 2; ++k) {
         if (c->evUpload[k]) cudaEventDestroy(c->evUpload[k]);
         if (c->ioStream[k]) { cudaStreamSynchronize(c->ioStream[k]); cudaStreamDestroy(c->ioStream[k]); }
@@ -503,6 +582,7 @@ int hmme_search_frame_async(hmme_ctx* c, const hmme_plane* cur, const hmme_plane
     // straight from the caller's (pageable) array: the runtime stages it before returning, and stream order protects dJobs,
     // so consecutive frames can be enqueued without a host synchronisation in between
     CU_TRY(c, cudaMemcpyAsync(c->dJobs, jobs, (size_t)njobs * sizeof(hmme_job), cudaMemcpyHostToDevice, c->stream));
+    c->lastSearchJobs = njobs;
     const char* refLo = static_cast<const char*>(ref->base);
     // planes carry 64 bytes of slack after the last row (hmme_plane_alloc adds it; required of external memory): the
     // 16-byte granular TMA row copies may run a few bytes past the window's last sample
@@ -529,6 +609,76 @@ int hmme_fetch_results_async(hmme_ctx* c, int njobs, int32_t* X, int32_t* Y, uin
     if (!c || njobs <= 0 || (size_t)njobs > c->jobCap) return fail(c, HMME_ERR_ARG, "hmme_fetch_results: bad job count");
     CU_TRY(c, cudaSetDevice(c->device));
     return fetch_async(c, njobs, X, Y, sad, cost);
+}
+
+// ---- fractional-pel refinement (TEncSearch::xPatternSearchFracDIF, TEncSearch.cpp:4294-4331) ------------------------------
+int hmme_refine_frac(hmme_ctx* c, const hmme_plane* cur, const hmme_plane* ref, const hmme_pu* pus, int npus, int useHad,
+                     hmme_frac_result* results, uint32_t* candCosts) {
+    if (!c) return HMME_ERR_ARG;
+    if (!pus || npus <= 0 || !results) return fail(c, HMME_ERR_ARG, "hmme_refine_frac: no PUs / null output");
+    int rc = check_frac_planes(c, cur, ref);
+    if (rc == HMME_OK) rc = check_pus(c, cur, ref, pus, npus);
+    if (rc != HMME_OK) return rc;
+    CU_TRY(c, cudaSetDevice(c->device));
+    rc = ensure_pus(c, (size_t)npus);
+    if (rc != HMME_OK) return rc;
+    static_assert(sizeof(hmme_pu) == sizeof(FracPu) && sizeof(hmme_frac_result) == sizeof(int4), "ABI structs mirror the kernel's");
+    CU_TRY(c, cudaMemcpyAsync(c->dPus, pus, (size_t)npus * sizeof(hmme_pu), cudaMemcpyHostToDevice, c->stream));
+    rc = enqueue_frac(c, cur, ref, npus, false, useHad, candCosts != nullptr);
+    if (rc != HMME_OK) return rc;
+    CU_TRY(c, cudaMemcpyAsync(results, c->dFrac, (size_t)npus * sizeof(int4), cudaMemcpyDeviceToHost, c->stream));
+    if (candCosts) CU_TRY(c, cudaMemcpyAsync(candCosts, c->dCand, (size_t)npus * 18 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    return sync_ctx(c);
+}
+
+int hmme_refine_frame_async(hmme_ctx* c, const hmme_plane* cur, const hmme_plane* ref, int njobs, const int32_t* predsQpel, int useHad) {
+    if (!c) return HMME_ERR_ARG;
+    if (njobs <= 0 || njobs != c->lastSearchJobs)
+        return fail(c, HMME_ERR_ARG, "hmme_refine_frame: job count must match the preceding hmme_search_frame on this context");
+    int rc = check_frac_planes(c, cur, ref);
+    if (rc != HMME_OK) return rc;
+    CU_TRY(c, cudaSetDevice(c->device));
+    const size_t npus = (size_t)njobs * HMME_NPARTS;
+    rc = ensure_pus(c, npus);
+    if (rc != HMME_OK) return rc;
+    if (predsQpel) {
+        if ((size_t)njobs > c->predCap) {
+            CU_TRY(c, cudaStreamSynchronize(c->stream));
+            cudaFree(c->dPreds); c->dPreds = nullptr; c->predCap = 0;
+            CU_TRY(c, cudaMalloc(&c->dPreds, c->jobCap * sizeof(int2)));
+            c->predCap = c->jobCap;
+        }
+        CU_TRY(c, cudaMemcpyAsync(c->dPreds, predsQpel, (size_t)njobs * sizeof(int2), cudaMemcpyHostToDevice, c->stream));
+    }
+    // winners of the integer search, still on the device: X, Y of [jobCap][593]
+    const int32_t* X = c->dRes;
+    const int32_t* Y = X + c->jobCap * HMME_NPARTS;
+    me_frac_build_kernel<<<(unsigned)((npus + 255) / 256), 256, 0, c->stream>>>(c->dJobs, X, Y, predsQpel ? c->dPreds : nullptr, c->dOrder, njobs,
+                                                                                c->dPus, c->dSlots);
+    c->launches += 1;
+    return enqueue_frac(c, cur, ref, (int)npus, true, useHad, false);
+}
+
+int hmme_fetch_frac_async(hmme_ctx* c, int njobs, hmme_frac_result* results) {
+    if (!c || !results || njobs <= 0 || (size_t)njobs * HMME_NPARTS > c->puCap) return fail(c, HMME_ERR_ARG, "hmme_fetch_frac: bad job count / null output");
+    CU_TRY(c, cudaSetDevice(c->device));
+    CU_TRY(c, cudaMemcpyAsync(results, c->dFrac, (size_t)njobs * HMME_NPARTS * sizeof(int4), cudaMemcpyDeviceToHost, c->stream));
+    return HMME_OK;
+}
+
+int hmme_refine_frame(hmme_ctx* c, const hmme_plane* cur, const hmme_plane* ref, int njobs, const int32_t* predsQpel, int useHad,
+                      hmme_frac_result* results) {
+    int rc = hmme_refine_frame_async(c, cur, ref, njobs, predsQpel, useHad);
+    if (rc == HMME_OK) rc = hmme_fetch_frac_async(c, njobs, results);
+    return rc != HMME_OK ? rc : sync_ctx(c);
+}
+
+int hmme_last_frac_ms(hmme_ctx* c, float* ms) {
+    if (!c || !ms) return HMME_ERR_ARG;
+    if (!c->evFracValid) return fail(c, HMME_ERR_ARG, "no refinement has been enqueued yet");
+    CU_TRY(c, cudaEventSynchronize(c->evF1));
+    CU_TRY(c, cudaEventElapsedTime(ms, c->evF0, c->evF1));
+    return HMME_OK;
 }
 
 int hmme_sync(hmme_ctx* c) {

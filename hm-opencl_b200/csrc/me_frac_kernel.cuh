@@ -1,0 +1,296 @@
+// me_frac_kernel.cuh -- fractional-pel refinement of prediction units after the integer search.
+//
+// Semantics: TEncSearch::xPatternSearchFracDIF (/root/reference/source/Lib/TLibEncoder/TEncSearch.cpp:4294-4331) =
+//   half-pel stage : 9 candidates around the integer MV (table s_acMvRefineH, :51-62), cost scale 1
+//   quarter stage  : 9 candidates around the half-pel winner (table s_acMvRefineQ, :64-75), cost scale 0
+//   each candidate : HEVC 8-tap luma interpolation, horizontal pass first with a 14-bit intermediate
+//                    (TComInterpolationFilter.cpp:57-63,155-250; which positions the reference's planes hold: TEncSearch.cpp:5386-5600),
+//                    distortion = Hadamard SATD in 8x8 blocks when both PU sides are multiples of 8, else 4x4 blocks
+//                    (TComRdCost::xGetHADs, TComRdCost.cpp:1537-1600), or plain SAD when HadamardME is off,
+//                    plus lambda * bits(mv - predictor) >> 16 (TComRdCost.h:166-185); strict '<' in table order (:816-872).
+// Nothing here is copied from the reference: every candidate sample is computed from the closed form
+//   h(r, c) = sum_k C[fx][k] * ref[r][c + ix + k - 3],   pred = clip255((sum_k C[fy][k] * h(r + iy + k - 3, c) + 2048) >> 12)
+// (ix = dx >> 2, fx = dx & 3; C[0] = {0,0,0,64,0,0,0,0} makes the integer cases fall out of the same arithmetic), which is what the
+// reference's plane bookkeeping evaluates (the tests pin this against the 18 candidate costs logged from the reference encoder).
+//
+// Mapping: one warp per PU, looping over its 8x8 tiles; both stages are 3x3 grids (dx in 3 values) x (dy in 3 values):
+//   H step : lane = (patch row 0..15, column half) -> 3 horizontal planes, two dp4a per sample (u8 samples x s8 taps)
+//   V step : lane = (dx index, column) -> the column of its plane in registers, 3 dy x 8 rows of 8-tap sums, difference against
+//            the current block and the vertical Hadamard pass, all in registers
+//   SATD   : transposed through warp-private shared memory, lane = (candidate, coefficient row) does the horizontal pass
+// No CTA-wide synchronisation; warps are independent and take PUs round-robin (callers order PUs large to small).
+#pragma once
+#include "me_common.cuh"
+
+namespace hmme {
+
+constexpr int kFracWarps = 4;
+constexpr int kFracThreads = kFracWarps * 32;
+
+struct FracPu { int x, y, w, h, mvx, mvy, predx, predy; };   // == hmme_pu (include/hmme_b200.h)
+
+struct FracParams {
+    const void* cur;            // picture sample (0,0); u8 or s16 (bi-prediction target 2*org - pred)
+    const uint8_t* ref;         // picture sample (0,0); 8-bit
+    long long curPitch, refPitch;
+    int curBytes;
+    const FracPu* pus;
+    const int* slots;           // optional: result index of PU n (whole-frame path: job * 593 + partition)
+    int npus;
+    uint32_t lambda;
+    int useHad;
+    int4* out;                  // {mv x, mv y (quarter pel), cost, distortion}
+    uint32_t* cand;             // optional [npus][18]: cost of every candidate in the reference's table order
+};
+
+// HEVC luma taps (TComInterpolationFilter.cpp:57-63), as ints and as packed signed bytes {k0..k3}, {k4..k7}
+__constant__ int kLumaTap[4][8] = {
+    {0, 0, 0, 64, 0, 0, 0, 0}, {-1, 4, -10, 58, 17, -5, 1, 0}, {-1, 4, -11, 40, 40, -11, 4, -1}, {0, 1, -5, 17, 58, -10, 4, -1}};
+__constant__ uint32_t kLumaPack[4][2] = {
+    {0x40000000u, 0x00000000u}, {0x3AF604FFu, 0x0001FB11u}, {0x28F504FFu, 0xFF04F528u}, {0x11FB0100u, 0xFF04F63Au}};
+
+struct __align__(16) FracScratch {
+    uint32_t ref[16][4];        // 16 x 16 reference samples: rows/cols -4..11 of the tile, displaced by the integer MV
+    int16_t cur[8][8];          // current tile, [column][row], zero outside the PU
+    int16_t h[3][8][24];        // horizontal planes [dx index][column][patch row], 16 used (+8: conflict-free 128-bit column loads)
+    int16_t t[9][72];           // vertically transformed differences [candidate][column * 8 + coefficient row] (+8 pad)
+};
+
+__device__ __forceinline__ int dp4a_us(uint32_t samples, uint32_t taps, int acc) {
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(samples), "r"(taps), "r"(acc));
+    return d;
+}
+
+template <int S0>
+__device__ __forceinline__ void frac_vfilter(const int (&v)[16], const int (&cf)[8], int (&pr)[8]) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        int a = 2048;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a += cf[k] * v[r + S0 + k];
+        a >>= 12;
+        pr[r] = min(max(a, 0), 255);
+    }
+}
+
+template <int N>
+__device__ __forceinline__ void hadamard_inplace(int* d) {
+#pragma unroll
+    for (int len = 1; len < N; len <<= 1)
+#pragma unroll
+        for (int i = 0; i < N; i += 2 * len)
+#pragma unroll
+            for (int j = i; j < i + len; ++j) { const int a = d[j], b = d[j + len]; d[j] = a + b; d[j + len] = a - b; }
+}
+
+constexpr int kFracSad = 0, kFracHad4 = 1, kFracHad8 = 2;
+
+// Distortion of the 9 candidates (dx[i], dy[j]) of one PU, summed over its tiles.  Result layout (per lane, 3 registers):
+//   Hadamard modes : candidate k = j*3+i in acc[k >> 2] on the lanes with (lane >> 3) == (k & 3)
+//   SAD mode       : candidate k in acc[j] on the lanes with (lane >> 3) == i
+template <int MODE>
+__device__ __forceinline__ void frac_eval(const FracParams& p, const FracPu& P, FracScratch& S, const int lane, const int (&dx)[3],
+                                          const int (&dy)[3], uint32_t (&acc)[3]) {
+    int ixm[3], iym[3], cV[3][8];
+    uint32_t cLo[3], cHi[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        ixm[i] = dx[i] >> 2; iym[i] = dy[i] >> 2;
+        cLo[i] = kLumaPack[dx[i] & 3][0]; cHi[i] = kLumaPack[dx[i] & 3][1];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) cV[i][k] = kLumaTap[dy[i] & 3][k];
+    }
+    acc[0] = acc[1] = acc[2] = 0;
+    const uint8_t* refPu = p.ref + (long long)(P.y + P.mvy - 4) * p.refPitch + (P.x + P.mvx - 4);
+
+    for (int ty = 0; ty < P.h; ty += 8) {
+        const int th = min(8, P.h - ty);
+        for (int tx = 0; tx < P.w; tx += 8) {
+            const int tw = min(8, P.w - tx);
+            {   // reference patch: lane = (row, half row of 8 samples)
+                const int row = lane >> 1, half = lane & 1;
+                const uint8_t* g = refPu + (long long)(ty + row) * p.refPitch + tx + half * 8;
+                const uint32_t w0 = g[0] | (g[1] << 8) | (g[2] << 16) | ((uint32_t)g[3] << 24);
+                const uint32_t w1 = g[4] | (g[5] << 8) | (g[6] << 16) | ((uint32_t)g[7] << 24);
+                *reinterpret_cast<uint2*>(&S.ref[row][half * 2]) = make_uint2(w0, w1);
+                // current tile, transposed: lane = (row, column pair)
+                const int r = lane >> 2, c0 = (lane & 3) * 2;
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int c = c0 + q;
+                    int v = 0;
+                    if (r < th && c < tw) {
+                        const long long o = (long long)(P.y + ty + r) * p.curPitch + P.x + tx + c;
+                        v = p.curBytes == 1 ? (int)static_cast<const uint8_t*>(p.cur)[o] : (int)static_cast<const int16_t*>(p.cur)[o];
+                    }
+                    S.cur[c][r] = (int16_t)v;
+                }
+            }
+            __syncwarp();
+            {   // H step: 4 columns x 3 planes per lane
+                const int row = lane >> 1, half = lane & 1;
+                const uint32_t W0 = S.ref[row][half], W1 = S.ref[row][half + 1], W2 = S.ref[row][half + 2];
+                uint32_t lo[5], hi[5];
+                lo[0] = W0; hi[0] = W1; lo[4] = W1; hi[4] = W2;
+#pragma unroll
+                for (int o = 1; o < 4; ++o) { lo[o] = __funnelshift_r(W0, W1, 8 * o); hi[o] = __funnelshift_r(W1, W2, 8 * o); }
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    int out[4];
+                    if (ixm[i] < 0) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) out[j] = dp4a_us(hi[j], cHi[i], dp4a_us(lo[j], cLo[i], 0));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) out[j] = dp4a_us(hi[j + 1], cHi[i], dp4a_us(lo[j + 1], cLo[i], 0));
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) S.h[i][half * 4 + j][row] = (int16_t)out[j];
+                }
+            }
+            __syncwarp();
+            {   // V step: lane = (dx index, column); lanes 24..31 only take part in the shuffles
+                const int di = lane >> 3, c = lane & 7;
+                const bool live = lane < 24;
+                int v[16], cu[8];
+                {
+                    const int dii = live ? di : 0;
+                    const uint4 a = *reinterpret_cast<const uint4*>(&S.h[dii][c][0]), b = *reinterpret_cast<const uint4*>(&S.h[dii][c][8]);
+                    const uint32_t wv[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) { v[2 * q] = (int)(int16_t)(wv[q] & 0xFFFFu); v[2 * q + 1] = (int)wv[q] >> 16; }
+                    const uint4 cc = *reinterpret_cast<const uint4*>(&S.cur[c][0]);
+                    const uint32_t wc[4] = {cc.x, cc.y, cc.z, cc.w};
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) { cu[2 * q] = (int)(int16_t)(wc[q] & 0xFFFFu); cu[2 * q + 1] = (int)wc[q] >> 16; }
+                }
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    int d[8];
+                    if (iym[j] < 0) frac_vfilter<0>(v, cV[j], d); else frac_vfilter<1>(v, cV[j], d);
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) d[r] = (live && r < th && c < tw) ? cu[r] - d[r] : 0;
+                    if (MODE == kFracSad) {
+                        uint32_t s = 0;
+#pragma unroll
+                        for (int r = 0; r < 8; ++r) s += (uint32_t)abs(d[r]);
+                        s += __shfl_xor_sync(0xFFFFFFFFu, s, 1); s += __shfl_xor_sync(0xFFFFFFFFu, s, 2); s += __shfl_xor_sync(0xFFFFFFFFu, s, 4);
+                        acc[j] += s;
+                    } else {
+                        if (MODE == kFracHad8) hadamard_inplace<8>(d);
+                        else { hadamard_inplace<4>(d); hadamard_inplace<4>(d + 4); }
+                        if (live) {
+                            uint4 pk;
+                            pk.x = __byte_perm(d[0], d[1], 0x5410); pk.y = __byte_perm(d[2], d[3], 0x5410);
+                            pk.z = __byte_perm(d[4], d[5], 0x5410); pk.w = __byte_perm(d[6], d[7], 0x5410);
+                            *reinterpret_cast<uint4*>(&S.t[j * 3 + di][c * 8]) = pk;
+                        }
+                    }
+                }
+            }
+            if (MODE != kFracSad) {
+                __syncwarp();
+                const int i = lane & 7;
+#pragma unroll
+                for (int pass = 0; pass < 3; ++pass) {
+                    const int k = pass * 4 + (lane >> 3);
+                    int e[8];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) e[c] = k < 9 ? (int)S.t[k][c * 8 + i] : 0;
+                    uint32_t tot;
+                    if (MODE == kFracHad8) {
+                        hadamard_inplace<8>(e);
+                        uint32_t s = 0;
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) s += (uint32_t)abs(e[c]);
+                        s += __shfl_xor_sync(0xFFFFFFFFu, s, 1); s += __shfl_xor_sync(0xFFFFFFFFu, s, 2); s += __shfl_xor_sync(0xFFFFFFFFu, s, 4);
+                        tot = (s + 2) >> 2;                                     // xCalcHADs8x8 rounding
+                    } else {
+                        hadamard_inplace<4>(e); hadamard_inplace<4>(e + 4);
+                        uint32_t sa = 0, sb = 0;
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) { sa += (uint32_t)abs(e[c]); sb += (uint32_t)abs(e[c + 4]); }
+                        sa += __shfl_xor_sync(0xFFFFFFFFu, sa, 1); sa += __shfl_xor_sync(0xFFFFFFFFu, sa, 2);
+                        sb += __shfl_xor_sync(0xFFFFFFFFu, sb, 1); sb += __shfl_xor_sync(0xFFFFFFFFu, sb, 2);
+                        uint32_t bl = ((sa + 1) >> 1) + ((sb + 1) >> 1);       // xCalcHADs4x4 rounding, per 4x4 block
+                        bl += __shfl_xor_sync(0xFFFFFFFFu, bl, 4);
+                        tot = bl;
+                    }
+                    acc[pass] += tot;
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// cost of the MV at quarter-pel position (qx, qy) against the predictor: TComRdCost::getCost(x, y) with any cost scale
+__device__ __forceinline__ uint32_t frac_mv_cost(uint32_t lambda, int qx, int qy, int predx, int predy) {
+    return (uint32_t)(lambda * (mv_bits(qx - predx) + mv_bits(qy - predy))) >> 16;
+}
+
+template <int MODE>
+__device__ __forceinline__ void frac_refine_pu(const FracParams& p, const FracPu& P, FracScratch& S, const int lane, const int n) {
+    // candidate of this lane in the 3x3 grid (lanes 0..8): row-major over (dy index, dx index)
+    const int gi = lane % 3, gj = (lane / 3) % 3;
+    const int srcLane = (MODE == kFracSad ? gi : (lane & 3)) * 8, srcReg = MODE == kFracSad ? gj : (lane >> 2);
+    // grid position -> index in the reference's candidate tables (TEncSearch.cpp:51-75); 4 bits each, grid position 0 lowest
+    const unsigned long long lutHalf = 0x827403615ull, lutQter = 0x827605413ull;
+    int cx = 0, cy = 0;                                   // stage centre, quarter-pel offset from the integer MV
+    uint32_t bestCost = 0, bestMvc = 0;
+#pragma unroll 1
+    for (int stage = 0; stage < 2; ++stage) {
+        const int step = stage == 0 ? 2 : 1;
+        const int dx[3] = {cx - step, cx, cx + step}, dy[3] = {cy - step, cy, cy + step};
+        uint32_t acc[3];
+        frac_eval<MODE>(p, P, S, lane, dx, dy, acc);
+        const uint32_t v0 = __shfl_sync(0xFFFFFFFFu, acc[0], srcLane & 31), v1 = __shfl_sync(0xFFFFFFFFu, acc[1], srcLane & 31),
+                       v2 = __shfl_sync(0xFFFFFFFFu, acc[2], srcLane & 31);
+        const uint32_t dist = srcReg == 0 ? v0 : (srcReg == 1 ? v1 : v2);
+        const int qx = 4 * P.mvx + cx + (gi - 1) * step, qy = 4 * P.mvy + cy + (gj - 1) * step;
+        const uint32_t mvc = frac_mv_cost(p.lambda, qx, qy, P.predx, P.predy);
+        const uint32_t cost = dist + mvc;
+        const uint32_t tIdx = (uint32_t)((stage == 0 ? lutHalf : lutQter) >> (4 * (lane < 9 ? lane : 0))) & 15u;
+        unsigned long long key = lane < 9 ? (((unsigned long long)cost << 8) | tIdx) : ~0ull;
+        if (p.cand && lane < 9) p.cand[(size_t)n * 18 + stage * 9 + tIdx] = cost;
+        unsigned long long m = key;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { const unsigned long long t = __shfl_xor_sync(0xFFFFFFFFu, m, o); m = t < m ? t : m; }
+        const int win = __ffs(__ballot_sync(0xFFFFFFFFu, key == m)) - 1;
+        cx += ((win % 3) - 1) * step; cy += ((win / 3) - 1) * step;
+        bestCost = __shfl_sync(0xFFFFFFFFu, cost, win);
+        bestMvc = __shfl_sync(0xFFFFFFFFu, mvc, win);
+    }
+    if (lane == 0) p.out[p.slots ? p.slots[n] : n] = make_int4(4 * P.mvx + cx, 4 * P.mvy + cy, (int)bestCost, (int)(bestCost - bestMvc));
+}
+
+__global__ void __launch_bounds__(kFracThreads) me_frac_kernel(const FracParams p) {
+    __shared__ FracScratch scratch[kFracWarps];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    FracScratch& S = scratch[warp];
+    const int nWarps = gridDim.x * kFracWarps;
+    for (int n = blockIdx.x * kFracWarps + warp; n < p.npus; n += nWarps) {
+        const FracPu P = p.pus[n];
+        if (!p.useHad) frac_refine_pu<kFracSad>(p, P, S, lane, n);
+        else if (((P.w | P.h) & 7) == 0) frac_refine_pu<kFracHad8>(p, P, S, lane, n);
+        else frac_refine_pu<kFracHad4>(p, P, S, lane, n);
+    }
+}
+
+// PU list of a whole frame from the winners of the preceding integer search: PU n = (job, partition), ordered by partition
+// area, large to small (order[] from the host), so that the round-robin over warps stays balanced.
+__global__ void me_frac_build_kernel(const int4* jobs, const int32_t* X, const int32_t* Y, const int2* preds, const int* order, int njobs,
+                                     FracPu* pus, int* slots) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= njobs * HMME_NPARTS) return;
+    const int part = order[n / njobs], job = n - (n / njobs) * njobs;
+    const int4 jb = jobs[job];
+    const PartRect r = part_rect(part);
+    const int slot = job * HMME_NPARTS + part;
+    const int2 pr = preds ? preds[job] : make_int2(0, 0);
+    pus[n] = FracPu{jb.x + r.x, jb.y + r.y, r.w, r.h, X[slot], Y[slot], pr.x, pr.y};
+    slots[n] = slot;
+}
+
+}  // namespace hmme

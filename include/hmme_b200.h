@@ -107,6 +107,31 @@ int hmme_plane_upload_s16_async(hmme_ctx* ctx, const hmme_plane* plane, const in
 int hmme_fetch_results_async(hmme_ctx* ctx, int njobs, int32_t* X, int32_t* Y, uint32_t* sad, uint32_t* cost);
 int hmme_sync(hmme_ctx* ctx);
 
+/* ---- fractional-pel refinement, the step right after the integer search:
+ * TEncSearch::xPatternSearchFracDIF (TEncSearch.cpp:4294-4331) = half-pel then quarter-pel refinement (xPatternRefinement,
+ * :816-872) over HEVC 8-tap interpolated samples (xExtDIFUpSamplingH/Q, :5386-5600; TComInterpolationFilter.cpp:155-250) with
+ * the Hadamard (TComRdCost::xGetHADs, TComRdCost.cpp:1537-1600) or SAD distortion plus lambda*bits(mv - predictor)>>16
+ * (TComRdCost.h:166-185).  lambda is the context's (hmme_set_lambda: m_uiLambdaMotionSAD has the same quantisation).
+ * A PU: luma rectangle (multiples of 4, up to 64), the integer-pel MV to refine and the quarter-pel predictor
+ * (TComRdCost::setPredictor).  cur may be an int16 plane (bi-prediction target), ref must be 8-bit.  The reference plane
+ * needs 4 samples (+ up to 4 of tile padding) around every MV-displaced PU.  useHad = HadamardME && !lossless. */
+typedef struct { int32_t x, y, w, h, mvx, mvy, predx, predy; } hmme_pu;
+/* final quarter-pel MV (4*integer + 2*half + quarter), ruiCost as xPatternSearchFracDIF returns it, and cost minus its MV part */
+typedef struct { int32_t mvx, mvy; uint32_t cost, dist; } hmme_frac_result;
+/* Host PU list -> results[npus]; candCosts is NULL or [npus][18]: the cost of each half- then quarter-pel candidate in the
+ * order of the reference's tables (TEncSearch.cpp:51-75), for tests.  Synchronous. */
+int hmme_refine_frac(hmme_ctx* ctx, const hmme_plane* cur, const hmme_plane* ref, const hmme_pu* pus, int npus, int useHad,
+                     hmme_frac_result* results, uint32_t* candCosts);
+/* All 593 partitions of every job of the preceding hmme_search_frame[_async] on this context, starting from that search's
+ * integer winners, which never leave the device.  predsQpel: NULL (zero predictor) or [njobs][2] quarter-pel predictors.
+ * results: [njobs][593].  The _async pair only enqueues (pair with hmme_sync). */
+int hmme_refine_frame(hmme_ctx* ctx, const hmme_plane* cur, const hmme_plane* ref, int njobs, const int32_t* predsQpel,
+                      int useHad, hmme_frac_result* results);
+int hmme_refine_frame_async(hmme_ctx* ctx, const hmme_plane* cur, const hmme_plane* ref, int njobs, const int32_t* predsQpel,
+                            int useHad);
+int hmme_fetch_frac_async(hmme_ctx* ctx, int njobs, hmme_frac_result* results);
+int hmme_last_frac_ms(hmme_ctx* ctx, float* refineKernelMs);
+
 /* ---- measurement hooks (bench.py / profiles): CUDA-event time of the dominant kernel of the most recent
  * search call on this context's stream, kernel launches issued so far, and the integer-ALU issue-rate
  * micro-benchmark that fixes the roofline denominator. */

@@ -1,0 +1,140 @@
+"""GPU parity tests of the fractional-pel refinement, through the C ABI: hmme_refine_frac /
+hmme_refine_frame against the CPU oracle and against the records logged from the reference encoder's own
+xPatternSearchFracDIF (tests/golden/frac_records.npz).  Bar: bit-exact MVs, costs and all 18 candidate costs."""
+import numpy as np
+import pytest
+
+from _pkg import hm
+from frac_util import load_records, pack_atlas
+from synth import frame_jobs, luma_frames, pad_plane
+
+pytestmark = pytest.mark.gpu
+
+SIZES = [(8, 4), (4, 8), (8, 8), (16, 4), (16, 12), (4, 16), (12, 16), (16, 8), (8, 16), (16, 16), (32, 8), (32, 24), (8, 32), (24, 32),
+         (32, 16), (16, 32), (32, 32), (64, 16), (64, 48), (16, 64), (48, 64), (64, 32), (32, 64), (64, 64)]
+
+
+@pytest.fixture(scope="module")
+def me():
+    m = hm.MotionEstimator(0, 64)
+    yield m
+    m.close()
+
+
+def planes(me, cur, ref, W, H, M):
+    pc = me.alloc_plane(1 if cur.dtype == np.uint8 else 2, W, H, M, M)
+    pr = me.alloc_plane(1, W, H, M, M)
+    me.upload(pc, cur); me.upload(pr, ref)
+    return pc, pr
+
+
+def check(res, cand, want, ctx):
+    for k, name in ((("mvx", "mvy"), "mvq"),):
+        got = np.stack([res[k[0]], res[k[1]]], 1)
+        assert np.array_equal(got, want[name]), (ctx, name, np.argwhere(got != want[name])[:5].tolist())
+    assert np.array_equal(res["cost"], want["cost"]), (ctx, "cost", np.argwhere(res["cost"] != want["cost"])[:5].tolist())
+    assert np.array_equal(res["dist"], want["dist"]), (ctx, "dist")
+    if cand is not None:
+        assert np.array_equal(cand, want["cand"]), (ctx, "cand", np.argwhere(cand != want["cand"])[:5].tolist())
+
+
+def test_reference_records_through_c_abi(me):
+    """The reference encoder's own inputs and outputs: winners, returned cost and each of the 18 candidate costs."""
+    recs = load_records()
+    n = 0
+    for had in (0, 1):
+        for bi in (0, 1):
+            for lam in sorted({r["lambda"] for r in recs if r["had"] == had and r["bi"] == bi}):
+                sub = [r for r in recs if r["had"] == had and r["bi"] == bi and r["lambda"] == lam]
+                cur, ref, (M, _), pus = pack_atlas(sub)
+                H, W = cur.shape[0] - 2 * M, cur.shape[1] - 2 * M
+                # uni-prediction records go through the 8-bit current plane, bi-prediction ones (2*org - pred) through int16
+                pc, pr = planes(me, cur.astype(np.uint8) if not bi else cur, ref.astype(np.uint8), W, H, M)
+                me.set_lambda_q16(lam)
+                res, cand = me.refine_frac(pc, pr, pus, bool(had), want_candidates=True)
+                for k, r in enumerate(sub):
+                    assert (int(res["mvx"][k]), int(res["mvy"][k])) == (2 * r["halfx"] + r["qterx"], 2 * r["halfy"] + r["qtery"]), (k, r["w"], r["h"])
+                    assert int(res["cost"][k]) == r["cost"]
+                    assert np.array_equal(cand[k], r["cand"]), (k, r["w"], r["h"], bi, had)
+                n += len(sub)
+                pc.free(); pr.free()
+    assert n == len(recs)
+
+
+@pytest.mark.parametrize("had,cur16,lam", [(1, 0, 460000), (1, 1, 1000000), (0, 0, 262144), (0, 1, 0), (1, 0, 0), (1, 0, 4500000)])
+def test_random_pus_vs_oracle(me, oracle, had, cur16, lam):
+    """Every PU size of the 593-partition layout plus odd multiples of 4, random integer MVs and predictors, textured content
+    with sub-pel structure; 8-bit and 16-bit (bi-prediction) current planes; Hadamard and SAD."""
+    rng = np.random.default_rng(1000 + had * 7 + cur16 * 3 + lam % 97)
+    W, H, M = 384, 256, 32
+    f = luma_frames(W + 2 * M, H + 2 * M, 2, seed=int(rng.integers(1 << 30)))
+    ref = np.ascontiguousarray(f[0].astype(np.int16))
+    cur = np.ascontiguousarray(f[1].astype(np.int16))
+    if cur16:
+        cur = np.ascontiguousarray((2 * cur - rng.integers(0, 256, cur.shape)).astype(np.int16))     # 2*org - pred in [-255, 510]
+    sizes = SIZES + [(20, 28), (4, 4), (60, 4), (4, 60), (28, 36), (64, 12), (40, 40)]
+    pus = []
+    for _ in range(14):
+        for (w, h) in sizes:
+            x, y = int(rng.integers(0, W - w)), int(rng.integers(0, H - h))
+            mvx = int(rng.integers(max(-M + 4 - x, -20), min(W + M - 12 - ((w + 7) & ~7) - x, 20) + 1))
+            mvy = int(rng.integers(max(-M + 4 - y, -20), min(H + M - 12 - ((h + 7) & ~7) - y, 20) + 1))
+            pus.append([x, y, w, h, mvx, mvy, int(rng.integers(-300, 300)), int(rng.integers(-300, 300))])
+    pus = np.array(pus, np.int32)
+    pc, pr = planes(me, cur.astype(np.uint8) if not cur16 else cur, ref.astype(np.uint8), W, H, M)
+    me.set_lambda_q16(lam)
+    res, cand = me.refine_frac(pc, pr, pus, bool(had), want_candidates=True)
+    want = oracle.refine_frac(cur, (M, M), ref, (M, M), pus, lam, bool(had))
+    check(res, cand, want, f"had={had} cur16={cur16} lam={lam}")
+    assert len({(int(a), int(b)) for a, b in zip(res["mvx"] - 4 * pus[:, 4], res["mvy"] - 4 * pus[:, 5])}) > 20    # many different winners
+    pc.free(); pr.free()
+
+
+def test_refine_frame_after_search(me, oracle):
+    """Whole-frame form: integer search, then all 593 partitions of every CTU refined from the winners left on the device,
+    with a per-job predictor; compared with the oracle fed the same integer MVs."""
+    W, H, R, M = 256, 128, 16, 40
+    f = luma_frames(W, H, 2, seed=42)
+    cur, ref = pad_plane(f[1], M, M), pad_plane(f[0], M, M)
+    jobs = frame_jobs(W, H, R)
+    lam = 460000
+    me.set_lambda_q16(lam)
+    pc, pr = planes(me, cur.astype(np.uint8), ref.astype(np.uint8), W, H, M)
+    X, Y, _, _ = me.search_frame(pc, pr, jobs, R)
+    preds = np.stack([np.arange(len(jobs)) * 3 - 9, 7 - np.arange(len(jobs)) * 2], 1).astype(np.int32)
+    for use_had, pp in ((True, preds), (False, None)):
+        res = me.refine_frame(pc, pr, len(jobs), pp, use_had)
+        rects = me.lib.partition_table()
+        pus = np.zeros((len(jobs), 593, 8), np.int32)
+        pus[:, :, 0] = jobs[:, None, 0] + rects[None, :, 0]
+        pus[:, :, 1] = jobs[:, None, 1] + rects[None, :, 1]
+        pus[:, :, 2] = rects[None, :, 2]
+        pus[:, :, 3] = rects[None, :, 3]
+        pus[:, :, 4], pus[:, :, 5] = X, Y
+        if pp is not None:
+            pus[:, :, 6], pus[:, :, 7] = pp[:, None, 0], pp[:, None, 1]
+        want = oracle.refine_frac(cur, (M, M), ref, (M, M), pus.reshape(-1, 8), lam, use_had)
+        check(res.reshape(-1), None, want, f"frame had={use_had}")
+    assert me.last_frac_ms() > 0
+    pc.free(); pr.free()
+
+
+def test_frac_errors(me):
+    W, H, M = 64, 64, 16
+    z = np.zeros((H + 2 * M, W + 2 * M), np.int16)
+    pc, pr = planes(me, z.astype(np.uint8), z.astype(np.uint8), W, H, M)
+    p16 = me.alloc_plane(2, W, H, M, M)
+    ok = np.array([[0, 0, 8, 8, 0, 0, 0, 0]], np.int32)
+    me.refine_frac(pc, pr, ok)
+    with pytest.raises(hm.HmmeError):          # 16-bit reference plane: not defined for this path
+        me.refine_frac(pc, p16, ok)
+    for bad in ([0, 0, 6, 8, 0, 0, 0, 0], [0, 0, 8, 68, 0, 0, 0, 0], [0, 0, 0, 8, 0, 0, 0, 0]):
+        with pytest.raises(hm.HmmeError):
+            me.refine_frac(pc, pr, np.array([bad], np.int32))
+    for bad in ([0, 0, 8, 8, -13, 0, 0, 0], [56, 56, 8, 8, 0, 13, 0, 0], [64 + 9, 0, 8, 8, 0, 0, 0, 0]):
+        with pytest.raises(hm.HmmeError) as e:
+            me.refine_frac(pc, pr, np.array([bad], np.int32))
+        assert e.value.code == -6
+    with pytest.raises(hm.HmmeError):          # refine_frame without a matching search on this context
+        me.refine_frame(pc, pr, 3)
+    pc.free(); pr.free(); p16.free()
