@@ -10,7 +10,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "hmme_b200.cu")
-DEPS = [SRC] + [os.path.join(HERE, "csrc", f) for f in ("me_common.cuh", "me_u8_kernel.cuh", "me_generic_kernel.cuh")] + [
+DEPS = [SRC] + sorted(os.path.join(HERE, "csrc", f) for f in os.listdir(os.path.join(HERE, "csrc")) if f.endswith(".cuh")) + [
     os.path.join(os.path.dirname(HERE), "include", "hmme_b200.h")]
 OUT = os.path.join(HERE, "libhmme_b200.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared",

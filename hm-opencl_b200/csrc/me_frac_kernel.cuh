@@ -86,12 +86,18 @@ __device__ __forceinline__ void hadamard_inplace(int* d) {
 
 constexpr int kFracSad = 0, kFracHad4 = 1, kFracHad8 = 2;
 
-// Distortion of the 9 candidates (dx[i], dy[j]) of one PU, summed over its tiles.  Result layout (per lane, 3 registers):
-//   Hadamard modes : candidate k = j*3+i in acc[k >> 2] on the lanes with (lane >> 3) == (k & 3)
-//   SAD mode       : candidate k in acc[j] on the lanes with (lane >> 3) == i
+__device__ __forceinline__ int frac_round_clip(int a) { return min(max(a >> 12, 0), 255); }
+
+// Distortion of the candidates (dx[i], dy[j]) of one PU, summed over its tiles.  halfStage: dx = dy = {-2, 0, 2}, where the two
+// outer rows (columns) of candidates read the same half-sample plane one row (column) apart and the centre needs no filter;
+// in the quarter stage the centre candidate is the half-pel winner, whose distortion is already known, so the Hadamard pass
+// skips it.  Result layout (per lane, 3 registers):
+//   Hadamard, half stage    : candidate g = j*3+i in acc[g >> 2] on the lanes with (lane >> 3) == (g & 3)
+//   Hadamard, quarter stage : same with k = g - (g > 4) in place of g (g = 4 is not computed)
+//   SAD mode                : candidate g in acc[j] on the lanes with (lane >> 3) == i
 template <int MODE>
-__device__ __forceinline__ void frac_eval(const FracParams& p, const FracPu& P, FracScratch& S, const int lane, const int (&dx)[3],
-                                          const int (&dy)[3], uint32_t (&acc)[3]) {
+__device__ __forceinline__ void frac_eval(const FracParams& p, const FracPu& P, FracScratch& S, const int lane, const bool halfStage,
+                                          const int (&dx)[3], const int (&dy)[3], uint32_t (&acc)[3]) {
     int ixm[3], iym[3], cV[3][8];
     uint32_t cLo[3], cHi[3];
 #pragma unroll
@@ -128,13 +134,14 @@ __device__ __forceinline__ void frac_eval(const FracParams& p, const FracPu& P, 
                 }
             }
             __syncwarp();
-            {   // H step: 4 columns x 3 planes per lane
+            {   // H step: 4 columns x 3 planes per lane; columns outside the PU become 0 (so does their prediction, and cur is 0 there)
                 const int row = lane >> 1, half = lane & 1;
                 const uint32_t W0 = S.ref[row][half], W1 = S.ref[row][half + 1], W2 = S.ref[row][half + 2];
                 uint32_t lo[5], hi[5];
                 lo[0] = W0; hi[0] = W1; lo[4] = W1; hi[4] = W2;
 #pragma unroll
                 for (int o = 1; o < 4; ++o) { lo[o] = __funnelshift_r(W0, W1, 8 * o); hi[o] = __funnelshift_r(W1, W2, 8 * o); }
+                const bool outside = MODE != kFracHad8 && half && tw < 8;
 #pragma unroll
                 for (int i = 0; i < 3; ++i) {
                     int out[4];
@@ -146,11 +153,11 @@ __device__ __forceinline__ void frac_eval(const FracParams& p, const FracPu& P, 
                         for (int j = 0; j < 4; ++j) out[j] = dp4a_us(hi[j + 1], cHi[i], dp4a_us(lo[j + 1], cLo[i], 0));
                     }
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) S.h[i][half * 4 + j][row] = (int16_t)out[j];
+                    for (int j = 0; j < 4; ++j) S.h[i][half * 4 + j][row] = outside ? (int16_t)0 : (int16_t)out[j];
                 }
             }
             __syncwarp();
-            {   // V step: lane = (dx index, column); lanes 24..31 only take part in the shuffles
+            {   // V step: lane = (dx index, column); lanes 24..31 compute on plane 0 and their results are never read
                 const int di = lane >> 3, c = lane & 7;
                 const bool live = lane < 24;
                 int v[16], cu[8];
@@ -165,12 +172,11 @@ __device__ __forceinline__ void frac_eval(const FracParams& p, const FracPu& P, 
 #pragma unroll
                     for (int q = 0; q < 4; ++q) { cu[2 * q] = (int)(int16_t)(wc[q] & 0xFFFFu); cu[2 * q + 1] = (int)wc[q] >> 16; }
                 }
+                // prediction column d[0..7] of candidate row j -> difference, vertical transform, hand-over
+                auto emit = [&](const int j, int (&d)[8]) {
 #pragma unroll
-                for (int j = 0; j < 3; ++j) {
-                    int d[8];
-                    if (iym[j] < 0) frac_vfilter<0>(v, cV[j], d); else frac_vfilter<1>(v, cV[j], d);
-#pragma unroll
-                    for (int r = 0; r < 8; ++r) d[r] = (live && r < th && c < tw) ? cu[r] - d[r] : 0;
+                    for (int r = 0; r < 8; ++r) d[r] = cu[r] - d[r];
+                    if (MODE != kFracHad8 && th < 8) { d[4] = 0; d[5] = 0; d[6] = 0; d[7] = 0; }
                     if (MODE == kFracSad) {
                         uint32_t s = 0;
 #pragma unroll
@@ -187,17 +193,48 @@ __device__ __forceinline__ void frac_eval(const FracParams& p, const FracPu& P, 
                             *reinterpret_cast<uint4*>(&S.t[j * 3 + di][c * 8]) = pk;
                         }
                     }
+                };
+                int d[8];
+                if (halfStage) {
+                    int o9[9];                                   // half-sample rows -1..7: dy = -2 reads 0..7 of them, dy = +2 reads 1..8
+#pragma unroll
+                    for (int r = 0; r < 9; ++r) {
+                        int a = 2048;
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) a += cV[0][k] * v[r + k];
+                        o9[r] = frac_round_clip(a);
+                    }
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) d[r] = o9[r];
+                    emit(0, d);
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) d[r] = o9[r + 1];
+                    emit(2, d);
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) d[r] = min(max((v[r + 4] + 32) >> 6, 0), 255);
+                    emit(1, d);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        if ((dy[j] & 3) == 0) {
+#pragma unroll
+                            for (int r = 0; r < 8; ++r) d[r] = min(max((v[r + 4] + 32) >> 6, 0), 255);
+                        } else if (iym[j] < 0) frac_vfilter<0>(v, cV[j], d);
+                        else frac_vfilter<1>(v, cV[j], d);
+                        emit(j, d);
+                    }
                 }
             }
             if (MODE != kFracSad) {
                 __syncwarp();
                 const int i = lane & 7;
-#pragma unroll
-                for (int pass = 0; pass < 3; ++pass) {
+                const int nPass = halfStage ? 3 : 2;
+                for (int pass = 0; pass < nPass; ++pass) {
                     const int k = pass * 4 + (lane >> 3);
+                    const int g = halfStage ? k : k + (k >= 4);         // quarter stage: the centre (4) is not evaluated
                     int e[8];
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) e[c] = k < 9 ? (int)S.t[k][c * 8 + i] : 0;
+                    for (int c = 0; c < 8; ++c) e[c] = g < 9 ? (int)S.t[g][c * 8 + i] : 0;
                     uint32_t tot;
                     if (MODE == kFracHad8) {
                         hadamard_inplace<8>(e);
@@ -217,7 +254,7 @@ __device__ __forceinline__ void frac_eval(const FracParams& p, const FracPu& P, 
                         bl += __shfl_xor_sync(0xFFFFFFFFu, bl, 4);
                         tot = bl;
                     }
-                    acc[pass] += tot;
+                    if (pass == 0) acc[0] += tot; else if (pass == 1) acc[1] += tot; else acc[2] += tot;
                 }
             }
             __syncwarp();
@@ -234,7 +271,6 @@ template <int MODE>
 __device__ __forceinline__ void frac_refine_pu(const FracParams& p, const FracPu& P, FracScratch& S, const int lane, const int n) {
     // candidate of this lane in the 3x3 grid (lanes 0..8): row-major over (dy index, dx index)
     const int gi = lane % 3, gj = (lane / 3) % 3;
-    const int srcLane = (MODE == kFracSad ? gi : (lane & 3)) * 8, srcReg = MODE == kFracSad ? gj : (lane >> 2);
     // grid position -> index in the reference's candidate tables (TEncSearch.cpp:51-75); 4 bits each, grid position 0 lowest
     const unsigned long long lutHalf = 0x827403615ull, lutQter = 0x827605413ull;
     int cx = 0, cy = 0;                                   // stage centre, quarter-pel offset from the integer MV
@@ -244,10 +280,14 @@ __device__ __forceinline__ void frac_refine_pu(const FracParams& p, const FracPu
         const int step = stage == 0 ? 2 : 1;
         const int dx[3] = {cx - step, cx, cx + step}, dy[3] = {cy - step, cy, cy + step};
         uint32_t acc[3];
-        frac_eval<MODE>(p, P, S, lane, dx, dy, acc);
+        frac_eval<MODE>(p, P, S, lane, stage == 0, dx, dy, acc);
+        // where frac_eval left the distortion of this lane's candidate (see its header)
+        const int gq = (lane < 9 ? lane : 0), kq = (MODE != kFracSad && stage == 1) ? gq - (gq > 4) : gq;
+        const int srcLane = (MODE == kFracSad ? gi : (kq & 3)) * 8, srcReg = MODE == kFracSad ? gj : (kq >> 2);
         const uint32_t v0 = __shfl_sync(0xFFFFFFFFu, acc[0], srcLane & 31), v1 = __shfl_sync(0xFFFFFFFFu, acc[1], srcLane & 31),
                        v2 = __shfl_sync(0xFFFFFFFFu, acc[2], srcLane & 31);
-        const uint32_t dist = srcReg == 0 ? v0 : (srcReg == 1 ? v1 : v2);
+        uint32_t dist = srcReg == 0 ? v0 : (srcReg == 1 ? v1 : v2);
+        if (MODE != kFracSad && stage == 1 && lane == 4) dist = bestCost - bestMvc;     // the half-pel winner, evaluated in stage 0
         const int qx = 4 * P.mvx + cx + (gi - 1) * step, qy = 4 * P.mvy + cy + (gj - 1) * step;
         const uint32_t mvc = frac_mv_cost(p.lambda, qx, qy, P.predx, P.predy);
         const uint32_t cost = dist + mvc;
