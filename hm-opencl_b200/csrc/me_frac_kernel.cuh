@@ -62,15 +62,34 @@ __device__ __forceinline__ int dp4a_us(uint32_t samples, uint32_t taps, int acc)
     return d;
 }
 
-template <int S0>
-__device__ __forceinline__ void frac_vfilter(const int (&v)[16], const int (&cf)[8], int (&pr)[8]) {
+__device__ __forceinline__ int dp2a_lo(uint32_t pair, uint32_t taps, int acc) {   // acc + pair.lo * taps.b0 + pair.hi * taps.b1
+    int d;
+    asm("dp2a.lo.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(pair), "r"(taps), "r"(acc));
+    return d;
+}
+__device__ __forceinline__ int dp2a_hi(uint32_t pair, uint32_t taps, int acc) {   // acc + pair.lo * taps.b2 + pair.hi * taps.b3
+    int d;
+    asm("dp2a.hi.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(pair), "r"(taps), "r"(acc));
+    return d;
+}
+__device__ __forceinline__ int frac_round_clip(int a) { return min(max(a >> 12, 0), 255); }
+
+// Vertical 8-tap pass over one column held as packed pairs of 16-bit rows (wv[q] = rows 2q, 2q+1): output r starts at row
+// r + S0.  An even start takes the taps as packed {k0..k3}, {k4..k7}; an odd start uses the same bytes moved up by one.
+template <int S0, int NOUT>
+__device__ __forceinline__ void frac_vfilter(const uint32_t (&wv)[8], const uint32_t ca, const uint32_t cb, int (&pr)[NOUT]) {
+    const uint32_t o1 = ca << 8, o2 = (ca >> 24) | (cb << 8), o3 = cb >> 24;
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
+    for (int r = 0; r < NOUT; ++r) {
+        const int s = r + S0, m = s >> 1;
         int a = 2048;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) a += cf[k] * v[r + S0 + k];
-        a >>= 12;
-        pr[r] = min(max(a, 0), 255);
+        if (s & 1) {
+            a = dp2a_lo(wv[m], o1, a); a = dp2a_hi(wv[m + 1], o1, a); a = dp2a_lo(wv[m + 2], o2, a); a = dp2a_hi(wv[m + 3], o2, a);
+            a = dp2a_lo(wv[m + 4], o3, a);
+        } else {
+            a = dp2a_lo(wv[m], ca, a); a = dp2a_hi(wv[m + 1], ca, a); a = dp2a_lo(wv[m + 2], cb, a); a = dp2a_hi(wv[m + 3], cb, a);
+        }
+        pr[r] = frac_round_clip(a);
     }
 }
 
@@ -86,8 +105,6 @@ __device__ __forceinline__ void hadamard_inplace(int* d) {
 
 constexpr int kFracSad = 0, kFracHad4 = 1, kFracHad8 = 2;
 
-__device__ __forceinline__ int frac_round_clip(int a) { return min(max(a >> 12, 0), 255); }
-
 // Distortion of the candidates (dx[i], dy[j]) of one PU, summed over its tiles.  halfStage: dx = dy = {-2, 0, 2}, where the two
 // outer rows (columns) of candidates read the same half-sample plane one row (column) apart and the centre needs no filter;
 // in the quarter stage the centre candidate is the half-pel winner, whose distortion is already known, so the Hadamard pass
@@ -98,14 +115,13 @@ __device__ __forceinline__ int frac_round_clip(int a) { return min(max(a >> 12, 
 template <int MODE>
 __device__ __forceinline__ void frac_eval(const FracParams& p, const FracPu& P, FracScratch& S, const int lane, const bool halfStage,
                                           const int (&dx)[3], const int (&dy)[3], uint32_t (&acc)[3]) {
-    int ixm[3], iym[3], cV[3][8];
-    uint32_t cLo[3], cHi[3];
+    int ixm[3], iym[3];
+    uint32_t cLo[3], cHi[3], vLo[3], vHi[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
         ixm[i] = dx[i] >> 2; iym[i] = dy[i] >> 2;
         cLo[i] = kLumaPack[dx[i] & 3][0]; cHi[i] = kLumaPack[dx[i] & 3][1];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) cV[i][k] = kLumaTap[dy[i] & 3][k];
+        vLo[i] = kLumaPack[dy[i] & 3][0]; vHi[i] = kLumaPack[dy[i] & 3][1];
     }
     acc[0] = acc[1] = acc[2] = 0;
     const uint8_t* refPu = p.ref + (long long)(P.y + P.mvy - 4) * p.refPitch + (P.x + P.mvx - 4);
@@ -136,12 +152,12 @@ __device__ __forceinline__ void frac_eval(const FracParams& p, const FracPu& P, 
             __syncwarp();
             {   // H step: 4 columns x 3 planes per lane; columns outside the PU become 0 (so does their prediction, and cur is 0 there)
                 const int row = lane >> 1, half = lane & 1;
-                const uint32_t W0 = S.ref[row][half], W1 = S.ref[row][half + 1], W2 = S.ref[row][half + 2];
+                const bool outside = MODE != kFracHad8 && half && tw < 8;       // zero samples -> zero planes
+                const uint32_t W0 = outside ? 0u : S.ref[row][half], W1 = outside ? 0u : S.ref[row][half + 1], W2 = outside ? 0u : S.ref[row][half + 2];
                 uint32_t lo[5], hi[5];
                 lo[0] = W0; hi[0] = W1; lo[4] = W1; hi[4] = W2;
 #pragma unroll
                 for (int o = 1; o < 4; ++o) { lo[o] = __funnelshift_r(W0, W1, 8 * o); hi[o] = __funnelshift_r(W1, W2, 8 * o); }
-                const bool outside = MODE != kFracHad8 && half && tw < 8;
 #pragma unroll
                 for (int i = 0; i < 3; ++i) {
                     int out[4];
@@ -153,20 +169,18 @@ __device__ __forceinline__ void frac_eval(const FracParams& p, const FracPu& P, 
                         for (int j = 0; j < 4; ++j) out[j] = dp4a_us(hi[j + 1], cHi[i], dp4a_us(lo[j + 1], cLo[i], 0));
                     }
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) S.h[i][half * 4 + j][row] = outside ? (int16_t)0 : (int16_t)out[j];
+                    for (int j = 0; j < 4; ++j) S.h[i][half * 4 + j][row] = (int16_t)out[j];
                 }
             }
             __syncwarp();
             {   // V step: lane = (dx index, column); lanes 24..31 compute on plane 0 and their results are never read
                 const int di = lane >> 3, c = lane & 7;
                 const bool live = lane < 24;
-                int v[16], cu[8];
+                int cu[8];
+                const int dii = live ? di : 0;
+                const uint4 ha = *reinterpret_cast<const uint4*>(&S.h[dii][c][0]), hb = *reinterpret_cast<const uint4*>(&S.h[dii][c][8]);
+                const uint32_t wv[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
                 {
-                    const int dii = live ? di : 0;
-                    const uint4 a = *reinterpret_cast<const uint4*>(&S.h[dii][c][0]), b = *reinterpret_cast<const uint4*>(&S.h[dii][c][8]);
-                    const uint32_t wv[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) { v[2 * q] = (int)(int16_t)(wv[q] & 0xFFFFu); v[2 * q + 1] = (int)wv[q] >> 16; }
                     const uint4 cc = *reinterpret_cast<const uint4*>(&S.cur[c][0]);
                     const uint32_t wc[4] = {cc.x, cc.y, cc.z, cc.w};
 #pragma unroll
@@ -180,7 +194,7 @@ __device__ __forceinline__ void frac_eval(const FracParams& p, const FracPu& P, 
                     if (MODE == kFracSad) {
                         uint32_t s = 0;
 #pragma unroll
-                        for (int r = 0; r < 8; ++r) s += (uint32_t)abs(d[r]);
+                        for (int r = 0; r < 8; ++r) s = __sad(d[r], 0, s);
                         s += __shfl_xor_sync(0xFFFFFFFFu, s, 1); s += __shfl_xor_sync(0xFFFFFFFFu, s, 2); s += __shfl_xor_sync(0xFFFFFFFFu, s, 4);
                         acc[j] += s;
                     } else {
@@ -195,32 +209,31 @@ __device__ __forceinline__ void frac_eval(const FracParams& p, const FracPu& P, 
                     }
                 };
                 int d[8];
+                // integer vertical phase: rows 4..11 of the column (patch rows 0..7 of the tile), rounded from the 14-bit intermediate
+                auto copy_rows = [&]() {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        d[2 * q] = min(max(((int)(int16_t)(wv[q + 2] & 0xFFFFu) + 32) >> 6, 0), 255);
+                        d[2 * q + 1] = min(max((((int)wv[q + 2] >> 16) + 32) >> 6, 0), 255);
+                    }
+                };
                 if (halfStage) {
                     int o9[9];                                   // half-sample rows -1..7: dy = -2 reads 0..7 of them, dy = +2 reads 1..8
-#pragma unroll
-                    for (int r = 0; r < 9; ++r) {
-                        int a = 2048;
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) a += cV[0][k] * v[r + k];
-                        o9[r] = frac_round_clip(a);
-                    }
+                    frac_vfilter<0, 9>(wv, vLo[0], vHi[0], o9);
 #pragma unroll
                     for (int r = 0; r < 8; ++r) d[r] = o9[r];
                     emit(0, d);
 #pragma unroll
                     for (int r = 0; r < 8; ++r) d[r] = o9[r + 1];
                     emit(2, d);
-#pragma unroll
-                    for (int r = 0; r < 8; ++r) d[r] = min(max((v[r + 4] + 32) >> 6, 0), 255);
+                    copy_rows();
                     emit(1, d);
                 } else {
 #pragma unroll
                     for (int j = 0; j < 3; ++j) {
-                        if ((dy[j] & 3) == 0) {
-#pragma unroll
-                            for (int r = 0; r < 8; ++r) d[r] = min(max((v[r + 4] + 32) >> 6, 0), 255);
-                        } else if (iym[j] < 0) frac_vfilter<0>(v, cV[j], d);
-                        else frac_vfilter<1>(v, cV[j], d);
+                        if ((dy[j] & 3) == 0) copy_rows();
+                        else if (iym[j] < 0) frac_vfilter<0, 8>(wv, vLo[j], vHi[j], d);
+                        else frac_vfilter<1, 8>(wv, vLo[j], vHi[j], d);
                         emit(j, d);
                     }
                 }
@@ -240,14 +253,14 @@ __device__ __forceinline__ void frac_eval(const FracParams& p, const FracPu& P, 
                         hadamard_inplace<8>(e);
                         uint32_t s = 0;
 #pragma unroll
-                        for (int c = 0; c < 8; ++c) s += (uint32_t)abs(e[c]);
+                        for (int c = 0; c < 8; ++c) s = __sad(e[c], 0, s);
                         s += __shfl_xor_sync(0xFFFFFFFFu, s, 1); s += __shfl_xor_sync(0xFFFFFFFFu, s, 2); s += __shfl_xor_sync(0xFFFFFFFFu, s, 4);
                         tot = (s + 2) >> 2;                                     // xCalcHADs8x8 rounding
                     } else {
                         hadamard_inplace<4>(e); hadamard_inplace<4>(e + 4);
                         uint32_t sa = 0, sb = 0;
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) { sa += (uint32_t)abs(e[c]); sb += (uint32_t)abs(e[c + 4]); }
+                        for (int c = 0; c < 4; ++c) { sa = __sad(e[c], 0, sa); sb = __sad(e[c + 4], 0, sb); }
                         sa += __shfl_xor_sync(0xFFFFFFFFu, sa, 1); sa += __shfl_xor_sync(0xFFFFFFFFu, sa, 2);
                         sb += __shfl_xor_sync(0xFFFFFFFFu, sb, 1); sb += __shfl_xor_sync(0xFFFFFFFFu, sb, 2);
                         uint32_t bl = ((sa + 1) >> 1) + ((sb + 1) >> 1);       // xCalcHADs4x4 rounding, per 4x4 block
