@@ -38,7 +38,8 @@ class PlaneDesc(C.Structure):
 
 
 def lib_path():
-    return os.path.join(_HERE, "libhmme_b200.so")
+    # HMME_B200_LIB: another build of the same library (kernel experiments); never a different implementation
+    return os.environ.get("HMME_B200_LIB") or os.path.join(_HERE, "libhmme_b200.so")
 
 
 class HmmeLib:
