@@ -145,6 +145,29 @@ def reference_cpu_me(R, clip, procs, fast_search=0):
     return sum(calls) / max(secs), max(secs), sum(calls), wall
 
 
+def reference_cpu_frac():
+    """The reference's own xPatternSearchFracDIF (TEncSearch.cpp:4294-4331), timed inside the instrumented reference encoder
+    (oracle/patch_cpume.py) on one core: default fast integer search (so the run is short), 416x240, I + P."""
+    import re
+    import tempfile
+    W, H = 416, 240
+    with tempfile.TemporaryDirectory() as d:
+        yuv = os.path.join(d, "clip.yuv")
+        with open(yuv, "wb") as fh:
+            for y in luma_frames(W, H, 2):
+                fh.write(y.tobytes())
+                fh.write(np.full((H // 2) * (W // 2) * 2, 128, np.uint8).tobytes())
+        r = subprocess.run([CPUME_BIN, "-c", CPUME_CFG, "-i", yuv, "-wdt", str(W), "-hgt", str(H), "-fr", "30", "-f", "2", "-q", "32",
+                            "-b", os.path.join(d, "o.hevc"), "-o", "", "--OpenCL=0", "--FastSearch=1", "--SearchRange=64"],
+                           stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    m = re.search(r"frac_seconds=([0-9.]+) frac_calls=(\d+) frac_pixels=(\d+)", r.stdout)
+    if not m:
+        raise RuntimeError("reference encoder did not report the fractional refinement:\n" + r.stdout[-1500:])
+    secs, calls, px = float(m.group(1)), int(m.group(2)), int(m.group(3))
+    return {"pu_refinements_per_s": calls / secs, "pu_pixels_per_s": px / secs, "cores": 1, "kind": "reference",
+            "sample": "%d xPatternSearchFracDIF calls (%d PU pixels) in %.3f s inside the reference encoder, 416x240 I+P, one core" % (calls, px, secs)}
+
+
 def cpu_baseline_entry(R, budget_s, all_cores=True):
     """cpu_baseline object: the reference's CPU ME when oracle/_ref holds its build, else the oracle port."""
     threads = os.cpu_count() or 1
@@ -289,6 +312,15 @@ def main():
                 self.me.search_frame_async(self.p_cur, self.p_ref, jobs, R)
                 self.me.fetch_results(njobs, self.outs, asynchronous=asynchronous)
 
+        def step_e2e_frac(self):
+            """Integer search + fractional refinement of all 593 partitions, host to host."""
+            if not hasattr(self, "frac_out"):
+                self.frac_out = torch.zeros((max(njobs, 1), NPARTS, 4), dtype=torch.int32).pin_memory().numpy()
+            self.upload_inputs(True)
+            self.me.search_frame_async(self.p_cur, self.p_ref, jobs, R)
+            self.me.fetch_results(njobs, self.outs, asynchronous=True)
+            self.me.refine_frame(self.p_cur, self.p_ref, njobs, None, True, asynchronous=True, out=self.frac_out)
+
     pipes = [Pipe(), Pipe()]
     me, ext, p_cur, p_ref = pipes[0].me, pipes[0].ext, pipes[0].p_cur, pipes[0].p_ref
     upload_inputs = pipes[0].upload_inputs
@@ -406,6 +438,57 @@ def main():
     if world > 1:
         dist.all_reduce(io, op=dist.ReduceOp.SUM)
 
+    # ------------------------------------------------------------------ next row: fractional-pel refinement
+    frac = None
+    if world == 1 and njobs and not args.virtual_world:
+        nfr = min(args.steps, 60)
+        fk, fk_sad = [], []
+        for s in range(nfr + 2):                            # kernel time: CUDA events inside the library, resident inputs
+            pc_, pr_ = sets[s % nsets]
+            me.search_frame_async(pc_, pr_, jobs, R)
+            me.refine_frame(pc_, pr_, njobs, None, True, asynchronous=True)
+            me.sync()
+            if s >= 2:
+                fk.append(me.last_frac_ms())
+        for s in range(6):
+            pc_, pr_ = sets[s % nsets]
+            me.search_frame_async(pc_, pr_, jobs, R)
+            me.refine_frame(pc_, pr_, njobs, None, False, asynchronous=True)
+            me.sync()
+            fk_sad.append(me.last_frac_ms())
+        barrier()
+        ev_a, ev_b = torch.cuda.Event(enable_timing=True), [torch.cuda.Event(enable_timing=True) for _ in pipes]
+        ev_a.record(pipes[0].ext)
+        for s in range(nfr):                                # search + refinement per frame, frames alternating over two contexts
+            pp = pipes[s & 1]
+            pc_, pr_ = sets[s % nsets]
+            pp.me.search_frame_async(pc_, pr_, jobs, R)
+            pp.me.refine_frame(pc_, pr_, njobs, None, True, asynchronous=True)
+        for pp, e_ in zip(pipes, ev_b):
+            e_.record(pp.ext)
+        barrier()
+        both_ms = max(ev_a.elapsed_time(e_) for e_ in ev_b) / nfr
+        for pp in pipes:
+            pp.step_e2e_frac(); pp.me.sync()
+        e0 = time.perf_counter()
+        for s in range(nfr):
+            pp = pipes[s & 1]
+            pp.me.sync()
+            pp.step_e2e_frac()
+        for pp in pipes:
+            pp.me.sync()
+        e2e_frac_ms = (time.perf_counter() - e0) * 1e3 / nfr
+        pu_px = njobs * 24 * 4096                           # sum of the 593 partition areas = 24 CTU areas
+        frac = {"scope": "fractional-pel refinement (xPatternSearchFracDIF: 9 half-pel + 9 quarter-pel candidates, 8-tap interpolation, Hadamard cost) "
+                         "of all 593 partitions of every CTU, from the integer winners left on the device",
+                "kernel": "me_frac_kernel", "pus_per_frame": njobs * NPARTS, "kernel_ms": float(np.mean(fk)), "kernel_ms_sad": float(np.mean(fk_sad)),
+                "pu_refinements_per_s": njobs * NPARTS / (np.mean(fk) * 1e-3), "pu_pixels_per_s": pu_px / (np.mean(fk) * 1e-3),
+                "search_plus_refine_ms_per_frame": both_ms, "search_plus_refine_frames_per_s": 1e3 / both_ms,
+                "e2e_ms_per_frame": e2e_frac_ms, "e2e_frames_per_s": 1e3 / e2e_frac_ms,
+                "e2e_d2h_bytes_per_step": 4 * njobs * NPARTS * 4 + njobs * NPARTS * 16, "steps": nfr,
+                "timer": "kernel_ms: CUDA events around me_frac_kernel on its stream; search_plus_refine: CUDA events around K frames alternating over two "
+                         "contexts, resident inputs; e2e: host wall clock, uploads + search + refine + all result arrays fetched, two contexts"}
+
     if rank == 0:
         total_cands = total_jobs * cands_per_job
         ms_per_step = total_ms / args.steps
@@ -449,8 +532,14 @@ def main():
                          "hbm": {"algorithmic_bytes_per_step": alg_bytes, "achieved_gbs": alg_bytes / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else 0.0,
                                  "peak_gbs": _measured_hbm()}},
         }
+        if frac:
+            out["frac_refine"] = frac
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"], _ = cpu_baseline_entry(R, 30.0)
+            if frac and os.path.exists(CPUME_BIN):
+                fr = reference_cpu_frac()
+                frac["cpu_reference"] = fr
+                frac["gpu_over_one_core"] = frac["pu_pixels_per_s"] / fr["pu_pixels_per_s"]
             if os.path.exists(CPUME_BIN):       # the reference's default (fast) integer search, for context: TZ evaluates ~600x fewer candidates
                 v, me_s, calls, wall = reference_cpu_me(R, (416, 240), 1, fast_search=1)
                 out["cpu_tz"] = {"value": v, "unit": "block-SAD evaluations/s", "cores": 1, "kind": "reference",

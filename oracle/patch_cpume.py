@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Instruments a SCRATCH COPY of the reference's TEncSearch.cpp for the CPU-ME baseline:
 wall-clock around the OpenCL=0 integer search calls of xMotionEstimation (TEncSearch.cpp:3774-3791: full search and TZ)
-and a counter of the DistFunc invocations made inside them (:390-426, :3878).  Arithmetic and control flow are untouched; the bitstream stays
+and a counter of the DistFunc invocations made inside them (:390-426, :3878), the same timer around the fractional-pel refinement
+(xPatternSearchFracDIF, :4294-4331), and optional logs (search-window placements, fractional-refinement records).  Arithmetic and control flow are untouched; the bitstream stays
 identical.  Used only by `make -C oracle encoders` on a temporary copy; nothing patched is ever committed."""
 import sys
 
@@ -22,7 +23,8 @@ once('#include "TEncSearch.h"', '''#include "TEncSearch.h"
 static double g_hmmeMeSeconds = 0.0;
 static unsigned long long g_hmmeDistCalls = 0, g_hmmeMeCalls = 0, g_hmmeInMe = 0;
 static double hmmeNow() { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + 1e-9 * t.tv_nsec; }
-static void hmmeReport() { printf("HMME_CPUME me_seconds=%.6f dist_calls=%llu me_calls=%llu\\n", g_hmmeMeSeconds, g_hmmeDistCalls, g_hmmeMeCalls); }
+static double g_hmmeFracSeconds = 0.0; static unsigned long long g_hmmeFracCalls = 0, g_hmmeFracPixels = 0;
+static void hmmeReport() { printf("HMME_CPUME me_seconds=%.6f dist_calls=%llu me_calls=%llu frac_seconds=%.6f frac_calls=%llu frac_pixels=%llu\\n", g_hmmeMeSeconds, g_hmmeDistCalls, g_hmmeMeCalls, g_hmmeFracSeconds, g_hmmeFracCalls, g_hmmeFracPixels); }
 static struct HmmeReportInit { HmmeReportInit() { atexit(hmmeReport); } } g_hmmeReportInit;''')
 once('          xPatternSearch      ( pcPatternKey, piRefY, iRefStride, &cMvSrchRngLT, &cMvSrchRngRB, rcMv, ruiCost );',
      '          { const double t0_ = hmmeNow(); g_hmmeInMe = 1; xPatternSearch      ( pcPatternKey, piRefY, iRefStride, &cMvSrchRngLT, &cMvSrchRngRB, rcMv, ruiCost ); g_hmmeInMe = 0; g_hmmeMeSeconds += hmmeNow() - t0_; ++g_hmmeMeCalls; }')
@@ -33,6 +35,12 @@ once('          xPatternSearchFast  ( pcCU, pcPatternKey, piRefY, iRefStride, &c
 n = s.count("m_cDistParam.DistFunc( &m_cDistParam )")
 assert n == 5, n
 s = s.replace("m_cDistParam.DistFunc( &m_cDistParam )", "(g_hmmeDistCalls += g_hmmeInMe, m_cDistParam.DistFunc( &m_cDistParam ))")
+# wall-clock around the fractional-pel refinement that follows every integer search (TEncSearch.cpp:3800)
+# (two call sites: xMotionEstimation :3798 and its per-PU twin used after the GPU table look-up :5738)
+n = s.count('xPatternSearchFracDIF( bIsLosslessCoded, pcPatternKey, piRefY, iRefStride, &rcMv, cMvHalf, cMvQter, ruiCost ,bBi );')
+assert n == 2, n
+s = s.replace('xPatternSearchFracDIF( bIsLosslessCoded, pcPatternKey, piRefY, iRefStride, &rcMv, cMvHalf, cMvQter, ruiCost ,bBi );',
+              '{ const double t0_ = hmmeNow(); xPatternSearchFracDIF( bIsLosslessCoded, pcPatternKey, piRefY, iRefStride, &rcMv, cMvHalf, cMvQter, ruiCost ,bBi ); g_hmmeFracSeconds += hmmeNow() - t0_; ++g_hmmeFracCalls; g_hmmeFracPixels += (unsigned long long)(iRoiWidth * iRoiHeight); }')
 # optional log of every search-window placement handed to the GPU path (golden for hmme_search_window_lt)
 once('            m_ppcOpenCLME->calcMotionVectors(piCtu, piRefY, iRefStride, iCtuStride, iSrchRng ,&cMvSrchRngLT);',
      '            if (getenv("HMME_LOG_LT")) { const TComMv& pm_ = bBi ? rcMv : cMvPred; printf("HMME_LT %d %d %d %d %d %d %d %d %d %d %d\\n", (int)pm_.getHor(), (int)pm_.getVer(), iSrchRng, '
