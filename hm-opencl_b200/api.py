@@ -21,7 +21,7 @@ EXPORTS = [
     "hmme_plane_alloc", "hmme_plane_free", "hmme_plane_upload_s16", "hmme_plane_upload_u8",
     "hmme_search_frame", "hmme_search_frame_async", "hmme_fetch_results", "hmme_sync",
     "hmme_plane_upload_s16_async", "hmme_fetch_results_async",
-    "hmme_refine_frac", "hmme_refine_frame", "hmme_refine_frame_async", "hmme_fetch_frac_async", "hmme_last_frac_ms",
+    "hmme_refine_pu", "hmme_refine_frac", "hmme_refine_frame", "hmme_refine_frame_async", "hmme_fetch_frac_async", "hmme_last_frac_ms",
     "hmme_last_kernel_ms", "hmme_kernel_launches", "hmme_measure_int_alu_peak", "hmme_partition_rect", "hmme_index_block", "hmme_search_window", "hmme_version",
 ]
 
@@ -81,6 +81,7 @@ class HmmeLib:
             "hmme_fetch_results_async": (i32, [vp, i32, vp, vp, vp, vp]),
             "hmme_plane_upload_s16_async": (i32, [vp, P(PlaneDesc), vp, i32]),
             "hmme_sync": (i32, [vp]),
+            "hmme_refine_pu": (i32, [vp, vp, i32, vp, i32, i32, i32, i32, i32, i32, i32, i32, P(C.c_int32), P(C.c_int32), P(u32), P(u32)]),
             "hmme_refine_frac": (i32, [vp, P(PlaneDesc), P(PlaneDesc), vp, i32, i32, vp, vp]),
             "hmme_refine_frame": (i32, [vp, P(PlaneDesc), P(PlaneDesc), i32, vp, i32, vp]),
             "hmme_refine_frame_async": (i32, [vp, P(PlaneDesc), P(PlaneDesc), i32, vp, i32]),
@@ -269,6 +270,20 @@ class MotionEstimator:
         self._chk(self.lib.L.hmme_refine_frac(self.h, C.byref(cur.desc), C.byref(ref.desc), pus.ctypes.data, n, int(bool(use_had)),
                                               res.ctypes.data, cand.ctypes.data if want_candidates else None))
         return (res, cand) if want_candidates else res
+
+    def refine_pu(self, cur_block, ref_plane, pu_x, pu_y, origin_x, origin_y, mv, pred, use_had=True):
+        """Host arrays, synchronous (the form xPatternSearchFracDIF has): cur_block (h, w) int16; ref_plane padded int16 plane
+        whose picture sample (0,0) sits at [origin_y, origin_x]; the PU is at picture position (pu_x, pu_y).
+        Returns (mvx, mvy quarter-pel, cost, dist)."""
+        cur_block = np.ascontiguousarray(cur_block, np.int16)
+        assert ref_plane.dtype == np.int16 and ref_plane.flags.c_contiguous
+        h, w = cur_block.shape
+        stride = ref_plane.shape[1]
+        off = int(((origin_y + pu_y) * stride + origin_x + pu_x) * 2)
+        mx, my, cost, dist = C.c_int32(), C.c_int32(), C.c_uint32(), C.c_uint32()
+        self._chk(self.lib.L.hmme_refine_pu(self.h, cur_block.ctypes.data, w, ref_plane.ctypes.data + off, stride, w, h, int(mv[0]), int(mv[1]),
+                                            int(pred[0]), int(pred[1]), int(bool(use_had)), C.byref(mx), C.byref(my), C.byref(cost), C.byref(dist)))
+        return mx.value, my.value, cost.value, dist.value
 
     def refine_frame(self, cur, ref, njobs, preds=None, use_had=True, asynchronous=False, out=None):
         """All 593 partitions of every job of the preceding search_frame[_async] on this context, from its integer winners

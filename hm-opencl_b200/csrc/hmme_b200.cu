@@ -631,6 +631,51 @@ int hmme_refine_frac(hmme_ctx* c, const hmme_plane* cur, const hmme_plane* ref, 
     return sync_ctx(c);
 }
 
+// One PU with HOST pointers, synchronous: the body of TEncSearch::xPatternSearchFracDIF as the encoder calls it
+// (pattern key block, piRefY at the PU origin, integer MV).  Stages the block and the MV-displaced reference patch
+// (4-sample apron) in the context's per-call buffers, like hmme_search_ctu stages its window.
+int hmme_refine_pu(hmme_ctx* c, const int16_t* cur, int curStride, const int16_t* refAtPu, int refStride, int w, int h, int mvx, int mvy,
+                   int predx, int predy, int useHad, int32_t* mvQpelX, int32_t* mvQpelY, uint32_t* cost, uint32_t* dist) {
+    if (!c) return HMME_ERR_ARG;
+    if (!cur || !refAtPu || !mvQpelX || !mvQpelY || !cost) return fail(c, HMME_ERR_ARG, "hmme_refine_pu: null pointer");
+    if (w <= 0 || h <= 0 || w > 64 || h > 64 || (w & 3) || (h & 3)) return fail(c, HMME_ERR_ARG, "hmme_refine_pu: width/height must be multiples of 4 in [4,64]");
+    CU_TRY(c, cudaSetDevice(c->device));
+    int rc = ensure_pus(c, 1);
+    if (rc != HMME_OK) return rc;
+    constexpr int kPatchPitch = 96;                           // >= 64 + 8 (apron) + 8 (tile padding), multiple of 16
+    const int pw = w + 8, ph = h + 8, w8 = (w + 7) & ~7, h8 = (h + 7) & ~7;
+    uint8_t* hp = static_cast<uint8_t*>(c->hWin);
+    int16_t* hc = static_cast<int16_t*>(c->hCurBlk);
+    std::memset(hp, 0, (size_t)kPatchPitch * (h8 + 8));
+    const int16_t* r0 = refAtPu + (long long)(mvy - 4) * refStride + (mvx - 4);
+    for (int y = 0; y < ph; ++y)
+        for (int x = 0; x < pw; ++x) {
+            const int v = r0[(long long)y * refStride + x];
+            if (v < 0 || v > 255) return fail(c, HMME_ERR_CONTENT, "hmme_refine_pu: reference samples outside [0,255] (8-bit video only)");
+            hp[y * kPatchPitch + x] = (uint8_t)v;
+        }
+    for (int y = 0; y < h; ++y) std::memcpy(hc + y * 64, cur + (long long)y * curStride, (size_t)w * sizeof(int16_t));
+    const hmme_pu pu{0, 0, w, h, 0, 0, predx - 4 * mvx, predy - 4 * mvy};      // the MV is folded into the patch origin; costs only see differences
+    CU_TRY(c, cudaMemcpyAsync(c->dWin, hp, (size_t)kPatchPitch * (h8 + 8), cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(c, cudaMemcpyAsync(c->dCurBlk, hc, 64 * 64 * sizeof(int16_t), cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(c, cudaMemcpyAsync(c->dPus, &pu, sizeof(pu), cudaMemcpyHostToDevice, c->stream));
+    (void)w8;
+    FracParams fp{};
+    fp.cur = c->dCurBlk; fp.ref = static_cast<const uint8_t*>(c->dWin) + 4 * kPatchPitch + 4;
+    fp.curPitch = 64; fp.refPitch = kPatchPitch; fp.curBytes = 2;
+    fp.pus = c->dPus; fp.slots = nullptr; fp.npus = 1; fp.lambda = c->lambda; fp.useHad = useHad ? 1 : 0;
+    fp.out = c->dFrac; fp.cand = nullptr;
+    me_frac_kernel<<<1, kFracThreads, 0, c->stream>>>(fp);
+    c->launches += 1;
+    CU_TRY(c, cudaGetLastError());
+    int4 res;
+    CU_TRY(c, cudaMemcpyAsync(&res, c->dFrac, sizeof(res), cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    *mvQpelX = res.x + 4 * mvx; *mvQpelY = res.y + 4 * mvy; *cost = (uint32_t)res.z;
+    if (dist) *dist = (uint32_t)res.w;
+    return HMME_OK;
+}
+
 int hmme_refine_frame_async(hmme_ctx* c, const hmme_plane* cur, const hmme_plane* ref, int njobs, const int32_t* predsQpel, int useHad) {
     if (!c) return HMME_ERR_ARG;
     if (njobs <= 0 || njobs != c->lastSearchJobs)

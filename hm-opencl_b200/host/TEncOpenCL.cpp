@@ -99,3 +99,25 @@ Void TEncOpenCL::calcMotionVectors(Pel* pelCtu, Pel* pelSearch, Int i_iRefStride
         abort();
     }
 }
+
+Distortion TEncOpenCL::refineFractional(Pel* pelKey, Int iKeyStride, Int iWidth, Int iHeight, Pel* piRefY, Int iRefStride, const TComMv& rcMvInt,
+                                        const TComMv& rcMvPred, Bool bUseHadamard, TComMv& rcMvHalf, TComMv& rcMvQter) {
+    if (!m_ctx || !enabled) {
+        fprintf(stderr, "FATAL: TEncOpenCL::refineFractional called without an initialised, enabled GPU context (there is no CPU fallback)\n");
+        abort();
+    }
+    int32_t qx = 0, qy = 0;
+    uint32_t cost = 0;
+    const int rc = hmme_refine_pu(m_ctx, pelKey, iKeyStride, piRefY, iRefStride, iWidth, iHeight, rcMvInt.getHor(), rcMvInt.getVer(),
+                                  rcMvPred.getHor(), rcMvPred.getVer(), bUseHadamard ? 1 : 0, &qx, &qy, &cost, NULL);
+    if (rc != HMME_OK) {
+        fprintf(stderr, "FATAL: hmme_refine_pu ( %d ): %s\n", rc, hmme_last_error(m_ctx));
+        abort();
+    }
+    // quarter-pel offset from the integer MV, in [-3, 3]: split as 2*half + qter with both parts in [-1, 1]
+    const int sx = qx - 4 * rcMvInt.getHor(), sy = qy - 4 * rcMvInt.getVer();
+    const int hx = sx / 2, hy = sy / 2;
+    rcMvHalf = TComMv((Short)hx, (Short)hy);
+    rcMvQter = TComMv((Short)(sx - 2 * hx), (Short)(sy - 2 * hy));
+    return (Distortion)cost;
+}

@@ -72,6 +72,12 @@ public:
     Bool            findDevices(Int device) { return findDevice(device); }   ///< the reference README's spelling
     Bool            createBuffers(UInt i_maxCtuWidth, UInt i_maxCtuHeight, Int i_searchRange);
     Void            calcMotionVectors(Pel* pelCtu, Pel* pelSearch, Int i_iRefStride, Int i_iCtuStride, Int i_areaSize, TComMv* pcMvSrchRngLT);
+    /// Addition to the reference's surface: the fractional-pel refinement of one PU on the GPU, with the
+    /// arguments TEncSearch::xPatternSearchFracDIF (TEncSearch.cpp:4294-4331) has at hand: pattern key block, piRefY at the PU origin,
+    /// integer MV, the predictor set in TComRdCost, HadamardME && !lossless.  Returns ruiCost; rcMvHalf / rcMvQter receive a
+    /// decomposition of the winning quarter-pel offset (only their sum (half << 1) + qter is used by the caller, :3800-3803).
+    Distortion      refineFractional(Pel* pelKey, Int iKeyStride, Int iWidth, Int iHeight, Pel* piRefY, Int iRefStride, const TComMv& rcMvInt,
+                                     const TComMv& rcMvPred, Bool bUseHadamard, TComMv& rcMvHalf, TComMv& rcMvQter);
 
     //======== getters and setters ================
     Int             getDeviceId         ()              { return deviceId; }

@@ -122,6 +122,13 @@ typedef struct { int32_t mvx, mvy; uint32_t cost, dist; } hmme_frac_result;
  * order of the reference's tables (TEncSearch.cpp:51-75), for tests.  Synchronous. */
 int hmme_refine_frac(hmme_ctx* ctx, const hmme_plane* cur, const hmme_plane* ref, const hmme_pu* pus, int npus, int useHad,
                      hmme_frac_result* results, uint32_t* candCosts);
+/* One PU with HOST pointers, synchronous -- what the body of xPatternSearchFracDIF needs: cur = the pattern key block (w x h,
+ * int16, stride curStride; 16-bit values allowed), refAtPu = piRefY, i.e. a pointer INTO the padded int16 reference plane at
+ * the PU origin (samples [mv-4, mv+w+3] x [mv-4, mv+h+3] around it are read), integer MV, quarter-pel predictor.  Returns the
+ * final quarter-pel MV (4*mv + 2*half + quarter), ruiCost, and optionally cost minus the MV cost. */
+int hmme_refine_pu(hmme_ctx* ctx, const int16_t* cur, int curStride, const int16_t* refAtPu, int refStride, int w, int h,
+                   int mvx, int mvy, int predx, int predy, int useHad, int32_t* mvQpelX, int32_t* mvQpelY, uint32_t* cost,
+                   uint32_t* dist);
 /* All 593 partitions of every job of the preceding hmme_search_frame[_async] on this context, starting from that search's
  * integer winners, which never leave the device.  predsQpel: NULL (zero predictor) or [njobs][2] quarter-pel predictors.
  * results: [njobs][593].  The _async pair only enqueues (pair with hmme_sync). */

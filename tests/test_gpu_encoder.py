@@ -15,6 +15,24 @@ from oracle.gen_encoder_golden import CASES, REFDIR, run_case
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BIN = os.path.join(REFDIR, "TAppEncoder_b200")
+BIN_FRAC = os.path.join(REFDIR, "TAppEncoder_b200frac")
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_bitstream_identical_with_fractional_refinement_on_gpu(name):
+    """Row f1 inside the encoder: every xPatternSearchFracDIF call (all PU sizes the RDO visits, uni- and bi-prediction)
+    goes through TEncOpenCL::refineFractional -> hmme_refine_pu; the bitstream must not change by a bit."""
+    if not os.path.exists(BIN_FRAC):
+        pytest.skip("oracle/_ref/TAppEncoder_b200frac was not built (needs /root/reference at build time)")
+    gold = json.load(open(os.path.join(ROOT, "tests/golden/encoder_bitstreams.json")))["cases"][name]
+    with tempfile.TemporaryDirectory() as d:
+        got = run_case(BIN_FRAC, name, os.path.join(REFDIR, "cfg", "encoder_lowdelay_P_main.cfg"), d)
+    assert got["bitstream_bytes"] == gold["bitstream_bytes"]
+    assert got["bitstream_md5"] == gold["bitstream_md5"]
+    assert got["recon_md5"] == gold["recon_md5"]
+    if got["decoded_ok"] is not None:
+        assert got["decoded_ok"] == got["frames"]
+    print(name, "GPU integer + fractional ME encode %.1f s" % got["seconds"])
 
 
 @pytest.mark.parametrize("name", sorted(CASES))

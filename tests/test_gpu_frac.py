@@ -138,3 +138,25 @@ def test_frac_errors(me):
     with pytest.raises(hm.HmmeError):          # refine_frame without a matching search on this context
         me.refine_frame(pc, pr, 3)
     pc.free(); pr.free(); p16.free()
+
+
+def test_refine_pu_host_pointers(me, oracle):
+    """hmme_refine_pu: the synchronous host-pointer form the encoder's xPatternSearchFracDIF body maps to."""
+    rng = np.random.default_rng(77)
+    W, H, M = 128, 96, 24
+    f = luma_frames(W + 2 * M, H + 2 * M, 2, seed=9)
+    ref = np.ascontiguousarray(f[0].astype(np.int16))
+    cur = np.ascontiguousarray((2 * f[1].astype(np.int16) - rng.integers(0, 256, f[1].shape)).astype(np.int16))
+    lam = 617503
+    me.set_lambda_q16(lam)
+    for (w, h) in SIZES:
+        x, y = int(rng.integers(0, W - w)), int(rng.integers(0, H - h))
+        mv = (int(rng.integers(-12, 13)), int(rng.integers(-12, 13)))
+        pred = (int(rng.integers(-100, 100)), int(rng.integers(-100, 100)))
+        for had in (True, False):
+            got = me.refine_pu(cur[M + y:M + y + h, M + x:M + x + w], ref, x, y, M, M, mv, pred, had)
+            want = oracle.refine_frac(cur, (M, M), ref, (M, M), np.array([[x, y, w, h, mv[0], mv[1], pred[0], pred[1]]], np.int32), lam, had)
+            assert got == (int(want["mvq"][0, 0]), int(want["mvq"][0, 1]), int(want["cost"][0]), int(want["dist"][0])), (w, h, had)
+    with pytest.raises(hm.HmmeError) as e:          # 10-bit-like content: not defined for this path
+        me.refine_pu(cur[M:M + 8, M:M + 8], ref + 300, 0, 0, M, M, (0, 0), (0, 0))
+    assert e.value.code == -5
