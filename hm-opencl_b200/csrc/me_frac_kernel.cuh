@@ -105,173 +105,183 @@ __device__ __forceinline__ void hadamard_inplace(int* d) {
 
 constexpr int kFracSad = 0, kFracHad4 = 1, kFracHad8 = 2;
 
-// Distortion of the candidates (dx[i], dy[j]) of one PU, summed over its tiles.  halfStage: dx = dy = {-2, 0, 2}, where the two
-// outer rows (columns) of candidates read the same half-sample plane one row (column) apart and the centre needs no filter;
-// in the quarter stage the centre candidate is the half-pel winner, whose distortion is already known, so the Hadamard pass
-// skips it.  Result layout (per lane, 3 registers):
+// Distortion of the candidates of one PU and one stage, summed over its tiles.
+//   HALF  : dx, dy in {-2, 0, 2} (all phases known at compile time): the two outer rows (columns) of candidates read the same
+//           half-sample plane one row (column) apart, the centre row is a rounding copy;
+//   !HALF : dx = cx + {-1, 0, 1}, dy = cy + {-1, 0, 1} around the half-pel winner (cx, cy); the centre candidate is that winner,
+//           whose distortion is already known, so the Hadamard pass skips it.
+// Result layout (per lane, 3 registers):
 //   Hadamard, half stage    : candidate g = j*3+i in acc[g >> 2] on the lanes with (lane >> 3) == (g & 3)
 //   Hadamard, quarter stage : same with k = g - (g > 4) in place of g (g = 4 is not computed)
 //   SAD mode                : candidate g in acc[j] on the lanes with (lane >> 3) == i
-template <int MODE>
-__device__ __forceinline__ void frac_eval(const FracParams& p, const FracPu& P, FracScratch& S, const int lane, const bool halfStage,
-                                          const int (&dx)[3], const int (&dy)[3], uint32_t (&acc)[3]) {
-    int ixm[3], iym[3];
+template <int MODE, bool HALF>
+__device__ __forceinline__ void frac_eval(const FracParams& p, const FracPu& P, FracScratch& S, const int lane, const int cx, const int cy,
+                                          uint32_t (&acc)[3]) {
+    const int step = HALF ? 2 : 1;
+    int hOff[3], vOff[3];                     // first tap of output 0 inside the patch row / column: 0 or 1 (= 1 + (d >> 2))
     uint32_t cLo[3], cHi[3], vLo[3], vHi[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-        ixm[i] = dx[i] >> 2; iym[i] = dy[i] >> 2;
-        cLo[i] = kLumaPack[dx[i] & 3][0]; cHi[i] = kLumaPack[dx[i] & 3][1];
-        vLo[i] = kLumaPack[dy[i] & 3][0]; vHi[i] = kLumaPack[dy[i] & 3][1];
+        const int dx = cx + (i - 1) * step, dy = cy + (i - 1) * step;
+        hOff[i] = 1 + (dx >> 2); vOff[i] = 1 + (dy >> 2);
+        cLo[i] = kLumaPack[dx & 3][0]; cHi[i] = kLumaPack[dx & 3][1];
+        vLo[i] = kLumaPack[dy & 3][0]; vHi[i] = kLumaPack[dy & 3][1];
     }
     acc[0] = acc[1] = acc[2] = 0;
     const uint8_t* refPu = p.ref + (long long)(P.y + P.mvy - 4) * p.refPitch + (P.x + P.mvx - 4);
+    const int rowL = lane >> 1, halfL = lane & 1;            // patch loader / H step role
+    const int curR = lane >> 2, curC = (lane & 3) * 2;       // current-tile loader role
 
-    for (int ty = 0; ty < P.h; ty += 8) {
-        const int th = min(8, P.h - ty);
-        for (int tx = 0; tx < P.w; tx += 8) {
-            const int tw = min(8, P.w - tx);
-            {   // reference patch: lane = (row, half row of 8 samples)
-                const int row = lane >> 1, half = lane & 1;
-                const uint8_t* g = refPu + (long long)(ty + row) * p.refPitch + tx + half * 8;
-                const uint32_t w0 = g[0] | (g[1] << 8) | (g[2] << 16) | ((uint32_t)g[3] << 24);
-                const uint32_t w1 = g[4] | (g[5] << 8) | (g[6] << 16) | ((uint32_t)g[7] << 24);
-                *reinterpret_cast<uint2*>(&S.ref[row][half * 2]) = make_uint2(w0, w1);
-                // current tile, transposed: lane = (row, column pair)
-                const int r = lane >> 2, c0 = (lane & 3) * 2;
+    // next tile's samples travel in registers while the current tile is being worked on
+    uint32_t nb[8]; int ncur[2];
+    auto fetch = [&](const int tx, const int ty) {
+        const uint8_t* g = refPu + (long long)(ty + rowL) * p.refPitch + tx + halfL * 8;
 #pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    const int c = c0 + q;
-                    int v = 0;
-                    if (r < th && c < tw) {
-                        const long long o = (long long)(P.y + ty + r) * p.curPitch + P.x + tx + c;
-                        v = p.curBytes == 1 ? (int)static_cast<const uint8_t*>(p.cur)[o] : (int)static_cast<const int16_t*>(p.cur)[o];
-                    }
-                    S.cur[c][r] = (int16_t)v;
-                }
+        for (int q = 0; q < 8; ++q) nb[q] = g[q];
+        const int tw = min(8, P.w - tx), th = min(8, P.h - ty);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            ncur[q] = 0;
+            if (curR < th && curC + q < tw) {
+                const long long o = (long long)(P.y + ty + curR) * p.curPitch + P.x + tx + curC + q;
+                ncur[q] = p.curBytes == 1 ? (int)static_cast<const uint8_t*>(p.cur)[o] : (int)static_cast<const int16_t*>(p.cur)[o];
             }
-            __syncwarp();
-            {   // H step: 4 columns x 3 planes per lane; columns outside the PU become 0 (so does their prediction, and cur is 0 there)
-                const int row = lane >> 1, half = lane & 1;
-                const bool outside = MODE != kFracHad8 && half && tw < 8;       // zero samples -> zero planes
-                const uint32_t W0 = outside ? 0u : S.ref[row][half], W1 = outside ? 0u : S.ref[row][half + 1], W2 = outside ? 0u : S.ref[row][half + 2];
-                uint32_t lo[5], hi[5];
-                lo[0] = W0; hi[0] = W1; lo[4] = W1; hi[4] = W2;
-#pragma unroll
-                for (int o = 1; o < 4; ++o) { lo[o] = __funnelshift_r(W0, W1, 8 * o); hi[o] = __funnelshift_r(W1, W2, 8 * o); }
-#pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    int out[4];
-                    if (ixm[i] < 0) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) out[j] = dp4a_us(hi[j], cHi[i], dp4a_us(lo[j], cLo[i], 0));
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) out[j] = dp4a_us(hi[j + 1], cHi[i], dp4a_us(lo[j + 1], cLo[i], 0));
-                    }
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) S.h[i][half * 4 + j][row] = (int16_t)out[j];
-                }
-            }
-            __syncwarp();
-            {   // V step: lane = (dx index, column); lanes 24..31 compute on plane 0 and their results are never read
-                const int di = lane >> 3, c = lane & 7;
-                const bool live = lane < 24;
-                int cu[8];
-                const int dii = live ? di : 0;
-                const uint4 ha = *reinterpret_cast<const uint4*>(&S.h[dii][c][0]), hb = *reinterpret_cast<const uint4*>(&S.h[dii][c][8]);
-                const uint32_t wv[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
-                {
-                    const uint4 cc = *reinterpret_cast<const uint4*>(&S.cur[c][0]);
-                    const uint32_t wc[4] = {cc.x, cc.y, cc.z, cc.w};
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) { cu[2 * q] = (int)(int16_t)(wc[q] & 0xFFFFu); cu[2 * q + 1] = (int)wc[q] >> 16; }
-                }
-                // prediction column d[0..7] of candidate row j -> difference, vertical transform, hand-over
-                auto emit = [&](const int j, int (&d)[8]) {
-#pragma unroll
-                    for (int r = 0; r < 8; ++r) d[r] = cu[r] - d[r];
-                    if (MODE != kFracHad8 && th < 8) { d[4] = 0; d[5] = 0; d[6] = 0; d[7] = 0; }
-                    if (MODE == kFracSad) {
-                        uint32_t s = 0;
-#pragma unroll
-                        for (int r = 0; r < 8; ++r) s = __sad(d[r], 0, s);
-                        s += __shfl_xor_sync(0xFFFFFFFFu, s, 1); s += __shfl_xor_sync(0xFFFFFFFFu, s, 2); s += __shfl_xor_sync(0xFFFFFFFFu, s, 4);
-                        acc[j] += s;
-                    } else {
-                        if (MODE == kFracHad8) hadamard_inplace<8>(d);
-                        else { hadamard_inplace<4>(d); hadamard_inplace<4>(d + 4); }
-                        if (live) {
-                            uint4 pk;
-                            pk.x = __byte_perm(d[0], d[1], 0x5410); pk.y = __byte_perm(d[2], d[3], 0x5410);
-                            pk.z = __byte_perm(d[4], d[5], 0x5410); pk.w = __byte_perm(d[6], d[7], 0x5410);
-                            *reinterpret_cast<uint4*>(&S.t[j * 3 + di][c * 8]) = pk;
-                        }
-                    }
-                };
-                int d[8];
-                // integer vertical phase: rows 4..11 of the column (patch rows 0..7 of the tile), rounded from the 14-bit intermediate
-                auto copy_rows = [&]() {
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        d[2 * q] = min(max(((int)(int16_t)(wv[q + 2] & 0xFFFFu) + 32) >> 6, 0), 255);
-                        d[2 * q + 1] = min(max((((int)wv[q + 2] >> 16) + 32) >> 6, 0), 255);
-                    }
-                };
-                if (halfStage) {
-                    int o9[9];                                   // half-sample rows -1..7: dy = -2 reads 0..7 of them, dy = +2 reads 1..8
-                    frac_vfilter<0, 9>(wv, vLo[0], vHi[0], o9);
-#pragma unroll
-                    for (int r = 0; r < 8; ++r) d[r] = o9[r];
-                    emit(0, d);
-#pragma unroll
-                    for (int r = 0; r < 8; ++r) d[r] = o9[r + 1];
-                    emit(2, d);
-                    copy_rows();
-                    emit(1, d);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 3; ++j) {
-                        if ((dy[j] & 3) == 0) copy_rows();
-                        else if (iym[j] < 0) frac_vfilter<0, 8>(wv, vLo[j], vHi[j], d);
-                        else frac_vfilter<1, 8>(wv, vLo[j], vHi[j], d);
-                        emit(j, d);
-                    }
-                }
-            }
-            if (MODE != kFracSad) {
-                __syncwarp();
-                const int i = lane & 7;
-                const int nPass = halfStage ? 3 : 2;
-                for (int pass = 0; pass < nPass; ++pass) {
-                    const int k = pass * 4 + (lane >> 3);
-                    const int g = halfStage ? k : k + (k >= 4);         // quarter stage: the centre (4) is not evaluated
-                    int e[8];
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) e[c] = g < 9 ? (int)S.t[g][c * 8 + i] : 0;
-                    uint32_t tot;
-                    if (MODE == kFracHad8) {
-                        hadamard_inplace<8>(e);
-                        uint32_t s = 0;
-#pragma unroll
-                        for (int c = 0; c < 8; ++c) s = __sad(e[c], 0, s);
-                        s += __shfl_xor_sync(0xFFFFFFFFu, s, 1); s += __shfl_xor_sync(0xFFFFFFFFu, s, 2); s += __shfl_xor_sync(0xFFFFFFFFu, s, 4);
-                        tot = (s + 2) >> 2;                                     // xCalcHADs8x8 rounding
-                    } else {
-                        hadamard_inplace<4>(e); hadamard_inplace<4>(e + 4);
-                        uint32_t sa = 0, sb = 0;
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) { sa = __sad(e[c], 0, sa); sb = __sad(e[c + 4], 0, sb); }
-                        sa += __shfl_xor_sync(0xFFFFFFFFu, sa, 1); sa += __shfl_xor_sync(0xFFFFFFFFu, sa, 2);
-                        sb += __shfl_xor_sync(0xFFFFFFFFu, sb, 1); sb += __shfl_xor_sync(0xFFFFFFFFu, sb, 2);
-                        uint32_t bl = ((sa + 1) >> 1) + ((sb + 1) >> 1);       // xCalcHADs4x4 rounding, per 4x4 block
-                        bl += __shfl_xor_sync(0xFFFFFFFFu, bl, 4);
-                        tot = bl;
-                    }
-                    if (pass == 0) acc[0] += tot; else if (pass == 1) acc[1] += tot; else acc[2] += tot;
-                }
-            }
-            __syncwarp();
         }
+    };
+    fetch(0, 0);
+    int tx = 0, ty = 0;
+    while (true) {
+        const int tw = min(8, P.w - tx), th = min(8, P.h - ty);
+        {
+            const uint32_t w0 = nb[0] | (nb[1] << 8) | (nb[2] << 16) | (nb[3] << 24), w1 = nb[4] | (nb[5] << 8) | (nb[6] << 16) | (nb[7] << 24);
+            *reinterpret_cast<uint2*>(&S.ref[rowL][halfL * 2]) = make_uint2(w0, w1);
+            S.cur[curC][curR] = (int16_t)ncur[0];
+            S.cur[curC + 1][curR] = (int16_t)ncur[1];
+        }
+        __syncwarp();
+        int ntx = tx + 8, nty = ty;
+        if (ntx >= P.w) { ntx = 0; nty += 8; }
+        const bool more = nty < P.h;
+        if (more) fetch(ntx, nty);
+        {   // H step: 4 columns x 3 planes per lane; columns outside the PU become 0 (so does their prediction, and cur is 0 there)
+            const bool outside = MODE != kFracHad8 && halfL && tw < 8;       // zero samples -> zero planes
+            const uint32_t W0 = outside ? 0u : S.ref[rowL][halfL], W1 = outside ? 0u : S.ref[rowL][halfL + 1], W2 = outside ? 0u : S.ref[rowL][halfL + 2];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                int out[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int o8 = 8 * (j + hOff[i]);                       // byte window start (x8): clamp mode makes 32 mean "next word"
+                    out[j] = dp4a_us(__funnelshift_rc(W1, W2, o8), cHi[i], dp4a_us(__funnelshift_rc(W0, W1, o8), cLo[i], 0));
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) S.h[i][halfL * 4 + j][rowL] = (int16_t)out[j];
+            }
+        }
+        __syncwarp();
+        {   // V step: lane = (dx index, column); lanes 24..31 compute on plane 0 and their results are never read
+            const int di = lane >> 3, c = lane & 7;
+            const bool live = lane < 24;
+            int cu[8];
+            const int dii = live ? di : 0;
+            const uint4 ha = *reinterpret_cast<const uint4*>(&S.h[dii][c][0]), hb = *reinterpret_cast<const uint4*>(&S.h[dii][c][8]);
+            const uint32_t wv[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
+            {
+                const uint4 cc = *reinterpret_cast<const uint4*>(&S.cur[c][0]);
+                const uint32_t wc[4] = {cc.x, cc.y, cc.z, cc.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { cu[2 * q] = (int)(int16_t)(wc[q] & 0xFFFFu); cu[2 * q + 1] = (int)wc[q] >> 16; }
+            }
+            // prediction column d[0..7] of candidate row j -> difference, vertical transform, hand-over
+            auto emit = [&](const int j, int (&d)[8]) {
+#pragma unroll
+                for (int r = 0; r < 8; ++r) d[r] = cu[r] - d[r];
+                if (MODE != kFracHad8 && th < 8) { d[4] = 0; d[5] = 0; d[6] = 0; d[7] = 0; }
+                if (MODE == kFracSad) {
+                    uint32_t s = 0;
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) s = __sad(d[r], 0, s);
+                    s += __shfl_xor_sync(0xFFFFFFFFu, s, 1); s += __shfl_xor_sync(0xFFFFFFFFu, s, 2); s += __shfl_xor_sync(0xFFFFFFFFu, s, 4);
+                    acc[j] += s;
+                } else {
+                    if (MODE == kFracHad8) hadamard_inplace<8>(d);
+                    else { hadamard_inplace<4>(d); hadamard_inplace<4>(d + 4); }
+                    uint4 pk;
+                    pk.x = __byte_perm(d[0], d[1], 0x5410); pk.y = __byte_perm(d[2], d[3], 0x5410);
+                    pk.z = __byte_perm(d[4], d[5], 0x5410); pk.w = __byte_perm(d[6], d[7], 0x5410);
+                    if (live) *reinterpret_cast<uint4*>(&S.t[j * 3 + di][c * 8]) = pk;
+                }
+            };
+            int d[8];
+            // integer vertical phase: rows 4..11 of the column (patch rows 0..7 of the tile), rounded from the 14-bit intermediate
+            auto copy_rows = [&]() {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    d[2 * q] = min(max(((int)(int16_t)(wv[q + 2] & 0xFFFFu) + 32) >> 6, 0), 255);
+                    d[2 * q + 1] = min(max((((int)wv[q + 2] >> 16) + 32) >> 6, 0), 255);
+                }
+            };
+            if (HALF) {
+                int o9[9];                                   // half-sample rows -1..7: dy = -2 reads 0..7 of them, dy = +2 reads 1..8
+                frac_vfilter<0, 9>(wv, vLo[0], vHi[0], o9);
+#pragma unroll
+                for (int r = 0; r < 8; ++r) d[r] = o9[r];
+                emit(0, d);
+#pragma unroll
+                for (int r = 0; r < 8; ++r) d[r] = o9[r + 1];
+                emit(2, d);
+                copy_rows();
+                emit(1, d);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    if (j == 1 && cy == 0) copy_rows();      // dy = 0: the only integer phase a quarter-pel row can have
+                    else {
+                        uint32_t ws[8];                      // column moved up by vOff rows, so that output r starts at row r
+#pragma unroll
+                        for (int q = 0; q < 7; ++q) ws[q] = __funnelshift_r(wv[q], wv[q + 1], 16 * vOff[j]);
+                        ws[7] = wv[7] >> (16 * vOff[j]);
+                        frac_vfilter<0, 8>(ws, vLo[j], vHi[j], d);
+                    }
+                    emit(j, d);
+                }
+            }
+        }
+        if (MODE != kFracSad) {
+            __syncwarp();
+            const int i = lane & 7;
+#pragma unroll
+            for (int pass = 0; pass < (HALF ? 3 : 2); ++pass) {
+                const int k = pass * 4 + (lane >> 3);
+                const int g = HALF ? k : k + (k >= 4);         // quarter stage: the centre (4) is not evaluated
+                int e[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) e[c] = g < 9 ? (int)S.t[g][c * 8 + i] : 0;
+                uint32_t tot;
+                if (MODE == kFracHad8) {
+                    hadamard_inplace<8>(e);
+                    uint32_t s = 0;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) s = __sad(e[c], 0, s);
+                    s += __shfl_xor_sync(0xFFFFFFFFu, s, 1); s += __shfl_xor_sync(0xFFFFFFFFu, s, 2); s += __shfl_xor_sync(0xFFFFFFFFu, s, 4);
+                    tot = (s + 2) >> 2;                                     // xCalcHADs8x8 rounding
+                } else {
+                    hadamard_inplace<4>(e); hadamard_inplace<4>(e + 4);
+                    uint32_t sa = 0, sb = 0;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) { sa = __sad(e[c], 0, sa); sb = __sad(e[c + 4], 0, sb); }
+                    sa += __shfl_xor_sync(0xFFFFFFFFu, sa, 1); sa += __shfl_xor_sync(0xFFFFFFFFu, sa, 2);
+                    sb += __shfl_xor_sync(0xFFFFFFFFu, sb, 1); sb += __shfl_xor_sync(0xFFFFFFFFu, sb, 2);
+                    uint32_t bl = ((sa + 1) >> 1) + ((sb + 1) >> 1);       // xCalcHADs4x4 rounding, per 4x4 block
+                    bl += __shfl_xor_sync(0xFFFFFFFFu, bl, 4);
+                    tot = bl;
+                }
+                acc[pass] += tot;
+            }
+        }
+        __syncwarp();
+        if (!more) break;
+        tx = ntx; ty = nty;
     }
 }
 
@@ -291,9 +301,9 @@ __device__ __forceinline__ void frac_refine_pu(const FracParams& p, const FracPu
 #pragma unroll 1
     for (int stage = 0; stage < 2; ++stage) {
         const int step = stage == 0 ? 2 : 1;
-        const int dx[3] = {cx - step, cx, cx + step}, dy[3] = {cy - step, cy, cy + step};
         uint32_t acc[3];
-        frac_eval<MODE>(p, P, S, lane, stage == 0, dx, dy, acc);
+        if (stage == 0) frac_eval<MODE, true>(p, P, S, lane, 0, 0, acc);
+        else frac_eval<MODE, false>(p, P, S, lane, cx, cy, acc);
         // where frac_eval left the distortion of this lane's candidate (see its header)
         const int gq = (lane < 9 ? lane : 0), kq = (MODE != kFracSad && stage == 1) ? gq - (gq > 4) : gq;
         const int srcLane = (MODE == kFracSad ? gi : (kq & 3)) * 8, srcReg = MODE == kFracSad ? gj : (kq >> 2);
