@@ -72,7 +72,7 @@ __device__ __forceinline__ int dp2a_hi(uint32_t pair, uint32_t taps, int acc) { 
     asm("dp2a.hi.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(pair), "r"(taps), "r"(acc));
     return d;
 }
-__device__ __forceinline__ int frac_round_clip(int a) { return min(max(a >> 12, 0), 255); }
+__device__ __forceinline__ int frac_round_clip(int a) { return __vimin_s32_relu(a >> 12, 255); }   // one VIMNMX.RELU: clip to [0, 255]
 
 // Vertical 8-tap pass over one column held as packed pairs of 16-bit rows (wv[q] = rows 2q, 2q+1): output r starts at row
 // r + S0.  An even start takes the taps as packed {k0..k3}, {k4..k7}; an odd start uses the same bytes moved up by one.
@@ -166,16 +166,29 @@ __device__ __forceinline__ void frac_eval(const FracParams& p, const FracPu& P, 
         {   // H step: 4 columns x 3 planes per lane; columns outside the PU become 0 (so does their prediction, and cur is 0 there)
             const bool outside = MODE != kFracHad8 && halfL && tw < 8;       // zero samples -> zero planes
             const uint32_t W0 = outside ? 0u : S.ref[rowL][halfL], W1 = outside ? 0u : S.ref[rowL][halfL + 1], W2 = outside ? 0u : S.ref[rowL][halfL + 2];
+            if (HALF) {
+                // dx = -2 and dx = +2 are the same half-sample row one column apart (5 windows serve both); dx = 0 is 64 * sample
+                int f[5];
 #pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                int out[4];
+                for (int o = 0; o < 5; ++o) f[o] = dp4a_us(__funnelshift_rc(W1, W2, 8 * o), cHi[0], dp4a_us(__funnelshift_rc(W0, W1, 8 * o), cLo[0], 0));
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const int o8 = 8 * (j + hOff[i]);                       // byte window start (x8): clamp mode makes 32 mean "next word"
-                    out[j] = dp4a_us(__funnelshift_rc(W1, W2, o8), cHi[i], dp4a_us(__funnelshift_rc(W0, W1, o8), cLo[i], 0));
+                    S.h[0][halfL * 4 + j][rowL] = (int16_t)f[j];
+                    S.h[2][halfL * 4 + j][rowL] = (int16_t)f[j + 1];
+                    S.h[1][halfL * 4 + j][rowL] = (int16_t)(((W1 >> (8 * j)) & 0xFFu) << 6);
                 }
+            } else {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) S.h[i][halfL * 4 + j][rowL] = (int16_t)out[j];
+                for (int i = 0; i < 3; ++i) {
+                    int out[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int o8 = 8 * (j + hOff[i]);                   // byte window start (x8): clamp mode makes 32 mean "next word"
+                        out[j] = dp4a_us(__funnelshift_rc(W1, W2, o8), cHi[i], dp4a_us(__funnelshift_rc(W0, W1, o8), cLo[i], 0));
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) S.h[i][halfL * 4 + j][rowL] = (int16_t)out[j];
+                }
             }
         }
         __syncwarp();
@@ -217,8 +230,8 @@ __device__ __forceinline__ void frac_eval(const FracParams& p, const FracPu& P, 
             auto copy_rows = [&]() {
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    d[2 * q] = min(max(((int)(int16_t)(wv[q + 2] & 0xFFFFu) + 32) >> 6, 0), 255);
-                    d[2 * q + 1] = min(max((((int)wv[q + 2] >> 16) + 32) >> 6, 0), 255);
+                    d[2 * q] = __vimin_s32_relu(((int)(int16_t)(wv[q + 2] & 0xFFFFu) + 32) >> 6, 255);
+                    d[2 * q + 1] = __vimin_s32_relu((((int)wv[q + 2] >> 16) + 32) >> 6, 255);
                 }
             };
             if (HALF) {
