@@ -317,9 +317,10 @@ def main():
             if not hasattr(self, "frac_out"):
                 self.frac_out = torch.zeros((max(njobs, 1), NPARTS, 4), dtype=torch.int32).pin_memory().numpy()
             self.upload_inputs(True)
-            self.me.search_frame_async(self.p_cur, self.p_ref, jobs, R)
-            self.me.fetch_results(njobs, self.outs, asynchronous=True)
-            self.me.refine_frame(self.p_cur, self.p_ref, njobs, None, True, asynchronous=True, out=self.frac_out)
+            if njobs:
+                self.me.search_frame_async(self.p_cur, self.p_ref, jobs, R)
+                self.me.fetch_results(njobs, self.outs, asynchronous=True)
+                self.me.refine_frame(self.p_cur, self.p_ref, njobs, None, True, asynchronous=True, out=self.frac_out)
 
     pipes = [Pipe(), Pipe()]
     me, ext, p_cur, p_ref = pipes[0].me, pipes[0].ext, pipes[0].p_cur, pipes[0].p_ref
@@ -440,30 +441,33 @@ def main():
 
     # ------------------------------------------------------------------ next row: fractional-pel refinement
     frac = None
-    if world == 1 and njobs and not args.virtual_world:
+    if not args.virtual_world:
         nfr = min(args.steps, 60)
         fk, fk_sad = [], []
-        for s in range(nfr + 2):                            # kernel time: CUDA events inside the library, resident inputs
+        for s in range(nfr + 2 if njobs else 0):           # kernel time: CUDA events inside the library, resident inputs
             pc_, pr_ = sets[s % nsets]
             me.search_frame_async(pc_, pr_, jobs, R)
             me.refine_frame(pc_, pr_, njobs, None, True, asynchronous=True)
             me.sync()
             if s >= 2:
                 fk.append(me.last_frac_ms())
-        for s in range(6):
+        for s in range(6 if njobs else 0):
             pc_, pr_ = sets[s % nsets]
             me.search_frame_async(pc_, pr_, jobs, R)
             me.refine_frame(pc_, pr_, njobs, None, False, asynchronous=True)
             me.sync()
             fk_sad.append(me.last_frac_ms())
+        if not njobs:
+            fk, fk_sad = [0.0], [0.0]
         barrier()
         ev_a, ev_b = torch.cuda.Event(enable_timing=True), [torch.cuda.Event(enable_timing=True) for _ in pipes]
         ev_a.record(pipes[0].ext)
         for s in range(nfr):                                # search + refinement per frame, frames alternating over two contexts
             pp = pipes[s & 1]
             pc_, pr_ = sets[s % nsets]
-            pp.me.search_frame_async(pc_, pr_, jobs, R)
-            pp.me.refine_frame(pc_, pr_, njobs, None, True, asynchronous=True)
+            if njobs:
+                pp.me.search_frame_async(pc_, pr_, jobs, R)
+                pp.me.refine_frame(pc_, pr_, njobs, None, True, asynchronous=True)
         for pp, e_ in zip(pipes, ev_b):
             e_.record(pp.ext)
         barrier()
@@ -477,15 +481,20 @@ def main():
             pp.step_e2e_frac()
         for pp in pipes:
             pp.me.sync()
+        barrier()
         e2e_frac_ms = (time.perf_counter() - e0) * 1e3 / nfr
-        pu_px = njobs * 24 * 4096                           # sum of the 593 partition areas = 24 CTU areas
+        ft = torch.tensor([float(np.mean(fk)), float(np.mean(fk_sad)), both_ms, e2e_frac_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ft, op=dist.ReduceOp.MAX)
+        fk, fk_sad, both_ms, e2e_frac_ms = [float(ft[0].item())], [float(ft[1].item())], float(ft[2].item()), float(ft[3].item())
+        pu_px = total_jobs * 24 * 4096                      # sum of the 593 partition areas = 24 CTU areas
         frac = {"scope": "fractional-pel refinement (xPatternSearchFracDIF: 9 half-pel + 9 quarter-pel candidates, 8-tap interpolation, Hadamard cost) "
                          "of all 593 partitions of every CTU, from the integer winners left on the device",
-                "kernel": "me_frac_kernel", "pus_per_frame": njobs * NPARTS, "kernel_ms": float(np.mean(fk)), "kernel_ms_sad": float(np.mean(fk_sad)),
-                "pu_refinements_per_s": njobs * NPARTS / (np.mean(fk) * 1e-3), "pu_pixels_per_s": pu_px / (np.mean(fk) * 1e-3),
+                "kernel": "me_frac_kernel", "pus_per_frame": total_jobs * NPARTS, "kernel_ms": float(np.mean(fk)), "kernel_ms_sad": float(np.mean(fk_sad)),
+                "pu_refinements_per_s": total_jobs * NPARTS / (np.mean(fk) * 1e-3), "pu_pixels_per_s": pu_px / (np.mean(fk) * 1e-3),
                 "search_plus_refine_ms_per_frame": both_ms, "search_plus_refine_frames_per_s": 1e3 / both_ms,
                 "e2e_ms_per_frame": e2e_frac_ms, "e2e_frames_per_s": 1e3 / e2e_frac_ms,
-                "e2e_d2h_bytes_per_step": 4 * njobs * NPARTS * 4 + njobs * NPARTS * 16, "steps": nfr,
+                "e2e_d2h_bytes_per_step": 4 * total_jobs * NPARTS * 4 + total_jobs * NPARTS * 16, "steps": nfr,
                 "timer": "kernel_ms: CUDA events around me_frac_kernel on its stream; search_plus_refine: CUDA events around K frames alternating over two "
                          "contexts, resident inputs; e2e: host wall clock, uploads + search + refine + all result arrays fetched, two contexts"}
 
