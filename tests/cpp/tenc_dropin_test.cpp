@@ -54,6 +54,32 @@ int main() {
                     }
             }
     }
-    printf("%s: %d calcMotionVectors calls, %d mismatches\n", bad ? "FAIL" : "PASS", calls, bad);
+    // the fractional-pel refinement as TEncSearch::xPatternSearchFracDIF would call it:
+    // pattern key block, piRefY at the PU origin, integer MV, predictor; a few PU shapes, 8-bit and 16-bit blocks
+    int fcalls = 0;
+    me.setLambda(49.3);
+    const int shapes[6][2] = {{64, 64}, {32, 24}, {16, 4}, {12, 16}, {8, 8}, {48, 64}};
+    for (int t = 0; t < 12; ++t) {
+        const int w = shapes[t % 6][0], h = shapes[t % 6][1], px = 16 + 8 * t, py = 24 + 4 * t;
+        Pel blk[64 * 64];
+        for (int r = 0; r < h; ++r)
+            for (int c = 0; c < w; ++c) {
+                const Pel v = cur[(size_t)(M + py + r) * S + M + px + c];
+                blk[r * 64 + c] = t >= 6 ? (Pel)(2 * v - (Pel)(lcg(seed) & 255)) : v;
+            }
+        const TComMv mvInt((Short)(3 - t), (Short)(t - 5)), pred((Short)(7 * t - 30), (Short)(11 - 3 * t));
+        Pel* refAtPu = &ref[(size_t)(M + py) * S + M + px];
+        TComMv half, qter;
+        const Distortion cost = me.refineFractional(blk, 64, w, h, refAtPu, S, mvInt, pred, (t & 1) == 0, half, qter);
+        const hmme_oracle_pu pu = {0, 0, w, h, mvInt.getHor(), mvInt.getVer(), pred.getHor(), pred.getVer()};
+        int32_t mvq[2], oh[2], oq[2]; uint32_t oc, od;
+        hmme_oracle_refine_frac(blk, 64, refAtPu, S, &pu, 1, hmme_oracle_lambda_q16(49.3), (t & 1) == 0, mvq, oh, oq, &oc, &od, NULL);
+        ++fcalls;
+        const int gx = 4 * mvInt.getHor() + 2 * half.getHor() + qter.getHor(), gy = 4 * mvInt.getVer() + 2 * half.getVer() + qter.getVer();
+        if (gx != mvq[0] || gy != mvq[1] || cost != oc || half.getHor() < -1 || half.getHor() > 1 || qter.getVer() < -1 || qter.getVer() > 1) {
+            if (bad++ < 10) printf("MISMATCH refineFractional %dx%d: got (%d,%d,%u) want (%d,%d,%u)\n", w, h, gx, gy, cost, mvq[0], mvq[1], oc);
+        }
+    }
+    printf("%s: %d calcMotionVectors calls, %d refineFractional calls, %d mismatches\n", bad ? "FAIL" : "PASS", calls, fcalls, bad);
     return bad ? 1 : 0;
 }

@@ -160,3 +160,54 @@ def test_refine_pu_host_pointers(me, oracle):
     with pytest.raises(hm.HmmeError) as e:          # 10-bit-like content: not defined for this path
         me.refine_pu(cur[M:M + 8, M:M + 8], ref + 300, 0, 0, M, M, (0, 0), (0, 0))
     assert e.value.code == -5
+
+
+def test_full_size_1080p_refine(me, oracle):
+    """BASELINE configuration: 1080p +-64 search, then all 284 640 PUs refined; every result obeys the size-independent
+    properties (offset within +-3 quarter samples, cost >= distortion), 24 sampled CTUs (14 232 PUs) equal the oracle."""
+    W, H, R, M = 1920, 1080, 64, 80
+    f = luma_frames(W, H, 2)
+    cur, ref = pad_plane(f[1], M, M), pad_plane(f[0], M, M)
+    jobs = frame_jobs(W, H, R)
+    lam = 460000
+    me.set_lambda_q16(lam)
+    pc, pr = planes(me, cur.astype(np.uint8), ref.astype(np.uint8), W, H, M)
+    X, Y, _, cost_int = me.search_frame(pc, pr, jobs, R)
+    res = me.refine_frame(pc, pr, len(jobs), None, True)
+    assert res.shape == (len(jobs), 593)
+    assert np.abs(res["mvx"] - 4 * X).max() <= 3 and np.abs(res["mvy"] - 4 * Y).max() <= 3
+    assert (res["cost"] >= res["dist"]).all()
+    pick = np.linspace(0, len(jobs) - 1, 24).astype(int)
+    rects = me.lib.partition_table()
+    pus = np.zeros((len(pick), 593, 8), np.int32)
+    pus[:, :, 0] = jobs[pick, None, 0] + rects[None, :, 0]
+    pus[:, :, 1] = jobs[pick, None, 1] + rects[None, :, 1]
+    pus[:, :, 2], pus[:, :, 3] = rects[None, :, 2], rects[None, :, 3]
+    pus[:, :, 4], pus[:, :, 5] = X[pick], Y[pick]
+    want = oracle.refine_frac(cur, (M, M), ref, (M, M), pus.reshape(-1, 8), lam, True)
+    check(res[pick].reshape(-1), None, want, "1080p sample")
+    pc.free(); pr.free()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_virtual_bands_refine_equal_whole_frame(me, world):
+    """Band sharding (the N-GPU layout of bench.py) leaves the refinement unchanged: each band searches and refines only its
+    own jobs; concatenated in rank order the results equal the single-GPU frame."""
+    W, H, R, M = 448, 320, 12, 32
+    f = luma_frames(W, H, 2, seed=10 + world)
+    cur, ref = pad_plane(f[1], M, M, np.uint8), pad_plane(f[0], M, M, np.uint8)
+    me.set_lambda_q16(460000)
+    pc, pr = planes(me, cur, ref, W, H, M)
+    jobs = frame_jobs(W, H, R)
+    me.search_frame(pc, pr, jobs, R)
+    whole = me.refine_frame(pc, pr, len(jobs), None, True)
+    parts = []
+    for rank in range(world):
+        bj, _ = hm.band_jobs(W, H, R, world, rank)
+        if len(bj):
+            me.search_frame(pc, pr, bj, R)
+            parts.append(me.refine_frame(pc, pr, len(bj), None, True))
+    got = np.concatenate(parts, 0)
+    for k in ("mvx", "mvy", "cost", "dist"):
+        assert np.array_equal(got[k], whole[k]), (world, k)
+    pc.free(); pr.free()
