@@ -8,6 +8,7 @@
 //   TEncSearch::xPatternSearchFracDIF (TEncSearch.cpp:4294-4331) -> hmme_refine_frac (PU list) / hmme_refine_frame (all partitions)
 // No OpenCL, no runtime compilation, no CPU fallback: every failure is an error code + message.
 #include <algorithm>
+#include <climits>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -116,6 +117,7 @@ struct hmme_ctx {
     int2* dPreds = nullptr; size_t predCap = 0;
     cudaEvent_t evF0 = nullptr, evF1 = nullptr; bool evFracValid = false;
     int lastSearchJobs = 0;       // job count of the most recent frame search (its winners feed hmme_refine_frame)
+    int lastBox[4] = {0, 0, 0, 0};   // picture-coordinate bounding box [x0, y0, x1, y1) of every sample that search could point a PU at
 };
 
 namespace {
@@ -583,6 +585,11 @@ int hmme_search_frame_async(hmme_ctx* c, const hmme_plane* cur, const hmme_plane
     // so consecutive frames can be enqueued without a host synchronisation in between
     CU_TRY(c, cudaMemcpyAsync(c->dJobs, jobs, (size_t)njobs * sizeof(hmme_job), cudaMemcpyHostToDevice, c->stream));
     c->lastSearchJobs = njobs;
+    c->lastBox[0] = c->lastBox[1] = INT32_MAX; c->lastBox[2] = c->lastBox[3] = INT32_MIN;
+    for (int j = 0; j < njobs; ++j) {
+        c->lastBox[0] = std::min(c->lastBox[0], jobs[j].ctuX + jobs[j].ltx); c->lastBox[1] = std::min(c->lastBox[1], jobs[j].ctuY + jobs[j].lty);
+        c->lastBox[2] = std::max(c->lastBox[2], jobs[j].ctuX + jobs[j].ltx + 2 * range + 64); c->lastBox[3] = std::max(c->lastBox[3], jobs[j].ctuY + jobs[j].lty + 2 * range + 64);
+    }
     const char* refLo = static_cast<const char*>(ref->base);
     // planes carry 64 bytes of slack after the last row (hmme_plane_alloc adds it; required of external memory): the
     // 16-byte granular TMA row copies may run a few bytes past the window's last sample
@@ -682,6 +689,10 @@ int hmme_refine_frame_async(hmme_ctx* c, const hmme_plane* cur, const hmme_plane
         return fail(c, HMME_ERR_ARG, "hmme_refine_frame: job count must match the preceding hmme_search_frame on this context");
     int rc = check_frac_planes(c, cur, ref);
     if (rc != HMME_OK) return rc;
+    // every MV the search can have returned keeps its PU inside lastBox; the filters add 4 samples and the kernel up to 4 of tile padding
+    if (c->lastBox[0] - 4 < -ref->marginX || c->lastBox[1] - 4 < -ref->marginY || c->lastBox[2] + 8 > ref->width + ref->marginX ||
+        c->lastBox[3] + 8 > ref->height + ref->marginY)
+        return fail(c, HMME_ERR_BOUNDS, "hmme_refine_frame: the search windows leave less than 8 samples of margin in the reference plane for the interpolation apron");
     CU_TRY(c, cudaSetDevice(c->device));
     const size_t npus = (size_t)njobs * HMME_NPARTS;
     rc = ensure_pus(c, npus);

@@ -137,6 +137,13 @@ def test_frac_errors(me):
         assert e.value.code == -6
     with pytest.raises(hm.HmmeError):          # refine_frame without a matching search on this context
         me.refine_frame(pc, pr, 3)
+    one = np.array([[0, 0, -12, -12]], np.int32)
+    me.search_frame(pc, pr, one, 12)            # window reaches 4 samples from the plane edge: no room for the 8-tap apron
+    with pytest.raises(hm.HmmeError) as e:
+        me.refine_frame(pc, pr, 1)
+    assert e.value.code == -6
+    me.search_frame(pc, pr, np.array([[0, 0, -8, -8]], np.int32), 8)
+    me.refine_frame(pc, pr, 1)
     pc.free(); pr.free(); p16.free()
 
 
