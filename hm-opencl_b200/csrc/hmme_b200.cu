@@ -113,7 +113,9 @@ struct hmme_ctx {
     // fractional-pel refinement (grown on demand)
     size_t puCap = 0;
     FracPu* dPus = nullptr; int* dSlots = nullptr; int4* dFrac = nullptr; uint32_t* dCand = nullptr;
-    int* dOrder = nullptr;        // 593 partition indices, large to small
+    int* dOrder = nullptr;        // 593 partition indices, by 8x8-tile count, large to small
+    int bigParts = 0;             // how many of them get a whole CTA in the small-batch form (kFracCoopTiles tiles or more)
+    int tilesPerCtu = 0;          // 8x8 tiles of all 593 partitions (1792)
     int2* dPreds = nullptr; size_t predCap = 0;
     cudaEvent_t evF0 = nullptr, evF1 = nullptr; bool evFracValid = false;
     int lastSearchJobs = 0;       // job count of the most recent frame search (its winners feed hmme_refine_frame)
@@ -191,7 +193,10 @@ int ensure_pus(hmme_ctx* c, size_t npus) {
         // partitions by area, large to small (stable), so that consecutive PUs of the whole-frame list cost about the same
         std::vector<int> order(HMME_NPARTS);
         for (int i = 0; i < HMME_NPARTS; ++i) order[i] = i;
-        std::stable_sort(order.begin(), order.end(), [](int a, int b) { const PartRect ra = part_rect(a), rb = part_rect(b); return ra.w * ra.h > rb.w * rb.h; });
+        auto tiles = [](int q) { const PartRect r = part_rect(q); return ((r.w + 7) / 8) * ((r.h + 7) / 8); };
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return tiles(a) > tiles(b); });
+        c->bigParts = 0; c->tilesPerCtu = 0;
+        for (int q : order) { c->bigParts += tiles(q) >= kFracCoopTiles; c->tilesPerCtu += tiles(q); }
         CU_TRY(c, cudaMalloc(&c->dOrder, HMME_NPARTS * sizeof(int)));
         CU_TRY(c, cudaMemcpy(c->dOrder, order.data(), HMME_NPARTS * sizeof(int), cudaMemcpyHostToDevice));
     }
@@ -223,20 +228,26 @@ int check_pus(hmme_ctx* c, const hmme_plane* cur, const hmme_plane* ref, const h
     return HMME_OK;
 }
 
-int enqueue_frac(hmme_ctx* c, const hmme_plane* cur, const hmme_plane* ref, int npus, bool slots, int useHad, bool wantCand) {
+int enqueue_frac(hmme_ctx* c, const hmme_plane* cur, const hmme_plane* ref, int npus, int nBig, long long totalTiles, bool slots, int useHad, bool wantCand) {
     if (wantCand && !c->dCand) CU_TRY(c, cudaMalloc(&c->dCand, c->puCap * 18 * sizeof(uint32_t)));
     FracParams fp{};
     fp.cur = origin_ptr(cur); fp.ref = reinterpret_cast<const uint8_t*>(origin_ptr(ref));
     fp.curPitch = cur->pitch; fp.refPitch = ref->pitch; fp.curBytes = cur->elemBytes;
-    fp.pus = c->dPus; fp.slots = slots ? c->dSlots : nullptr; fp.npus = npus;
+    // Large PUs get a CTA each only when the batch is too small for longest-first scheduling to hide a 64-tile PU running on one
+    // warp (measured at 1080p: 8 / 30 CTU jobs 0.094 -> 0.035 ms / 0.115 -> 0.086 ms, but 60 jobs 0.156 -> 0.160 and 480 jobs 1.14 -> 1.21)
+    static const int coopEnv = std::getenv("HMME_FRAC_COOP") ? std::atoi(std::getenv("HMME_FRAC_COOP")) : -1;   // experiments: 0 never, 1 always
+    const bool coop = nBig > 0 && (coopEnv >= 0 ? coopEnv != 0 : totalTiles < 32LL * c->prop.multiProcessorCount * 16);
+    if (!coop) nBig = 0;
+    fp.pus = c->dPus; fp.slots = slots ? c->dSlots : nullptr; fp.npus = npus; fp.nBig = nBig;
     fp.lambda = c->lambda; fp.useHad = useHad ? 1 : 0;
     fp.out = c->dFrac; fp.cand = wantCand ? c->dCand : nullptr;
     // about one PU per warp: CTAs start in index order, so with the list ordered large to small the hardware's CTA scheduler does
     // longest-first load balancing (measured 1080p: 16 CTAs per SM 1.25 ms, 32: 1.20, 128 and more: 1.14; one resident wave: 1.30)
     static const int perSm = std::getenv("HMME_FRAC_CTAS_PER_SM") ? std::max(1, std::atoi(std::getenv("HMME_FRAC_CTAS_PER_SM"))) : 256;
-    const int ctas = std::max(1, std::min((npus + kFracWarps - 1) / kFracWarps, c->prop.multiProcessorCount * perSm));
+    const int ctas = std::max(1, nBig + std::min((npus - nBig + kFracWarps - 1) / kFracWarps, c->prop.multiProcessorCount * perSm));
     CU_TRY(c, cudaEventRecord(c->evF0, c->stream));
-    me_frac_kernel<<<ctas, kFracThreads, 0, c->stream>>>(fp);
+    if (coop) me_frac_coop_kernel<<<ctas, kFracThreads, 0, c->stream>>>(fp);
+    else me_frac_kernel<<<ctas, kFracThreads, 0, c->stream>>>(fp);
     CU_TRY(c, cudaEventRecord(c->evF1, c->stream));
     c->evFracValid = true;
     c->launches += 1;
@@ -632,8 +643,19 @@ int hmme_refine_frac(hmme_ctx* c, const hmme_plane* cur, const hmme_plane* ref, 
     rc = ensure_pus(c, (size_t)npus);
     if (rc != HMME_OK) return rc;
     static_assert(sizeof(hmme_pu) == sizeof(FracPu) && sizeof(hmme_frac_result) == sizeof(int4), "ABI structs mirror the kernel's");
-    CU_TRY(c, cudaMemcpyAsync(c->dPus, pus, (size_t)npus * sizeof(hmme_pu), cudaMemcpyHostToDevice, c->stream));
-    rc = enqueue_frac(c, cur, ref, npus, false, useHad, candCosts != nullptr);
+    // PUs by 8x8-tile count, large to small (longest-first scheduling; the large ones get a CTA each); results go back to list order
+    auto tiles = [&](int i) { return ((pus[i].w + 7) / 8) * ((pus[i].h + 7) / 8); };
+    std::vector<int> idx(npus);
+    for (int i = 0; i < npus; ++i) idx[i] = i;
+    std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return tiles(a) > tiles(b); });
+    std::vector<hmme_pu> sorted(npus);
+    int nBig = 0;
+    long long totalTiles = 0;
+    for (int i = 0; i < npus; ++i) { sorted[i] = pus[idx[i]]; nBig += tiles(idx[i]) >= kFracCoopTiles; totalTiles += tiles(idx[i]); }
+    CU_TRY(c, cudaMemcpyAsync(c->dPus, sorted.data(), (size_t)npus * sizeof(hmme_pu), cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(c, cudaMemcpyAsync(c->dSlots, idx.data(), (size_t)npus * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));           // the two vectors are pageable and go out of scope
+    rc = enqueue_frac(c, cur, ref, npus, nBig, totalTiles, true, useHad, candCosts != nullptr);
     if (rc != HMME_OK) return rc;
     CU_TRY(c, cudaMemcpyAsync(results, c->dFrac, (size_t)npus * sizeof(int4), cudaMemcpyDeviceToHost, c->stream));
     if (candCosts) CU_TRY(c, cudaMemcpyAsync(candCosts, c->dCand, (size_t)npus * 18 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
@@ -668,13 +690,14 @@ int hmme_refine_pu(hmme_ctx* c, const int16_t* cur, int curStride, const int16_t
     CU_TRY(c, cudaMemcpyAsync(c->dWin, hp, (size_t)kPatchPitch * (h8 + 8), cudaMemcpyHostToDevice, c->stream));
     CU_TRY(c, cudaMemcpyAsync(c->dCurBlk, hc, 64 * 64 * sizeof(int16_t), cudaMemcpyHostToDevice, c->stream));
     CU_TRY(c, cudaMemcpyAsync(c->dPus, &pu, sizeof(pu), cudaMemcpyHostToDevice, c->stream));
-    (void)w8;
     FracParams fp{};
     fp.cur = c->dCurBlk; fp.ref = static_cast<const uint8_t*>(c->dWin) + 4 * kPatchPitch + 4;
     fp.curPitch = 64; fp.refPitch = kPatchPitch; fp.curBytes = 2;
-    fp.pus = c->dPus; fp.slots = nullptr; fp.npus = 1; fp.lambda = c->lambda; fp.useHad = useHad ? 1 : 0;
+    fp.pus = c->dPus; fp.slots = nullptr; fp.npus = 1; fp.nBig = (w8 / 8) * (h8 / 8) >= kFracCoopTiles ? 1 : 0;
+    fp.lambda = c->lambda; fp.useHad = useHad ? 1 : 0;
     fp.out = c->dFrac; fp.cand = nullptr;
-    me_frac_kernel<<<1, kFracThreads, 0, c->stream>>>(fp);
+    if (fp.nBig) me_frac_coop_kernel<<<1, kFracThreads, 0, c->stream>>>(fp);
+    else me_frac_kernel<<<1, kFracThreads, 0, c->stream>>>(fp);
     c->launches += 1;
     CU_TRY(c, cudaGetLastError());
     int4 res;
@@ -714,7 +737,7 @@ int hmme_refine_frame_async(hmme_ctx* c, const hmme_plane* cur, const hmme_plane
     me_frac_build_kernel<<<(unsigned)((npus + 255) / 256), 256, 0, c->stream>>>(c->dJobs, X, Y, predsQpel ? c->dPreds : nullptr, c->dOrder, njobs,
                                                                                 c->dPus, c->dSlots);
     c->launches += 1;
-    return enqueue_frac(c, cur, ref, (int)npus, true, useHad, false);
+    return enqueue_frac(c, cur, ref, (int)npus, njobs * c->bigParts, (long long)njobs * c->tilesPerCtu, true, useHad, false);
 }
 
 int hmme_fetch_frac_async(hmme_ctx* c, int njobs, hmme_frac_result* results) {

@@ -26,6 +26,7 @@ namespace hmme {
 
 constexpr int kFracWarps = 4;
 constexpr int kFracThreads = kFracWarps * 32;
+constexpr int kFracCoopTiles = 8;      // PUs of this many 8x8 tiles or more are shared by the 4 warps of a CTA
 
 struct FracPu { int x, y, w, h, mvx, mvy, predx, predy; };   // == hmme_pu (include/hmme_b200.h)
 
@@ -37,6 +38,7 @@ struct FracParams {
     const FracPu* pus;
     const int* slots;           // optional: result index of PU n (whole-frame path: job * 593 + partition)
     int npus;
+    int nBig;                   // PUs [0, nBig) have at least kFracCoopTiles tiles and get a whole CTA each (one per CTA, 4 warps share the tiles)
     uint32_t lambda;
     int useHad;
     int4* out;                  // {mv x, mv y (quarter pel), cost, distortion}
@@ -114,9 +116,10 @@ constexpr int kFracSad = 0, kFracHad4 = 1, kFracHad8 = 2;
 //   Hadamard, half stage    : candidate g = j*3+i in acc[g >> 2] on the lanes with (lane >> 3) == (g & 3)
 //   Hadamard, quarter stage : same with k = g - (g > 4) in place of g (g = 4 is not computed)
 //   SAD mode                : candidate g in acc[j] on the lanes with (lane >> 3) == i
-template <int MODE, bool HALF>
+template <int MODE, bool HALF, bool COOP>
 __device__ __forceinline__ void frac_eval(const FracParams& p, const FracPu& P, FracScratch& S, const int lane, const int cx, const int cy,
                                           uint32_t (&acc)[3]) {
+    const int t0 = COOP ? (int)(threadIdx.x >> 5) : 0, tstep = COOP ? kFracWarps : 1;
     const int step = HALF ? 2 : 1;
     int hOff[3], vOff[3];                     // first tap of output 0 inside the patch row / column: 0 or 1 (= 1 + (d >> 2))
     uint32_t cLo[3], cHi[3], vLo[3], vHi[3];
@@ -148,8 +151,11 @@ __device__ __forceinline__ void frac_eval(const FracParams& p, const FracPu& P, 
             }
         }
     };
-    fetch(0, 0);
-    int tx = 0, ty = 0;
+    // this warp's tiles: t0, t0 + tstep, ... in raster order over the PU
+    const int ntxT = (P.w + 7) >> 3, nT = ntxT * ((P.h + 7) >> 3);
+    const int rcp = (65536 + ntxT - 1) / ntxT;               // t / ntxT == (t * rcp) >> 16 for t < 128, ntxT <= 8
+    int t = t0, ty = ((t * rcp) >> 16) * 8, tx = t * 8 - ty * ntxT;
+    fetch(tx, ty);
     while (true) {
         const int tw = min(8, P.w - tx), th = min(8, P.h - ty);
         {
@@ -159,9 +165,10 @@ __device__ __forceinline__ void frac_eval(const FracParams& p, const FracPu& P, 
             S.cur[curC + 1][curR] = (int16_t)ncur[1];
         }
         __syncwarp();
-        int ntx = tx + 8, nty = ty;
-        if (ntx >= P.w) { ntx = 0; nty += 8; }
-        const bool more = nty < P.h;
+        int tn = t + tstep, ntx, nty;
+        bool more;
+        if (COOP) { nty = ((tn * rcp) >> 16) * 8; ntx = tn * 8 - nty * ntxT; more = tn < nT; }
+        else { ntx = tx + 8; nty = ty; if (ntx >= P.w) { ntx = 0; nty += 8; } more = nty < P.h; }   // raster walk, no index arithmetic
         if (more) fetch(ntx, nty);
         {   // H step: 4 columns x 3 planes per lane; columns outside the PU become 0 (so does their prediction, and cur is 0 there)
             const bool outside = MODE != kFracHad8 && halfL && tw < 8;       // zero samples -> zero planes
@@ -294,7 +301,7 @@ __device__ __forceinline__ void frac_eval(const FracParams& p, const FracPu& P, 
         }
         __syncwarp();
         if (!more) break;
-        tx = ntx; ty = nty;
+        t = tn; tx = ntx; ty = nty;
     }
 }
 
@@ -303,8 +310,11 @@ __device__ __forceinline__ uint32_t frac_mv_cost(uint32_t lambda, int qx, int qy
     return (uint32_t)(lambda * (mv_bits(qx - predx) + mv_bits(qy - predy))) >> 16;
 }
 
-template <int MODE>
-__device__ __forceinline__ void frac_refine_pu(const FracParams& p, const FracPu& P, FracScratch& S, const int lane, const int n) {
+template <int MODE, bool COOP>
+__device__ __forceinline__ void frac_refine_pu(const FracParams& p, const FracPu& P, FracScratch& S, const int lane, const int n, uint32_t* red) {
+    constexpr bool coop = COOP;
+    const int warp = threadIdx.x >> 5;
+    const int slot = p.slots ? p.slots[n] : n;
     // candidate of this lane in the 3x3 grid (lanes 0..8): row-major over (dy index, dx index)
     const int gi = lane % 3, gj = (lane / 3) % 3;
     // grid position -> index in the reference's candidate tables (TEncSearch.cpp:51-75); 4 bits each, grid position 0 lowest
@@ -315,8 +325,16 @@ __device__ __forceinline__ void frac_refine_pu(const FracParams& p, const FracPu
     for (int stage = 0; stage < 2; ++stage) {
         const int step = stage == 0 ? 2 : 1;
         uint32_t acc[3];
-        if (stage == 0) frac_eval<MODE, true>(p, P, S, lane, 0, 0, acc);
-        else frac_eval<MODE, false>(p, P, S, lane, cx, cy, acc);
+        if (stage == 0) frac_eval<MODE, true, COOP>(p, P, S, lane, 0, 0, acc);
+        else frac_eval<MODE, false, COOP>(p, P, S, lane, cx, cy, acc);
+        if (coop) {                                        // CTA-uniform: the four warps hold partial sums over their tiles
+            uint32_t* r = red + stage * (kFracWarps * 3 * 32);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) r[(warp * 3 + k) * 32 + lane] = acc[k];
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < 3; ++k) acc[k] = r[k * 32 + lane] + r[(3 + k) * 32 + lane] + r[(6 + k) * 32 + lane] + r[(9 + k) * 32 + lane];
+        }
         // where frac_eval left the distortion of this lane's candidate (see its header)
         const int gq = (lane < 9 ? lane : 0), kq = (MODE != kFracSad && stage == 1) ? gq - (gq > 4) : gq;
         const int srcLane = (MODE == kFracSad ? gi : (kq & 3)) * 8, srcReg = MODE == kFracSad ? gj : (kq >> 2);
@@ -329,7 +347,7 @@ __device__ __forceinline__ void frac_refine_pu(const FracParams& p, const FracPu
         const uint32_t cost = dist + mvc;
         const uint32_t tIdx = (uint32_t)((stage == 0 ? lutHalf : lutQter) >> (4 * (lane < 9 ? lane : 0))) & 15u;
         unsigned long long key = lane < 9 ? (((unsigned long long)cost << 8) | tIdx) : ~0ull;
-        if (p.cand && lane < 9) p.cand[(size_t)n * 18 + stage * 9 + tIdx] = cost;
+        if (p.cand && lane < 9 && (!coop || warp == 0)) p.cand[(size_t)slot * 18 + stage * 9 + tIdx] = cost;
         unsigned long long m = key;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { const unsigned long long t = __shfl_xor_sync(0xFFFFFFFFu, m, o); m = t < m ? t : m; }
@@ -338,26 +356,43 @@ __device__ __forceinline__ void frac_refine_pu(const FracParams& p, const FracPu
         bestCost = __shfl_sync(0xFFFFFFFFu, cost, win);
         bestMvc = __shfl_sync(0xFFFFFFFFu, mvc, win);
     }
-    if (lane == 0) p.out[p.slots ? p.slots[n] : n] = make_int4(4 * P.mvx + cx, 4 * P.mvy + cy, (int)bestCost, (int)(bestCost - bestMvc));
+    if (lane == 0 && (!coop || warp == 0)) p.out[slot] = make_int4(4 * P.mvx + cx, 4 * P.mvy + cy, (int)bestCost, (int)(bestCost - bestMvc));
 }
 
+template <bool COOP>
+__device__ __forceinline__ void frac_dispatch(const FracParams& p, FracScratch& S, const int lane, const int n, uint32_t* red) {
+    const FracPu P = p.pus[n];
+    if (!p.useHad) frac_refine_pu<kFracSad, COOP>(p, P, S, lane, n, red);
+    else if (((P.w | P.h) & 7) == 0) frac_refine_pu<kFracHad8, COOP>(p, P, S, lane, n, red);
+    else frac_refine_pu<kFracHad4, COOP>(p, P, S, lane, n, red);
+}
+
+// Throughput form: every warp refines PUs on its own (nBig is 0).
 __global__ void __launch_bounds__(kFracThreads) me_frac_kernel(const FracParams p) {
     __shared__ FracScratch scratch[kFracWarps];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    FracScratch& S = scratch[warp];
-    const int nWarps = gridDim.x * kFracWarps;
-    for (int n = blockIdx.x * kFracWarps + warp; n < p.npus; n += nWarps) {
-        const FracPu P = p.pus[n];
-        if (!p.useHad) frac_refine_pu<kFracSad>(p, P, S, lane, n);
-        else if (((P.w | P.h) & 7) == 0) frac_refine_pu<kFracHad8>(p, P, S, lane, n);
-        else frac_refine_pu<kFracHad4>(p, P, S, lane, n);
+    const int stride = (int)gridDim.x * kFracWarps;
+    for (int n = (int)blockIdx.x * kFracWarps + warp; n < p.npus; n += stride) frac_dispatch<false>(p, scratch[warp], lane, n, nullptr);
+}
+
+// Latency form for small batches (a band of a frame on one of several GPUs, a single PU from the encoder): the first nBig PUs
+// (kFracCoopTiles tiles or more) get a CTA each, whose four warps share the tiles and add up their partial sums per stage.
+__global__ void __launch_bounds__(kFracThreads) me_frac_coop_kernel(const FracParams p) {
+    __shared__ FracScratch scratch[kFracWarps];
+    __shared__ uint32_t red[2 * kFracWarps * 3 * 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if ((int)blockIdx.x < p.nBig) {
+        frac_dispatch<true>(p, scratch[warp], lane, blockIdx.x, red);
+        return;
     }
+    const int stride = ((int)gridDim.x - p.nBig) * kFracWarps;
+    for (int n = p.nBig + ((int)blockIdx.x - p.nBig) * kFracWarps + warp; n < p.npus; n += stride) frac_dispatch<false>(p, scratch[warp], lane, n, nullptr);
 }
 
 // PU list of a whole frame from the winners of the preceding integer search: PU n = (job, partition), ordered by partition
 // area, large to small (order[] from the host), so that the round-robin over warps stays balanced.
 __global__ void me_frac_build_kernel(const int4* jobs, const int32_t* X, const int32_t* Y, const int2* preds, const int* order, int njobs,
-                                     FracPu* pus, int* slots) {
+                                     FracPu* pus, int* slots) {   // order[] is by tile count, so the cooperative PUs come first
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= njobs * HMME_NPARTS) return;
     const int part = order[n / njobs], job = n - (n / njobs) * njobs;

@@ -20,6 +20,8 @@ me.set_lambda_q16(460000)
 pc, pr = me.alloc_plane(1, W, H, M, M), me.alloc_plane(1, W, H, M, M)
 me.upload(pc, cur); me.upload(pr, ref)
 jobs = frame_jobs(W, H, R)
+if len(sys.argv) > 1:                      # first N jobs only (the band one of N GPUs would get)
+    jobs = jobs[:int(sys.argv[1])]
 out = {}
 for had in (1, 0):
     ms = []
