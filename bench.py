@@ -110,6 +110,7 @@ def cpu_oracle_throughput(W, H, R, margin, njobs_sample, threads):
     return cands * NPARTS / dt, dt, len(pick)
 
 
+FRAC_OPS_PER_CTU = 24020326        # see DESIGN.md 3.4 (sum over the 593 partitions)
 CPUME_BIN = os.path.join(ROOT, "oracle", "_ref", "TAppEncoder_cpume")
 CPUME_CFG = os.path.join(ROOT, "oracle", "_ref", "cfg", "encoder_lowdelay_P_main.cfg")
 
@@ -460,18 +461,16 @@ def main():
         if not njobs:
             fk, fk_sad = [0.0], [0.0]
         barrier()
-        ev_a, ev_b = torch.cuda.Event(enable_timing=True), [torch.cuda.Event(enable_timing=True) for _ in pipes]
-        ev_a.record(pipes[0].ext)
-        for s in range(nfr):                                # search + refinement per frame, frames alternating over two contexts
-            pp = pipes[s & 1]
-            pc_, pr_ = sets[s % nsets]
-            if njobs:
-                pp.me.search_frame_async(pc_, pr_, jobs, R)
-                pp.me.refine_frame(pc_, pr_, njobs, None, True, asynchronous=True)
-        for pp, e_ in zip(pipes, ev_b):
-            e_.record(pp.ext)
+        ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev_a.record(ext)
+        for s in range(nfr):                                # search + refinement per frame, one context: the two kernels of a frame
+            pc_, pr_ = sets[s % nsets]                      # depend on each other and both fill the GPU, so there is nothing to overlap
+            if njobs:                                       # (two contexts with deep queues showed erratic CTA interleaving: 2.5-5 ms)
+                me.search_frame_async(pc_, pr_, jobs, R)
+                me.refine_frame(pc_, pr_, njobs, None, True, asynchronous=True)
+        ev_b.record(ext)
         barrier()
-        both_ms = max(ev_a.elapsed_time(e_) for e_ in ev_b) / nfr
+        both_ms = ev_a.elapsed_time(ev_b) / nfr
         for pp in pipes:
             pp.step_e2e_frac(); pp.me.sync()
         e0 = time.perf_counter()
@@ -488,6 +487,10 @@ def main():
             dist.all_reduce(ft, op=dist.ReduceOp.MAX)
         fk, fk_sad, both_ms, e2e_frac_ms = [float(ft[0].item())], [float(ft[1].item())], float(ft[2].item()), float(ft[3].item())
         pu_px = total_jobs * 24 * 4096                      # sum of the 593 partition areas = 24 CTU areas
+        # algorithmic operations of the reference's own scheme per CTU (all 593 partitions, half-pel winner at the centre): filter MACs over
+        # the plane sizes of xExtDIFUpSamplingH/Q + 8 (8x8 Hadamard) or 6 (4x4) operations per pixel and candidate; formula in DESIGN.md 3.4
+        frac_ops = FRAC_OPS_PER_CTU * njobs
+        frac_peak = 2.0 * peak["lane_ops_per_s"]            # both integer pipes (ALU + FMA-heavy/IMAD), each at the measured 64 lanes/clk/SM
         frac = {"scope": "fractional-pel refinement (xPatternSearchFracDIF: 9 half-pel + 9 quarter-pel candidates, 8-tap interpolation, Hadamard cost) "
                          "of all 593 partitions of every CTU, from the integer winners left on the device",
                 "kernel": "me_frac_kernel", "pus_per_frame": total_jobs * NPARTS, "kernel_ms": float(np.mean(fk)), "kernel_ms_sad": float(np.mean(fk_sad)),
@@ -495,8 +498,11 @@ def main():
                 "search_plus_refine_ms_per_frame": both_ms, "search_plus_refine_frames_per_s": 1e3 / both_ms,
                 "e2e_ms_per_frame": e2e_frac_ms, "e2e_frames_per_s": 1e3 / e2e_frac_ms,
                 "e2e_d2h_bytes_per_step": 4 * total_jobs * NPARTS * 4 + total_jobs * NPARTS * 16, "steps": nfr,
-                "timer": "kernel_ms: CUDA events around me_frac_kernel on its stream; search_plus_refine: CUDA events around K frames alternating over two "
-                         "contexts, resident inputs; e2e: host wall clock, uploads + search + refine + all result arrays fetched, two contexts"}
+                "roofline": {"bound": "int_issue", "achieved": frac_ops / (np.mean(fk) * 1e-3) / 1e12 if np.mean(fk) > 0 else 0.0, "peak": frac_peak / 1e12,
+                             "unit": "T int-op/s", "frac": (frac_ops / (np.mean(fk) * 1e-3)) / frac_peak if np.mean(fk) > 0 and frac_peak else None,
+                             "ops_per_ctu": FRAC_OPS_PER_CTU, "peak_source": "2 x the live-measured integer-ALU issue rate (ALU and FMA-heavy pipes issue concurrently)"},
+                "timer": "kernel_ms: CUDA events around me_frac_kernel on its stream; search_plus_refine: CUDA events around K frames on one context/stream, "
+                         "resident inputs; e2e: host wall clock, uploads + search + refine + all result arrays fetched, two contexts"}
 
     if rank == 0:
         total_cands = total_jobs * cands_per_job
