@@ -21,7 +21,7 @@ EXPORTS = [
     "hmme_plane_alloc", "hmme_plane_free", "hmme_plane_upload_s16", "hmme_plane_upload_u8",
     "hmme_search_frame", "hmme_search_frame_async", "hmme_fetch_results", "hmme_sync",
     "hmme_plane_upload_s16_async", "hmme_fetch_results_async",
-    "hmme_refine_pu", "hmme_refine_frac", "hmme_refine_frame", "hmme_refine_frame_async", "hmme_fetch_frac_async", "hmme_last_frac_ms",
+    "hmme_refine_pu", "hmme_refine_frac", "hmme_refine_frame", "hmme_refine_frame_async", "hmme_fetch_frac_async", "hmme_last_frac_ms", "hmme_mc_cost",
     "hmme_last_kernel_ms", "hmme_kernel_launches", "hmme_measure_int_alu_peak", "hmme_partition_rect", "hmme_index_block", "hmme_search_window", "hmme_version",
 ]
 
@@ -87,6 +87,7 @@ class HmmeLib:
             "hmme_refine_frame_async": (i32, [vp, P(PlaneDesc), P(PlaneDesc), i32, vp, i32]),
             "hmme_fetch_frac_async": (i32, [vp, i32, vp]),
             "hmme_last_frac_ms": (i32, [vp, P(C.c_float)]),
+            "hmme_mc_cost": (i32, [vp, P(PlaneDesc), P(PlaneDesc), vp, i32, i32, vp]),
             "hmme_last_kernel_ms": (i32, [vp, P(C.c_float)]),
             "hmme_kernel_launches": (C.c_uint64, [vp]),
             "hmme_measure_int_alu_peak": (i32, [vp, P(C.c_double), P(C.c_double), P(C.c_double)]),
@@ -300,6 +301,14 @@ class MotionEstimator:
         res = out if out is not None else np.zeros((njobs, NUM_CTU_PARTS), self.FRAC_DTYPE)
         self._chk(self.lib.L.hmme_refine_frame(self.h, C.byref(cur.desc), C.byref(ref.desc), int(njobs), pp, int(bool(use_had)), res.ctypes.data))
         return res
+
+    def mc_cost(self, cur, ref, pus, use_had=False):
+        """Distortion of the motion-compensated uni-prediction (xGetTemplateCost / uni merge candidates): pus (n, 6) int32 rows
+        {x, y, w, h, mvx, mvy (QUARTER pel, already clipped)}.  Returns (n,) uint32: SAD, or Hadamard SATD with use_had."""
+        pus = np.ascontiguousarray(pus, np.int32).reshape(-1, 6)
+        out = np.zeros(pus.shape[0], np.uint32)
+        self._chk(self.lib.L.hmme_mc_cost(self.h, C.byref(cur.desc), C.byref(ref.desc), pus.ctypes.data, pus.shape[0], int(bool(use_had)), out.ctypes.data))
+        return out
 
     def last_frac_ms(self):
         ms = C.c_float()

@@ -708,6 +708,39 @@ int hmme_refine_pu(hmme_ctx* c, const int16_t* cur, int curStride, const int16_t
     return HMME_OK;
 }
 
+// ---- distortion of motion-compensated uni-prediction at quarter-pel MVs (xGetTemplateCost / uni-directional merge candidates)
+int hmme_mc_cost(hmme_ctx* c, const hmme_plane* cur, const hmme_plane* ref, const hmme_mc_pu* pus, int npus, int useHad, uint32_t* dist) {
+    if (!c) return HMME_ERR_ARG;
+    if (!pus || npus <= 0 || !dist) return fail(c, HMME_ERR_ARG, "hmme_mc_cost: no PUs / null output");
+    int rc = check_frac_planes(c, cur, ref);
+    if (rc != HMME_OK) return rc;
+    for (int n = 0; n < npus; ++n) {                        // same geometry rules as the refinement, around the integer part of the MV
+        const hmme_mc_pu& u = pus[n];
+        const hmme_pu g{u.x, u.y, u.w, u.h, u.mvQpelX >> 2, u.mvQpelY >> 2, 0, 0};
+        rc = check_pus(c, cur, ref, &g, 1);
+        if (rc != HMME_OK) { c->err = "PU " + std::to_string(n) + " of hmme_mc_cost: " + c->err; return rc; }
+    }
+    CU_TRY(c, cudaSetDevice(c->device));
+    rc = ensure_pus(c, (size_t)npus);                       // dPus (32 B per entry) holds the 24-byte records, dFrac the results
+    if (rc != HMME_OK) return rc;
+    static_assert(sizeof(hmme_mc_pu) == sizeof(McPu) && sizeof(McPu) <= sizeof(FracPu), "ABI struct mirrors the kernel's");
+    CU_TRY(c, cudaMemcpyAsync(c->dPus, pus, (size_t)npus * sizeof(hmme_mc_pu), cudaMemcpyHostToDevice, c->stream));
+    McParams mp{};
+    mp.cur = origin_ptr(cur); mp.ref = reinterpret_cast<const uint8_t*>(origin_ptr(ref));
+    mp.curPitch = cur->pitch; mp.refPitch = ref->pitch; mp.curBytes = cur->elemBytes;
+    mp.pus = reinterpret_cast<const McPu*>(c->dPus); mp.npus = npus; mp.useHad = useHad ? 1 : 0;
+    mp.out = reinterpret_cast<uint32_t*>(c->dFrac);
+    const int ctas = std::max(1, std::min((npus + kFracWarps - 1) / kFracWarps, c->prop.multiProcessorCount * 64));
+    CU_TRY(c, cudaEventRecord(c->evF0, c->stream));
+    me_mc_cost_kernel<<<ctas, kFracThreads, 0, c->stream>>>(mp);
+    CU_TRY(c, cudaEventRecord(c->evF1, c->stream));
+    c->evFracValid = true;
+    c->launches += 1;
+    CU_TRY(c, cudaGetLastError());
+    CU_TRY(c, cudaMemcpyAsync(dist, c->dFrac, (size_t)npus * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    return sync_ctx(c);
+}
+
 int hmme_refine_frame_async(hmme_ctx* c, const hmme_plane* cur, const hmme_plane* ref, int njobs, const int32_t* predsQpel, int useHad) {
     if (!c) return HMME_ERR_ARG;
     if (njobs <= 0 || njobs != c->lastSearchJobs)

@@ -404,4 +404,156 @@ __global__ void me_frac_build_kernel(const int4* jobs, const int32_t* X, const i
     slots[n] = slot;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// Distortion of the motion-compensated uni-prediction of a PU at a given QUARTER-PEL MV: the arithmetic
+// of TEncSearch::xGetTemplateCost (TEncSearch.cpp:3634-3674: xPredInterBlk + SAD, the AMVP candidate check) and of the uni-directional
+// candidates of xMergeEstimation / xGetInterPredictionError (:2814-2836, Hadamard).  Same interpolation and distortion code as the
+// refinement above with a single candidate, so one warp works on four 8x8 tiles at a time: lane = (tile, column) in the V step and
+// (tile, coefficient row) in the Hadamard pass.
+struct McPu { int x, y, w, h, mvqx, mvqy; };               // == hmme_mc_pu
+
+struct McParams {
+    const void* cur; const uint8_t* ref;
+    long long curPitch, refPitch;
+    int curBytes;
+    const McPu* pus;
+    int npus;
+    int useHad;
+    uint32_t* out;
+};
+
+struct __align__(16) McScratch {
+    uint32_t ref[4][16][4];
+    int16_t cur[4][8][8];
+    int16_t h[4][8][24];
+    int16_t t[4][72];
+};
+
+template <int MODE>
+__device__ __forceinline__ uint32_t mc_cost_pu(const McParams& p, const McPu& P, McScratch& S, const int lane) {
+    const int fx = P.mvqx & 3, fy = P.mvqy & 3;
+    const uint32_t cLo = kLumaPack[fx][0], cHi = kLumaPack[fx][1], vLo = kLumaPack[fy][0], vHi = kLumaPack[fy][1];
+    // patch origin: the integer part of the MV is folded in, so taps of output 0 always start at patch index 1
+    const uint8_t* refPu = p.ref + (long long)(P.y + (P.mvqy >> 2) - 4) * p.refPitch + (P.x + (P.mvqx >> 2) - 4);
+    const int ntxT = (P.w + 7) >> 3, nT = ntxT * ((P.h + 7) >> 3);
+    const int rcp = (65536 + ntxT - 1) / ntxT;
+    const int rowL = lane >> 1, halfL = lane & 1, curR = lane >> 2, curC = (lane & 3) * 2;
+    uint32_t acc = 0;
+    for (int g = 0; g < nT; g += 4) {
+#pragma unroll
+        for (int s4 = 0; s4 < 4; ++s4) {                      // patches and current tiles of up to four tiles
+            const int t = g + s4;
+            uint32_t w0 = 0, w1 = 0; int c0 = 0, c1 = 0;
+            if (t < nT) {
+                const int ty = ((t * rcp) >> 16) * 8, tx = t * 8 - ty * ntxT;
+                const int tw = min(8, P.w - tx), th = min(8, P.h - ty);
+                const uint8_t* q = refPu + (long long)(ty + rowL) * p.refPitch + tx + halfL * 8;
+                w0 = q[0] | (q[1] << 8) | (q[2] << 16) | ((uint32_t)q[3] << 24);
+                w1 = q[4] | (q[5] << 8) | (q[6] << 16) | ((uint32_t)q[7] << 24);
+                if (curR < th) {
+                    const long long o = (long long)(P.y + ty + curR) * p.curPitch + P.x + tx + curC;
+                    if (curC < tw) c0 = p.curBytes == 1 ? (int)static_cast<const uint8_t*>(p.cur)[o] : (int)static_cast<const int16_t*>(p.cur)[o];
+                    if (curC + 1 < tw) c1 = p.curBytes == 1 ? (int)static_cast<const uint8_t*>(p.cur)[o + 1] : (int)static_cast<const int16_t*>(p.cur)[o + 1];
+                }
+            }
+            *reinterpret_cast<uint2*>(&S.ref[s4][rowL][halfL * 2]) = make_uint2(w0, w1);
+            S.cur[s4][curC][curR] = (int16_t)c0;
+            S.cur[s4][curC + 1][curR] = (int16_t)c1;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int s4 = 0; s4 < 4; ++s4) {                      // H step, one plane per tile
+            const uint32_t W0 = S.ref[s4][rowL][halfL], W1 = S.ref[s4][rowL][halfL + 1], W2 = S.ref[s4][rowL][halfL + 2];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int o8 = 8 * (j + 1);
+                const int out = dp4a_us(__funnelshift_rc(W1, W2, o8), cHi, dp4a_us(__funnelshift_rc(W0, W1, o8), cLo, 0));
+                S.h[s4][halfL * 4 + j][rowL] = (int16_t)out;
+            }
+        }
+        __syncwarp();
+        {   // V step: lane = (tile, column)
+            const int s4 = lane >> 3, c = lane & 7;
+            const int t = g + s4;
+            const int ty = ((t * rcp) >> 16) * 8, tx = t * 8 - ty * ntxT;
+            const int tw = min(8, P.w - tx), th = min(8, P.h - ty);
+            const uint4 ha = *reinterpret_cast<const uint4*>(&S.h[s4][c][0]), hb = *reinterpret_cast<const uint4*>(&S.h[s4][c][8]);
+            const uint32_t wv[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
+            const uint4 cc = *reinterpret_cast<const uint4*>(&S.cur[s4][c][0]);
+            const uint32_t wc[4] = {cc.x, cc.y, cc.z, cc.w};
+            int d[8];
+            if (fy == 0) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    d[2 * q] = __vimin_s32_relu(((int)(int16_t)(wv[q + 2] & 0xFFFFu) + 32) >> 6, 255);
+                    d[2 * q + 1] = __vimin_s32_relu((((int)wv[q + 2] >> 16) + 32) >> 6, 255);
+                }
+            } else frac_vfilter<1, 8>(wv, vLo, vHi, d);
+            const bool inside = t < nT && c < tw;              // columns right of a 4-wide tile and tiles past the last one contribute nothing
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int cu0 = (int)(int16_t)(wc[q] & 0xFFFFu), cu1 = (int)wc[q] >> 16;
+                d[2 * q] = inside ? cu0 - d[2 * q] : 0;
+                d[2 * q + 1] = inside ? cu1 - d[2 * q + 1] : 0;
+            }
+            if (MODE != kFracHad8 && th < 8) { d[4] = 0; d[5] = 0; d[6] = 0; d[7] = 0; }
+            if (MODE == kFracSad) {
+                uint32_t sm = 0;
+#pragma unroll
+                for (int r = 0; r < 8; ++r) sm = __sad(d[r], 0, sm);
+                acc += sm;                                       // summed over all lanes at the end
+            } else {
+                if (MODE == kFracHad8) hadamard_inplace<8>(d);
+                else { hadamard_inplace<4>(d); hadamard_inplace<4>(d + 4); }
+                uint4 pk;
+                pk.x = __byte_perm(d[0], d[1], 0x5410); pk.y = __byte_perm(d[2], d[3], 0x5410);
+                pk.z = __byte_perm(d[4], d[5], 0x5410); pk.w = __byte_perm(d[6], d[7], 0x5410);
+                *reinterpret_cast<uint4*>(&S.t[s4][c * 8]) = pk;
+            }
+        }
+        if (MODE != kFracSad) {
+            __syncwarp();
+            const int s4 = lane >> 3, i = lane & 7;
+            int e[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) e[c] = (int)S.t[s4][c * 8 + i];
+            if (MODE == kFracHad8) {
+                hadamard_inplace<8>(e);
+                uint32_t sm = 0;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) sm = __sad(e[c], 0, sm);
+                sm += __shfl_xor_sync(0xFFFFFFFFu, sm, 1); sm += __shfl_xor_sync(0xFFFFFFFFu, sm, 2); sm += __shfl_xor_sync(0xFFFFFFFFu, sm, 4);
+                if (i == 0) acc += (sm + 2) >> 2;
+            } else {
+                hadamard_inplace<4>(e); hadamard_inplace<4>(e + 4);
+                uint32_t sa = 0, sb = 0;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) { sa = __sad(e[c], 0, sa); sb = __sad(e[c + 4], 0, sb); }
+                sa += __shfl_xor_sync(0xFFFFFFFFu, sa, 1); sa += __shfl_xor_sync(0xFFFFFFFFu, sa, 2);
+                sb += __shfl_xor_sync(0xFFFFFFFFu, sb, 1); sb += __shfl_xor_sync(0xFFFFFFFFu, sb, 2);
+                if ((i & 3) == 0) acc += ((sa + 1) >> 1) + ((sb + 1) >> 1);
+            }
+        }
+        __syncwarp();
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);
+    return acc;
+}
+
+__global__ void __launch_bounds__(kFracThreads) me_mc_cost_kernel(const McParams p) {
+    __shared__ McScratch scratch[kFracWarps];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    McScratch& S = scratch[warp];
+    const int stride = (int)gridDim.x * kFracWarps;
+    for (int n = (int)blockIdx.x * kFracWarps + warp; n < p.npus; n += stride) {
+        const McPu P = p.pus[n];
+        uint32_t d;
+        if (!p.useHad) d = mc_cost_pu<kFracSad>(p, P, S, lane);
+        else if (((P.w | P.h) & 7) == 0) d = mc_cost_pu<kFracHad8>(p, P, S, lane);
+        else d = mc_cost_pu<kFracHad4>(p, P, S, lane);
+        if (lane == 0) p.out[n] = d;
+    }
+}
+
 }  // namespace hmme

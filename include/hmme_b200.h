@@ -137,7 +137,17 @@ int hmme_refine_frame(hmme_ctx* ctx, const hmme_plane* cur, const hmme_plane* re
 int hmme_refine_frame_async(hmme_ctx* ctx, const hmme_plane* cur, const hmme_plane* ref, int njobs, const int32_t* predsQpel,
                             int useHad);
 int hmme_fetch_frac_async(hmme_ctx* ctx, int njobs, hmme_frac_result* results);
-int hmme_last_frac_ms(hmme_ctx* ctx, float* refineKernelMs);
+int hmme_last_frac_ms(hmme_ctx* ctx, float* refineKernelMs);   /* most recent refinement or hmme_mc_cost kernel */
+
+/* ---- distortion of the motion-compensated uni-prediction of PUs at given QUARTER-PEL MVs: the
+ * arithmetic inside TEncSearch::xGetTemplateCost (TEncSearch.cpp:3634-3674: xPredInterBlk + SAD of each AMVP candidate; the
+ * floating-point calcRdCost on top stays with the caller) and of the uni-directional candidates of xMergeEstimation /
+ * xGetInterPredictionError (:2814-2836, Hadamard when HadamardME).  The MV must already be clipped (TComDataCU::clipMv).
+ * dist[i] = SAD (useHad = 0) or Hadamard SATD (xGetHADs) between the current block and the prediction.  Same plane rules as
+ * hmme_refine_frac, around the integer part of the MV.  Synchronous. */
+typedef struct { int32_t x, y, w, h, mvQpelX, mvQpelY; } hmme_mc_pu;
+int hmme_mc_cost(hmme_ctx* ctx, const hmme_plane* cur, const hmme_plane* ref, const hmme_mc_pu* pus, int npus, int useHad,
+                 uint32_t* dist);
 
 /* ---- measurement hooks (bench.py / profiles): CUDA-event time of the dominant kernel of the most recent
  * search call on this context's stream, kernel launches issued so far, and the integer-ALU issue-rate

@@ -134,3 +134,19 @@ int hmme_oracle_refine_frac(const int16_t* curOrigin, int curStride, const int16
     }
     return 0;
 }
+
+/* Distortion of the motion-compensated uni-prediction at a quarter-pel MV:
+ * TEncSearch::xGetTemplateCost (TEncSearch.cpp:3634-3674) = xPredInterBlk (TComPrediction.cpp, uni-directional: the same two-pass
+ * 8-tap interpolation with final rounding) + TComRdCost::getDistPart(DF_SAD) (TComRdCost.cpp:433-455); with useHad the distortion
+ * of xGetInterPredictionError (TEncSearch.cpp:2814-2836).  The MV is taken as given (the caller has applied clipMv). */
+int hmme_oracle_mc_cost(const int16_t* curOrigin, int curStride, const int16_t* refOrigin, int refStride,
+                        const hmme_oracle_mc_pu* pus, int npus, int useHad, uint32_t* dist) {
+    for (int n = 0; n < npus; ++n) {
+        const hmme_oracle_mc_pu* P = &pus[n];
+        if (P->w <= 0 || P->h <= 0 || P->w > 64 || P->h > 64 || (P->w & 3) || (P->h & 3)) return -1;
+        int16_t pred[64 * 64];
+        predict(refOrigin + (long)P->y * refStride + P->x, refStride, P->mvqx, P->mvqy, P->w, P->h, pred);
+        dist[n] = distortion(curOrigin + (long)P->y * curStride + P->x, curStride, pred, P->w, P->h, useHad);
+    }
+    return 0;
+}

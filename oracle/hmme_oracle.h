@@ -89,6 +89,12 @@ int hmme_oracle_refine_frac(const int16_t* curOrigin, int curStride, const int16
                             int32_t* mvq, int32_t* half, int32_t* qter, uint32_t* cost, uint32_t* dist,
                             uint32_t* cand /* optional [npus][18]: cost of each half- then quarter-pel candidate */);
 
+/* Distortion (SAD, or Hadamard SATD with useHad) between the current block and the motion-compensated uni-prediction at a
+ * QUARTER-PEL MV: the arithmetic of xGetTemplateCost / the uni-directional merge candidates (hmme_frac_oracle.c has the citations). */
+typedef struct { int32_t x, y, w, h, mvqx, mvqy; } hmme_oracle_mc_pu;
+int hmme_oracle_mc_cost(const int16_t* curOrigin, int curStride, const int16_t* refOrigin, int refStride,
+                        const hmme_oracle_mc_pu* pus, int npus, int useHad, uint32_t* dist);
+
 #ifdef __cplusplus
 }
 #endif

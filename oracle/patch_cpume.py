@@ -85,6 +85,30 @@ once("""  ruiCost = xPatternRefinement( pcPatternKey, baseRefMv, 1, rcMvQter, !b
     }
   }
 }""")
+# optional binary log of AMVP template costs (golden records for the motion-compensated-cost oracle, SURVEY row f3): block, reference
+# patch around the integer part of the clipped candidate MV, the MV, and the SAD xGetTemplateCost computed before its rate term
+once("""  uiCost = m_pcRdCost->getDistPart( pcCU->getSlice()->getSPS()->getBitDepth(CHANNEL_TYPE_LUMA), pcTemplateCand->getAddr(COMPONENT_Y, uiPartAddr), pcTemplateCand->getStride(COMPONENT_Y), pcOrgYuv->getAddr(COMPONENT_Y, uiPartAddr), pcOrgYuv->getStride(COMPONENT_Y), iSizeX, iSizeY, COMPONENT_Y, DF_SAD );
+""", """  uiCost = m_pcRdCost->getDistPart( pcCU->getSlice()->getSPS()->getBitDepth(CHANNEL_TYPE_LUMA), pcTemplateCand->getAddr(COMPONENT_Y, uiPartAddr), pcTemplateCand->getStride(COMPONENT_Y), pcOrgYuv->getAddr(COMPONENT_Y, uiPartAddr), pcOrgYuv->getStride(COMPONENT_Y), iSizeX, iSizeY, COMPONENT_Y, DF_SAD );
+  if (const char* logName_ = getenv("HMME_LOG_MC"))
+  {
+    static FILE* f_ = fopen(logName_, "wb");
+    static std::map<int, int> seen_;
+    static const int cap_ = getenv("HMME_LOG_FRAC_CAP") ? atoi(getenv("HMME_LOG_FRAC_CAP")) : 8;
+    static const int stride_ = getenv("HMME_LOG_FRAC_STRIDE") ? atoi(getenv("HMME_LOG_FRAC_STRIDE")) : 29;
+    const int n_ = seen_[(iSizeX * 100 + iSizeY) * 16 + (cMvCand.getHor() & 3) * 4 + (cMvCand.getVer() & 3)]++;
+    if (f_ && !(pcCU->getSlice()->testWeightPred() && pcCU->getSlice()->getSliceType()==P_SLICE) && n_ % stride_ == 0 && n_ / stride_ < cap_)
+    {
+      const int hdr_[8] = { 0x4d434f53, iSizeX, iSizeY, cMvCand.getHor(), cMvCand.getVer(), (int)uiCost, 0, 0 };
+      fwrite(hdr_, sizeof(int), 8, f_);
+      Pel* org_ = pcOrgYuv->getAddr(COMPONENT_Y, uiPartAddr);
+      for (int r_ = 0; r_ < iSizeY; ++r_) fwrite(org_ + r_ * pcOrgYuv->getStride(COMPONENT_Y), sizeof(Pel), iSizeX, f_);
+      const Int rs_ = pcPicYuvRef->getStride(COMPONENT_Y);
+      Pel* ref_ = pcPicYuvRef->getAddr(COMPONENT_Y, pcCU->getCtuRsAddr(), pcCU->getZorderIdxInCtu() + uiPartAddr) + (cMvCand.getVer() >> 2) * rs_ + (cMvCand.getHor() >> 2);
+      for (int r_ = -4; r_ < iSizeY + 4; ++r_) fwrite(ref_ + r_ * rs_ - 4, sizeof(Pel), iSizeX + 8, f_);
+      fflush(f_);
+    }
+  }
+""")
 open(path, "w").write(s)
 # the log reads the predictor and lambda straight from TComRdCost: open its first private section in the scratch copy
 import os

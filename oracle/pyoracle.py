@@ -43,6 +43,8 @@ class Oracle:
         L.hmme_oracle_search_frame.restype = C.c_int
         L.hmme_oracle_search_frame.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int,
                                                C.c_uint32, C.c_int] + [C.c_void_p] * 4
+        L.hmme_oracle_mc_cost.restype = C.c_int
+        L.hmme_oracle_mc_cost.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.hmme_oracle_refine_frac.restype = C.c_int
         L.hmme_oracle_refine_frac.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_uint32,
                                               C.c_int] + [C.c_void_p] * 6
@@ -108,6 +110,19 @@ class Oracle:
         rc = self.lib.hmme_oracle_refine_frac(cur_plane.ctypes.data + co, cs, ref_plane.ctypes.data + ro, rs, pus.ctypes.data, n,
                                               C.c_uint32(lam), int(bool(use_had)), out["mvq"].ctypes.data, out["half"].ctypes.data,
                                               out["qter"].ctypes.data, out["cost"].ctypes.data, out["dist"].ctypes.data, out["cand"].ctypes.data)
+        assert rc == 0
+        return out
+
+
+    def mc_cost(self, cur_plane, cur_origin, ref_plane, ref_origin, pus, use_had=False):
+        """Distortion of the motion-compensated uni-prediction; pus (n,6) int32 rows {x, y, w, h, mvx, mvy (quarter pel)}."""
+        pus = np.ascontiguousarray(pus, np.int32).reshape(-1, 6)
+        assert cur_plane.dtype == np.int16 and ref_plane.dtype == np.int16 and cur_plane.flags.c_contiguous and ref_plane.flags.c_contiguous
+        out = np.zeros(pus.shape[0], np.uint32)
+        cs, rs = cur_plane.shape[1], ref_plane.shape[1]
+        rc = self.lib.hmme_oracle_mc_cost(cur_plane.ctypes.data + int((cur_origin[1] * cs + cur_origin[0]) * 2), cs,
+                                          ref_plane.ctypes.data + int((ref_origin[1] * rs + ref_origin[0]) * 2), rs,
+                                          pus.ctypes.data, pus.shape[0], int(bool(use_had)), out.ctypes.data)
         assert rc == 0
         return out
 

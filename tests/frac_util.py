@@ -46,3 +46,35 @@ def pack_atlas(recs, cell=80, per_row=8, margin=16):
         ref[margin + y - 4:margin + y + h + 4, margin + x - 4:margin + x + w + 4] = r["patch"]
         pus[k] = [x, y, w, h, 0, 0, r["predx"] - 4 * r["mvx"], r["predy"] - 4 * r["mvy"]]
     return cur, ref, (margin, margin), pus
+
+
+def load_mc_records():
+    """Records logged from the reference's xGetTemplateCost (tests/golden/mc_records.npz, oracle/gen_mc_golden.py)."""
+    d = np.load(os.path.join(ROOT, "tests", "golden", "mc_records.npz"))
+    hdr, cur, patch = d["hdr"], d["cur"], d["patch"]
+    out, pc, pp = [], 0, 0
+    for i in range(hdr.shape[0]):
+        w, h = int(hdr[i, 1]), int(hdr[i, 2])
+        out.append(dict(w=w, h=h, mvx=int(hdr[i, 3]), mvy=int(hdr[i, 4]), sad=int(np.uint32(hdr[i, 5])),
+                        cur=cur[pc:pc + w * h].reshape(h, w), patch=patch[pp:pp + (w + 8) * (h + 8)].reshape(h + 8, w + 8)))
+        pc += w * h
+        pp += (w + 8) * (h + 8)
+    return out
+
+
+def pack_mc_atlas(recs, cell=80, per_row=8, margin=16):
+    """Like pack_atlas: record k in its own cell; the patch is pasted at the PU position, so the PU carries only the fractional
+    part of the logged MV (its integer part is already folded into where the patch was cut)."""
+    n = len(recs)
+    rows = (n + per_row - 1) // per_row
+    W, H = per_row * cell, rows * cell
+    cur = np.zeros((H + 2 * margin, W + 2 * margin), np.int16)
+    ref = np.zeros_like(cur)
+    pus = np.zeros((n, 6), np.int32)
+    for k, r in enumerate(recs):
+        x, y = (k % per_row) * cell + 8, (k // per_row) * cell + 8
+        w, h = r["w"], r["h"]
+        cur[margin + y:margin + y + h, margin + x:margin + x + w] = r["cur"]
+        ref[margin + y - 4:margin + y + h + 4, margin + x - 4:margin + x + w + 4] = r["patch"]
+        pus[k] = [x, y, w, h, r["mvx"] & 3, r["mvy"] & 3]
+    return cur, ref, (margin, margin), pus

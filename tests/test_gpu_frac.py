@@ -218,3 +218,43 @@ def test_virtual_bands_refine_equal_whole_frame(me, world):
     for k in ("mvx", "mvy", "cost", "dist"):
         assert np.array_equal(got[k], whole[k]), (world, k)
     pc.free(); pr.free()
+
+
+def test_mc_cost_reference_records(me):
+    """hmme_mc_cost against the SADs the reference encoder's xGetTemplateCost computed (row f3)."""
+    from frac_util import load_mc_records, pack_mc_atlas
+    recs = load_mc_records()
+    cur, ref, (M, _), pus = pack_mc_atlas(recs)
+    H, W = cur.shape[0] - 2 * M, cur.shape[1] - 2 * M
+    pc, pr = planes(me, cur.astype(np.uint8), ref.astype(np.uint8), W, H, M)
+    got = me.mc_cost(pc, pr, pus, False)
+    assert np.array_equal(got, np.array([r["sad"] for r in recs], np.uint32)), np.argwhere(got != np.array([r["sad"] for r in recs]))[:5]
+    pc.free(); pr.free()
+
+
+@pytest.mark.parametrize("had,cur16", [(0, 0), (1, 0), (1, 1), (0, 1)])
+def test_mc_cost_random_vs_oracle(me, oracle, had, cur16):
+    """Every PU size, random quarter-pel MVs (all phases, both signs), SAD and Hadamard, 8-bit and 16-bit current planes."""
+    rng = np.random.default_rng(300 + 2 * had + cur16)
+    W, H, M = 384, 256, 32
+    f = luma_frames(W + 2 * M, H + 2 * M, 2, seed=int(rng.integers(1 << 30)))
+    ref = np.ascontiguousarray(f[0].astype(np.int16))
+    cur = np.ascontiguousarray(f[1].astype(np.int16))
+    if cur16:
+        cur = np.ascontiguousarray((2 * cur - rng.integers(0, 256, cur.shape)).astype(np.int16))
+    pus = []
+    for _ in range(12):
+        for (w, h) in SIZES + [(20, 28), (4, 4), (60, 4), (64, 12), (40, 40)]:
+            x, y = int(rng.integers(0, W - w)), int(rng.integers(0, H - h))
+            ix = int(rng.integers(max(-M + 4 - x, -20), min(W + M - 12 - ((w + 7) & ~7) - x, 20)))
+            iy = int(rng.integers(max(-M + 4 - y, -20), min(H + M - 12 - ((h + 7) & ~7) - y, 20)))
+            pus.append([x, y, w, h, 4 * ix + int(rng.integers(0, 4)), 4 * iy + int(rng.integers(0, 4))])
+    pus = np.array(pus, np.int32)
+    pc, pr = planes(me, cur.astype(np.uint8) if not cur16 else cur, ref.astype(np.uint8), W, H, M)
+    got = me.mc_cost(pc, pr, pus, bool(had))
+    want = oracle.mc_cost(cur, (M, M), ref, (M, M), pus, bool(had))
+    assert np.array_equal(got, want), (had, cur16, np.argwhere(got != want)[:5].tolist())
+    with pytest.raises(hm.HmmeError) as e:
+        me.mc_cost(pc, pr, np.array([[0, 0, 8, 8, -4 * (M + 1), 0]], np.int32))
+    assert e.value.code == -6
+    pc.free(); pr.free()
