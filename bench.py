@@ -504,6 +504,28 @@ def main():
                 "timer": "kernel_ms: CUDA events around me_frac_kernel on its stream; search_plus_refine: CUDA events around K frames on one context/stream, "
                          "resident inputs; e2e: host wall clock, uploads + search + refine + all result arrays fetched, two contexts"}
 
+    # ------------------------------------------------------------------ row f3: motion-compensated distortion at quarter-pel MVs
+    mc = None
+    if world == 1 and njobs and not args.virtual_world:
+        rng = np.random.default_rng(7)
+        rects = me.lib.partition_table()
+        mpus = np.zeros((njobs, NPARTS, 6), np.int32)
+        mpus[:, :, 0] = jobs[:, None, 0] + rects[None, :, 0]
+        mpus[:, :, 1] = jobs[:, None, 1] + rects[None, :, 1]
+        mpus[:, :, 2], mpus[:, :, 3] = rects[None, :, 2], rects[None, :, 3]
+        mpus[:, :, 4:6] = rng.integers(-4 * (R - 8), 4 * (R - 8), size=(njobs, NPARTS, 2))     # any quarter-pel MV inside the search range
+        km = {}
+        for name, had in (("sad", False), ("hadamard", True)):
+            t = []
+            for s in range(4):
+                me.mc_cost(sets[s % nsets][0], sets[s % nsets][1], mpus.reshape(-1, 6), had)
+                t.append(me.last_frac_ms())
+            km[name] = float(np.mean(t[1:]))
+        mc = {"scope": "distortion of the motion-compensated uni-prediction (8-tap interpolation at a quarter-pel MV) of all 593 partitions of every CTU: "
+                       "the arithmetic of xGetTemplateCost (SAD) / uni-directional merge candidates (Hadamard)",
+              "kernel": "me_mc_cost_kernel", "pus": njobs * NPARTS, "kernel_ms_sad": km["sad"], "kernel_ms_hadamard": km["hadamard"],
+              "pu_pixels_per_s_sad": njobs * 24 * 4096 / (km["sad"] * 1e-3), "timer": "CUDA events around the kernel on its stream, resident planes"}
+
     if rank == 0:
         total_cands = total_jobs * cands_per_job
         ms_per_step = total_ms / args.steps
@@ -549,6 +571,8 @@ def main():
         }
         if frac:
             out["frac_refine"] = frac
+        if mc:
+            out["mc_cost"] = mc
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"], _ = cpu_baseline_entry(R, 30.0)
             if frac and os.path.exists(CPUME_BIN):
