@@ -22,6 +22,7 @@ EXPORTS = [
     "hmme_search_frame", "hmme_search_frame_async", "hmme_fetch_results", "hmme_sync",
     "hmme_plane_upload_s16_async", "hmme_fetch_results_async",
     "hmme_refine_pu", "hmme_refine_frac", "hmme_refine_frame", "hmme_refine_frame_async", "hmme_fetch_frac_async", "hmme_last_frac_ms", "hmme_mc_cost",
+    "hmme_graph_begin", "hmme_graph_end", "hmme_graph_launch", "hmme_graph_destroy",
     "hmme_last_kernel_ms", "hmme_kernel_launches", "hmme_measure_int_alu_peak", "hmme_partition_rect", "hmme_index_block", "hmme_search_window", "hmme_version",
 ]
 
@@ -87,6 +88,10 @@ class HmmeLib:
             "hmme_refine_frame_async": (i32, [vp, P(PlaneDesc), P(PlaneDesc), i32, vp, i32]),
             "hmme_fetch_frac_async": (i32, [vp, i32, vp]),
             "hmme_last_frac_ms": (i32, [vp, P(C.c_float)]),
+            "hmme_graph_begin": (i32, [vp]),
+            "hmme_graph_end": (i32, [vp, P(vp)]),
+            "hmme_graph_launch": (i32, [vp, vp]),
+            "hmme_graph_destroy": (None, [vp]),
             "hmme_mc_cost": (i32, [vp, P(PlaneDesc), P(PlaneDesc), vp, i32, i32, vp]),
             "hmme_last_kernel_ms": (i32, [vp, P(C.c_float)]),
             "hmme_kernel_launches": (C.c_uint64, [vp]),
@@ -257,6 +262,21 @@ class MotionEstimator:
 
     def sync(self):
         self._chk(self.lib.L.hmme_sync(self.h))
+
+    # -- CUDA graphs: record the asynchronous calls of a step once, replay them with one call
+    def graph_begin(self):
+        self._chk(self.lib.L.hmme_graph_begin(self.h))
+
+    def graph_end(self):
+        g = C.c_void_p()
+        self._chk(self.lib.L.hmme_graph_end(self.h, C.byref(g)))
+        return g
+
+    def graph_launch(self, g):
+        self._chk(self.lib.L.hmme_graph_launch(self.h, g))
+
+    def graph_destroy(self, g):
+        self.lib.L.hmme_graph_destroy(g)
 
     # -- fractional-pel refinement (TEncSearch::xPatternSearchFracDIF, TEncSearch.cpp:4294-4331)
     FRAC_DTYPE = np.dtype([("mvx", np.int32), ("mvy", np.int32), ("cost", np.uint32), ("dist", np.uint32)])

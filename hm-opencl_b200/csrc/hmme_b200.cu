@@ -118,8 +118,16 @@ struct hmme_ctx {
     int tilesPerCtu = 0;          // 8x8 tiles of all 593 partitions (1792)
     int2* dPreds = nullptr; size_t predCap = 0;
     cudaEvent_t evF0 = nullptr, evF1 = nullptr; bool evFracValid = false;
+    bool capturing = false;       // between hmme_graph_begin and hmme_graph_end: the asynchronous calls are recorded, not run
+    cudaEvent_t evFork = nullptr, evJoin[2] = {nullptr, nullptr};
     int lastSearchJobs = 0;       // job count of the most recent frame search (its winners feed hmme_refine_frame)
     int lastBox[4] = {0, 0, 0, 0};   // picture-coordinate bounding box [x0, y0, x1, y1) of every sample that search could point a PU at
+};
+
+struct hmme_graph {
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    hmme_ctx* owner = nullptr;
 };
 
 namespace {
@@ -433,6 +441,8 @@ void hmme_destroy(hmme_ctx* c) {
     cudaFreeHost(c->hWin); cudaFree(c->dWin); cudaFreeHost(c->hCurBlk); cudaFree(c->dCurBlk);
     cudaFree(c->dStage[0]); cudaFree(c->dStage[1]); cudaFree(c->dFlag); cudaFreeHost(c->hFlag);
     cudaFree(c->dPus); cudaFree(c->dSlots); cudaFree(c->dFrac); cudaFree(c->dCand); cudaFree(c->dOrder); cudaFree(c->dPreds);
+    if (c->evFork) cudaEventDestroy(c->evFork);
+    for (int k = 0; k < 2; ++k) if (c->evJoin[k]) cudaEventDestroy(c->evJoin[k]);
     if (c->evF0) cudaEventDestroy(c->evF0);
     if (c->evF1) cudaEventDestroy(c->evF1);
     for (int k = 0; k < 2; ++k) {
@@ -554,7 +564,7 @@ int hmme_plane_upload_s16_async(hmme_ctx* c, const hmme_plane* p, const int16_t*
     // the tiny narrowing kernels are scheduled as soon as an SM frees a slot, even while another context's search kernel
     // fills the device.  Searches already enqueued on this context may still read the plane: wait for them first; the
     // next search waits for this upload.
-    CU_TRY(c, cudaStreamWaitEvent(io, c->evSearch, 0));
+    if (!c->capturing) CU_TRY(c, cudaStreamWaitEvent(io, c->evSearch, 0));   // inside a graph the whole previous launch has completed (stream order)
     if (p->pitch != cols) CU_TRY(c, cudaMemsetAsync(c->dStage[sb], 0, n * 2, io));   // pitch padding columns must read as in-range samples
     CU_TRY(c, copy_rows_h2d(c->dStage[sb], (size_t)p->pitch * 2, src, (size_t)hostStride * 2, (size_t)cols * 2, rows, io));
     me_narrow_kernel<<<(unsigned)((n / 8 + 255) / 256 + 1), 256, 0, io>>>(c->dStage[sb], static_cast<uint8_t*>(p->base), n, c->dFlag);
@@ -596,7 +606,11 @@ int hmme_search_frame_async(hmme_ctx* c, const hmme_plane* cur, const hmme_plane
     if (rc != HMME_OK) return rc;
     // straight from the caller's (pageable) array: the runtime stages it before returning, and stream order protects dJobs,
     // so consecutive frames can be enqueued without a host synchronisation in between
-    CU_TRY(c, cudaMemcpyAsync(c->dJobs, jobs, (size_t)njobs * sizeof(hmme_job), cudaMemcpyHostToDevice, c->stream));
+    if (c->capturing) {                                     // a graph replays the copy: it has to read page-locked memory the library owns
+        std::memcpy(c->hJobs, jobs, (size_t)njobs * sizeof(hmme_job));
+        CU_TRY(c, cudaMemcpyAsync(c->dJobs, c->hJobs, (size_t)njobs * sizeof(hmme_job), cudaMemcpyHostToDevice, c->stream));
+    } else
+        CU_TRY(c, cudaMemcpyAsync(c->dJobs, jobs, (size_t)njobs * sizeof(hmme_job), cudaMemcpyHostToDevice, c->stream));
     c->lastSearchJobs = njobs;
     c->lastBox[0] = c->lastBox[1] = INT32_MAX; c->lastBox[2] = c->lastBox[3] = INT32_MIN;
     for (int j = 0; j < njobs; ++j) {
@@ -793,6 +807,71 @@ int hmme_last_frac_ms(hmme_ctx* c, float* ms) {
     CU_TRY(c, cudaEventSynchronize(c->evF1));
     CU_TRY(c, cudaEventElapsedTime(ms, c->evF0, c->evF1));
     return HMME_OK;
+}
+
+// ---- CUDA graphs: a launch-bound step (narrow bands on many GPUs: ~25 runtime calls for 0.16 ms of kernels) recorded once, replayed
+// with one call.  Between begin and end the asynchronous calls of this context are captured instead of executed; their host
+// buffers must be page-locked and stay where they are, device buffers must already have their final size (run the step once first).
+int hmme_graph_begin(hmme_ctx* c) {
+    if (!c) return HMME_ERR_ARG;
+    if (c->capturing) return fail(c, HMME_ERR_ARG, "hmme_graph_begin: already capturing");
+    CU_TRY(c, cudaSetDevice(c->device));
+    if (!c->evFork) {
+        CU_TRY(c, cudaEventCreateWithFlags(&c->evFork, cudaEventDisableTiming));
+        for (int k = 0; k < 2; ++k) CU_TRY(c, cudaEventCreateWithFlags(&c->evJoin[k], cudaEventDisableTiming));
+    }
+    int rc = sync_ctx(c);
+    if (rc != HMME_OK) return rc;
+    CU_TRY(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed));
+    c->capturing = true;
+    // the io streams join the capture by depending on the origin stream
+    CU_TRY(c, cudaEventRecord(c->evFork, c->stream));
+    for (int k = 0; k < 2; ++k) CU_TRY(c, cudaStreamWaitEvent(c->ioStream[k], c->evFork, 0));
+    return HMME_OK;
+}
+
+int hmme_graph_end(hmme_ctx* c, hmme_graph** out) {
+    if (!c || !out) return HMME_ERR_ARG;
+    *out = nullptr;
+    if (!c->capturing) return fail(c, HMME_ERR_ARG, "hmme_graph_end: not capturing");
+    c->capturing = false;
+    cudaGraph_t g = nullptr;
+    cudaError_t e = cudaSuccess;
+    for (int k = 0; k < 2 && e == cudaSuccess; ++k) {       // every forked stream has to flow back into the origin stream
+        e = cudaEventRecord(c->evJoin[k], c->ioStream[k]);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(c->stream, c->evJoin[k], 0);
+    }
+    const cudaError_t e2 = cudaStreamEndCapture(c->stream, &g);
+    if (e != cudaSuccess || e2 != cudaSuccess || !g) {
+        if (g) cudaGraphDestroy(g);
+        cudaGetLastError();
+        return fail(c, HMME_ERR_CUDA, std::string("graph capture failed: ") + cudaGetErrorString(e != cudaSuccess ? e : e2));
+    }
+    hmme_graph* h = new hmme_graph;
+    h->graph = g; h->owner = c;
+    e = cudaGraphInstantiate(&h->exec, g, 0);
+    if (e != cudaSuccess) { cudaGraphDestroy(g); delete h; return fail(c, HMME_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e)); }
+    *out = h;
+    return HMME_OK;
+}
+
+int hmme_graph_launch(hmme_ctx* c, hmme_graph* g) {
+    if (!c || !g || g->owner != c || !g->exec) return fail(c, HMME_ERR_ARG, "hmme_graph_launch: graph does not belong to this context");
+    if (c->capturing) return fail(c, HMME_ERR_ARG, "hmme_graph_launch: capturing");
+    CU_TRY(c, cudaSetDevice(c->device));
+    CU_TRY(c, cudaGraphLaunch(g->exec, c->stream));
+    CU_TRY(c, cudaEventRecord(c->evSearch, c->stream));     // later uploads outside graphs order themselves after this launch
+    c->contentCheckPending = true;
+    c->evValid = false; c->evFracValid = false;             // the timing events were recorded inside the graph: not readable
+    return HMME_OK;
+}
+
+void hmme_graph_destroy(hmme_graph* g) {
+    if (!g) return;
+    if (g->owner && g->owner->device >= 0) cudaSetDevice(g->owner->device);
+    if (g->exec) cudaGraphExecDestroy(g->exec);
+    if (g->graph) cudaGraphDestroy(g->graph);
+    delete g;
 }
 
 int hmme_sync(hmme_ctx* c) {

@@ -107,6 +107,18 @@ int hmme_plane_upload_s16_async(hmme_ctx* ctx, const hmme_plane* plane, const in
 int hmme_fetch_results_async(hmme_ctx* ctx, int njobs, int32_t* X, int32_t* Y, uint32_t* sad, uint32_t* cost);
 int hmme_sync(hmme_ctx* ctx);
 
+/* ---- CUDA graphs for launch-bound steps (many GPUs, narrow bands: tens of runtime calls for a fraction of a millisecond of
+ * kernels).  hmme_graph_begin .. hmme_graph_end records the asynchronous calls made on this context in between
+ * (hmme_plane_upload_s16_async, hmme_search_frame_async, hmme_fetch_results_async, hmme_refine_frame_async,
+ * hmme_fetch_frac_async) instead of running them; hmme_graph_launch replays them with one call on the context's stream.
+ * Host buffers must be page-locked and keep their addresses (their CONTENT is read / written at every launch); run the step
+ * once before capturing so that every device buffer has its final size.  Synchronous calls are not allowed while capturing. */
+typedef struct hmme_graph hmme_graph;
+int hmme_graph_begin(hmme_ctx* ctx);
+int hmme_graph_end(hmme_ctx* ctx, hmme_graph** out);
+int hmme_graph_launch(hmme_ctx* ctx, hmme_graph* graph);
+void hmme_graph_destroy(hmme_graph* graph);
+
 /* ---- fractional-pel refinement, the step right after the integer search:
  * TEncSearch::xPatternSearchFracDIF (TEncSearch.cpp:4294-4331) = half-pel then quarter-pel refinement (xPatternRefinement,
  * :816-872) over HEVC 8-tap interpolated samples (xExtDIFUpSamplingH/Q, :5386-5600; TComInterpolationFilter.cpp:155-250) with

@@ -336,3 +336,59 @@ def test_virtual_bands_equal_whole_frame(me, world):
         pb.free()
     assert_same(hm.merge_bands(parts), whole, f"world={world}")
     pc.free(); pr.free()
+
+
+def test_cuda_graph_replays_a_whole_step(me, oracle):
+    """hmme_graph_*: upload both planes, search, refine, fetch everything recorded once; every replay reads the CURRENT content of
+    the page-locked host buffers and must give what the ordinary calls give (here: what the oracle gives)."""
+    import torch
+    W, H, R, M = 256, 128, 16, 40
+    lam = 460000
+    me.set_lambda_q16(lam)
+    jobs = frame_jobs(W, H, R)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()   # noqa: E731
+    h_cur, h_ref = pin(np.zeros((H + 2 * M, W + 2 * M), np.int16)), pin(np.zeros((H + 2 * M, W + 2 * M), np.int16))
+    outs = [pin(np.zeros((len(jobs), 593), t)) for t in (np.int32, np.int32, np.uint32, np.uint32)]
+    fr = pin(np.zeros((len(jobs), 593, 4), np.int32))
+    pc, pr = me.alloc_plane(1, W, H, M, M), me.alloc_plane(1, W, H, M, M)
+
+    def step():
+        me.upload(pr, h_ref, asynchronous=True)
+        me.upload(pc, h_cur, asynchronous=True)
+        me.search_frame_async(pc, pr, jobs, R)
+        me.fetch_results(len(jobs), outs, asynchronous=True)
+        me.refine_frame(pc, pr, len(jobs), None, True, asynchronous=True, out=fr)
+
+    step(); me.sync()                                    # sizes every device buffer
+    me.graph_begin()
+    step()
+    g = me.graph_end()
+    launches0 = me.kernel_launches
+    for seed in (1, 2, 3):
+        f = luma_frames(W, H, 2, seed=seed)
+        h_cur[:] = pad_plane(f[1], M, M); h_ref[:] = pad_plane(f[0], M, M)
+        for o in outs:
+            o[:] = 0
+        fr[:] = 0
+        me.graph_launch(g)
+        me.sync()
+        want = oracle.search_frame(h_cur, (M, M), h_ref, (M, M), jobs, R, lam, nthreads=4)
+        assert_same(outs, want, f"graph replay {seed}")
+        rects = me.lib.partition_table()
+        pus = np.zeros((len(jobs), 593, 8), np.int32)
+        pus[:, :, 0] = jobs[:, None, 0] + rects[None, :, 0]
+        pus[:, :, 1] = jobs[:, None, 1] + rects[None, :, 1]
+        pus[:, :, 2], pus[:, :, 3] = rects[None, :, 2], rects[None, :, 3]
+        pus[:, :, 4], pus[:, :, 5] = want[0], want[1]
+        wf = oracle.refine_frac(h_cur, (M, M), h_ref, (M, M), pus.reshape(-1, 8), lam, True)
+        assert np.array_equal(fr[:, :, :2].reshape(-1, 2), wf["mvq"]) and np.array_equal(fr[:, :, 2].reshape(-1).view(np.uint32), wf["cost"])
+    assert me.kernel_launches == launches0               # replays are not counted as library launches made by the caller
+    h_ref[0, 0] = 300                                    # content errors of replayed uploads still surface at the next sync
+    me.graph_launch(g)
+    with pytest.raises(hm.HmmeError) as e:
+        me.sync()
+    assert e.value.code == -5
+    me.graph_destroy(g)
+    with pytest.raises(hm.HmmeError):                    # end without begin
+        me.graph_end()
+    pc.free(); pr.free()
