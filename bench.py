@@ -223,6 +223,9 @@ def main():
     ap.add_argument("--ref-dist", default="broadcast", choices=["allgather", "broadcast"],
                     help="N > 1: how the reference plane reaches every GPU: rank 0 uploads all of it and NCCL broadcasts (default), or each "
                          "rank uploads 1/N of it and NCCL all-gathers (faster when steps are serial, no gain once frames are pipelined)")
+    ap.add_argument("--graphs", action="store_true", help="e2e: replay CUDA graphs of the step (hmme_graph_*) instead of issuing it call by call; measured: "
+                                                          "same at N = 1 (1.269 ms), 0.187 vs 0.191 ms for an 8-GPU-sized band on one GPU, slower at N = 2 "
+                                                          "(0.74 vs 0.66 ms: the split around the NCCL broadcast loses overlap), hence off by default")
     ap.add_argument("--virtual-world", type=int, default=0, help="experiments: on ONE GPU, run only the band rank 0 would get in a world of this size")
     args = ap.parse_args()
     if args.impl == "reference":          # each step is seconds of single-threaded CPU encoders: keep the default run short
@@ -312,6 +315,43 @@ def main():
             if njobs:
                 self.me.search_frame_async(self.p_cur, self.p_ref, jobs, R)
                 self.me.fetch_results(njobs, self.outs, asynchronous=asynchronous)
+
+        def build_graphs(self):
+            """The pipelined e2e step recorded as CUDA graphs (hmme_graph_*): at N = 8 a step is ~25 runtime calls for 0.16 ms of
+            kernels.  One graph when the reference needs no collective, else {upload reference} -> NCCL -> {upload current, search, fetch}."""
+            self.g_ref = self.g_main = None
+            if world == 1:
+                self.me.graph_begin()
+                self.step_e2e(True)
+                self.g_main = self.me.graph_end()
+                return
+            uploads_ref = (self.p_ref_slice is not None) if args.ref_dist == "allgather" else rank == 0
+            if uploads_ref:
+                self.me.graph_begin()
+                if args.ref_dist == "allgather":
+                    self.me.upload(self.p_ref_slice, n_ref[s0:s1], origin_x=margin, origin_y=0, asynchronous=True)
+                else:
+                    self.me.upload(self.p_ref, n_ref, asynchronous=True)
+                self.g_ref = self.me.graph_end()
+            if band_h and njobs:
+                self.me.graph_begin()
+                self.me.upload(self.p_cur_band, n_cur_band, origin_x=margin, origin_y=0, asynchronous=True)
+                self.me.search_frame_async(self.p_cur, self.p_ref, jobs, R)
+                self.me.fetch_results(njobs, self.outs, asynchronous=True)
+                self.g_main = self.me.graph_end()
+
+        def step_e2e_graph(self):
+            if self.g_ref is not None:
+                self.me.graph_launch(self.g_ref)
+            if world > 1:
+                with torch.cuda.stream(self.ext):
+                    if args.ref_dist == "allgather":
+                        full = self.t_ref[:slice_rows * world * pitch]
+                        dist.all_gather_into_tensor(full, full[rank * slice_rows * pitch:(rank + 1) * slice_rows * pitch])
+                    else:
+                        dist.broadcast(self.t_ref, src=0)
+            if self.g_main is not None:
+                self.me.graph_launch(self.g_main)
 
         def step_e2e_frac(self):
             """Integer search + fractional refinement of all 593 partitions, host to host."""
@@ -420,11 +460,23 @@ def main():
         pipes[0].step_e2e(False)
     barrier()
     serial_ms = (time.perf_counter() - e0) * 1e3
+    use_graphs = args.graphs
+    if use_graphs:
+        for pp in pipes:
+            pp.me.sync()
+            pp.build_graphs()
+        for pp in pipes:                               # one replay each before the clock starts
+            pp.step_e2e_graph()
+            pp.me.sync()
+        barrier()
     e0 = time.perf_counter()
     for s in range(args.steps):
         pp = pipes[s & 1]
         pp.me.sync()                                   # this context's previous frame (two steps ago) is complete
-        pp.step_e2e(True)
+        if use_graphs:
+            pp.step_e2e_graph()
+        else:
+            pp.step_e2e(True)
     for pp in pipes:
         pp.me.sync()
     barrier()
@@ -557,7 +609,8 @@ def main():
                     "ms_per_step": e2e_ms / args.steps,
                     "serial_ms_per_step": serial_ms / args.steps, "serial_frames_per_s": 1e3 / (serial_ms / args.steps),
                     "timer": "host wall clock around K x {upload both int16 planes from pinned memory (+ NCCL broadcast), search, fetch four result arrays}, "
-                             "frames alternating over two contexts/streams so copies overlap kernels; serial_* = one context, each step waits for its results; max over ranks"},
+                             "frames alternating over two contexts/streams so copies overlap kernels" + ("; each context's step is recorded once as CUDA graph(s) and replayed (hmme_graph_*)" if use_graphs else "") +
+                             "; serial_* = one context, call by call, each step waits for its results; max over ranks"},
             "roofline": {"bound": "int_alu", "kernel": "me_u8_tile_kernel", "achieved": achieved / 1e12, "peak": peak["lane_ops_per_s"] / 1e12,
                          "unit": "T int-lane-op/s", "frac": achieved / peak["lane_ops_per_s"] if peak["lane_ops_per_s"] else None,
                          "traffic": _ncu_traffic(args.workload) if world == 1 else None,

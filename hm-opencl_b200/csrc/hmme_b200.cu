@@ -847,9 +847,30 @@ int hmme_graph_end(hmme_ctx* c, hmme_graph** out) {
         cudaGetLastError();
         return fail(c, HMME_ERR_CUDA, std::string("graph capture failed: ") + cudaGetErrorString(e != cudaSuccess ? e : e2));
     }
+    // Captured kernel nodes do not keep the priority of the io streams they were recorded on; give the small kernels that must
+    // slip in between another context's search CTAs (narrowing, finalisation, PU list) their high priority back.
+    {
+        size_t nn = 0;
+        cudaGraphGetNodes(g, nullptr, &nn);
+        std::vector<cudaGraphNode_t> nodes(nn);
+        if (nn) cudaGraphGetNodes(g, nodes.data(), &nn);
+        int prLo = 0, prHi = 0;
+        cudaDeviceGetStreamPriorityRange(&prLo, &prHi);
+        for (cudaGraphNode_t nd : nodes) {
+            cudaGraphNodeType ty;
+            if (cudaGraphNodeGetType(nd, &ty) != cudaSuccess || ty != cudaGraphNodeTypeKernel) continue;
+            cudaKernelNodeParams kp{};
+            if (cudaGraphKernelNodeGetParams(nd, &kp) != cudaSuccess) continue;
+            const bool small = kp.func == (void*)me_narrow_kernel || kp.func == (void*)me_finalize_kernel || kp.func == (void*)me_frac_build_kernel;
+            cudaLaunchAttributeValue v{};
+            v.priority = small ? prHi : prLo;
+            cudaGraphKernelNodeSetAttribute(nd, cudaLaunchAttributePriority, &v);
+        }
+        cudaGetLastError();
+    }
     hmme_graph* h = new hmme_graph;
     h->graph = g; h->owner = c;
-    e = cudaGraphInstantiate(&h->exec, g, 0);
+    e = cudaGraphInstantiateWithFlags(&h->exec, g, cudaGraphInstantiateFlagUseNodePriority);
     if (e != cudaSuccess) { cudaGraphDestroy(g); delete h; return fail(c, HMME_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e)); }
     *out = h;
     return HMME_OK;
