@@ -21,7 +21,7 @@ EXPORTS = [
     "hmme_plane_alloc", "hmme_plane_free", "hmme_plane_upload_s16", "hmme_plane_upload_u8",
     "hmme_search_frame", "hmme_search_frame_async", "hmme_fetch_results", "hmme_sync",
     "hmme_plane_upload_s16_async", "hmme_fetch_results_async",
-    "hmme_refine_pu", "hmme_refine_frac", "hmme_refine_frame", "hmme_refine_frame_async", "hmme_fetch_frac_async", "hmme_last_frac_ms", "hmme_mc_cost",
+    "hmme_refine_pu", "hmme_refine_frac", "hmme_refine_frame", "hmme_refine_frame_async", "hmme_fetch_frac_async", "hmme_last_frac_ms", "hmme_mc_cost", "hmme_mc_cost_pu",
     "hmme_graph_begin", "hmme_graph_end", "hmme_graph_launch", "hmme_graph_destroy",
     "hmme_last_kernel_ms", "hmme_kernel_launches", "hmme_measure_int_alu_peak", "hmme_partition_rect", "hmme_index_block", "hmme_search_window", "hmme_version",
 ]
@@ -92,6 +92,7 @@ class HmmeLib:
             "hmme_graph_end": (i32, [vp, P(vp)]),
             "hmme_graph_launch": (i32, [vp, vp]),
             "hmme_graph_destroy": (None, [vp]),
+            "hmme_mc_cost_pu": (i32, [vp, vp, i32, vp, i32, i32, i32, i32, i32, i32, P(u32)]),
             "hmme_mc_cost": (i32, [vp, P(PlaneDesc), P(PlaneDesc), vp, i32, i32, vp]),
             "hmme_last_kernel_ms": (i32, [vp, P(C.c_float)]),
             "hmme_kernel_launches": (C.c_uint64, [vp]),
@@ -329,6 +330,18 @@ class MotionEstimator:
         out = np.zeros(pus.shape[0], np.uint32)
         self._chk(self.lib.L.hmme_mc_cost(self.h, C.byref(cur.desc), C.byref(ref.desc), pus.ctypes.data, pus.shape[0], int(bool(use_had)), out.ctypes.data))
         return out
+
+    def mc_cost_pu(self, cur_block, ref_plane, pu_x, pu_y, origin_x, origin_y, mv_qpel, use_had=False):
+        """Host arrays, synchronous: distortion of the prediction of one PU at a clipped quarter-pel MV (xGetTemplateCost's arguments)."""
+        cur_block = np.ascontiguousarray(cur_block, np.int16)
+        assert ref_plane.dtype == np.int16 and ref_plane.flags.c_contiguous
+        h, w = cur_block.shape
+        stride = ref_plane.shape[1]
+        off = int(((origin_y + pu_y) * stride + origin_x + pu_x) * 2)
+        d = C.c_uint32()
+        self._chk(self.lib.L.hmme_mc_cost_pu(self.h, cur_block.ctypes.data, w, ref_plane.ctypes.data + off, stride, w, h, int(mv_qpel[0]), int(mv_qpel[1]),
+                                             int(bool(use_had)), C.byref(d)))
+        return d.value
 
     def last_frac_ms(self):
         ms = C.c_float()

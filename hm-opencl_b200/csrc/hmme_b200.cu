@@ -755,6 +755,46 @@ int hmme_mc_cost(hmme_ctx* c, const hmme_plane* cur, const hmme_plane* ref, cons
     return sync_ctx(c);
 }
 
+// One PU with HOST pointers, synchronous: what xGetTemplateCost has at hand (original block, reference plane at the PU origin,
+// the clipped candidate MV).  Staged like hmme_refine_pu, around the integer part of the MV.
+int hmme_mc_cost_pu(hmme_ctx* c, const int16_t* cur, int curStride, const int16_t* refAtPu, int refStride, int w, int h, int mvQpelX,
+                    int mvQpelY, int useHad, uint32_t* dist) {
+    if (!c) return HMME_ERR_ARG;
+    if (!cur || !refAtPu || !dist) return fail(c, HMME_ERR_ARG, "hmme_mc_cost_pu: null pointer");
+    if (w <= 0 || h <= 0 || w > 64 || h > 64 || (w & 3) || (h & 3)) return fail(c, HMME_ERR_ARG, "hmme_mc_cost_pu: width/height must be multiples of 4 in [4,64]");
+    CU_TRY(c, cudaSetDevice(c->device));
+    int rc = ensure_pus(c, 1);
+    if (rc != HMME_OK) return rc;
+    constexpr int kPatchPitch = 96;
+    const int pw = w + 8, ph = h + 8, h8 = (h + 7) & ~7;
+    uint8_t* hp = static_cast<uint8_t*>(c->hWin);
+    int16_t* hc = static_cast<int16_t*>(c->hCurBlk);
+    std::memset(hp, 0, (size_t)kPatchPitch * (h8 + 8));
+    const int16_t* r0 = refAtPu + (long long)((mvQpelY >> 2) - 4) * refStride + ((mvQpelX >> 2) - 4);
+    for (int y = 0; y < ph; ++y)
+        for (int x = 0; x < pw; ++x) {
+            const int v = r0[(long long)y * refStride + x];
+            if (v < 0 || v > 255) return fail(c, HMME_ERR_CONTENT, "hmme_mc_cost_pu: reference samples outside [0,255] (8-bit video only)");
+            hp[y * kPatchPitch + x] = (uint8_t)v;
+        }
+    for (int y = 0; y < h; ++y) std::memcpy(hc + y * 64, cur + (long long)y * curStride, (size_t)w * sizeof(int16_t));
+    const hmme_mc_pu pu{0, 0, w, h, mvQpelX & 3, mvQpelY & 3};       // the integer part is where the patch was cut
+    CU_TRY(c, cudaMemcpyAsync(c->dWin, hp, (size_t)kPatchPitch * (h8 + 8), cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(c, cudaMemcpyAsync(c->dCurBlk, hc, 64 * 64 * sizeof(int16_t), cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(c, cudaMemcpyAsync(c->dPus, &pu, sizeof(pu), cudaMemcpyHostToDevice, c->stream));
+    McParams mp{};
+    mp.cur = c->dCurBlk; mp.ref = static_cast<const uint8_t*>(c->dWin) + 4 * kPatchPitch + 4;
+    mp.curPitch = 64; mp.refPitch = kPatchPitch; mp.curBytes = 2;
+    mp.pus = reinterpret_cast<const McPu*>(c->dPus); mp.npus = 1; mp.useHad = useHad ? 1 : 0;
+    mp.out = reinterpret_cast<uint32_t*>(c->dFrac);
+    me_mc_cost_kernel<<<1, kFracThreads, 0, c->stream>>>(mp);
+    c->launches += 1;
+    CU_TRY(c, cudaGetLastError());
+    CU_TRY(c, cudaMemcpyAsync(dist, c->dFrac, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    return HMME_OK;
+}
+
 int hmme_refine_frame_async(hmme_ctx* c, const hmme_plane* cur, const hmme_plane* ref, int njobs, const int32_t* predsQpel, int useHad) {
     if (!c) return HMME_ERR_ARG;
     if (njobs <= 0 || njobs != c->lastSearchJobs)

@@ -121,3 +121,19 @@ Distortion TEncOpenCL::refineFractional(Pel* pelKey, Int iKeyStride, Int iWidth,
     rcMvQter = TComMv((Short)(sx - 2 * hx), (Short)(sy - 2 * hy));
     return (Distortion)cost;
 }
+
+Distortion TEncOpenCL::templateDistortion(Pel* pelOrg, Int iOrgStride, Int iWidth, Int iHeight, Pel* piRefY, Int iRefStride, const TComMv& rcMvClipped,
+                                          Bool bUseHadamard) {
+    if (!m_ctx || !enabled) {
+        fprintf(stderr, "FATAL: TEncOpenCL::templateDistortion called without an initialised, enabled GPU context (there is no CPU fallback)\n");
+        abort();
+    }
+    uint32_t dist = 0;
+    const int rc = hmme_mc_cost_pu(m_ctx, pelOrg, iOrgStride, piRefY, iRefStride, iWidth, iHeight, rcMvClipped.getHor(), rcMvClipped.getVer(),
+                                   bUseHadamard ? 1 : 0, &dist);
+    if (rc != HMME_OK) {
+        fprintf(stderr, "FATAL: hmme_mc_cost_pu ( %d ): %s\n", rc, hmme_last_error(m_ctx));
+        abort();
+    }
+    return (Distortion)dist;
+}

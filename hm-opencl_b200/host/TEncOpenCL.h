@@ -79,6 +79,12 @@ public:
     Distortion      refineFractional(Pel* pelKey, Int iKeyStride, Int iWidth, Int iHeight, Pel* piRefY, Int iRefStride, const TComMv& rcMvInt,
                                      const TComMv& rcMvPred, Bool bUseHadamard, TComMv& rcMvHalf, TComMv& rcMvQter);
 
+    /// Addition: SAD (or Hadamard SATD) between the original block and the uni-directional motion-compensated
+    /// prediction at an already clipped quarter-pel MV -- the distortion TEncSearch::xGetTemplateCost (TEncSearch.cpp:3634-3674)
+    /// computes with xPredInterBlk + getDistPart(DF_SAD) before it adds its rate term.
+    Distortion      templateDistortion(Pel* pelOrg, Int iOrgStride, Int iWidth, Int iHeight, Pel* piRefY, Int iRefStride, const TComMv& rcMvClipped,
+                                       Bool bUseHadamard);
+
     //======== getters and setters ================
     Int             getDeviceId         ()              { return deviceId; }
     Void            setDeviceId         ( Int i )       { deviceId = i; }

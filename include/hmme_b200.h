@@ -160,6 +160,10 @@ int hmme_last_frac_ms(hmme_ctx* ctx, float* refineKernelMs);   /* most recent re
 typedef struct { int32_t x, y, w, h, mvQpelX, mvQpelY; } hmme_mc_pu;
 int hmme_mc_cost(hmme_ctx* ctx, const hmme_plane* cur, const hmme_plane* ref, const hmme_mc_pu* pus, int npus, int useHad,
                  uint32_t* dist);
+/* One PU with HOST pointers, synchronous (the arguments xGetTemplateCost has): cur = original block (int16, stride curStride),
+ * refAtPu = pointer into the padded int16 reference plane at the PU origin, clipped quarter-pel MV. */
+int hmme_mc_cost_pu(hmme_ctx* ctx, const int16_t* cur, int curStride, const int16_t* refAtPu, int refStride, int w, int h,
+                    int mvQpelX, int mvQpelY, int useHad, uint32_t* dist);
 
 /* ---- measurement hooks (bench.py / profiles): CUDA-event time of the dominant kernel of the most recent
  * search call on this context's stream, kernel launches issued so far, and the integer-ALU issue-rate

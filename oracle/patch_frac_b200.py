@@ -2,7 +2,8 @@
 """Routes the reference encoder's fractional-pel refinement through the B200 library in a SCRATCH COPY of the reference sources
 (bitstream-parity build `_ref/TAppEncoder_b200frac`, SURVEY.md section 8 row f1): the body of TEncSearch::xPatternSearchFracDIF
 (TEncSearch.cpp:4294-4331) becomes one call of TEncOpenCL::refineFractional when GPU ME is enabled, and TComRdCost gets a getter
-for the predictor the call needs.  This is the integration a maintainer would write; nothing
+for the predictor the call needs; TEncSearch::xGetTemplateCost (:3634-3674, the AMVP candidate check) takes its SAD from
+TEncOpenCL::templateDistortion.  This is the integration a maintainer would write (INTEGRATION.md section 5); nothing
 patched is ever committed."""
 import os
 import sys
@@ -21,6 +22,20 @@ s = s.replace(old, """  if ( m_ppcOpenCLME && m_ppcOpenCLME->isEnabled() )
                                                m_pcEncCfg->getUseHADME() && !bIsLosslessCoded, rcMvHalf, rcMvQter );
     m_pcRdCost->setCostScale( 0 );          // the state the CPU body leaves behind
     return;
+  }
+""" + old)
+# row f3: the AMVP candidate check (xGetTemplateCost, TEncSearch.cpp:3634-3674) takes its SAD from the library as well
+old = """  // prediction pattern
+  if ( pcCU->getSlice()->testWeightPred() && pcCU->getSlice()->getSliceType()==P_SLICE )
+  {
+    xPredInterBlk( COMPONENT_Y, pcCU, pcPicYuvRef, uiPartAddr, &cMvCand, iSizeX, iSizeY, pcTemplateCand, true,"""
+assert s.count(old) == 1
+s = s.replace(old, """  if ( m_ppcOpenCLME && m_ppcOpenCLME->isEnabled() && !( pcCU->getSlice()->testWeightPred() && pcCU->getSlice()->getSliceType()==P_SLICE ) )
+  {
+    uiCost = m_ppcOpenCLME->templateDistortion( pcOrgYuv->getAddr(COMPONENT_Y, uiPartAddr), pcOrgYuv->getStride(COMPONENT_Y), iSizeX, iSizeY,
+                                                pcPicYuvRef->getAddr(COMPONENT_Y, pcCU->getCtuRsAddr(), pcCU->getZorderIdxInCtu() + uiPartAddr),
+                                                pcPicYuvRef->getStride(COMPONENT_Y), cMvCand, false );
+    return (UInt) m_pcRdCost->calcRdCost( m_auiMVPIdxCost[iMVPIdx][iMVPNum], uiCost, false, DF_SAD );
   }
 """ + old)
 open(path, "w").write(s)

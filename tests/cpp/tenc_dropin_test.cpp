@@ -80,6 +80,21 @@ int main() {
             if (bad++ < 10) printf("MISMATCH refineFractional %dx%d: got (%d,%d,%u) want (%d,%d,%u)\n", w, h, gx, gy, cost, mvq[0], mvq[1], oc);
         }
     }
-    printf("%s: %d calcMotionVectors calls, %d refineFractional calls, %d mismatches\n", bad ? "FAIL" : "PASS", calls, fcalls, bad);
+    // the AMVP candidate check's distortion as TEncSearch::xGetTemplateCost would ask for it
+    int tcalls = 0;
+    for (int t = 0; t < 12; ++t) {
+        const int w = shapes[t % 6][0], h = shapes[t % 6][1], px = 24 + 8 * t, py = 20 + 4 * t;
+        Pel blk[64 * 64];
+        for (int r = 0; r < h; ++r) memcpy(blk + 64 * r, &cur[(size_t)(M + py + r) * S + M + px], w * sizeof(Pel));
+        const TComMv mv((Short)(13 * t - 70), (Short)(41 - 9 * t));
+        Pel* refAtPu = &ref[(size_t)(M + py) * S + M + px];
+        const Distortion d = me.templateDistortion(blk, 64, w, h, refAtPu, S, mv, (t & 1) != 0);
+        const hmme_oracle_mc_pu pu = {0, 0, w, h, mv.getHor(), mv.getVer()};
+        uint32_t od;
+        hmme_oracle_mc_cost(blk, 64, refAtPu, S, &pu, 1, (t & 1) != 0, &od);
+        ++tcalls;
+        if (d != od && bad++ < 10) printf("MISMATCH templateDistortion %dx%d: got %u want %u\n", w, h, d, od);
+    }
+    printf("%s: %d calcMotionVectors calls, %d refineFractional calls, %d templateDistortion calls, %d mismatches\n", bad ? "FAIL" : "PASS", calls, fcalls, tcalls, bad);
     return bad ? 1 : 0;
 }

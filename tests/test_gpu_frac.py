@@ -258,3 +258,19 @@ def test_mc_cost_random_vs_oracle(me, oracle, had, cur16):
         me.mc_cost(pc, pr, np.array([[0, 0, 8, 8, -4 * (M + 1), 0]], np.int32))
     assert e.value.code == -6
     pc.free(); pr.free()
+
+
+def test_mc_cost_pu_host_pointers(me, oracle):
+    """hmme_mc_cost_pu: the synchronous host-pointer form xGetTemplateCost's body maps to."""
+    rng = np.random.default_rng(78)
+    W, H, M = 128, 96, 24
+    f = luma_frames(W + 2 * M, H + 2 * M, 2, seed=19)
+    ref = np.ascontiguousarray(f[0].astype(np.int16))
+    cur = np.ascontiguousarray(f[1].astype(np.int16))
+    for (w, h) in SIZES:
+        x, y = int(rng.integers(0, W - w)), int(rng.integers(0, H - h))
+        mv = (int(rng.integers(-50, 51)), int(rng.integers(-50, 51)))
+        for had in (False, True):
+            got = me.mc_cost_pu(cur[M + y:M + y + h, M + x:M + x + w], ref, x, y, M, M, mv, had)
+            want = int(oracle.mc_cost(cur, (M, M), ref, (M, M), np.array([[x, y, w, h, mv[0], mv[1]]], np.int32), had)[0])
+            assert got == want, (w, h, mv, had)
