@@ -21,7 +21,7 @@ EXPORTS = [
     "hmme_plane_alloc", "hmme_plane_free", "hmme_plane_upload_s16", "hmme_plane_upload_u8",
     "hmme_search_frame", "hmme_search_frame_async", "hmme_fetch_results", "hmme_sync",
     "hmme_plane_upload_s16_async", "hmme_fetch_results_async",
-    "hmme_refine_pu", "hmme_refine_frac", "hmme_refine_frame", "hmme_refine_frame_async", "hmme_fetch_frac_async", "hmme_last_frac_ms", "hmme_mc_cost", "hmme_mc_cost_pu",
+    "hmme_refine_pu", "hmme_refine_frac", "hmme_refine_frame", "hmme_refine_frame_async", "hmme_fetch_frac_async", "hmme_last_frac_ms", "hmme_mc_cost", "hmme_mc_cost_pu", "hmme_mc_cost_bi", "hmme_mc_cost_bi_pu",
     "hmme_graph_begin", "hmme_graph_end", "hmme_graph_launch", "hmme_graph_destroy",
     "hmme_last_kernel_ms", "hmme_kernel_launches", "hmme_measure_int_alu_peak", "hmme_partition_rect", "hmme_index_block", "hmme_search_window", "hmme_version",
 ]
@@ -93,6 +93,8 @@ class HmmeLib:
             "hmme_graph_launch": (i32, [vp, vp]),
             "hmme_graph_destroy": (None, [vp]),
             "hmme_mc_cost_pu": (i32, [vp, vp, i32, vp, i32, i32, i32, i32, i32, i32, P(u32)]),
+            "hmme_mc_cost_bi": (i32, [vp, P(PlaneDesc), P(PlaneDesc), P(PlaneDesc), vp, i32, i32, vp]),
+            "hmme_mc_cost_bi_pu": (i32, [vp, vp, i32, vp, i32, i32, i32, vp, i32, i32, i32, i32, i32, i32, P(u32)]),
             "hmme_mc_cost": (i32, [vp, P(PlaneDesc), P(PlaneDesc), vp, i32, i32, vp]),
             "hmme_last_kernel_ms": (i32, [vp, P(C.c_float)]),
             "hmme_kernel_launches": (C.c_uint64, [vp]),
@@ -330,6 +332,26 @@ class MotionEstimator:
         out = np.zeros(pus.shape[0], np.uint32)
         self._chk(self.lib.L.hmme_mc_cost(self.h, C.byref(cur.desc), C.byref(ref.desc), pus.ctypes.data, pus.shape[0], int(bool(use_had)), out.ctypes.data))
         return out
+
+    def mc_cost_bi(self, cur, ref0, ref1, pus, use_had=False):
+        """Bi-directional form: pus (n, 8) int32 rows {x, y, w, h, mv0x, mv0y, mv1x, mv1y} (quarter pel, clipped)."""
+        pus = np.ascontiguousarray(pus, np.int32).reshape(-1, 8)
+        out = np.zeros(pus.shape[0], np.uint32)
+        self._chk(self.lib.L.hmme_mc_cost_bi(self.h, C.byref(cur.desc), C.byref(ref0.desc), C.byref(ref1.desc), pus.ctypes.data, pus.shape[0],
+                                             int(bool(use_had)), out.ctypes.data))
+        return out
+
+    def mc_cost_bi_pu(self, cur_block, ref0_plane, ref1_plane, pu_x, pu_y, origin_x, origin_y, mv0, mv1, use_had=False):
+        """Host arrays, synchronous, two reference planes of equal geometry."""
+        cur_block = np.ascontiguousarray(cur_block, np.int16)
+        h, w = cur_block.shape
+        s0, s1 = ref0_plane.shape[1], ref1_plane.shape[1]
+        o0 = int(((origin_y + pu_y) * s0 + origin_x + pu_x) * 2)
+        o1 = int(((origin_y + pu_y) * s1 + origin_x + pu_x) * 2)
+        d = C.c_uint32()
+        self._chk(self.lib.L.hmme_mc_cost_bi_pu(self.h, cur_block.ctypes.data, w, ref0_plane.ctypes.data + o0, s0, int(mv0[0]), int(mv0[1]),
+                                                ref1_plane.ctypes.data + o1, s1, int(mv1[0]), int(mv1[1]), w, h, int(bool(use_had)), C.byref(d)))
+        return d.value
 
     def mc_cost_pu(self, cur_block, ref_plane, pu_x, pu_y, origin_x, origin_y, mv_qpel, use_had=False):
         """Host arrays, synchronous: distortion of the prediction of one PU at a clipped quarter-pel MV (xGetTemplateCost's arguments)."""

@@ -722,31 +722,40 @@ int hmme_refine_pu(hmme_ctx* c, const int16_t* cur, int curStride, const int16_t
     return HMME_OK;
 }
 
-// ---- distortion of motion-compensated uni-prediction at quarter-pel MVs (xGetTemplateCost / uni-directional merge candidates)
-int hmme_mc_cost(hmme_ctx* c, const hmme_plane* cur, const hmme_plane* ref, const hmme_mc_pu* pus, int npus, int useHad, uint32_t* dist) {
-    if (!c) return HMME_ERR_ARG;
-    if (!pus || npus <= 0 || !dist) return fail(c, HMME_ERR_ARG, "hmme_mc_cost: no PUs / null output");
+// ---- distortion of motion-compensated prediction at quarter-pel MVs (xGetTemplateCost / merge candidates / xGetInterPredictionError)
+namespace {
+
+// pus: npus records of 6 (uni) or 8 (bi) ints; ref1 is the second reference plane of bi-directional PUs
+int mc_cost_planes(hmme_ctx* c, const hmme_plane* cur, const hmme_plane* ref, const hmme_plane* ref1, const int32_t* pus, int npus, int useHad,
+                   uint32_t* dist, const char* who) {
+    const bool bi = ref1 != nullptr;
+    const int stride = bi ? 8 : 6;
+    if (!pus || npus <= 0 || !dist) return fail(c, HMME_ERR_ARG, std::string(who) + ": no PUs / null output");
     int rc = check_frac_planes(c, cur, ref);
+    if (rc == HMME_OK && bi) rc = check_frac_planes(c, cur, ref1);
     if (rc != HMME_OK) return rc;
-    for (int n = 0; n < npus; ++n) {                        // same geometry rules as the refinement, around the integer part of the MV
-        const hmme_mc_pu& u = pus[n];
-        const hmme_pu g{u.x, u.y, u.w, u.h, u.mvQpelX >> 2, u.mvQpelY >> 2, 0, 0};
-        rc = check_pus(c, cur, ref, &g, 1);
-        if (rc != HMME_OK) { c->err = "PU " + std::to_string(n) + " of hmme_mc_cost: " + c->err; return rc; }
-    }
+    for (int n = 0; n < npus; ++n)                          // same geometry rules as the refinement, around the integer part of each MV
+        for (int l = 0; l < (bi ? 2 : 1); ++l) {
+            const int32_t* u = pus + (size_t)n * stride;
+            const hmme_pu g{u[0], u[1], u[2], u[3], u[4 + 2 * l] >> 2, u[5 + 2 * l] >> 2, 0, 0};
+            rc = check_pus(c, cur, l ? ref1 : ref, &g, 1);
+            if (rc != HMME_OK) { c->err = "PU " + std::to_string(n) + " of " + who + ": " + c->err; return rc; }
+        }
     CU_TRY(c, cudaSetDevice(c->device));
-    rc = ensure_pus(c, (size_t)npus);                       // dPus (32 B per entry) holds the 24-byte records, dFrac the results
+    rc = ensure_pus(c, (size_t)npus);                       // dPus (32 B per entry) holds the 24- or 32-byte records, dFrac the results
     if (rc != HMME_OK) return rc;
-    static_assert(sizeof(hmme_mc_pu) == sizeof(McPu) && sizeof(McPu) <= sizeof(FracPu), "ABI struct mirrors the kernel's");
-    CU_TRY(c, cudaMemcpyAsync(c->dPus, pus, (size_t)npus * sizeof(hmme_mc_pu), cudaMemcpyHostToDevice, c->stream));
+    static_assert(sizeof(hmme_mc_pu) == 24 && sizeof(hmme_mc_bi_pu) == 32 && sizeof(FracPu) == 32, "record sizes");
+    CU_TRY(c, cudaMemcpyAsync(c->dPus, pus, (size_t)npus * stride * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
     McParams mp{};
     mp.cur = origin_ptr(cur); mp.ref = reinterpret_cast<const uint8_t*>(origin_ptr(ref));
-    mp.curPitch = cur->pitch; mp.refPitch = ref->pitch; mp.curBytes = cur->elemBytes;
-    mp.pus = reinterpret_cast<const McPu*>(c->dPus); mp.npus = npus; mp.useHad = useHad ? 1 : 0;
+    mp.ref1 = bi ? reinterpret_cast<const uint8_t*>(origin_ptr(ref1)) : nullptr;
+    mp.curPitch = cur->pitch; mp.refPitch = ref->pitch; mp.ref1Pitch = bi ? ref1->pitch : 0; mp.curBytes = cur->elemBytes;
+    mp.pus = reinterpret_cast<const int*>(c->dPus); mp.npus = npus; mp.useHad = useHad ? 1 : 0;
     mp.out = reinterpret_cast<uint32_t*>(c->dFrac);
     const int ctas = std::max(1, std::min((npus + kFracWarps - 1) / kFracWarps, c->prop.multiProcessorCount * 64));
     CU_TRY(c, cudaEventRecord(c->evF0, c->stream));
-    me_mc_cost_kernel<<<ctas, kFracThreads, 0, c->stream>>>(mp);
+    if (bi) me_mc_cost_kernel<true><<<ctas, kFracThreads, 0, c->stream>>>(mp);
+    else me_mc_cost_kernel<false><<<ctas, kFracThreads, 0, c->stream>>>(mp);
     CU_TRY(c, cudaEventRecord(c->evF1, c->stream));
     c->evFracValid = true;
     c->launches += 1;
@@ -755,44 +764,81 @@ int hmme_mc_cost(hmme_ctx* c, const hmme_plane* cur, const hmme_plane* ref, cons
     return sync_ctx(c);
 }
 
-// One PU with HOST pointers, synchronous: what xGetTemplateCost has at hand (original block, reference plane at the PU origin,
-// the clipped candidate MV).  Staged like hmme_refine_pu, around the integer part of the MV.
-int hmme_mc_cost_pu(hmme_ctx* c, const int16_t* cur, int curStride, const int16_t* refAtPu, int refStride, int w, int h, int mvQpelX,
-                    int mvQpelY, int useHad, uint32_t* dist) {
-    if (!c) return HMME_ERR_ARG;
-    if (!cur || !refAtPu || !dist) return fail(c, HMME_ERR_ARG, "hmme_mc_cost_pu: null pointer");
-    if (w <= 0 || h <= 0 || w > 64 || h > 64 || (w & 3) || (h & 3)) return fail(c, HMME_ERR_ARG, "hmme_mc_cost_pu: width/height must be multiples of 4 in [4,64]");
+// One PU with HOST pointers: stages the block and one or two MV-displaced reference patches (4-sample apron) in the context's per-call
+// buffers, like hmme_refine_pu.  The integer part of each MV is folded into where its patch is cut.
+int mc_cost_host(hmme_ctx* c, const int16_t* cur, int curStride, const int16_t* const refAtPu[2], const int refStride[2], const int mv[2][2],
+                 int nLists, int w, int h, int useHad, uint32_t* dist, const char* who) {
+    if (!cur || !refAtPu[0] || (nLists == 2 && !refAtPu[1]) || !dist) return fail(c, HMME_ERR_ARG, std::string(who) + ": null pointer");
+    if (w <= 0 || h <= 0 || w > 64 || h > 64 || (w & 3) || (h & 3)) return fail(c, HMME_ERR_ARG, std::string(who) + ": width/height must be multiples of 4 in [4,64]");
     CU_TRY(c, cudaSetDevice(c->device));
     int rc = ensure_pus(c, 1);
     if (rc != HMME_OK) return rc;
     constexpr int kPatchPitch = 96;
     const int pw = w + 8, ph = h + 8, h8 = (h + 7) & ~7;
+    const size_t patchBytes = (size_t)kPatchPitch * (h8 + 8);   // <= 96 * 80; the staging window holds at least 80 * 80 * 2 bytes
     uint8_t* hp = static_cast<uint8_t*>(c->hWin);
     int16_t* hc = static_cast<int16_t*>(c->hCurBlk);
-    std::memset(hp, 0, (size_t)kPatchPitch * (h8 + 8));
-    const int16_t* r0 = refAtPu + (long long)((mvQpelY >> 2) - 4) * refStride + ((mvQpelX >> 2) - 4);
-    for (int y = 0; y < ph; ++y)
-        for (int x = 0; x < pw; ++x) {
-            const int v = r0[(long long)y * refStride + x];
-            if (v < 0 || v > 255) return fail(c, HMME_ERR_CONTENT, "hmme_mc_cost_pu: reference samples outside [0,255] (8-bit video only)");
-            hp[y * kPatchPitch + x] = (uint8_t)v;
-        }
+    if (2 * patchBytes > c->winElems * 2) return fail(c, HMME_ERR_RANGE, std::string(who) + ": staging window too small");
+    std::memset(hp, 0, nLists * patchBytes);
+    for (int l = 0; l < nLists; ++l) {
+        const int16_t* r0 = refAtPu[l] + (long long)((mv[l][1] >> 2) - 4) * refStride[l] + ((mv[l][0] >> 2) - 4);
+        for (int y = 0; y < ph; ++y)
+            for (int x = 0; x < pw; ++x) {
+                const int v = r0[(long long)y * refStride[l] + x];
+                if (v < 0 || v > 255) return fail(c, HMME_ERR_CONTENT, std::string(who) + ": reference samples outside [0,255] (8-bit video only)");
+                hp[l * patchBytes + y * kPatchPitch + x] = (uint8_t)v;
+            }
+    }
     for (int y = 0; y < h; ++y) std::memcpy(hc + y * 64, cur + (long long)y * curStride, (size_t)w * sizeof(int16_t));
-    const hmme_mc_pu pu{0, 0, w, h, mvQpelX & 3, mvQpelY & 3};       // the integer part is where the patch was cut
-    CU_TRY(c, cudaMemcpyAsync(c->dWin, hp, (size_t)kPatchPitch * (h8 + 8), cudaMemcpyHostToDevice, c->stream));
+    const int32_t pu[8] = {0, 0, w, h, mv[0][0] & 3, mv[0][1] & 3, nLists == 2 ? (mv[1][0] & 3) : 0, nLists == 2 ? (mv[1][1] & 3) : 0};
+    CU_TRY(c, cudaMemcpyAsync(c->dWin, hp, nLists * patchBytes, cudaMemcpyHostToDevice, c->stream));
     CU_TRY(c, cudaMemcpyAsync(c->dCurBlk, hc, 64 * 64 * sizeof(int16_t), cudaMemcpyHostToDevice, c->stream));
-    CU_TRY(c, cudaMemcpyAsync(c->dPus, &pu, sizeof(pu), cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(c, cudaMemcpyAsync(c->dPus, pu, sizeof(pu), cudaMemcpyHostToDevice, c->stream));
     McParams mp{};
     mp.cur = c->dCurBlk; mp.ref = static_cast<const uint8_t*>(c->dWin) + 4 * kPatchPitch + 4;
-    mp.curPitch = 64; mp.refPitch = kPatchPitch; mp.curBytes = 2;
-    mp.pus = reinterpret_cast<const McPu*>(c->dPus); mp.npus = 1; mp.useHad = useHad ? 1 : 0;
+    mp.ref1 = static_cast<const uint8_t*>(c->dWin) + patchBytes + 4 * kPatchPitch + 4;
+    mp.curPitch = 64; mp.refPitch = kPatchPitch; mp.ref1Pitch = kPatchPitch; mp.curBytes = 2;
+    mp.pus = reinterpret_cast<const int*>(c->dPus); mp.npus = 1; mp.useHad = useHad ? 1 : 0;
     mp.out = reinterpret_cast<uint32_t*>(c->dFrac);
-    me_mc_cost_kernel<<<1, kFracThreads, 0, c->stream>>>(mp);
+    if (nLists == 2) me_mc_cost_kernel<true><<<1, kFracThreads, 0, c->stream>>>(mp);
+    else me_mc_cost_kernel<false><<<1, kFracThreads, 0, c->stream>>>(mp);
     c->launches += 1;
     CU_TRY(c, cudaGetLastError());
     CU_TRY(c, cudaMemcpyAsync(dist, c->dFrac, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
     CU_TRY(c, cudaStreamSynchronize(c->stream));
     return HMME_OK;
+}
+
+}  // namespace
+
+int hmme_mc_cost(hmme_ctx* c, const hmme_plane* cur, const hmme_plane* ref, const hmme_mc_pu* pus, int npus, int useHad, uint32_t* dist) {
+    if (!c) return HMME_ERR_ARG;
+    return mc_cost_planes(c, cur, ref, nullptr, reinterpret_cast<const int32_t*>(pus), npus, useHad, dist, "hmme_mc_cost");
+}
+
+int hmme_mc_cost_bi(hmme_ctx* c, const hmme_plane* cur, const hmme_plane* ref0, const hmme_plane* ref1, const hmme_mc_bi_pu* pus, int npus,
+                    int useHad, uint32_t* dist) {
+    if (!c) return HMME_ERR_ARG;
+    if (!ref1) return fail(c, HMME_ERR_ARG, "hmme_mc_cost_bi: null second reference plane");
+    return mc_cost_planes(c, cur, ref0, ref1, reinterpret_cast<const int32_t*>(pus), npus, useHad, dist, "hmme_mc_cost_bi");
+}
+
+int hmme_mc_cost_pu(hmme_ctx* c, const int16_t* cur, int curStride, const int16_t* refAtPu, int refStride, int w, int h, int mvQpelX,
+                    int mvQpelY, int useHad, uint32_t* dist) {
+    if (!c) return HMME_ERR_ARG;
+    const int16_t* const refs[2] = {refAtPu, nullptr};
+    const int strides[2] = {refStride, 0};
+    const int mv[2][2] = {{mvQpelX, mvQpelY}, {0, 0}};
+    return mc_cost_host(c, cur, curStride, refs, strides, mv, 1, w, h, useHad, dist, "hmme_mc_cost_pu");
+}
+
+int hmme_mc_cost_bi_pu(hmme_ctx* c, const int16_t* cur, int curStride, const int16_t* ref0AtPu, int ref0Stride, int mv0QpelX, int mv0QpelY,
+                       const int16_t* ref1AtPu, int ref1Stride, int mv1QpelX, int mv1QpelY, int w, int h, int useHad, uint32_t* dist) {
+    if (!c) return HMME_ERR_ARG;
+    const int16_t* const refs[2] = {ref0AtPu, ref1AtPu};
+    const int strides[2] = {ref0Stride, ref1Stride};
+    const int mv[2][2] = {{mv0QpelX, mv0QpelY}, {mv1QpelX, mv1QpelY}};
+    return mc_cost_host(c, cur, curStride, refs, strides, mv, 2, w, h, useHad, dist, "hmme_mc_cost_bi_pu");
 }
 
 int hmme_refine_frame_async(hmme_ctx* c, const hmme_plane* cur, const hmme_plane* ref, int njobs, const int32_t* predsQpel, int useHad) {

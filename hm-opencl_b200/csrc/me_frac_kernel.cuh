@@ -78,20 +78,20 @@ __device__ __forceinline__ int frac_round_clip(int a) { return __vimin_s32_relu(
 
 // Vertical 8-tap pass over one column held as packed pairs of 16-bit rows (wv[q] = rows 2q, 2q+1): output r starts at row
 // r + S0.  An even start takes the taps as packed {k0..k3}, {k4..k7}; an odd start uses the same bytes moved up by one.
-template <int S0, int NOUT>
+template <int S0, int NOUT, bool RAW = false>
 __device__ __forceinline__ void frac_vfilter(const uint32_t (&wv)[8], const uint32_t ca, const uint32_t cb, int (&pr)[NOUT]) {
     const uint32_t o1 = ca << 8, o2 = (ca >> 24) | (cb << 8), o3 = cb >> 24;
 #pragma unroll
     for (int r = 0; r < NOUT; ++r) {
         const int s = r + S0, m = s >> 1;
-        int a = 2048;
+        int a = RAW ? 0 : 2048;
         if (s & 1) {
             a = dp2a_lo(wv[m], o1, a); a = dp2a_hi(wv[m + 1], o1, a); a = dp2a_lo(wv[m + 2], o2, a); a = dp2a_hi(wv[m + 3], o2, a);
             a = dp2a_lo(wv[m + 4], o3, a);
         } else {
             a = dp2a_lo(wv[m], ca, a); a = dp2a_hi(wv[m + 1], ca, a); a = dp2a_lo(wv[m + 2], cb, a); a = dp2a_hi(wv[m + 3], cb, a);
         }
-        pr[r] = frac_round_clip(a);
+        pr[r] = RAW ? (a >> 6) : frac_round_clip(a);          // RAW: the 14-bit bi-prediction intermediate (+8192), TComInterpolationFilter.cpp:203-224
     }
 }
 
@@ -410,32 +410,47 @@ __global__ void me_frac_build_kernel(const int4* jobs, const int32_t* X, const i
 // candidates of xMergeEstimation / xGetInterPredictionError (:2814-2836, Hadamard).  Same interpolation and distortion code as the
 // refinement above with a single candidate, so one warp works on four 8x8 tiles at a time: lane = (tile, column) in the V step and
 // (tile, coefficient row) in the Hadamard pass.
-struct McPu { int x, y, w, h, mvqx, mvqy; };               // == hmme_mc_pu
-
 struct McParams {
-    const void* cur; const uint8_t* ref;
-    long long curPitch, refPitch;
+    const void* cur; const uint8_t* ref; const uint8_t* ref1;     // ref1: second reference plane of bi-directional PUs
+    long long curPitch, refPitch, ref1Pitch;
     int curBytes;
-    const McPu* pus;
+    const int* pus;            // uni: {x, y, w, h, mvx, mvy}; bi: {x, y, w, h, mv0x, mv0y, mv1x, mv1y} (quarter pel, clipped)
     int npus;
     int useHad;
     uint32_t* out;
 };
 
+template <bool BI>
 struct __align__(16) McScratch {
-    uint32_t ref[4][16][4];
+    uint32_t ref[BI ? 2 : 1][4][16][4];
     int16_t cur[4][8][8];
-    int16_t h[4][8][24];
+    int16_t h[BI ? 2 : 1][4][8][24];
     int16_t t[4][72];
 };
 
-template <int MODE>
-__device__ __forceinline__ uint32_t mc_cost_pu(const McParams& p, const McPu& P, McScratch& S, const int lane) {
-    const int fx = P.mvqx & 3, fy = P.mvqy & 3;
-    const uint32_t cLo = kLumaPack[fx][0], cHi = kLumaPack[fx][1], vLo = kLumaPack[fy][0], vHi = kLumaPack[fy][1];
-    // patch origin: the integer part of the MV is folded in, so taps of output 0 always start at patch index 1
-    const uint8_t* refPu = p.ref + (long long)(P.y + (P.mvqy >> 2) - 4) * p.refPitch + (P.x + (P.mvqx >> 2) - 4);
-    const int ntxT = (P.w + 7) >> 3, nT = ntxT * ((P.h + 7) >> 3);
+// Bi-directional PUs (TComPrediction::xPredInterBi, TComPrediction.cpp:603-651): each list gives the 14-bit intermediate
+// q = (sum_k C[fy][k] * h(r + k - 3)) >> 6 (xPredInterBlk with bi = true; its -8192 offsets cancel against addAvg's), the prediction
+// is clip255((q0 + q1 + 64) >> 7) (TComYuv::addAvg, TComYuv.cpp:352-410).
+template <int MODE, bool BI>
+__device__ __forceinline__ uint32_t mc_cost_pu(const McParams& p, const int n, McScratch<BI>& S, const int lane) {
+    constexpr int NL = BI ? 2 : 1;
+    const int* pu = p.pus + (size_t)n * (BI ? 8 : 6);
+    const int Px = pu[0], Py = pu[1], Pw = pu[2], Ph = pu[3];
+    uint32_t cLo[NL], cHi[NL], vLo[NL], vHi[NL];
+    int fyL[NL];
+    const uint8_t* refPu[NL];
+    long long pitchL[NL];
+#pragma unroll
+    for (int l = 0; l < NL; ++l) {
+        const int mx = pu[4 + 2 * l], my = pu[5 + 2 * l];
+        cLo[l] = kLumaPack[mx & 3][0]; cHi[l] = kLumaPack[mx & 3][1];
+        vLo[l] = kLumaPack[my & 3][0]; vHi[l] = kLumaPack[my & 3][1];
+        fyL[l] = my & 3;
+        pitchL[l] = l ? p.ref1Pitch : p.refPitch;
+        // patch origin: the integer part of the MV is folded in, so taps of output 0 always start at patch index 1
+        refPu[l] = (l ? p.ref1 : p.ref) + (long long)(Py + (my >> 2) - 4) * pitchL[l] + (Px + (mx >> 2) - 4);
+    }
+    const int ntxT = (Pw + 7) >> 3, nT = ntxT * ((Ph + 7) >> 3);
     const int rcp = (65536 + ntxT - 1) / ntxT;
     const int rowL = lane >> 1, halfL = lane & 1, curR = lane >> 2, curC = (lane & 3) * 2;
     uint32_t acc = 0;
@@ -443,52 +458,80 @@ __device__ __forceinline__ uint32_t mc_cost_pu(const McParams& p, const McPu& P,
 #pragma unroll
         for (int s4 = 0; s4 < 4; ++s4) {                      // patches and current tiles of up to four tiles
             const int t = g + s4;
-            uint32_t w0 = 0, w1 = 0; int c0 = 0, c1 = 0;
+            uint32_t w0[NL], w1[NL]; int c0 = 0, c1 = 0;
+#pragma unroll
+            for (int l = 0; l < NL; ++l) { w0[l] = 0; w1[l] = 0; }
             if (t < nT) {
                 const int ty = ((t * rcp) >> 16) * 8, tx = t * 8 - ty * ntxT;
-                const int tw = min(8, P.w - tx), th = min(8, P.h - ty);
-                const uint8_t* q = refPu + (long long)(ty + rowL) * p.refPitch + tx + halfL * 8;
-                w0 = q[0] | (q[1] << 8) | (q[2] << 16) | ((uint32_t)q[3] << 24);
-                w1 = q[4] | (q[5] << 8) | (q[6] << 16) | ((uint32_t)q[7] << 24);
+                const int tw = min(8, Pw - tx), th = min(8, Ph - ty);
+#pragma unroll
+                for (int l = 0; l < NL; ++l) {
+                    const uint8_t* q = refPu[l] + (long long)(ty + rowL) * pitchL[l] + tx + halfL * 8;
+                    w0[l] = q[0] | (q[1] << 8) | (q[2] << 16) | ((uint32_t)q[3] << 24);
+                    w1[l] = q[4] | (q[5] << 8) | (q[6] << 16) | ((uint32_t)q[7] << 24);
+                }
                 if (curR < th) {
-                    const long long o = (long long)(P.y + ty + curR) * p.curPitch + P.x + tx + curC;
+                    const long long o = (long long)(Py + ty + curR) * p.curPitch + Px + tx + curC;
                     if (curC < tw) c0 = p.curBytes == 1 ? (int)static_cast<const uint8_t*>(p.cur)[o] : (int)static_cast<const int16_t*>(p.cur)[o];
                     if (curC + 1 < tw) c1 = p.curBytes == 1 ? (int)static_cast<const uint8_t*>(p.cur)[o + 1] : (int)static_cast<const int16_t*>(p.cur)[o + 1];
                 }
             }
-            *reinterpret_cast<uint2*>(&S.ref[s4][rowL][halfL * 2]) = make_uint2(w0, w1);
+#pragma unroll
+            for (int l = 0; l < NL; ++l) *reinterpret_cast<uint2*>(&S.ref[l][s4][rowL][halfL * 2]) = make_uint2(w0[l], w1[l]);
             S.cur[s4][curC][curR] = (int16_t)c0;
             S.cur[s4][curC + 1][curR] = (int16_t)c1;
         }
         __syncwarp();
 #pragma unroll
-        for (int s4 = 0; s4 < 4; ++s4) {                      // H step, one plane per tile
-            const uint32_t W0 = S.ref[s4][rowL][halfL], W1 = S.ref[s4][rowL][halfL + 1], W2 = S.ref[s4][rowL][halfL + 2];
+        for (int l = 0; l < NL; ++l)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int o8 = 8 * (j + 1);
-                const int out = dp4a_us(__funnelshift_rc(W1, W2, o8), cHi, dp4a_us(__funnelshift_rc(W0, W1, o8), cLo, 0));
-                S.h[s4][halfL * 4 + j][rowL] = (int16_t)out;
+            for (int s4 = 0; s4 < 4; ++s4) {                  // H step, one plane per tile and list
+                const uint32_t W0 = S.ref[l][s4][rowL][halfL], W1 = S.ref[l][s4][rowL][halfL + 1], W2 = S.ref[l][s4][rowL][halfL + 2];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int o8 = 8 * (j + 1);
+                    const int out = dp4a_us(__funnelshift_rc(W1, W2, o8), cHi[l], dp4a_us(__funnelshift_rc(W0, W1, o8), cLo[l], 0));
+                    S.h[l][s4][halfL * 4 + j][rowL] = (int16_t)out;
+                }
             }
-        }
         __syncwarp();
         {   // V step: lane = (tile, column)
             const int s4 = lane >> 3, c = lane & 7;
             const int t = g + s4;
             const int ty = ((t * rcp) >> 16) * 8, tx = t * 8 - ty * ntxT;
-            const int tw = min(8, P.w - tx), th = min(8, P.h - ty);
-            const uint4 ha = *reinterpret_cast<const uint4*>(&S.h[s4][c][0]), hb = *reinterpret_cast<const uint4*>(&S.h[s4][c][8]);
-            const uint32_t wv[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
+            const int tw = min(8, Pw - tx), th = min(8, Ph - ty);
+            int d[8];
+            if (!BI) {
+                const uint4 ha = *reinterpret_cast<const uint4*>(&S.h[0][s4][c][0]), hb = *reinterpret_cast<const uint4*>(&S.h[0][s4][c][8]);
+                const uint32_t wv[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
+                if (fyL[0] == 0) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        d[2 * q] = __vimin_s32_relu(((int)(int16_t)(wv[q + 2] & 0xFFFFu) + 32) >> 6, 255);
+                        d[2 * q + 1] = __vimin_s32_relu((((int)wv[q + 2] >> 16) + 32) >> 6, 255);
+                    }
+                } else frac_vfilter<1, 8>(wv, vLo[0], vHi[0], d);
+            } else {
+                int qs[8];
+#pragma unroll
+                for (int r = 0; r < 8; ++r) qs[r] = 64;                     // addAvg rounding
+#pragma unroll
+                for (int l = 0; l < NL; ++l) {
+                    const uint4 ha = *reinterpret_cast<const uint4*>(&S.h[l][s4][c][0]), hb = *reinterpret_cast<const uint4*>(&S.h[l][s4][c][8]);
+                    const uint32_t wv[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
+                    int q8[8];
+                    if (fyL[l] == 0) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) { q8[2 * q] = (int)(int16_t)(wv[q + 2] & 0xFFFFu); q8[2 * q + 1] = (int)wv[q + 2] >> 16; }
+                    } else frac_vfilter<1, 8, true>(wv, vLo[l], vHi[l], q8);
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) qs[r] += q8[r];
+                }
+#pragma unroll
+                for (int r = 0; r < 8; ++r) d[r] = __vimin_s32_relu(qs[r] >> 7, 255);
+            }
             const uint4 cc = *reinterpret_cast<const uint4*>(&S.cur[s4][c][0]);
             const uint32_t wc[4] = {cc.x, cc.y, cc.z, cc.w};
-            int d[8];
-            if (fy == 0) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    d[2 * q] = __vimin_s32_relu(((int)(int16_t)(wv[q + 2] & 0xFFFFu) + 32) >> 6, 255);
-                    d[2 * q + 1] = __vimin_s32_relu((((int)wv[q + 2] >> 16) + 32) >> 6, 255);
-                }
-            } else frac_vfilter<1, 8>(wv, vLo, vHi, d);
             const bool inside = t < nT && c < tw;              // columns right of a 4-wide tile and tiles past the last one contribute nothing
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -541,17 +584,18 @@ __device__ __forceinline__ uint32_t mc_cost_pu(const McParams& p, const McPu& P,
     return acc;
 }
 
+template <bool BI>
 __global__ void __launch_bounds__(kFracThreads) me_mc_cost_kernel(const McParams p) {
-    __shared__ McScratch scratch[kFracWarps];
+    __shared__ McScratch<BI> scratch[kFracWarps];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    McScratch& S = scratch[warp];
+    McScratch<BI>& S = scratch[warp];
     const int stride = (int)gridDim.x * kFracWarps;
     for (int n = (int)blockIdx.x * kFracWarps + warp; n < p.npus; n += stride) {
-        const McPu P = p.pus[n];
+        const int w = p.pus[(size_t)n * (BI ? 8 : 6) + 2], h = p.pus[(size_t)n * (BI ? 8 : 6) + 3];
         uint32_t d;
-        if (!p.useHad) d = mc_cost_pu<kFracSad>(p, P, S, lane);
-        else if (((P.w | P.h) & 7) == 0) d = mc_cost_pu<kFracHad8>(p, P, S, lane);
-        else d = mc_cost_pu<kFracHad4>(p, P, S, lane);
+        if (!p.useHad) d = mc_cost_pu<kFracSad, BI>(p, n, S, lane);
+        else if (((w | h) & 7) == 0) d = mc_cost_pu<kFracHad8, BI>(p, n, S, lane);
+        else d = mc_cost_pu<kFracHad4, BI>(p, n, S, lane);
         if (lane == 0) p.out[n] = d;
     }
 }

@@ -160,6 +160,17 @@ int hmme_last_frac_ms(hmme_ctx* ctx, float* refineKernelMs);   /* most recent re
 typedef struct { int32_t x, y, w, h, mvQpelX, mvQpelY; } hmme_mc_pu;
 int hmme_mc_cost(hmme_ctx* ctx, const hmme_plane* cur, const hmme_plane* ref, const hmme_mc_pu* pus, int npus, int useHad,
                  uint32_t* dist);
+/* Bi-directional PUs (merge candidates / the motion-estimation result that xGetInterPredictionError evaluates through
+ * TComPrediction::xPredInterBi, TComPrediction.cpp:603-651): each list contributes its 14-bit intermediate, the prediction is
+ * TComYuv::addAvg's clip((p0 + p1 + offset) >> 7) (TComYuv.cpp:352-410).  ref0 / ref1 are the two reference planes, the MVs are
+ * clipped quarter-pel MVs.  Identical motion (same picture, same MV) is the caller's case to route to hmme_mc_cost
+ * (TComPrediction::xCheckIdenticalMotion, :501-516). */
+typedef struct { int32_t x, y, w, h, mv0QpelX, mv0QpelY, mv1QpelX, mv1QpelY; } hmme_mc_bi_pu;
+int hmme_mc_cost_bi(hmme_ctx* ctx, const hmme_plane* cur, const hmme_plane* ref0, const hmme_plane* ref1, const hmme_mc_bi_pu* pus,
+                    int npus, int useHad, uint32_t* dist);
+int hmme_mc_cost_bi_pu(hmme_ctx* ctx, const int16_t* cur, int curStride, const int16_t* ref0AtPu, int ref0Stride, int mv0QpelX,
+                       int mv0QpelY, const int16_t* ref1AtPu, int ref1Stride, int mv1QpelX, int mv1QpelY, int w, int h, int useHad,
+                       uint32_t* dist);
 /* One PU with HOST pointers, synchronous (the arguments xGetTemplateCost has): cur = original block (int16, stride curStride),
  * refAtPu = pointer into the padded int16 reference plane at the PU origin, clipped quarter-pel MV. */
 int hmme_mc_cost_pu(hmme_ctx* ctx, const int16_t* cur, int curStride, const int16_t* refAtPu, int refStride, int w, int h,

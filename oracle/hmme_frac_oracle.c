@@ -150,3 +150,42 @@ int hmme_oracle_mc_cost(const int16_t* curOrigin, int curStride, const int16_t* 
     }
     return 0;
 }
+
+/* 14-bit bi-prediction intermediate of one list, plus 8192: xPredInterBlk with bi = true (TComPrediction.cpp:669-707) stores
+ * h - 8192 (fy == 0), sum_k C[fy][k]*ref - 8192 (fx == 0) or ((sum_k C[fy][k]*(h - 8192)) >> 6) (both fractional,
+ * TComInterpolationFilter.cpp:203-224) -- in every case (sum_k C[fy][k] * h(r + k - 3) >> 6) - 8192 with h the horizontal sums. */
+static void predict_raw(const int16_t* ref0, int stride, int dx, int dy, int w, int h, int* out /* w*h */) {
+    const int ix = dx >> 2, fx = dx & 3, iy = dy >> 2, fy = dy & 3;
+    int* hp = (int*)malloc(sizeof(int) * (size_t)w * (size_t)(h + 8));
+    for (int r = -3; r < h + 5; ++r)
+        for (int c = 0; c < w; ++c) {
+            const int16_t* s = ref0 + (long)(r + iy) * stride + c + ix;
+            int acc = 0;
+            for (int k = 0; k < 8; ++k) acc += kLuma[fx][k] * s[k - 3];
+            hp[(r + 3) * w + c] = acc;
+        }
+    for (int r = 0; r < h; ++r)
+        for (int c = 0; c < w; ++c) {
+            int acc = 0;
+            for (int k = 0; k < 8; ++k) acc += kLuma[fy][k] * hp[(r + k) * w + c];
+            out[r * w + c] = acc >> 6;
+        }
+    free(hp);
+}
+
+/* Bi-directional PUs: TComPrediction::xPredInterBi (TComPrediction.cpp:603-651) + TComYuv::addAvg (TComYuv.cpp:352-410):
+ * pred = clip255((p0 + p1 + 64 + 2*8192) >> 7) with p = the intermediates above; the 8192 offsets cancel. */
+int hmme_oracle_mc_cost_bi(const int16_t* curOrigin, int curStride, const int16_t* ref0Origin, int ref0Stride,
+                           const int16_t* ref1Origin, int ref1Stride, const hmme_oracle_mc_bi_pu* pus, int npus, int useHad, uint32_t* dist) {
+    for (int n = 0; n < npus; ++n) {
+        const hmme_oracle_mc_bi_pu* P = &pus[n];
+        if (P->w <= 0 || P->h <= 0 || P->w > 64 || P->h > 64 || (P->w & 3) || (P->h & 3)) return -1;
+        static __thread int q0[64 * 64], q1[64 * 64];
+        int16_t pred[64 * 64];
+        predict_raw(ref0Origin + (long)P->y * ref0Stride + P->x, ref0Stride, P->mv0x, P->mv0y, P->w, P->h, q0);
+        predict_raw(ref1Origin + (long)P->y * ref1Stride + P->x, ref1Stride, P->mv1x, P->mv1y, P->w, P->h, q1);
+        for (int i = 0; i < P->w * P->h; ++i) pred[i] = (int16_t)clip255((q0[i] + q1[i] + 64) >> 7);
+        dist[n] = distortion(curOrigin + (long)P->y * curStride + P->x, curStride, pred, P->w, P->h, useHad);
+    }
+    return 0;
+}

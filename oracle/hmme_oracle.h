@@ -95,6 +95,11 @@ typedef struct { int32_t x, y, w, h, mvqx, mvqy; } hmme_oracle_mc_pu;
 int hmme_oracle_mc_cost(const int16_t* curOrigin, int curStride, const int16_t* refOrigin, int refStride,
                         const hmme_oracle_mc_pu* pus, int npus, int useHad, uint32_t* dist);
 
+/* Bi-directional form: two reference planes, two clipped quarter-pel MVs (xPredInterBi + addAvg). */
+typedef struct { int32_t x, y, w, h, mv0x, mv0y, mv1x, mv1y; } hmme_oracle_mc_bi_pu;
+int hmme_oracle_mc_cost_bi(const int16_t* curOrigin, int curStride, const int16_t* ref0Origin, int ref0Stride,
+                           const int16_t* ref1Origin, int ref1Stride, const hmme_oracle_mc_bi_pu* pus, int npus, int useHad, uint32_t* dist);
+
 #ifdef __cplusplus
 }
 #endif

@@ -45,6 +45,8 @@ class Oracle:
                                                C.c_uint32, C.c_int] + [C.c_void_p] * 4
         L.hmme_oracle_mc_cost.restype = C.c_int
         L.hmme_oracle_mc_cost.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.hmme_oracle_mc_cost_bi.restype = C.c_int
+        L.hmme_oracle_mc_cost_bi.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.hmme_oracle_refine_frac.restype = C.c_int
         L.hmme_oracle_refine_frac.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_uint32,
                                               C.c_int] + [C.c_void_p] * 6
@@ -123,6 +125,21 @@ class Oracle:
         rc = self.lib.hmme_oracle_mc_cost(cur_plane.ctypes.data + int((cur_origin[1] * cs + cur_origin[0]) * 2), cs,
                                           ref_plane.ctypes.data + int((ref_origin[1] * rs + ref_origin[0]) * 2), rs,
                                           pus.ctypes.data, pus.shape[0], int(bool(use_had)), out.ctypes.data)
+        assert rc == 0
+        return out
+
+
+    def mc_cost_bi(self, cur_plane, cur_origin, ref0_plane, ref1_plane, ref_origin, pus, use_had=False):
+        """Bi-directional form; pus (n,8) int32 rows {x, y, w, h, mv0x, mv0y, mv1x, mv1y}; both reference planes share ref_origin."""
+        pus = np.ascontiguousarray(pus, np.int32).reshape(-1, 8)
+        for a in (cur_plane, ref0_plane, ref1_plane):
+            assert a.dtype == np.int16 and a.flags.c_contiguous
+        out = np.zeros(pus.shape[0], np.uint32)
+        cs, r0s, r1s = cur_plane.shape[1], ref0_plane.shape[1], ref1_plane.shape[1]
+        rc = self.lib.hmme_oracle_mc_cost_bi(cur_plane.ctypes.data + int((cur_origin[1] * cs + cur_origin[0]) * 2), cs,
+                                             ref0_plane.ctypes.data + int((ref_origin[1] * r0s + ref_origin[0]) * 2), r0s,
+                                             ref1_plane.ctypes.data + int((ref_origin[1] * r1s + ref_origin[0]) * 2), r1s,
+                                             pus.ctypes.data, pus.shape[0], int(bool(use_had)), out.ctypes.data)
         assert rc == 0
         return out
 

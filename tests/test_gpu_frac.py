@@ -274,3 +274,33 @@ def test_mc_cost_pu_host_pointers(me, oracle):
             got = me.mc_cost_pu(cur[M + y:M + y + h, M + x:M + x + w], ref, x, y, M, M, mv, had)
             want = int(oracle.mc_cost(cur, (M, M), ref, (M, M), np.array([[x, y, w, h, mv[0], mv[1]]], np.int32), had)[0])
             assert got == want, (w, h, mv, had)
+
+
+@pytest.mark.parametrize("had", [0, 1])
+def test_mc_cost_bi_vs_oracle(me, oracle, had):
+    """Bi-directional PUs (two reference planes, xPredInterBi + addAvg rounding): plane form and host-pointer form."""
+    rng = np.random.default_rng(500 + had)
+    W, H, M = 320, 192, 32
+    f = luma_frames(W + 2 * M, H + 2 * M, 3, seed=int(rng.integers(1 << 30)))
+    ref0, ref1, cur = (np.ascontiguousarray(f[k].astype(np.int16)) for k in (0, 2, 1))
+    pus = []
+    for _ in range(8):
+        for (w, h) in SIZES + [(20, 28), (4, 4), (40, 40)]:
+            x, y = int(rng.integers(0, W - w)), int(rng.integers(0, H - h))
+            mv = []
+            for _l in range(2):
+                ix = int(rng.integers(max(-M + 4 - x, -20), min(W + M - 12 - ((w + 7) & ~7) - x, 20)))
+                iy = int(rng.integers(max(-M + 4 - y, -20), min(H + M - 12 - ((h + 7) & ~7) - y, 20)))
+                mv += [4 * ix + int(rng.integers(0, 4)), 4 * iy + int(rng.integers(0, 4))]
+            pus.append([x, y, w, h] + mv)
+    pus = np.array(pus, np.int32)
+    pc = me.alloc_plane(1, W, H, M, M); p0 = me.alloc_plane(1, W, H, M, M); p1 = me.alloc_plane(1, W, H, M, M)
+    me.upload(pc, cur.astype(np.uint8)); me.upload(p0, ref0.astype(np.uint8)); me.upload(p1, ref1.astype(np.uint8))
+    got = me.mc_cost_bi(pc, p0, p1, pus, bool(had))
+    want = oracle.mc_cost_bi(cur, (M, M), ref0, ref1, (M, M), pus, bool(had))
+    assert np.array_equal(got, want), (had, np.argwhere(got != want)[:5].tolist())
+    for k in range(0, len(pus), 7):                   # host-pointer form on a subset
+        x, y, w, h, a, b, c_, d = (int(v) for v in pus[k])
+        g = me.mc_cost_bi_pu(cur[M + y:M + y + h, M + x:M + x + w], ref0, ref1, x, y, M, M, (a, b), (c_, d), bool(had))
+        assert g == int(want[k]), (k, w, h)
+    pc.free(); p0.free(); p1.free()
