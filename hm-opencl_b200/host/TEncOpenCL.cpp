@@ -137,3 +137,21 @@ Distortion TEncOpenCL::templateDistortion(Pel* pelOrg, Int iOrgStride, Int iWidt
     }
     return (Distortion)dist;
 }
+
+Distortion TEncOpenCL::interPredictionError(Pel* pelOrg, Int iOrgStride, Int iWidth, Int iHeight, Pel* piRefY0, Int iRefStride0, const TComMv& rcMv0,
+                                            Pel* piRefY1, Int iRefStride1, const TComMv& rcMv1, Bool bUseHadamard) {
+    if (!m_ctx || !enabled) {
+        fprintf(stderr, "FATAL: TEncOpenCL::interPredictionError called without an initialised, enabled GPU context (there is no CPU fallback)\n");
+        abort();
+    }
+    uint32_t dist = 0;
+    const int rc = piRefY1
+        ? hmme_mc_cost_bi_pu(m_ctx, pelOrg, iOrgStride, piRefY0, iRefStride0, rcMv0.getHor(), rcMv0.getVer(), piRefY1, iRefStride1, rcMv1.getHor(),
+                             rcMv1.getVer(), iWidth, iHeight, bUseHadamard ? 1 : 0, &dist)
+        : hmme_mc_cost_pu(m_ctx, pelOrg, iOrgStride, piRefY0, iRefStride0, iWidth, iHeight, rcMv0.getHor(), rcMv0.getVer(), bUseHadamard ? 1 : 0, &dist);
+    if (rc != HMME_OK) {
+        fprintf(stderr, "FATAL: hmme_mc_cost%s_pu ( %d ): %s\n", piRefY1 ? "_bi" : "", rc, hmme_last_error(m_ctx));
+        abort();
+    }
+    return (Distortion)dist;
+}

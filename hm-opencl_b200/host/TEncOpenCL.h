@@ -85,6 +85,11 @@ public:
     Distortion      templateDistortion(Pel* pelOrg, Int iOrgStride, Int iWidth, Int iHeight, Pel* piRefY, Int iRefStride, const TComMv& rcMvClipped,
                                        Bool bUseHadamard);
 
+    /// Addition (row f3): the distortion TEncSearch::xGetInterPredictionError (TEncSearch.cpp:2814-2836) computes after motionCompensation, for a
+    /// uni-directional PU (piRefY1 == NULL) or a bi-directional one (xPredInterBi + addAvg); MVs already clipped, plane pointers at the PU origin.
+    Distortion      interPredictionError(Pel* pelOrg, Int iOrgStride, Int iWidth, Int iHeight, Pel* piRefY0, Int iRefStride0, const TComMv& rcMv0,
+                                         Pel* piRefY1, Int iRefStride1, const TComMv& rcMv1, Bool bUseHadamard);
+
     //======== getters and setters ================
     Int             getDeviceId         ()              { return deviceId; }
     Void            setDeviceId         ( Int i )       { deviceId = i; }

@@ -109,6 +109,45 @@ once("""  uiCost = m_pcRdCost->getDistPart( pcCU->getSlice()->getSPS()->getBitDe
     }
   }
 """)
+# optional binary log of inter-prediction errors (merge candidates and the motion-estimation result, uni- and bi-directional; golden
+# records for the bi-directional oracle, SURVEY row f3): what xGetInterPredictionError computed and the samples it computed it from
+once("""  ruiErr = cDistParam.DistFunc( &cDistParam );
+}""", """  ruiErr = cDistParam.DistFunc( &cDistParam );
+  if (const char* logName_ = getenv("HMME_LOG_IPE"))
+  {
+    static FILE* f_ = fopen(logName_, "wb");
+    static std::map<int, int> seen_;
+    static const int cap_ = getenv("HMME_LOG_IPE_CAP") ? atoi(getenv("HMME_LOG_IPE_CAP")) : 4;
+    static const int stride_ = getenv("HMME_LOG_IPE_STRIDE") ? atoi(getenv("HMME_LOG_IPE_STRIDE")) : 5;
+    const Int ri0_ = pcCU->getCUMvField(REF_PIC_LIST_0)->getRefIdx(uiAbsPartIdx), ri1_ = pcCU->getCUMvField(REF_PIC_LIST_1)->getRefIdx(uiAbsPartIdx);
+    const bool bi_ = ri0_ >= 0 && ri1_ >= 0 && !xCheckIdenticalMotion(pcCU, uiAbsPartIdx);
+    const bool wp_ = (pcCU->getSlice()->getPPS()->getUseWP() && pcCU->getSlice()->getSliceType() == P_SLICE) || (pcCU->getSlice()->getPPS()->getWPBiPred() && pcCU->getSlice()->getSliceType() == B_SLICE);
+    const int n_ = seen_[(iWidth * 100 + iHeight) * 2 + (bi_ ? 1 : 0)]++;
+    if (f_ && !wp_ && n_ % stride_ == 0 && n_ / stride_ < cap_)
+    {
+      int lists_[2], nl_ = 0;
+      if (bi_) { lists_[0] = 0; lists_[1] = 1; nl_ = 2; } else { lists_[0] = ri0_ >= 0 ? 0 : 1; nl_ = 1; }
+      TComMv mv_[2]; Pel* rp_[2] = {0, 0}; Int rs_[2] = {0, 0};
+      for (int l_ = 0; l_ < nl_; ++l_)
+      {
+        const RefPicList e_ = lists_[l_] ? REF_PIC_LIST_1 : REF_PIC_LIST_0;
+        mv_[l_] = pcCU->getCUMvField(e_)->getMv(uiAbsPartIdx);
+        pcCU->clipMv(mv_[l_]);
+        TComPicYuv* py_ = pcCU->getSlice()->getRefPic(e_, pcCU->getCUMvField(e_)->getRefIdx(uiAbsPartIdx))->getPicYuvRec();
+        rs_[l_] = py_->getStride(COMPONENT_Y);
+        rp_[l_] = py_->getAddr(COMPONENT_Y, pcCU->getCtuRsAddr(), pcCU->getZorderIdxInCtu() + uiAbsPartIdx) + (mv_[l_].getVer() >> 2) * rs_[l_] + (mv_[l_].getHor() >> 2);
+      }
+      const int hdr_[12] = { 0x49504552, iWidth, iHeight, nl_, (m_pcEncCfg->getUseHADME() && (pcCU->getCUTransquantBypass(iPartIdx) == 0)) ? 1 : 0,
+                             mv_[0].getHor(), mv_[0].getVer(), nl_ == 2 ? mv_[1].getHor() : 0, nl_ == 2 ? mv_[1].getVer() : 0, (int)ruiErr, 0, 0 };
+      fwrite(hdr_, sizeof(int), 12, f_);
+      Pel* org_ = pcYuvOrg->getAddr(COMPONENT_Y, uiAbsPartIdx);
+      for (int r_ = 0; r_ < iHeight; ++r_) fwrite(org_ + r_ * pcYuvOrg->getStride(COMPONENT_Y), sizeof(Pel), iWidth, f_);
+      for (int l_ = 0; l_ < nl_; ++l_)
+        for (int r_ = -4; r_ < iHeight + 4; ++r_) fwrite(rp_[l_] + r_ * rs_[l_] - 4, sizeof(Pel), iWidth + 8, f_);
+      fflush(f_);
+    }
+  }
+}""")
 open(path, "w").write(s)
 # the log reads the predictor and lambda straight from TComRdCost: open its first private section in the scratch copy
 import os

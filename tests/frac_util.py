@@ -78,3 +78,39 @@ def pack_mc_atlas(recs, cell=80, per_row=8, margin=16):
         ref[margin + y - 4:margin + y + h + 4, margin + x - 4:margin + x + w + 4] = r["patch"]
         pus[k] = [x, y, w, h, r["mvx"] & 3, r["mvy"] & 3]
     return cur, ref, (margin, margin), pus
+
+
+def load_ipe_records():
+    """Records logged from the reference's xGetInterPredictionError (merge candidates, ME result; uni- and bi-directional)."""
+    d = np.load(os.path.join(ROOT, "tests", "golden", "mc_records.npz"))
+    hdr, cur, patch = d["ipe_hdr"], d["ipe_cur"], d["ipe_patch"]
+    out, pc, pp = [], 0, 0
+    for i in range(hdr.shape[0]):
+        w, h, nl = int(hdr[i, 1]), int(hdr[i, 2]), int(hdr[i, 3])
+        r = dict(w=w, h=h, lists=nl, had=int(hdr[i, 4]), mv0=(int(hdr[i, 5]), int(hdr[i, 6])), mv1=(int(hdr[i, 7]), int(hdr[i, 8])),
+                 dist=int(np.uint32(hdr[i, 9])), cur=cur[pc:pc + w * h].reshape(h, w), patches=[])
+        pc += w * h
+        for _ in range(nl):
+            r["patches"].append(patch[pp:pp + (w + 8) * (h + 8)].reshape(h + 8, w + 8))
+            pp += (w + 8) * (h + 8)
+        out.append(r)
+    return out
+
+
+def pack_ipe_atlas(recs, cell=80, per_row=8, margin=16):
+    """Records (all with the same number of lists) -> cur plane, one reference plane per list, origin, PU rows (6 or 8 ints)."""
+    n, nl = len(recs), recs[0]["lists"]
+    rows = (n + per_row - 1) // per_row
+    W, H = per_row * cell, rows * cell
+    cur = np.zeros((H + 2 * margin, W + 2 * margin), np.int16)
+    refs = [np.zeros_like(cur) for _ in range(nl)]
+    pus = np.zeros((n, 4 + 2 * nl), np.int32)
+    for k, r in enumerate(recs):
+        x, y = (k % per_row) * cell + 8, (k // per_row) * cell + 8
+        w, h = r["w"], r["h"]
+        cur[margin + y:margin + y + h, margin + x:margin + x + w] = r["cur"]
+        for l in range(nl):
+            refs[l][margin + y - 4:margin + y + h + 4, margin + x - 4:margin + x + w + 4] = r["patches"][l]
+        mv = [r["mv0"][0] & 3, r["mv0"][1] & 3] + ([r["mv1"][0] & 3, r["mv1"][1] & 3] if nl == 2 else [])
+        pus[k] = [x, y, w, h] + mv
+    return cur, refs, (margin, margin), pus

@@ -304,3 +304,28 @@ def test_mc_cost_bi_vs_oracle(me, oracle, had):
         g = me.mc_cost_bi_pu(cur[M + y:M + y + h, M + x:M + x + w], ref0, ref1, x, y, M, M, (a, b), (c_, d), bool(had))
         assert g == int(want[k]), (k, w, h)
     pc.free(); p0.free(); p1.free()
+
+
+def test_inter_prediction_error_reference_records(me):
+    """hmme_mc_cost / hmme_mc_cost_bi against what the reference encoder's xGetInterPredictionError computed."""
+    from frac_util import load_ipe_records, pack_ipe_atlas
+    recs = load_ipe_records()
+    n = 0
+    for nl in (1, 2):
+        for had in (0, 1):
+            sub = [r for r in recs if r["lists"] == nl and r["had"] == had]
+            if not sub:
+                continue
+            cur, refs, (M, _), pus = pack_ipe_atlas(sub)
+            H, W = cur.shape[0] - 2 * M, cur.shape[1] - 2 * M
+            pc = me.alloc_plane(1, W, H, M, M); me.upload(pc, cur.astype(np.uint8))
+            prs = []
+            for r_ in refs:
+                p_ = me.alloc_plane(1, W, H, M, M); me.upload(p_, r_.astype(np.uint8)); prs.append(p_)
+            got = me.mc_cost(pc, prs[0], pus, bool(had)) if nl == 1 else me.mc_cost_bi(pc, prs[0], prs[1], pus, bool(had))
+            assert np.array_equal(got, np.array([r["dist"] for r in sub], np.uint32)), (nl, had)
+            n += len(sub)
+            pc.free()
+            for p_ in prs:
+                p_.free()
+    assert n == len(recs)
