@@ -21,8 +21,9 @@ BIN_FRAC = os.path.join(REFDIR, "TAppEncoder_b200frac")
 @pytest.mark.parametrize("name", sorted(CASES))
 def test_bitstream_identical_with_fractional_refinement_on_gpu(name):
     """Rows f1 and f3 inside the encoder: every xPatternSearchFracDIF call (all PU sizes the RDO visits, uni- and bi-prediction)
-    goes through TEncOpenCL::refineFractional -> hmme_refine_pu, and every xGetTemplateCost (AMVP candidate check) takes its SAD
-    from TEncOpenCL::templateDistortion -> hmme_mc_cost_pu; the bitstream must not change by a bit."""
+    goes through TEncOpenCL::refineFractional -> hmme_refine_pu, every xGetTemplateCost (AMVP candidate check) takes its SAD
+    from TEncOpenCL::templateDistortion -> hmme_mc_cost_pu, and every xGetInterPredictionError (merge candidates, ME result; uni- and
+    bi-directional) its distortion from TEncOpenCL::interPredictionError; the bitstream must not change by a bit."""
     if not os.path.exists(BIN_FRAC):
         pytest.skip("oracle/_ref/TAppEncoder_b200frac was not built (needs /root/reference at build time)")
     gold = json.load(open(os.path.join(ROOT, "tests/golden/encoder_bitstreams.json")))["cases"][name]
