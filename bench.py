@@ -573,9 +573,15 @@ def main():
                 me.mc_cost(sets[s % nsets][0], sets[s % nsets][1], mpus.reshape(-1, 6), had)
                 t.append(me.last_frac_ms())
             km[name] = float(np.mean(t[1:]))
+        bpus = np.concatenate([mpus, rng.integers(-4 * (R - 8), 4 * (R - 8), size=(njobs, NPARTS, 2)).astype(np.int32)], axis=2).reshape(-1, 8)
+        tb = []
+        for s in range(3):                                   # bi-directional: the reference plane and the current plane stand in for the two lists
+            me.mc_cost_bi(sets[s % nsets][0], sets[s % nsets][1], sets[s % nsets][0], bpus, True)
+            tb.append(me.last_frac_ms())
+        km["bi_hadamard"] = float(np.mean(tb[1:]))
         mc = {"scope": "distortion of the motion-compensated uni-prediction (8-tap interpolation at a quarter-pel MV) of all 593 partitions of every CTU: "
                        "the arithmetic of xGetTemplateCost (SAD) / uni-directional merge candidates (Hadamard)",
-              "kernel": "me_mc_cost_kernel", "pus": njobs * NPARTS, "kernel_ms_sad": km["sad"], "kernel_ms_hadamard": km["hadamard"],
+              "kernel": "me_mc_cost_kernel", "pus": njobs * NPARTS, "kernel_ms_sad": km["sad"], "kernel_ms_hadamard": km["hadamard"], "kernel_ms_bi_hadamard": km["bi_hadamard"],
               "pu_pixels_per_s_sad": njobs * 24 * 4096 / (km["sad"] * 1e-3), "timer": "CUDA events around the kernel on its stream, resident planes"}
 
     if rank == 0:

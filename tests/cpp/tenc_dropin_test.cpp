@@ -95,6 +95,30 @@ int main() {
         ++tcalls;
         if (d != od && bad++ < 10) printf("MISMATCH templateDistortion %dx%d: got %u want %u\n", w, h, d, od);
     }
-    printf("%s: %d calcMotionVectors calls, %d refineFractional calls, %d templateDistortion calls, %d mismatches\n", bad ? "FAIL" : "PASS", calls, fcalls, tcalls, bad);
+    // merge candidates / ME result as TEncSearch::xGetInterPredictionError would ask: bi-directional over two reference planes (cur doubles as
+    // the second one), and the uni-directional form through the same method
+    int icalls = 0;
+    for (int t = 0; t < 12; ++t) {
+        const int w = shapes[t % 6][0], h = shapes[t % 6][1], px = 32 + 8 * t, py = 16 + 4 * t;
+        Pel blk[64 * 64];
+        for (int r = 0; r < h; ++r) memcpy(blk + 64 * r, &ref[(size_t)(M + py + r + 1) * S + M + px + 1], w * sizeof(Pel));
+        const TComMv mv0((Short)(9 * t - 40), (Short)(23 - 5 * t)), mv1((Short)(31 - 7 * t), (Short)(3 * t - 14));
+        Pel* r0 = &ref[(size_t)(M + py) * S + M + px];
+        Pel* r1 = &cur[(size_t)(M + py) * S + M + px];
+        const bool bi = (t % 3) != 0, had = (t & 1) == 0;
+        const Distortion d = me.interPredictionError(blk, 64, w, h, r0, S, mv0, bi ? r1 : NULL, S, mv1, had);
+        uint32_t od;
+        if (bi) {
+            const hmme_oracle_mc_bi_pu pu = {0, 0, w, h, mv0.getHor(), mv0.getVer(), mv1.getHor(), mv1.getVer()};
+            hmme_oracle_mc_cost_bi(blk, 64, r0, S, r1, S, &pu, 1, had, &od);
+        } else {
+            const hmme_oracle_mc_pu pu = {0, 0, w, h, mv0.getHor(), mv0.getVer()};
+            hmme_oracle_mc_cost(blk, 64, r0, S, &pu, 1, had, &od);
+        }
+        ++icalls;
+        if (d != od && bad++ < 10) printf("MISMATCH interPredictionError %dx%d bi=%d: got %u want %u\n", w, h, (int)bi, d, od);
+    }
+    printf("%s: %d calcMotionVectors calls, %d refineFractional, %d templateDistortion, %d interPredictionError calls, %d mismatches\n",
+           bad ? "FAIL" : "PASS", calls, fcalls, tcalls, icalls, bad);
     return bad ? 1 : 0;
 }
