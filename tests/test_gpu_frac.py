@@ -329,3 +329,44 @@ def test_inter_prediction_error_reference_records(me):
             for p_ in prs:
                 p_.free()
     assert n == len(recs)
+
+
+def test_fuzz_refine_and_mc(me, oracle):
+    """Random plane sizes, margins, PU lists (any multiples of 4 up to 64, PUs touching the plane borders so that aprons live in the
+    margins), lambdas, modes and batch sizes -- small batches take the cooperative kernel, large ones the throughput kernel.
+    Soak with HMME_FUZZ_ITERS / HMME_FUZZ_SEED."""
+    import os
+    g = np.random.default_rng(int(os.environ.get("HMME_FUZZ_SEED", "2027")))
+    for it in range(int(os.environ.get("HMME_FUZZ_ITERS", "40"))):
+        W, H = 16 * int(g.integers(5, 20)), 16 * int(g.integers(5, 14))
+        M = 16 + 4 * int(g.integers(0, 6))
+        cur16 = bool(g.integers(0, 2))
+        had = bool(g.integers(0, 2))
+        lam = int(g.choice([0, 65536, 460000, 1000000, 4500000, 0xFFFFFFFF]))
+        ref = np.ascontiguousarray(g.integers(0, 256, (H + 2 * M, W + 2 * M)).astype(np.int16))
+        k = int(g.integers(1, 4))
+        ref = np.ascontiguousarray(np.clip((ref + np.roll(ref, k, 0) + np.roll(ref, k, 1) + np.roll(ref, -k, 1)) // 4 * 2 - 100, 0, 255).astype(np.int16))
+        cur = np.ascontiguousarray(np.roll(ref, (int(g.integers(-2, 3)), int(g.integers(-2, 3))), (0, 1)) + g.integers(-6, 7, ref.shape).astype(np.int16))
+        cur = np.ascontiguousarray((np.clip(cur, 0, 255) if not cur16 else np.clip(2 * cur - 128, -255, 510)).astype(np.int16))
+        n = int(g.choice([1, 3, 17, 200, 1500]))
+        pus, mcs = [], []
+        for _ in range(n):
+            w, h = 4 * int(g.integers(1, 17)), 4 * int(g.integers(1, 17))
+            x, y = int(g.integers(0, W - w + 1)), int(g.integers(0, H - h + 1))
+            w8, h8 = (w + 7) & ~7, (h + 7) & ~7
+            mvx = int(g.integers(-M + 4 - x, W + M - 4 - w8 - x + 1))     # the whole legal range, borders included
+            mvy = int(g.integers(-M + 4 - y, H + M - 4 - h8 - y + 1))
+            mvx, mvy = max(-60, min(60, mvx)), max(-60, min(60, mvy))
+            pus.append([x, y, w, h, mvx, mvy, int(g.integers(-400, 400)), int(g.integers(-400, 400))])
+            fx, fy = (int(g.integers(0, 4)), int(g.integers(0, 4)))
+            ex, ey = min(mvx, W + M - 4 - w8 - x - 1), min(mvy, H + M - 4 - h8 - y - 1)   # a fractional MV reads one more sample
+            mcs.append([x, y, w, h, 4 * ex + fx, 4 * ey + fy])
+        pus, mcs = np.array(pus, np.int32), np.array(mcs, np.int32)
+        pc, pr = planes(me, cur.astype(np.uint8) if not cur16 else cur, ref.astype(np.uint8), W, H, M)
+        me.set_lambda_q16(lam)
+        res, cand = me.refine_frac(pc, pr, pus, had, want_candidates=True)
+        want = oracle.refine_frac(cur, (M, M), ref, (M, M), pus, lam, had)
+        check(res, cand, want, f"fuzz {it}: {W}x{H} M={M} n={n} had={had} cur16={cur16} lam={lam}")
+        got = me.mc_cost(pc, pr, mcs, had)
+        assert np.array_equal(got, oracle.mc_cost(cur, (M, M), ref, (M, M), mcs, had)), f"fuzz {it} mc"
+        pc.free(); pr.free()
