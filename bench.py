@@ -251,7 +251,15 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL kernels on a high-priority stream: the reference-plane broadcast of one context slips in between the search CTAs of the
+        # other context instead of queueing behind them (HMME_NCCL_LOW_PRIORITY=1 restores the default for comparison)
+        pg_opts = None
+        if not os.environ.get("HMME_NCCL_LOW_PRIORITY"):
+            try:
+                pg_opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+            except Exception:
+                pg_opts = None
+        dist.init_process_group("nccl", device_id=dev, pg_options=pg_opts)
 
     W, H, R, margin = workload_geometry(args.workload)
     ncx, ncy = W // 64, H // 64
@@ -315,6 +323,37 @@ def main():
             if njobs:
                 self.me.search_frame_async(self.p_cur, self.p_ref, jobs, R)
                 self.me.fetch_results(njobs, self.outs, asynchronous=asynchronous)
+
+        def bind(self):
+            """Pre-marshalled calls of the pipelined e2e step (same C entry points as upload / search_frame_async / fetch_results):
+            at N = 8 a step is 0.16 ms of kernels, so the Python argument handling of every call counts."""
+            m = self.me
+            self.b_sync = m.bind_sync()
+            self.b_ref = None
+            if world > 1 and args.ref_dist == "allgather":
+                if self.p_ref_slice is not None:
+                    self.b_ref = m.bind_upload(self.p_ref_slice, n_ref[s0:s1], origin_x=margin, origin_y=0)
+            elif rank == 0:
+                self.b_ref = m.bind_upload(self.p_ref, n_ref)
+            self.b_cur = m.bind_upload(self.p_cur_band, n_cur_band, origin_x=margin, origin_y=0) if band_h else None
+            self.b_search = m.bind_search(self.p_cur, self.p_ref, jobs, R) if njobs else None
+            self.b_fetch = m.bind_fetch(njobs, self.outs) if njobs else None
+
+        def step_e2e_bound(self):
+            if self.b_ref is not None:
+                self.b_ref()
+            if world > 1:
+                with torch.cuda.stream(self.ext):
+                    if args.ref_dist == "allgather":
+                        full = self.t_ref[:slice_rows * world * pitch]
+                        dist.all_gather_into_tensor(full, full[rank * slice_rows * pitch:(rank + 1) * slice_rows * pitch])
+                    else:
+                        dist.broadcast(self.t_ref, src=0)
+            if self.b_cur is not None:
+                self.b_cur()
+            if self.b_search is not None:
+                self.b_search()
+                self.b_fetch()
 
         def build_graphs(self):
             """The pipelined e2e step recorded as CUDA graphs (hmme_graph_*): at N = 8 a step is ~25 runtime calls for 0.16 ms of
@@ -469,14 +508,17 @@ def main():
             pp.step_e2e_graph()
             pp.me.sync()
         barrier()
+    for pp in pipes:
+        pp.bind()
+    barrier()
     e0 = time.perf_counter()
     for s in range(args.steps):
         pp = pipes[s & 1]
-        pp.me.sync()                                   # this context's previous frame (two steps ago) is complete
+        pp.b_sync()                                    # this context's previous frame (two steps ago) is complete
         if use_graphs:
             pp.step_e2e_graph()
         else:
-            pp.step_e2e(True)
+            pp.step_e2e_bound()
     for pp in pipes:
         pp.me.sync()
     barrier()

@@ -266,6 +266,42 @@ class MotionEstimator:
     def sync(self):
         self._chk(self.lib.L.hmme_sync(self.h))
 
+    # -- pre-marshalled asynchronous calls for launch-bound loops: the same C entry points, their ctypes arguments built once
+    def _bound(self, fn, *args):
+        chk = self._chk
+
+        def call():
+            chk(fn(*args))
+        call.keepalive = args
+        return call
+
+    def bind_upload(self, plane, host, origin_x=None, origin_y=None):
+        """Zero-argument callable = upload(plane, host, ..., asynchronous=True); `host` (int16, page-locked) must stay alive and in place."""
+        d = plane.desc
+        ox = d.marginX if origin_x is None else origin_x
+        oy = d.marginY if origin_y is None else origin_y
+        assert host.dtype == np.int16 and host.ndim == 2 and host.flags.c_contiguous
+        assert oy >= d.marginY and ox >= d.marginX and host.shape[0] - oy >= d.height + d.marginY and host.shape[1] - ox >= d.width + d.marginX
+        off = int(oy * host.shape[1] + ox) * host.itemsize
+        f = self._bound(self.lib.L.hmme_plane_upload_s16_async, self.h, C.byref(d), C.c_void_p(host.ctypes.data + off), C.c_int(host.shape[1]))
+        f.host = host
+        return f
+
+    def bind_search(self, cur, ref, jobs, rng):
+        jobs = np.ascontiguousarray(jobs, np.int32).reshape(-1, 4)
+        f = self._bound(self.lib.L.hmme_search_frame_async, self.h, C.byref(cur.desc), C.byref(ref.desc), C.c_void_p(jobs.ctypes.data),
+                        C.c_int(jobs.shape[0]), C.c_int(int(rng)))
+        f.jobs = jobs
+        return f
+
+    def bind_fetch(self, njobs, outs):
+        f = self._bound(self.lib.L.hmme_fetch_results_async, self.h, C.c_int(njobs), *[C.c_void_p(o.ctypes.data) for o in outs])
+        f.outs = outs
+        return f
+
+    def bind_sync(self):
+        return self._bound(self.lib.L.hmme_sync, self.h)
+
     # -- CUDA graphs: record the asynchronous calls of a step once, replay them with one call
     def graph_begin(self):
         self._chk(self.lib.L.hmme_graph_begin(self.h))
