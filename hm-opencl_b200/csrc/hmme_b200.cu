@@ -421,7 +421,7 @@ int hmme_create(hmme_ctx** out, int device, int maxCtuW, int maxCtuH, int maxSea
     if (const char* e = std::getenv("HMME_FAST_RG")) c->forceRG = std::atoi(e);
     if (const char* e = std::getenv("HMME_STAGGER")) c->stagger = std::max(0, std::atoi(e));
     const size_t side = (size_t)2 * maxSearchRange + 64 + 16;
-    c->winElems = side * side;
+    c->winElems = std::max(side * side, (size_t)96 * 80);   // also stages the one or two 96-pitch reference patches of the per-PU calls
     if ((e = cudaMallocHost(&c->hWin, c->winElems * 2)) != cudaSuccess || (e = cudaMalloc(&c->dWin, c->winElems * 2 + 64)) != cudaSuccess ||
         (e = cudaMallocHost(&c->hCurBlk, 4096 * 2)) != cudaSuccess || (e = cudaMalloc(&c->dCurBlk, 4096 * 2)) != cudaSuccess ||
         (e = cudaMalloc(&c->dFlag, sizeof(int))) != cudaSuccess || (e = cudaMallocHost(&c->hFlag, sizeof(int))) != cudaSuccess)
