@@ -370,3 +370,23 @@ def test_fuzz_refine_and_mc(me, oracle):
         got = me.mc_cost(pc, pr, mcs, had)
         assert np.array_equal(got, oracle.mc_cost(cur, (M, M), ref, (M, M), mcs, had)), f"fuzz {it} mc"
         pc.free(); pr.free()
+
+
+def test_per_pu_calls_on_a_small_range_context(oracle):
+    """A context created for a tiny search range still stages 64x64 PUs (two patches for the bi-directional call)."""
+    m = hm.MotionEstimator(0, 1)
+    try:
+        rng = np.random.default_rng(3)
+        M = 16
+        ref0 = np.ascontiguousarray(rng.integers(0, 256, (64 + 2 * M, 64 + 2 * M)).astype(np.int16))
+        ref1 = np.ascontiguousarray(rng.integers(0, 256, ref0.shape).astype(np.int16))
+        cur = np.ascontiguousarray(rng.integers(0, 256, ref0.shape).astype(np.int16))
+        m.set_lambda_q16(460000)
+        got = m.mc_cost_bi_pu(cur[M:M + 64, M:M + 64], ref0, ref1, 0, 0, M, M, (5, -7), (-9, 14), True)
+        want = int(oracle.mc_cost_bi(cur, (M, M), ref0, ref1, (M, M), np.array([[0, 0, 64, 64, 5, -7, -9, 14]], np.int32), True)[0])
+        assert got == want
+        g2 = m.refine_pu(cur[M:M + 64, M:M + 64], ref0, 0, 0, M, M, (2, -1), (3, 3), True)
+        w2 = oracle.refine_frac(cur, (M, M), ref0, (M, M), np.array([[0, 0, 64, 64, 2, -1, 3, 3]], np.int32), 460000, True)
+        assert g2 == (int(w2["mvq"][0, 0]), int(w2["mvq"][0, 1]), int(w2["cost"][0]), int(w2["dist"][0]))
+    finally:
+        m.close()
