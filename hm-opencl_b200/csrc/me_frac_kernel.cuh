@@ -458,10 +458,11 @@ __device__ __forceinline__ uint32_t mc_cost_pu(const McParams& p, const int n, M
 #pragma unroll
         for (int s4 = 0; s4 < 4; ++s4) {                      // patches and current tiles of up to four tiles
             const int t = g + s4;
-            uint32_t w0[NL], w1[NL]; int c0 = 0, c1 = 0;
+            if (t >= nT) break;                                // warp-uniform: tiles past the last one are masked in the V step, their
+            uint32_t w0[NL], w1[NL]; int c0 = 0, c1 = 0;       // shared memory may hold anything
 #pragma unroll
             for (int l = 0; l < NL; ++l) { w0[l] = 0; w1[l] = 0; }
-            if (t < nT) {
+            {
                 const int ty = ((t * rcp) >> 16) * 8, tx = t * 8 - ty * ntxT;
                 const int tw = min(8, Pw - tx), th = min(8, Ph - ty);
 #pragma unroll
@@ -486,6 +487,7 @@ __device__ __forceinline__ uint32_t mc_cost_pu(const McParams& p, const int n, M
         for (int l = 0; l < NL; ++l)
 #pragma unroll
             for (int s4 = 0; s4 < 4; ++s4) {                  // H step, one plane per tile and list
+                if (g + s4 >= nT) break;
                 const uint32_t W0 = S.ref[l][s4][rowL][halfL], W1 = S.ref[l][s4][rowL][halfL + 1], W2 = S.ref[l][s4][rowL][halfL + 2];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
