@@ -752,7 +752,7 @@ int mc_cost_planes(hmme_ctx* c, const hmme_plane* cur, const hmme_plane* ref, co
     mp.curPitch = cur->pitch; mp.refPitch = ref->pitch; mp.ref1Pitch = bi ? ref1->pitch : 0; mp.curBytes = cur->elemBytes;
     mp.pus = reinterpret_cast<const int*>(c->dPus); mp.npus = npus; mp.useHad = useHad ? 1 : 0;
     mp.out = reinterpret_cast<uint32_t*>(c->dFrac);
-    const int ctas = std::max(1, std::min((npus + kFracWarps - 1) / kFracWarps, c->prop.multiProcessorCount * 64));
+    const int ctas = std::max(1, std::min((npus + kFracWarps - 1) / kFracWarps, c->prop.multiProcessorCount * 512));   // one PU per warp (the list is not ordered here)
     CU_TRY(c, cudaEventRecord(c->evF0, c->stream));
     if (bi) me_mc_cost_kernel<true><<<ctas, kFracThreads, 0, c->stream>>>(mp);
     else me_mc_cost_kernel<false><<<ctas, kFracThreads, 0, c->stream>>>(mp);
