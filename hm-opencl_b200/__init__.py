@@ -7,5 +7,5 @@ loader at the repository root:  `from _pkg import hm`  (or importlib, see _pkg.p
 There is no CPU path in this package: if the CUDA library is missing or no B200 is present,
 construction raises.  The oracle under oracle/ is test infrastructure and is never imported here.
 """
-from .api import (HmmeError, HmmeLib, MotionEstimator, Plane, TEncOpenCL, NUM_CTU_PARTS, lib_path)  # noqa: F401
+from .api import (Group, HmmeError, HmmeLib, MotionEstimator, Plane, TEncOpenCL, NUM_CTU_PARTS, lib_path)  # noqa: F401
 from .sharding import band_ctus, band_jobs, band_reference_rows, band_rows, merge_bands  # noqa: F401,E402

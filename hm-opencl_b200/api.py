@@ -23,6 +23,11 @@ EXPORTS = [
     "hmme_plane_upload_s16_async", "hmme_fetch_results_async",
     "hmme_refine_pu", "hmme_refine_frac", "hmme_refine_frame", "hmme_refine_frame_async", "hmme_fetch_frac_async", "hmme_last_frac_ms", "hmme_mc_cost", "hmme_mc_cost_pu", "hmme_mc_cost_bi", "hmme_mc_cost_bi_pu",
     "hmme_graph_begin", "hmme_graph_end", "hmme_graph_launch", "hmme_graph_destroy",
+    "hmme_plane_upload_u8_async", "hmme_plane_upload_rect_async",
+    "hmme_table_create", "hmme_table_destroy", "hmme_search_frame_table_async", "hmme_table_fetch_async", "hmme_table_device_ptr",
+    "hmme_group_create", "hmme_group_unique_id", "hmme_group_create_rank", "hmme_group_destroy", "hmme_group_last_error", "hmme_group_size",
+    "hmme_group_set_lambda_q16", "hmme_group_configure", "hmme_group_search_frame_async", "hmme_group_sync", "hmme_group_search_frame",
+    "hmme_group_band", "hmme_group_context", "hmme_group_last_kernel_ms", "hmme_group_kernel_launches", "hmme_band_split", "hmme_band_extent",
     "hmme_last_kernel_ms", "hmme_kernel_launches", "hmme_measure_int_alu_peak", "hmme_partition_rect", "hmme_index_block", "hmme_search_window", "hmme_version",
 ]
 
@@ -96,6 +101,30 @@ class HmmeLib:
             "hmme_mc_cost_bi": (i32, [vp, P(PlaneDesc), P(PlaneDesc), P(PlaneDesc), vp, i32, i32, vp]),
             "hmme_mc_cost_bi_pu": (i32, [vp, vp, i32, vp, i32, i32, i32, vp, i32, i32, i32, i32, i32, i32, P(u32)]),
             "hmme_mc_cost": (i32, [vp, P(PlaneDesc), P(PlaneDesc), vp, i32, i32, vp]),
+            "hmme_plane_upload_u8_async": (i32, [vp, P(PlaneDesc), vp, i32]),
+            "hmme_plane_upload_rect_async": (i32, [vp, P(PlaneDesc), vp, i32, i32, i32, i32, i32, i32]),
+            "hmme_table_create": (i32, [vp, P(vp), i32, i32]),
+            "hmme_table_destroy": (None, [vp]),
+            "hmme_search_frame_table_async": (i32, [vp, P(PlaneDesc), P(PlaneDesc), vp, i32, i32, vp, i32]),
+            "hmme_table_fetch_async": (i32, [vp, vp, i32, i32, i32, vp, vp, vp, vp]),
+            "hmme_table_device_ptr": (vp, [vp, i32, i32]),
+            "hmme_group_create": (i32, [P(vp), P(C.c_int), i32, i32]),
+            "hmme_group_unique_id": (i32, [vp, C.c_size_t]),
+            "hmme_group_create_rank": (i32, [P(vp), i32, i32, i32, vp, i32]),
+            "hmme_group_destroy": (None, [vp]),
+            "hmme_group_last_error": (C.c_char_p, [vp]),
+            "hmme_group_size": (i32, [vp, P(C.c_int), P(C.c_int)]),
+            "hmme_group_set_lambda_q16": (i32, [vp, u32]),
+            "hmme_group_configure": (i32, [vp, i32, i32, i32, i32, i32]),
+            "hmme_group_search_frame_async": (i32, [vp, i32, vp, i32, vp, i32, i32, vp, i32, i32, vp, vp, vp, vp]),
+            "hmme_group_sync": (i32, [vp, i32]),
+            "hmme_group_search_frame": (i32, [vp, vp, i32, vp, i32, i32, vp, i32, i32, vp, vp, vp, vp]),
+            "hmme_group_band": (i32, [vp, i32, i32, P(C.c_int), P(C.c_int)]),
+            "hmme_group_context": (vp, [vp, i32, i32]),
+            "hmme_group_last_kernel_ms": (i32, [vp, i32, P(C.c_float)]),
+            "hmme_group_kernel_launches": (C.c_uint64, [vp]),
+            "hmme_band_split": (i32, [i32, i32, i32, P(C.c_int), P(C.c_int)]),
+            "hmme_band_extent": (i32, [vp, i32, i32, vp, vp]),
             "hmme_last_kernel_ms": (i32, [vp, P(C.c_float)]),
             "hmme_kernel_launches": (C.c_uint64, [vp]),
             "hmme_measure_int_alu_peak": (i32, [vp, P(C.c_double), P(C.c_double), P(C.c_double)]),
@@ -124,6 +153,23 @@ class HmmeLib:
         v = [C.c_int() for _ in range(4)]
         assert self.L.hmme_search_window(pred_hor_qpel, pred_ver_qpel, rng, cu_x, cu_y, pic_w, pic_h, *[C.byref(q) for q in v]) == 0
         return tuple(q.value for q in v)      # ltx, lty, rbx, rby
+
+    def band_split(self, njobs, world, rank):
+        """Jobs [first, first + count) of njobs belong to `rank` of `world` (hmme_band_split: the split the group uses)."""
+        f, n = C.c_int(), C.c_int()
+        rc = self.L.hmme_band_split(int(njobs), int(world), int(rank), C.byref(f), C.byref(n))
+        if rc != 0:
+            raise HmmeError(rc, "hmme_band_split: bad argument")
+        return f.value, n.value
+
+    def band_extent(self, jobs, rng):
+        """Picture rectangles (x0, y0, x1, y1) a job range reads: its CTUs of the current frame, band + halo of the reference."""
+        jobs = np.ascontiguousarray(jobs, np.int32).reshape(-1, 4)
+        cr, rr = np.zeros(4, np.int32), np.zeros(4, np.int32)
+        rc = self.L.hmme_band_extent(jobs.ctypes.data, jobs.shape[0], int(rng), cr.ctypes.data, rr.ctypes.data)
+        if rc != 0:
+            raise HmmeError(rc, "hmme_band_extent: bad argument")
+        return tuple(int(v) for v in cr), tuple(int(v) for v in rr)
 
     def device_count(self):
         n = C.c_int(0)
@@ -235,9 +281,41 @@ class MotionEstimator:
             fn = self.lib.L.hmme_plane_upload_s16_async if asynchronous else self.lib.L.hmme_plane_upload_s16
             self._chk(fn(self.h, C.byref(d), host.ctypes.data + off, host.shape[1]))
         elif host.dtype == np.uint8:
-            self._chk(self.lib.L.hmme_plane_upload_u8(self.h, C.byref(d), host.ctypes.data + off, host.shape[1]))
+            fn = self.lib.L.hmme_plane_upload_u8_async if asynchronous else self.lib.L.hmme_plane_upload_u8
+            self._chk(fn(self.h, C.byref(d), host.ctypes.data + off, host.shape[1]))
         else:
             raise TypeError("plane uploads take int16 (HM Pel) or uint8 arrays")
+
+    def upload_rect(self, plane, host, rect, origin_x=None, origin_y=None):
+        """Asynchronous upload of the picture rectangle rect = (x0, y0, x1, y1) only (hmme_plane_upload_rect_async)."""
+        d = plane.desc
+        ox = d.marginX if origin_x is None else origin_x
+        oy = d.marginY if origin_y is None else origin_y
+        assert host.ndim == 2 and host.flags.c_contiguous and host.dtype in (np.int16, np.uint8)
+        x0, y0, x1, y1 = (int(v) for v in rect)
+        assert oy + y0 >= 0 and ox + x0 >= 0 and oy + y1 <= host.shape[0] and ox + x1 <= host.shape[1]
+        off = int(oy * host.shape[1] + ox) * host.itemsize
+        self._chk(self.lib.L.hmme_plane_upload_rect_async(self.h, C.byref(d), host.ctypes.data + off, host.shape[1], host.itemsize, x0, y0, x1, y1))
+
+    # -- device-resident result tables (allMotionVectors / allRuiCost for every CTU of a picture, one slot per list / reference / hypothesis)
+    def create_table(self, slots, jobs_per_slot):
+        t = C.c_void_p()
+        self._chk(self.lib.L.hmme_table_create(self.h, C.byref(t), int(slots), int(jobs_per_slot)))
+        return t
+
+    def destroy_table(self, t):
+        self.lib.L.hmme_table_destroy(t)
+
+    def search_frame_table(self, cur, ref, jobs, rng, table, slot):
+        jobs = np.ascontiguousarray(jobs, np.int32).reshape(-1, 4)
+        self._chk(self.lib.L.hmme_search_frame_table_async(self.h, C.byref(cur.desc), C.byref(ref.desc), jobs.ctypes.data, jobs.shape[0], int(rng), table, int(slot)))
+        self._keep_jobs = jobs
+
+    def table_fetch(self, table, slot, first, njobs, out=None):
+        out = out or self._outs(njobs)
+        self._chk(self.lib.L.hmme_table_fetch_async(self.h, table, int(slot), int(first), int(njobs), *[o.ctypes.data for o in out]))
+        self.sync()
+        return tuple(out)
 
     # -- whole-frame batch
     @staticmethod
@@ -415,6 +493,121 @@ class MotionEstimator:
         a, b, c = C.c_double(), C.c_double(), C.c_double()
         self._chk(self.lib.L.hmme_measure_int_alu_peak(self.h, C.byref(a), C.byref(b), C.byref(c)))
         return {"lane_ops_per_s": a.value, "lanes_per_clk_sm": b.value, "sm_mhz": c.value}
+
+
+class Group:
+    """hmme_group: one frame over several GPUs behind the C ABI (band split, band + halo or NCCL-broadcast reference distribution,
+    results into one host table).  devices=[...] drives them from this process; rank/world/unique_id makes this process one rank of
+    a one-process-per-GPU job (torchrun)."""
+    BAND_HALO, BROADCAST = 0, 1
+
+    def __init__(self, devices=None, max_search_range=64, device=None, rank=None, world=None, unique_id=None):
+        self.lib = HmmeLib.get()
+        g = C.c_void_p()
+        if rank is None:
+            devs = (C.c_int * len(devices))(*devices)
+            rc = self.lib.L.hmme_group_create(C.byref(g), devs, len(devices), max_search_range)
+        else:
+            self._uid = (C.c_char * 128).from_buffer_copy(bytes(unique_id)) if unique_id is not None else None
+            rc = self.lib.L.hmme_group_create_rank(C.byref(g), int(device), int(rank), int(world), self._uid, max_search_range)
+        if rc != 0:
+            raise HmmeError(rc, self.lib.L.hmme_group_last_error(None).decode())
+        self.g = g
+        w, n = C.c_int(), C.c_int()
+        self.lib.L.hmme_group_size(g, C.byref(w), C.byref(n))
+        self.world, self.nlocal = w.value, n.value
+
+    @staticmethod
+    def unique_id():
+        buf = (C.c_char * 128)()
+        rc = HmmeLib.get().L.hmme_group_unique_id(buf, 128)
+        if rc != 0:
+            raise HmmeError(rc, HmmeLib.get().L.hmme_group_last_error(None).decode())
+        return bytes(buf)
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise HmmeError(rc, self.lib.L.hmme_group_last_error(self.g).decode())
+
+    def close(self):
+        if getattr(self, "g", None):
+            self.lib.L.hmme_group_destroy(self.g)
+            self.g = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_lambda_q16(self, v):
+        self._chk(self.lib.L.hmme_group_set_lambda_q16(self.g, C.c_uint32(int(v))))
+
+    def configure(self, width, height, margin_x, margin_y, ref_dist=0):
+        self._chk(self.lib.L.hmme_group_configure(self.g, int(width), int(height), int(margin_x), int(margin_y), int(ref_dist)))
+
+    @staticmethod
+    def _origin(host, ox, oy):
+        assert host.ndim == 2 and host.flags.c_contiguous and host.dtype in (np.int16, np.uint8)
+        return C.c_void_p(host.ctypes.data + int(oy * host.shape[1] + ox) * host.itemsize)
+
+    def bind_frame(self, slot, cur, cur_origin, ref, ref_origin, jobs, rng, outs):
+        """Zero-argument callable = hmme_group_search_frame_async with every argument marshalled once (launch-bound loops).  cur / ref:
+        host planes (int16 or uint8, same type) whose picture sample (0,0) is at [origin_y, origin_x] = *_origin[::-1]."""
+        assert cur.dtype == ref.dtype
+        jobs = np.ascontiguousarray(jobs, np.int32).reshape(-1, 4)
+        args = (self.g, C.c_int(slot), self._origin(cur, *cur_origin), C.c_int(cur.shape[1]), self._origin(ref, *ref_origin), C.c_int(ref.shape[1]),
+                C.c_int(cur.itemsize), C.c_void_p(jobs.ctypes.data), C.c_int(jobs.shape[0]), C.c_int(int(rng)), *[C.c_void_p(o.ctypes.data) for o in outs])
+        fn, chk = self.lib.L.hmme_group_search_frame_async, self._chk
+
+        def call():
+            chk(fn(*args))
+        call.keepalive = (cur, ref, jobs, outs, args)
+        return call
+
+    def search_frame_async(self, slot, cur, cur_origin, ref, ref_origin, jobs, rng, outs):
+        f = self.bind_frame(slot, cur, cur_origin, ref, ref_origin, jobs, rng, outs)
+        f()
+        self._keep = f
+
+    def sync(self, slot=-1):
+        self._chk(self.lib.L.hmme_group_sync(self.g, int(slot)))
+
+    def bind_sync(self, slot):
+        fn, chk, g, s = self.lib.L.hmme_group_sync, self._chk, self.g, C.c_int(slot)
+        return lambda: chk(fn(g, s))
+
+    def search_frame(self, cur, cur_origin, ref, ref_origin, jobs, rng):
+        jobs = np.ascontiguousarray(jobs, np.int32).reshape(-1, 4)
+        outs = MotionEstimator._outs(jobs.shape[0])
+        self.search_frame_async(0, cur, cur_origin, ref, ref_origin, jobs, rng, outs)
+        self.sync(0)
+        return tuple(outs)
+
+    def band(self, njobs, local_index=0):
+        f, n = C.c_int(), C.c_int()
+        self._chk(self.lib.L.hmme_group_band(self.g, int(njobs), int(local_index), C.byref(f), C.byref(n)))
+        return f.value, n.value
+
+    def context(self, local_index=0, slot=0):
+        """The per-GPU MotionEstimator behind a slot (borrowed: do not close)."""
+        h = self.lib.L.hmme_group_context(self.g, int(local_index), int(slot))
+        if not h:
+            raise HmmeError(-1, "no such context")
+        me = MotionEstimator.__new__(MotionEstimator)
+        me.lib, me.h, me.max_search_range = self.lib, None, 0
+        me.__dict__["h"] = C.c_void_p(h)
+        me.close = lambda: None
+        return me
+
+    def last_kernel_ms(self, slot=0):
+        ms = C.c_float()
+        self._chk(self.lib.L.hmme_group_last_kernel_ms(self.g, int(slot), C.byref(ms)))
+        return ms.value
+
+    @property
+    def kernel_launches(self):
+        return int(self.lib.L.hmme_group_kernel_launches(self.g))
 
 
 class TEncOpenCL:

@@ -10,7 +10,8 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "hmme_b200.cu")
-DEPS = [SRC] + sorted(os.path.join(HERE, "csrc", f) for f in os.listdir(os.path.join(HERE, "csrc")) if f.endswith(".cuh")) + [
+SRCS = [SRC, os.path.join(HERE, "csrc", "hmme_group.cu")]
+DEPS = SRCS + sorted(os.path.join(HERE, "csrc", f) for f in os.listdir(os.path.join(HERE, "csrc")) if f.endswith(".cuh")) + [
     os.path.join(os.path.dirname(HERE), "include", "hmme_b200.h")]
 OUT = os.path.join(HERE, "libhmme_b200.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared",
@@ -28,7 +29,7 @@ def build(force=False, quiet=True):
     if not (force or stale()):
         return OUT
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", OUT, SRC]
+    cmd = [nvcc] + NVCC_FLAGS + ["-o", OUT] + SRCS + ["-ldl"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     log = os.path.join(HERE, "build.log")
     with open(log, "w") as f:

@@ -20,6 +20,7 @@
 #include <cuda_runtime.h>
 
 #include "../../include/hmme_b200.h"
+#include "hmme_internal.cuh"
 #include "me_common.cuh"
 #include "me_frac_kernel.cuh"
 #include "me_generic_kernel.cuh"
@@ -55,20 +56,34 @@ size_t fast_smem_bytes(int tw, int th, int yb) {
 //   waves(k) * (rounds(k) + c),  waves = ceil(CTAs / sms),  rounds = ceil(tw * k / 32),  c ~ 4 rounds of per-tile overhead
 FastGeom fast_geometry(int W, int yb, int njobs, int sms, int forceRG) {
     FastGeom g{};
-    g.nTx = (W + kMaxTileW - 1) / kMaxTileW;
-    g.tw = (W + g.nTx - 1) / g.nTx;
+    const int nTxMin = (W + kMaxTileW - 1) / kMaxTileW;
     const int nRGjob = (W + yb - 1) / yb;
-    int maxRG = std::max(1, std::min(kMaxTileCands / (g.tw * yb), nRGjob));
-    while (maxRG > 1 && fast_smem_bytes(g.tw, maxRG * yb, yb) > kSmemBudget) --maxRG;
-    int bestK = maxRG;
-    double bestCost = 1e300;
-    const bool fullWave = (long long)njobs * g.nTx * ((nRGjob + maxRG - 1) / maxRG) >= sms;
-    for (int k = maxRG; k >= 1 && !fullWave; --k) {
-        const long long ctas = (long long)njobs * g.nTx * ((nRGjob + k - 1) / k);
-        const double cost = (double)((ctas + sms - 1) / sms) * ((g.tw * k + 31) / 32 + 4.0);
-        if (cost < bestCost * 0.995) { bestCost = cost; bestK = k; }      // prefer the larger tile unless clearly worse
+    auto max_rg = [&](int tw) {
+        int m = std::max(1, std::min(kMaxTileCands / (tw * yb), nRGjob));
+        while (m > 1 && fast_smem_bytes(tw, m * yb, yb) > kSmemBudget) --m;
+        return m;
+    };
+    int bestNx = nTxMin, bestTw = (W + nTxMin - 1) / nTxMin;
+    int bestK = max_rg(bestTw);
+    const bool fullWave = (long long)njobs * nTxMin * ((nRGjob + bestK - 1) / bestK) >= sms;
+    if (!fullWave) {
+        // Small launch (the encoder's per-CTU call is ONE job): split columns as well as rows so that the job reaches every SM.
+        // cost = waves * (rounds + c): rounds = ceil(units / 32) with units = tw * k (lane = candidate column x row group),
+        // c ~ 4 rounds of per-tile staging.  +-64, one job: 129 x 3 tiles (43 CTAs, 5 rounds) -> 43 x 3 tiles (129 CTAs, 2 rounds).
+        double bestCost = 1e300;
+        for (int nx = nTxMin; nx <= 4 * nTxMin && nx <= W; ++nx) {
+            const int tw = (W + nx - 1) / nx;
+            if ((W + tw - 1) / tw != nx) continue;                        // this column count does not change the tile width
+            const int maxRG = max_rg(tw);
+            for (int k = maxRG; k >= 1; --k) {
+                const long long ctas = (long long)njobs * nx * ((nRGjob + k - 1) / k);
+                const double cost = (double)((ctas + sms - 1) / sms) * ((tw * k + 31) / 32 + 4.0);
+                if (cost < bestCost * 0.995) { bestCost = cost; bestK = k; bestNx = nx; bestTw = tw; }   // prefer the larger tile unless clearly worse
+            }
+        }
     }
-    if (forceRG >= 1 && forceRG <= maxRG) bestK = forceRG;
+    if (forceRG >= 1 && forceRG <= max_rg(bestTw)) bestK = forceRG;
+    g.nTx = bestNx; g.tw = bestTw;
     g.th = bestK * yb;
     g.nTy = (nRGjob + bestK - 1) / bestK;
     g.smemBytes = fast_smem_bytes(g.tw, g.th, yb);
@@ -77,73 +92,15 @@ FastGeom fast_geometry(int W, int yb, int njobs, int sms, int forceRG) {
 
 }  // namespace
 
-struct hmme_ctx {
-    int device = -1;
-    cudaStream_t stream = nullptr;      // compute: search kernels and result copies
-    cudaStream_t ioStream[2] = {nullptr, nullptr};   // high priority, one per staging buffer: a frame's two plane uploads copy back to back
-                                                      // instead of the second copy queueing behind the first plane's narrowing kernel;
-                                                      // ioStream[0] also runs the finalize kernel
-    cudaEvent_t evUpload[2] = {nullptr, nullptr}, evSearch = nullptr, evFinal = nullptr;   // io -> compute and compute -> io ordering
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    bool evValid = false;
-    cudaDeviceProp prop{};
-    std::string err;
-    uint32_t lambda = 0;
-    int maxRange = 0;
-    uint64_t launches = 0;
-    int stagger = 1300;          // cycles of start skew between the two warp groups of the packed kernel (HMME_STAGGER env overrides)
-    int forceRG = 0;             // HMME_FAST_RG env: force the number of row groups per tile (experiments)
-    // job / result buffers (grown on demand)
-    size_t jobCap = 0;
-    int4* dJobs = nullptr;
-    unsigned long long* dBest = nullptr;   // arg-min scratch, kept all "no winner" between searches
-    int32_t* dRes = nullptr;      // [4][jobCap][593]: X, Y, sad, cost
-    hmme_job* hJobs = nullptr;    // pinned
-    // per-CTU synchronous path staging
-    size_t winElems = 0;          // (2*maxRange+64+16)^2
-    void* hWin = nullptr;         // pinned, int16-sized
-    void* dWin = nullptr;
-    void* hCurBlk = nullptr;      // pinned 64x64 int16
-    void* dCurBlk = nullptr;
-    // upload staging
-    int16_t* dStage[2] = {nullptr, nullptr}; size_t stageElems[2] = {0, 0}; int stageNext = 0;   // two staging buffers: a frame's reference
-                                                                                                  // and current plane copy back to back
-    int* dFlag = nullptr; int* hFlag = nullptr;
-    bool contentCheckPending = false;   // an _async 8-bit upload has not had its range flag read back yet
-    // fractional-pel refinement (grown on demand)
-    size_t puCap = 0;
-    FracPu* dPus = nullptr; int* dSlots = nullptr; int4* dFrac = nullptr; uint32_t* dCand = nullptr;
-    int* dOrder = nullptr;        // 593 partition indices, by 8x8-tile count, large to small
-    int bigParts = 0;             // how many of them get a whole CTA in the small-batch form (kFracCoopTiles tiles or more)
-    int tilesPerCtu = 0;          // 8x8 tiles of all 593 partitions (1792)
-    int2* dPreds = nullptr; size_t predCap = 0;
-    cudaEvent_t evF0 = nullptr, evF1 = nullptr; bool evFracValid = false;
-    bool capturing = false;       // between hmme_graph_begin and hmme_graph_end: the asynchronous calls are recorded, not run
-    cudaEvent_t evFork = nullptr, evJoin[2] = {nullptr, nullptr};
-    int lastSearchJobs = 0;       // job count of the most recent frame search (its winners feed hmme_refine_frame)
-    int lastBox[4] = {0, 0, 0, 0};   // picture-coordinate bounding box [x0, y0, x1, y1) of every sample that search could point a PU at
-};
-
-struct hmme_graph {
-    cudaGraph_t graph = nullptr;
-    cudaGraphExec_t exec = nullptr;
-    hmme_ctx* owner = nullptr;
-};
-
-namespace {
-
-int fail(hmme_ctx* c, int code, const std::string& msg) {
+int hmme_fail(hmme_ctx* c, int code, const std::string& msg) {
     if (c) c->err = msg;
     else { std::lock_guard<std::mutex> l(g_errMu); g_createErr = msg; }
     return code;
 }
 
-#define CU_TRY(c, expr)                                                                                      \
-    do {                                                                                                     \
-        cudaError_t e_ = (expr);                                                                             \
-        if (e_ != cudaSuccess)                                                                               \
-            return fail((c), HMME_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));            \
-    } while (0)
+namespace {
+
+inline int fail(hmme_ctx* c, int code, const std::string& msg) { return hmme_fail(c, code, msg); }
 
 int ensure_jobs(hmme_ctx* c, size_t njobs) {
     if (njobs <= c->jobCap) return HMME_OK;
@@ -160,6 +117,7 @@ int ensure_jobs(hmme_ctx* c, size_t njobs) {
     CU_TRY(c, cudaMalloc(&c->dRes, 4 * cap * HMME_NPARTS * sizeof(int32_t)));
     CU_TRY(c, cudaMallocHost(&c->hJobs, cap * sizeof(hmme_job)));
     c->jobCap = cap;
+    ++c->bufGen;                                            // graphs recorded against the old buffers must not be replayed
     return HMME_OK;
 }
 
@@ -217,6 +175,7 @@ int ensure_pus(hmme_ctx* c, size_t npus) {
     CU_TRY(c, cudaMalloc(&c->dSlots, cap * sizeof(int)));
     CU_TRY(c, cudaMalloc(&c->dFrac, cap * sizeof(int4)));
     c->puCap = cap;
+    ++c->bufGen;
     return HMME_OK;
 }
 
@@ -233,6 +192,13 @@ int check_pus(hmme_ctx* c, const hmme_plane* cur, const hmme_plane* ref, const h
             u.y + u.mvy + h8 + 4 > ref->height + ref->marginY)
             return fail(c, HMME_ERR_BOUNDS, "PU " + std::to_string(n) + ": interpolation apron leaves the reference plane (needs 4 samples + tile padding)");
     }
+    return HMME_OK;
+}
+
+// "last reader" marker: uploads enqueued later wait for everything the compute stream holds up to here (searches, refinements
+// and distortion kernels all read planes an upload may overwrite)
+int mark_compute(hmme_ctx* c) {
+    if (!c->capturing) CU_TRY(c, cudaEventRecord(c->evCompute, c->stream));
     return HMME_OK;
 }
 
@@ -253,14 +219,14 @@ int enqueue_frac(hmme_ctx* c, const hmme_plane* cur, const hmme_plane* ref, int 
     // longest-first load balancing (measured 1080p: 16 CTAs per SM 1.25 ms, 32: 1.20, 128 and more: 1.14; one resident wave: 1.30)
     static const int perSm = std::getenv("HMME_FRAC_CTAS_PER_SM") ? std::max(1, std::atoi(std::getenv("HMME_FRAC_CTAS_PER_SM"))) : 256;
     const int ctas = std::max(1, nBig + std::min((npus - nBig + kFracWarps - 1) / kFracWarps, c->prop.multiProcessorCount * perSm));
-    CU_TRY(c, cudaEventRecord(c->evF0, c->stream));
+    if (!c->capturing) CU_TRY(c, cudaEventRecord(c->evF0, c->stream));
     if (coop) me_frac_coop_kernel<<<ctas, kFracThreads, 0, c->stream>>>(fp);
     else me_frac_kernel<<<ctas, kFracThreads, 0, c->stream>>>(fp);
-    CU_TRY(c, cudaEventRecord(c->evF1, c->stream));
-    c->evFracValid = true;
+    if (!c->capturing) CU_TRY(c, cudaEventRecord(c->evF1, c->stream));
+    c->evFracValid = !c->capturing;
     c->launches += 1;
     CU_TRY(c, cudaGetLastError());
-    return HMME_OK;
+    return mark_compute(c);
 }
 
 int check_frac_planes(hmme_ctx* c, const hmme_plane* cur, const hmme_plane* ref) {
@@ -277,17 +243,29 @@ void launch_generic(hmme_ctx* c, const GenericParams& gp, int njobs) {
     me_generic_kernel<TC, TR><<<njobs * gp.nChunks, kGenThreads, 0, c->stream>>>(gp);
 }
 
-// Enqueue search -> finalize for njobs jobs already present in c->dJobs.  The arg-min scratch is in its reset state before and
+// Where a search reads its jobs and leaves its results.  Default: the context's own buffers ([4][jobCap][593]); a device-resident
+// table slot (hmme_table) or the compact per-CTU buffer of hmme_search_ctu otherwise.
+struct SearchIO {
+    const int4* jobs; int32_t* X; int32_t* Y; uint32_t* S; uint32_t* Cst;
+    bool finalizeInline;       // finalisation on the compute stream itself (latency path: no cross-stream events)
+};
+
+SearchIO default_io(hmme_ctx* c) {
+    SearchIO io{};
+    io.jobs = c->dJobs;
+    io.X = c->dRes; io.Y = io.X + c->jobCap * HMME_NPARTS;
+    io.S = reinterpret_cast<uint32_t*>(io.Y + c->jobCap * HMME_NPARTS); io.Cst = io.S + c->jobCap * HMME_NPARTS;
+    io.finalizeInline = false;
+    return io;
+}
+
+// Enqueue search -> finalize for njobs jobs already present at io.jobs.  The arg-min scratch is in its reset state before and
 // after (me_init_kernel once per allocation, me_finalize_kernel restores it).
-int enqueue_search(hmme_ctx* c, const void* curOrigin, int curElem, long long curPitch, const void* refOrigin, int refElem,
+int enqueue_search(hmme_ctx* c, const SearchIO& io, const void* curOrigin, int curElem, long long curPitch, const void* refOrigin, int refElem,
                    long long refPitch, const void* refLo, const void* refHi, int njobs, int R) {
     const int W = 2 * R + 1;
     const size_t nres = (size_t)njobs * HMME_NPARTS;
-    int32_t* X = c->dRes;
-    int32_t* Y = X + c->jobCap * HMME_NPARTS;
-    uint32_t* S = reinterpret_cast<uint32_t*>(Y + c->jobCap * HMME_NPARTS);
-    uint32_t* Cst = S + c->jobCap * HMME_NPARTS;
-    CU_TRY(c, cudaEventRecord(c->ev0, c->stream));
+    if (!c->capturing) CU_TRY(c, cudaEventRecord(c->ev0, c->stream));   // timing events stay out of captured graphs
     if (curElem == 1 && refElem == 1) {
         constexpr int yb = HMME_FAST_YB;             // candidate rows per thread (3: measured best; 2 is 17 % slower, 4 does not fit)
         const FastGeom g = fast_geometry(W, yb, njobs, c->prop.multiProcessorCount, c->forceRG);
@@ -297,20 +275,18 @@ int enqueue_search(hmme_ctx* c, const void* curOrigin, int curElem, long long cu
         fp.refLo = static_cast<const uint8_t*>(refLo);
         fp.refHi = static_cast<const uint8_t*>(refHi);
         fp.curPitch = curPitch; fp.refPitch = refPitch;
-        fp.jobs = c->dJobs; fp.best = c->dBest; fp.lambda = c->lambda; fp.W = W;
+        fp.jobs = io.jobs; fp.best = c->dBest; fp.lambda = c->lambda; fp.W = W;
         fp.tw = g.tw; fp.th = g.th; fp.nTx = g.nTx; fp.nTy = g.nTy; fp.stagger = c->stagger;
         const unsigned grid = (unsigned)(njobs * g.nTx * g.nTy);
-        auto launch = [&](auto kernel) -> cudaError_t {
-            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smemBytes);
-            if (e != cudaSuccess) return e;
-            kernel<<<grid, kFastThreads, g.smemBytes, c->stream>>>(fp);
-            return cudaSuccess;
-        };
-        CU_TRY(c, launch(me_u8_tile_kernel<HMME_FAST_YB>));
+        if (g.smemBytes > c->fastSmemSet) {           // the opt-in only ever has to grow
+            CU_TRY(c, cudaFuncSetAttribute(me_u8_tile_kernel<HMME_FAST_YB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
+            c->fastSmemSet = kSmemBudget;
+        }
+        me_u8_tile_kernel<HMME_FAST_YB><<<grid, kFastThreads, g.smemBytes, c->stream>>>(fp);
     } else {
         GenericParams gp{};
         gp.cur = curOrigin; gp.ref = refOrigin; gp.curPitch = curPitch; gp.refPitch = refPitch;
-        gp.jobs = c->dJobs; gp.best = c->dBest; gp.lambda = c->lambda; gp.W = W;
+        gp.jobs = io.jobs; gp.best = c->dBest; gp.lambda = c->lambda; gp.W = W;
         const int nCand = W * W;
         int nChunks = std::max(1, std::min((nCand + 63) / 64, (4 * c->prop.multiProcessorCount + njobs - 1) / njobs));
         gp.chunk = (nCand + nChunks - 1) / nChunks;
@@ -321,18 +297,22 @@ int enqueue_search(hmme_ctx* c, const void* curOrigin, int curElem, long long cu
         else launch_generic<int16_t, int16_t>(c, gp, njobs);
     }
     CU_TRY(c, cudaEventRecord(c->ev1, c->stream));
-    c->evValid = true;
+    c->evValid = !c->capturing;
+    c->launches += 2;
+    if (io.finalizeInline) {
+        me_finalize_kernel<<<(unsigned)((nres + 255) / 256), 256, 0, c->stream>>>(c->dBest, io.jobs, njobs, W, c->lambda, io.X, io.Y, io.S, io.Cst);
+        CU_TRY(c, cudaGetLastError());
+        return mark_compute(c);
+    }
     // Finalisation (keys -> X, Y, sad, cost; keys handed back in their reset state) runs on a high-priority stream: a tiny
     // kernel on the compute stream would queue behind every pending CTA of another context's search, delaying the result
     // copy -- and with it the host -- by a whole search.
     CU_TRY(c, cudaStreamWaitEvent(c->ioStream[0], c->ev1, 0));
-    me_finalize_kernel<<<(unsigned)((nres + 255) / 256), 256, 0, c->ioStream[0]>>>(c->dBest, c->dJobs, njobs, W, c->lambda, X, Y, S, Cst);
+    me_finalize_kernel<<<(unsigned)((nres + 255) / 256), 256, 0, c->ioStream[0]>>>(c->dBest, io.jobs, njobs, W, c->lambda, io.X, io.Y, io.S, io.Cst);
     CU_TRY(c, cudaEventRecord(c->evFinal, c->ioStream[0]));
     CU_TRY(c, cudaStreamWaitEvent(c->stream, c->evFinal, 0));
-    c->launches += 2;
     CU_TRY(c, cudaGetLastError());
-    CU_TRY(c, cudaEventRecord(c->evSearch, c->stream));
-    return HMME_OK;
+    return mark_compute(c);
 }
 
 // stream sync + deferred content check of asynchronous 8-bit uploads
@@ -363,12 +343,6 @@ int fetch_async(hmme_ctx* c, int njobs, int32_t* X, int32_t* Y, uint32_t* sad, u
 int fetch(hmme_ctx* c, int njobs, int32_t* X, int32_t* Y, uint32_t* sad, uint32_t* cost) {
     const int rc = fetch_async(c, njobs, X, Y, sad, cost);
     return rc != HMME_OK ? rc : sync_ctx(c);
-}
-
-// host rows -> device rows; one linear copy when both sides have the same pitch
-cudaError_t copy_rows_h2d(void* dst, size_t dpitch, const void* src, size_t spitch, size_t rowBytes, size_t rows, cudaStream_t s) {
-    if (dpitch == spitch) return cudaMemcpyAsync(dst, src, spitch * (rows - 1) + rowBytes, cudaMemcpyHostToDevice, s);
-    return cudaMemcpy2DAsync(dst, dpitch, src, spitch, rowBytes, rows, cudaMemcpyHostToDevice, s);
 }
 
 }  // namespace
@@ -414,15 +388,16 @@ int hmme_create(hmme_ctx** out, int device, int maxCtuW, int maxCtuH, int maxSea
     if ((e = cudaEventCreate(&c->ev0)) != cudaSuccess || (e = cudaEventCreate(&c->ev1)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&c->evUpload[0], cudaEventDisableTiming)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&c->evUpload[1], cudaEventDisableTiming)) != cudaSuccess ||
-        (e = cudaEventCreateWithFlags(&c->evSearch, cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&c->evCompute, cudaEventDisableTiming)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&c->evFinal, cudaEventDisableTiming)) != cudaSuccess)
         return bail(std::string("cudaEventCreate: ") + cudaGetErrorString(e), HMME_ERR_CUDA);
     c->maxRange = maxSearchRange;
     if (const char* e = std::getenv("HMME_FAST_RG")) c->forceRG = std::atoi(e);
     if (const char* e = std::getenv("HMME_STAGGER")) c->stagger = std::max(0, std::atoi(e));
     const size_t side = (size_t)2 * maxSearchRange + 64 + 16;
-    c->winElems = std::max(side * side, (size_t)96 * 80);   // also stages the one or two 96-pitch reference patches of the per-PU calls
+    c->winElems = std::max(side * side, (size_t)96 * 80) + 4128;   // + {job | 64x64 block} of hmme_search_ctu; also stages the one or two 96-pitch reference patches of the per-PU calls
     if ((e = cudaMallocHost(&c->hWin, c->winElems * 2)) != cudaSuccess || (e = cudaMalloc(&c->dWin, c->winElems * 2 + 64)) != cudaSuccess ||
+        (e = cudaMallocHost(&c->hCtuRes, 4 * HMME_NPARTS * sizeof(int32_t))) != cudaSuccess || (e = cudaMalloc(&c->dCtuRes, 4 * HMME_NPARTS * sizeof(int32_t))) != cudaSuccess ||
         (e = cudaMallocHost(&c->hCurBlk, 4096 * 2)) != cudaSuccess || (e = cudaMalloc(&c->dCurBlk, 4096 * 2)) != cudaSuccess ||
         (e = cudaMalloc(&c->dFlag, sizeof(int))) != cudaSuccess || (e = cudaMallocHost(&c->hFlag, sizeof(int))) != cudaSuccess)
         return bail(std::string("buffer allocation: ") + cudaGetErrorString(e), HMME_ERR_CUDA);
@@ -438,7 +413,7 @@ void hmme_destroy(hmme_ctx* c) {
     if (c->device >= 0) cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->dJobs); cudaFree(c->dBest); cudaFree(c->dRes); cudaFreeHost(c->hJobs);
-    cudaFreeHost(c->hWin); cudaFree(c->dWin); cudaFreeHost(c->hCurBlk); cudaFree(c->dCurBlk);
+    cudaFreeHost(c->hWin); cudaFree(c->dWin); cudaFreeHost(c->hCurBlk); cudaFree(c->dCurBlk); cudaFreeHost(c->hCtuRes); cudaFree(c->dCtuRes);
     cudaFree(c->dStage[0]); cudaFree(c->dStage[1]); cudaFree(c->dFlag); cudaFreeHost(c->hFlag);
     cudaFree(c->dPus); cudaFree(c->dSlots); cudaFree(c->dFrac); cudaFree(c->dCand); cudaFree(c->dOrder); cudaFree(c->dPreds);
     if (c->evFork) cudaEventDestroy(c->evFork);
@@ -449,7 +424,7 @@ void hmme_destroy(hmme_ctx* c) {
         if (c->evUpload[k]) cudaEventDestroy(c->evUpload[k]);
         if (c->ioStream[k]) { cudaStreamSynchronize(c->ioStream[k]); cudaStreamDestroy(c->ioStream[k]); }
     }
-    if (c->evSearch) cudaEventDestroy(c->evSearch);
+    if (c->evCompute) cudaEventDestroy(c->evCompute);
     if (c->evFinal) cudaEventDestroy(c->evFinal);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -475,46 +450,66 @@ int hmme_set_lambda(hmme_ctx* c, double lambda) {
 int hmme_set_lambda_q16(hmme_ctx* c, uint32_t v) { if (!c) return HMME_ERR_ARG; c->lambda = v; return HMME_OK; }
 uint32_t hmme_get_lambda_q16(hmme_ctx* c) { return c ? c->lambda : 0; }
 
+// classify + narrow one row of int16 samples (vectorises: distinct source and destination)
+static inline uint32_t narrow_row(const int16_t* __restrict__ src, uint8_t* __restrict__ dst, int n) {
+    uint32_t o = 0;
+    for (int q = 0; q < n; ++q) { o |= (uint16_t)src[q]; dst[q] = (uint8_t)src[q]; }
+    return o;
+}
+
 int hmme_search_ctu(hmme_ctx* c, const int16_t* cur, int curStride, const int16_t* refAtCtu, int refStride, int range, int ltx,
                     int lty, int32_t* X, int32_t* Y, uint32_t* sad, uint32_t* cost) {
     if (!c) return HMME_ERR_ARG;
     if (!cur || !refAtCtu || !X || !Y || !sad || curStride < 64) return fail(c, HMME_ERR_ARG, "hmme_search_ctu: null pointer or stride < 64");
     if (range < 0 || range > c->maxRange) return fail(c, HMME_ERR_RANGE, "search range " + std::to_string(range) + " exceeds the context's " + std::to_string(c->maxRange));
+    if (c->capturing) return fail(c, HMME_ERR_ARG, "hmme_search_ctu is synchronous: not allowed while capturing a graph");
     CU_TRY(c, cudaSetDevice(c->device));
-    int rc = ensure_jobs(c, 1);
-    if (rc != HMME_OK) return rc;
     const int side = 2 * range + 64;                 // TEncOpenCL.cpp:256 areaStride
     const int wp = (side + 15) & ~15;
-    // gather block + window with the reference's linear addressing (TEncOpenCL.cpp:251,275-277) and classify the content
-    int16_t* hc = static_cast<int16_t*>(c->hCurBlk);
-    int16_t* hw = static_cast<int16_t*>(c->hWin);
+    // One page-locked staging block {job | 64x64 block | window rows}, gathered with the reference's linear addressing
+    // (TEncOpenCL.cpp:251,275-277), narrowed to 8 bit on the way when the content allows (every encoder call except the
+    // bi-prediction refinement, whose block is 2*org - pred), moved with ONE copy.
+    char* hs = static_cast<char*>(c->hWin);
+    char* ds = static_cast<char*>(c->dWin);
+    constexpr size_t kCurOff = 64, kWinOff = 64 + 8192;
     uint32_t orAll = 0;
-    for (int r = 0; r < 64; ++r)
-        for (int q = 0; q < 64; ++q) { const int16_t v = cur[(size_t)r * curStride + q]; hc[r * 64 + q] = v; orAll |= (uint16_t)v; }
-    const int16_t* w0 = refAtCtu + (ptrdiff_t)refStride * lty + ltx;
-    for (int r = 0; r < side; ++r) {
-        const int16_t* src = w0 + (ptrdiff_t)r * refStride;
-        int16_t* dst = hw + (size_t)r * wp;
-        for (int q = 0; q < side; ++q) { dst[q] = src[q]; orAll |= (uint16_t)src[q]; }
-        for (int q = side; q < wp; ++q) dst[q] = 0;
+    {
+        uint8_t* hc8 = reinterpret_cast<uint8_t*>(hs + kCurOff);
+        for (int r = 0; r < 64; ++r) orAll |= narrow_row(cur + (size_t)r * curStride, hc8 + r * 64, 64);
+        const int16_t* w0 = refAtCtu + (ptrdiff_t)refStride * lty + ltx;
+        uint8_t* hw8 = reinterpret_cast<uint8_t*>(hs + kWinOff);
+        if (!(orAll & 0xFF00u))
+            for (int r = 0; r < side; ++r) orAll |= narrow_row(w0 + (ptrdiff_t)r * refStride, hw8 + (size_t)r * wp, side);
     }
     const bool eight = (orAll & 0xFF00u) == 0;
     const int elem = eight ? 1 : 2;
-    if (eight) {                                      // narrow in place on the host staging (front to back is safe)
-        uint8_t* hc8 = reinterpret_cast<uint8_t*>(hc);
-        for (int i = 0; i < 4096; ++i) hc8[i] = (uint8_t)hc[i];
-        uint8_t* hw8 = reinterpret_cast<uint8_t*>(hw);
-        for (size_t i = 0; i < (size_t)side * wp; ++i) hw8[i] = (uint8_t)hw[i];
+    if (!eight) {
+        int16_t* hc = reinterpret_cast<int16_t*>(hs + kCurOff);
+        for (int r = 0; r < 64; ++r) std::memcpy(hc + r * 64, cur + (size_t)r * curStride, 128);
+        const int16_t* w0 = refAtCtu + (ptrdiff_t)refStride * lty + ltx;
+        int16_t* hw = reinterpret_cast<int16_t*>(hs + kWinOff);
+        for (int r = 0; r < side; ++r) std::memcpy(hw + (size_t)r * wp, w0 + (ptrdiff_t)r * refStride, (size_t)side * 2);
     }
-    CU_TRY(c, cudaMemcpyAsync(c->dCurBlk, hc, 4096 * elem, cudaMemcpyHostToDevice, c->stream));
-    CU_TRY(c, cudaMemcpyAsync(c->dWin, hw, (size_t)side * wp * elem, cudaMemcpyHostToDevice, c->stream));
-    c->hJobs[0] = hmme_job{0, 0, ltx, lty};
-    CU_TRY(c, cudaMemcpyAsync(c->dJobs, c->hJobs, sizeof(hmme_job), cudaMemcpyHostToDevice, c->stream));
+    *reinterpret_cast<hmme_job*>(hs) = hmme_job{0, 0, ltx, lty};
+    const size_t winBytes = (size_t)side * wp * elem;
+    CU_TRY(c, cudaMemcpyAsync(ds, hs, kWinOff + winBytes, cudaMemcpyHostToDevice, c->stream));
     // virtual origin: sample (ctu + lt) is element 0 of the staged window
-    const char* refOrigin = static_cast<const char*>(c->dWin) - ((ptrdiff_t)lty * wp + ltx) * elem;
-    rc = enqueue_search(c, c->dCurBlk, elem, 64, refOrigin, elem, wp, c->dWin, static_cast<const char*>(c->dWin) + (size_t)side * wp * elem + 64, 1, range);
+    const char* dWin = ds + kWinOff;
+    const char* refOrigin = dWin - ((ptrdiff_t)lty * wp + ltx) * elem;
+    SearchIO io{};
+    io.jobs = reinterpret_cast<const int4*>(ds);
+    io.X = c->dCtuRes; io.Y = io.X + HMME_NPARTS;
+    io.S = reinterpret_cast<uint32_t*>(io.Y + HMME_NPARTS); io.Cst = io.S + HMME_NPARTS;
+    io.finalizeInline = true;
+    int rc = enqueue_search(c, io, ds + kCurOff, elem, 64, refOrigin, elem, wp, dWin, dWin + winBytes + 64, 1, range);
     if (rc != HMME_OK) return rc;
-    return fetch(c, 1, X, Y, sad, cost);
+    CU_TRY(c, cudaMemcpyAsync(c->hCtuRes, c->dCtuRes, 4 * HMME_NPARTS * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    const int32_t* hr = c->hCtuRes;
+    std::memcpy(X, hr, HMME_NPARTS * 4); std::memcpy(Y, hr + HMME_NPARTS, HMME_NPARTS * 4);
+    std::memcpy(sad, hr + 2 * HMME_NPARTS, HMME_NPARTS * 4);
+    if (cost) std::memcpy(cost, hr + 3 * HMME_NPARTS, HMME_NPARTS * 4);
+    return HMME_OK;
 }
 
 int hmme_plane_alloc(hmme_ctx* c, hmme_plane* out, int elemBytes, int width, int height, int marginX, int marginY) {
@@ -525,6 +520,7 @@ int hmme_plane_alloc(hmme_ctx* c, hmme_plane* out, int elemBytes, int width, int
     p.elemBytes = elemBytes; p.width = width; p.height = height; p.marginX = marginX; p.marginY = marginY;
     p.pitch = (width + 2 * marginX + 15) & ~15;       // 16-element pitch keeps every row 16-byte aligned (TMA-ready)
     CU_TRY(c, cudaMalloc(&p.base, plane_elems(&p) * elemBytes + 64));
+    CU_TRY(c, cudaMemset(p.base, 0, plane_elems(&p) * elemBytes + 64));   // pitch padding and slack read as defined samples
     *out = p;
     return HMME_OK;
 }
@@ -538,41 +534,69 @@ int hmme_plane_free(hmme_ctx* c, hmme_plane* p) {
     return HMME_OK;
 }
 
-int hmme_plane_upload_s16_async(hmme_ctx* c, const hmme_plane* p, const int16_t* hostOrigin, int hostStride) {
-    if (!c || !hostOrigin) return fail(c, HMME_ERR_ARG, "hmme_plane_upload_s16: null pointer");
+// Host rectangle -> device plane.  [x0, x1) x [y0, y1) are picture coordinates (negative / beyond the picture = margin samples,
+// which must exist on the host side as they do in TComPicYuv).  Equal sample sizes: one strided DMA straight into the plane.
+// int16 host -> 8-bit plane: DMA into a dense staging buffer, then me_narrow_rect_kernel (content check deferred to the next
+// synchronising call).  Everything runs on one of the two high-priority io streams, ordered
+//   after  every compute call already enqueued on this context (it may still read the plane: evCompute),
+//   after  the previous upload on the other io stream (two uploads to the same plane keep their order),
+//   before every compute call enqueued later (the compute stream waits on evUpload).
+static int upload_rect(hmme_ctx* c, const hmme_plane* p, const void* hostOrigin, int hostStride, int hostElem, int x0, int y0, int x1, int y1,
+                       const char* who) {
+    if (!c || !hostOrigin) return fail(c, HMME_ERR_ARG, std::string(who) + ": null pointer");
     int rc = check_plane(c, p, "upload target");
     if (rc != HMME_OK) return rc;
+    if (hostElem != 1 && hostElem != 2) return fail(c, HMME_ERR_ARG, std::string(who) + ": host samples must be 1 or 2 bytes");
+    if (hostElem == 1 && p->elemBytes == 2) return fail(c, HMME_ERR_ARG, std::string(who) + ": an int16 plane takes int16 host samples");
+    if (x0 >= x1 || y0 >= y1 || x0 < -p->marginX || y0 < -p->marginY || x1 > p->width + p->marginX || y1 > p->height + p->marginY)
+        return fail(c, HMME_ERR_ARG, std::string(who) + ": rectangle empty or outside the padded plane");
+    if (hostStride < x1 - x0) return fail(c, HMME_ERR_ARG, std::string(who) + ": host stride smaller than the rectangle");
     CU_TRY(c, cudaSetDevice(c->device));
-    const int rows = p->height + 2 * p->marginY, cols = p->width + 2 * p->marginX;
-    const int16_t* src = hostOrigin - (ptrdiff_t)p->marginY * hostStride - p->marginX;
-    if (p->elemBytes == 2) {
-        CU_TRY(c, copy_rows_h2d(p->base, (size_t)p->pitch * 2, src, (size_t)hostStride * 2, (size_t)cols * 2, rows, c->stream));
-        return HMME_OK;
-    }
-    const size_t n = plane_elems(p);
+    const int rows = y1 - y0, cols = x1 - x0;
+    const char* src = static_cast<const char*>(hostOrigin) + ((ptrdiff_t)y0 * hostStride + x0) * hostElem;
+    char* dst = static_cast<char*>(p->base) + ((size_t)(p->marginY + y0) * p->pitch + (size_t)(p->marginX + x0)) * p->elemBytes;
     const int sb = c->stageNext;
     c->stageNext ^= 1;
     cudaStream_t io = c->ioStream[sb];
-    if (c->stageElems[sb] < n) {
-        CU_TRY(c, cudaStreamSynchronize(io));
-        if (c->dStage[sb]) cudaFree(c->dStage[sb]);
-        c->dStage[sb] = nullptr; c->stageElems[sb] = 0;
-        CU_TRY(c, cudaMalloc(&c->dStage[sb], n * 2));
-        c->stageElems[sb] = n;
+    if (!c->capturing) CU_TRY(c, cudaStreamWaitEvent(io, c->evCompute, 0));   // inside a graph the whole previous launch has completed (stream order)
+    if (c->uploadValid[sb ^ 1]) CU_TRY(c, cudaStreamWaitEvent(io, c->evUpload[sb ^ 1], 0));
+    if (hostElem == p->elemBytes) {
+        CU_TRY(c, cudaMemcpy2DAsync(dst, (size_t)p->pitch * hostElem, src, (size_t)hostStride * hostElem, (size_t)cols * hostElem, rows,
+                                    cudaMemcpyHostToDevice, io));
+    } else {
+        const int spitch = (cols + 7) & ~7;
+        const size_t n = (size_t)spitch * rows;
+        if (c->stageElems[sb] < n) {
+            if (c->capturing) return fail(c, HMME_ERR_ARG, std::string(who) + ": staging buffer would grow while capturing (run the step once first)");
+            CU_TRY(c, cudaStreamSynchronize(io));
+            if (c->dStage[sb]) cudaFree(c->dStage[sb]);
+            c->dStage[sb] = nullptr; c->stageElems[sb] = 0;
+            CU_TRY(c, cudaMalloc(&c->dStage[sb], n * 2));
+            c->stageElems[sb] = n;
+            ++c->bufGen;
+        }
+        CU_TRY(c, cudaMemcpy2DAsync(c->dStage[sb], (size_t)spitch * 2, src, (size_t)hostStride * 2, (size_t)cols * 2, rows, cudaMemcpyHostToDevice, io));
+        const long long threads = (long long)((cols + 7) >> 3) * rows;
+        me_narrow_rect_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, io>>>(c->dStage[sb], spitch, reinterpret_cast<uint8_t*>(dst), p->pitch, cols,
+                                                                               rows, c->dFlag);
+        c->launches += 1;
+        CU_TRY(c, cudaGetLastError());
+        c->contentCheckPending = true;                      // sticky device flag, read back at the next synchronising call
     }
-    // Uploads run on high-priority io streams (one per staging buffer): the copies of a frame's two planes start at once and
-    // the tiny narrowing kernels are scheduled as soon as an SM frees a slot, even while another context's search kernel
-    // fills the device.  Searches already enqueued on this context may still read the plane: wait for them first; the
-    // next search waits for this upload.
-    if (!c->capturing) CU_TRY(c, cudaStreamWaitEvent(io, c->evSearch, 0));   // inside a graph the whole previous launch has completed (stream order)
-    if (p->pitch != cols) CU_TRY(c, cudaMemsetAsync(c->dStage[sb], 0, n * 2, io));   // pitch padding columns must read as in-range samples
-    CU_TRY(c, copy_rows_h2d(c->dStage[sb], (size_t)p->pitch * 2, src, (size_t)hostStride * 2, (size_t)cols * 2, rows, io));
-    me_narrow_kernel<<<(unsigned)((n / 8 + 255) / 256 + 1), 256, 0, io>>>(c->dStage[sb], static_cast<uint8_t*>(p->base), n, c->dFlag);
-    c->launches += 1;
     CU_TRY(c, cudaEventRecord(c->evUpload[sb], io));
+    c->uploadValid[sb] = true;
     CU_TRY(c, cudaStreamWaitEvent(c->stream, c->evUpload[sb], 0));
-    c->contentCheckPending = true;                      // sticky device flag, read back at the next synchronising call
     return HMME_OK;
+}
+
+int hmme_plane_upload_rect_async(hmme_ctx* c, const hmme_plane* p, const void* hostOrigin, int hostStride, int hostElemBytes, int x0, int y0,
+                                 int x1, int y1) {
+    return upload_rect(c, p, hostOrigin, hostStride, hostElemBytes, x0, y0, x1, y1, "hmme_plane_upload_rect");
+}
+
+int hmme_plane_upload_s16_async(hmme_ctx* c, const hmme_plane* p, const int16_t* hostOrigin, int hostStride) {
+    if (!p) return fail(c, HMME_ERR_ARG, "hmme_plane_upload_s16: null plane");
+    return upload_rect(c, p, hostOrigin, hostStride, 2, -p->marginX, -p->marginY, p->width + p->marginX, p->height + p->marginY, "hmme_plane_upload_s16");
 }
 
 int hmme_plane_upload_s16(hmme_ctx* c, const hmme_plane* p, const int16_t* hostOrigin, int hostStride) {
@@ -580,17 +604,15 @@ int hmme_plane_upload_s16(hmme_ctx* c, const hmme_plane* p, const int16_t* hostO
     return rc != HMME_OK ? rc : sync_ctx(c);
 }
 
-int hmme_plane_upload_u8(hmme_ctx* c, const hmme_plane* p, const uint8_t* hostOrigin, int hostStride) {
-    if (!c || !hostOrigin) return fail(c, HMME_ERR_ARG, "hmme_plane_upload_u8: null pointer");
-    int rc = check_plane(c, p, "upload target");
-    if (rc != HMME_OK) return rc;
+int hmme_plane_upload_u8_async(hmme_ctx* c, const hmme_plane* p, const uint8_t* hostOrigin, int hostStride) {
+    if (!p) return fail(c, HMME_ERR_ARG, "hmme_plane_upload_u8: null plane");
     if (p->elemBytes != 1) return fail(c, HMME_ERR_ARG, "hmme_plane_upload_u8 needs an 8-bit plane");
-    CU_TRY(c, cudaSetDevice(c->device));
-    const int rows = p->height + 2 * p->marginY, cols = p->width + 2 * p->marginX;
-    const uint8_t* src = hostOrigin - (ptrdiff_t)p->marginY * hostStride - p->marginX;
-    CU_TRY(c, copy_rows_h2d(p->base, (size_t)p->pitch, src, (size_t)hostStride, (size_t)cols, rows, c->stream));
-    CU_TRY(c, cudaStreamSynchronize(c->stream));
-    return HMME_OK;
+    return upload_rect(c, p, hostOrigin, hostStride, 1, -p->marginX, -p->marginY, p->width + p->marginX, p->height + p->marginY, "hmme_plane_upload_u8");
+}
+
+int hmme_plane_upload_u8(hmme_ctx* c, const hmme_plane* p, const uint8_t* hostOrigin, int hostStride) {
+    const int rc = hmme_plane_upload_u8_async(c, p, hostOrigin, hostStride);
+    return rc != HMME_OK ? rc : sync_ctx(c);
 }
 
 int hmme_search_frame_async(hmme_ctx* c, const hmme_plane* cur, const hmme_plane* ref, const hmme_job* jobs, int njobs, int range) {
@@ -606,9 +628,12 @@ int hmme_search_frame_async(hmme_ctx* c, const hmme_plane* cur, const hmme_plane
     if (rc != HMME_OK) return rc;
     // straight from the caller's (pageable) array: the runtime stages it before returning, and stream order protects dJobs,
     // so consecutive frames can be enqueued without a host synchronisation in between
-    if (c->capturing) {                                     // a graph replays the copy: it has to read page-locked memory the library owns
-        std::memcpy(c->hJobs, jobs, (size_t)njobs * sizeof(hmme_job));
-        CU_TRY(c, cudaMemcpyAsync(c->dJobs, c->hJobs, (size_t)njobs * sizeof(hmme_job), cudaMemcpyHostToDevice, c->stream));
+    if (c->capturing) {                                     // a graph replays the copy: it reads a page-locked copy that the graph owns
+        void* hj = nullptr;
+        CU_TRY(c, cudaMallocHost(&hj, (size_t)njobs * sizeof(hmme_job)));
+        c->captureBufs.push_back(hj);
+        std::memcpy(hj, jobs, (size_t)njobs * sizeof(hmme_job));
+        CU_TRY(c, cudaMemcpyAsync(c->dJobs, hj, (size_t)njobs * sizeof(hmme_job), cudaMemcpyHostToDevice, c->stream));
     } else
         CU_TRY(c, cudaMemcpyAsync(c->dJobs, jobs, (size_t)njobs * sizeof(hmme_job), cudaMemcpyHostToDevice, c->stream));
     c->lastSearchJobs = njobs;
@@ -620,8 +645,89 @@ int hmme_search_frame_async(hmme_ctx* c, const hmme_plane* cur, const hmme_plane
     const char* refLo = static_cast<const char*>(ref->base);
     // planes carry 64 bytes of slack after the last row (hmme_plane_alloc adds it; required of external memory): the
     // 16-byte granular TMA row copies may run a few bytes past the window's last sample
-    return enqueue_search(c, origin_ptr(cur), cur->elemBytes, cur->pitch, origin_ptr(ref), ref->elemBytes, ref->pitch, refLo,
+    return enqueue_search(c, default_io(c), origin_ptr(cur), cur->elemBytes, cur->pitch, origin_ptr(ref), ref->elemBytes, ref->pitch, refLo,
                           refLo + plane_elems(ref) * ref->elemBytes + 64, njobs, range);
+}
+
+// ---- device-resident result tables: the reference keeps allMotionVectors[2][33][593] / allRuiCost for ONE
+// CTU on the host (TEncSearch.h:114-115); a table holds the same 593-entry records for every CTU of a picture and every (list, reference
+// index) slot in HBM, so that a B picture's two lists (and several window hypotheses per list) coexist and sub-CU lookups or the
+// fractional refinement can read them without a host round trip.
+struct hmme_table {
+    hmme_ctx* owner = nullptr;
+    int slots = 0, jobsPerSlot = 0;
+    int32_t* dRes = nullptr;       // [slots][4][jobsPerSlot][593]: X, Y, sad, cost
+    int4* dJobs = nullptr;         // [slots][jobsPerSlot]: the jobs each slot was searched with
+    std::vector<int> njobs, range; // per slot, 0 = never searched
+};
+
+int hmme_table_create(hmme_ctx* c, hmme_table** out, int slots, int jobsPerSlot) {
+    if (!c || !out || slots <= 0 || jobsPerSlot <= 0) return fail(c, HMME_ERR_ARG, "hmme_table_create: bad argument");
+    *out = nullptr;
+    CU_TRY(c, cudaSetDevice(c->device));
+    int rc = ensure_jobs(c, (size_t)jobsPerSlot);          // the arg-min scratch must cover a whole slot
+    if (rc != HMME_OK) return rc;
+    hmme_table* t = new hmme_table;
+    t->owner = c; t->slots = slots; t->jobsPerSlot = jobsPerSlot; t->njobs.assign(slots, 0); t->range.assign(slots, 0);
+    const size_t n = (size_t)slots * jobsPerSlot;
+    if (cudaMalloc(&t->dRes, n * 4 * HMME_NPARTS * sizeof(int32_t)) != cudaSuccess || cudaMalloc(&t->dJobs, n * sizeof(int4)) != cudaSuccess) {
+        cudaFree(t->dRes); delete t; cudaGetLastError();
+        return fail(c, HMME_ERR_CUDA, "hmme_table_create: out of device memory");
+    }
+    *out = t;
+    return HMME_OK;
+}
+
+void hmme_table_destroy(hmme_table* t) {
+    if (!t) return;
+    if (t->owner) { cudaSetDevice(t->owner->device); cudaStreamSynchronize(t->owner->stream); cudaStreamSynchronize(t->owner->ioStream[0]); }
+    cudaFree(t->dRes); cudaFree(t->dJobs);
+    delete t;
+}
+
+int hmme_search_frame_table_async(hmme_ctx* c, const hmme_plane* cur, const hmme_plane* ref, const hmme_job* jobs, int njobs, int range,
+                                  hmme_table* t, int slot) {
+    if (!c) return HMME_ERR_ARG;
+    if (!t || t->owner != c || slot < 0 || slot >= t->slots) return fail(c, HMME_ERR_ARG, "hmme_search_frame_table: table does not belong to this context / bad slot");
+    if (!jobs || njobs <= 0 || njobs > t->jobsPerSlot) return fail(c, HMME_ERR_ARG, "hmme_search_frame_table: job count exceeds the table's jobs per slot");
+    if (range < 0 || range > 1024) return fail(c, HMME_ERR_RANGE, "search range out of [0,1024]");
+    if (c->capturing) return fail(c, HMME_ERR_ARG, "hmme_search_frame_table: not available while capturing a graph");
+    int rc = check_plane(c, cur, "current");
+    if (rc == HMME_OK) rc = check_plane(c, ref, "reference");
+    if (rc == HMME_OK) rc = check_jobs(c, cur, ref, jobs, njobs, range);
+    if (rc != HMME_OK) return rc;
+    CU_TRY(c, cudaSetDevice(c->device));
+    int4* dj = t->dJobs + (size_t)slot * t->jobsPerSlot;
+    CU_TRY(c, cudaMemcpyAsync(dj, jobs, (size_t)njobs * sizeof(hmme_job), cudaMemcpyHostToDevice, c->stream));
+    SearchIO io{};
+    const size_t plane = (size_t)t->jobsPerSlot * HMME_NPARTS;
+    io.jobs = dj;
+    io.X = t->dRes + (size_t)slot * 4 * plane; io.Y = io.X + plane;
+    io.S = reinterpret_cast<uint32_t*>(io.Y + plane); io.Cst = io.S + plane;
+    io.finalizeInline = false;
+    t->njobs[slot] = njobs; t->range[slot] = range;
+    const char* refLo = static_cast<const char*>(ref->base);
+    return enqueue_search(c, io, origin_ptr(cur), cur->elemBytes, cur->pitch, origin_ptr(ref), ref->elemBytes, ref->pitch, refLo,
+                          refLo + plane_elems(ref) * ref->elemBytes + 64, njobs, range);
+}
+
+int hmme_table_fetch_async(hmme_ctx* c, hmme_table* t, int slot, int firstJob, int njobs, int32_t* X, int32_t* Y, uint32_t* sad, uint32_t* cost) {
+    if (!c) return HMME_ERR_ARG;
+    if (!t || t->owner != c || slot < 0 || slot >= t->slots || firstJob < 0 || njobs <= 0 || firstJob + njobs > t->njobs[slot])
+        return fail(c, HMME_ERR_ARG, "hmme_table_fetch: bad slot or job range (the slot holds " + std::to_string(t && slot >= 0 && slot < t->slots ? t->njobs[slot] : 0) + " jobs)");
+    CU_TRY(c, cudaSetDevice(c->device));
+    const size_t plane = (size_t)t->jobsPerSlot * HMME_NPARTS, n = (size_t)njobs * HMME_NPARTS;
+    const int32_t* base = t->dRes + (size_t)slot * 4 * plane + (size_t)firstJob * HMME_NPARTS;
+    void* outs[4] = {X, Y, sad, cost};
+    for (int k = 0; k < 4; ++k)
+        if (outs[k]) CU_TRY(c, cudaMemcpyAsync(outs[k], base + k * plane, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    return HMME_OK;
+}
+
+const void* hmme_table_device_ptr(hmme_table* t, int slot, int array) {
+    if (!t || slot < 0 || slot >= t->slots || array < 0 || array > 3) return nullptr;
+    const size_t plane = (size_t)t->jobsPerSlot * HMME_NPARTS;
+    return t->dRes + (size_t)slot * 4 * plane + (size_t)array * plane;
 }
 
 int hmme_fetch_results(hmme_ctx* c, int njobs, int32_t* X, int32_t* Y, uint32_t* sad, uint32_t* cost) {
@@ -760,6 +866,7 @@ int mc_cost_planes(hmme_ctx* c, const hmme_plane* cur, const hmme_plane* ref, co
     c->evFracValid = true;
     c->launches += 1;
     CU_TRY(c, cudaGetLastError());
+    { const int rcm = mark_compute(c); if (rcm != HMME_OK) return rcm; }
     CU_TRY(c, cudaMemcpyAsync(dist, c->dFrac, (size_t)npus * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
     return sync_ctx(c);
 }
@@ -908,6 +1015,7 @@ int hmme_graph_begin(hmme_ctx* c) {
     }
     int rc = sync_ctx(c);
     if (rc != HMME_OK) return rc;
+    c->uploadValid[0] = c->uploadValid[1] = false;          // events recorded before the capture are not part of it
     CU_TRY(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed));
     c->capturing = true;
     // the io streams join the capture by depending on the origin stream
@@ -928,8 +1036,13 @@ int hmme_graph_end(hmme_ctx* c, hmme_graph** out) {
         if (e == cudaSuccess) e = cudaStreamWaitEvent(c->stream, c->evJoin[k], 0);
     }
     const cudaError_t e2 = cudaStreamEndCapture(c->stream, &g);
+    // events recorded while capturing belong to the graph: nothing outside may wait on or time them
+    c->evValid = false; c->evFracValid = false; c->uploadValid[0] = c->uploadValid[1] = false;
+    std::vector<void*> bufs;
+    bufs.swap(c->captureBufs);
     if (e != cudaSuccess || e2 != cudaSuccess || !g) {
         if (g) cudaGraphDestroy(g);
+        for (void* b : bufs) cudaFreeHost(b);
         cudaGetLastError();
         return fail(c, HMME_ERR_CUDA, std::string("graph capture failed: ") + cudaGetErrorString(e != cudaSuccess ? e : e2));
     }
@@ -955,9 +1068,10 @@ int hmme_graph_end(hmme_ctx* c, hmme_graph** out) {
         cudaGetLastError();
     }
     hmme_graph* h = new hmme_graph;
-    h->graph = g; h->owner = c;
+    h->graph = g; h->owner = c; h->bufGen = c->bufGen; h->pinned.swap(bufs);
     e = cudaGraphInstantiateWithFlags(&h->exec, g, cudaGraphInstantiateFlagUseNodePriority);
-    if (e != cudaSuccess) { cudaGraphDestroy(g); delete h; return fail(c, HMME_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e)); }
+    if (e != cudaSuccess) { hmme_graph_destroy(h); return fail(c, HMME_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e)); }
+    CU_TRY(c, cudaEventRecord(c->evCompute, c->stream));    // outside the capture again: later uploads have a valid event to wait on
     *out = h;
     return HMME_OK;
 }
@@ -965,9 +1079,11 @@ int hmme_graph_end(hmme_ctx* c, hmme_graph** out) {
 int hmme_graph_launch(hmme_ctx* c, hmme_graph* g) {
     if (!c || !g || g->owner != c || !g->exec) return fail(c, HMME_ERR_ARG, "hmme_graph_launch: graph does not belong to this context");
     if (c->capturing) return fail(c, HMME_ERR_ARG, "hmme_graph_launch: capturing");
+    if (g->bufGen != c->bufGen)
+        return fail(c, HMME_ERR_ARG, "hmme_graph_launch: a device buffer of this context was reallocated after the graph was recorded; record it again");
     CU_TRY(c, cudaSetDevice(c->device));
     CU_TRY(c, cudaGraphLaunch(g->exec, c->stream));
-    CU_TRY(c, cudaEventRecord(c->evSearch, c->stream));     // later uploads outside graphs order themselves after this launch
+    CU_TRY(c, cudaEventRecord(c->evCompute, c->stream));     // later uploads outside graphs order themselves after this launch
     c->contentCheckPending = true;
     c->evValid = false; c->evFracValid = false;             // the timing events were recorded inside the graph: not readable
     return HMME_OK;
@@ -978,6 +1094,7 @@ void hmme_graph_destroy(hmme_graph* g) {
     if (g->owner && g->owner->device >= 0) cudaSetDevice(g->owner->device);
     if (g->exec) cudaGraphExecDestroy(g->exec);
     if (g->graph) cudaGraphDestroy(g->graph);
+    for (void* b : g->pinned) cudaFreeHost(b);
     delete g;
 }
 

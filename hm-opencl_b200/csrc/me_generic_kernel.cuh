@@ -175,6 +175,38 @@ __global__ void me_narrow_kernel(const int16_t* __restrict__ src, uint8_t* __res
     if (bad) atomicOr(flag, 1);
 }
 
+// Same narrowing for a rectangle: src = dense staging rows of `spitch` int16 (spitch a multiple of 8, so every row starts 16-byte
+// aligned), dst = the rectangle's top-left sample inside an 8-bit plane of pitch `dpitch`.  One thread per 8 samples of a row.
+__global__ void me_narrow_rect_kernel(const int16_t* __restrict__ src, int spitch, uint8_t* __restrict__ dst, long long dpitch, int cols, int rows,
+                                      int* flag) {
+    const int perRow = (cols + 7) >> 3;
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= (long long)perRow * rows) return;
+    const int r = (int)(t / perRow), q = (int)(t - (long long)r * perRow) * 8;
+    const int16_t* s = src + (size_t)r * spitch + q;
+    uint8_t* d = dst + r * dpitch + q;
+    bool bad = false;
+    if (q + 8 <= cols) {
+        const uint4 v = *reinterpret_cast<const uint4*>(s);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        uint32_t lo = 0, hi = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            bad |= (w[k] & 0xFF00FF00u) != 0;
+            const uint32_t two = (w[k] & 0xFFu) | ((w[k] >> 8) & 0xFF00u);
+            if (k < 2) lo |= two << (16 * k); else hi |= two << (16 * (k - 2));
+        }
+        if ((reinterpret_cast<uintptr_t>(d) & 7) == 0) *reinterpret_cast<uint2*>(d) = make_uint2(lo, hi);
+        else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { d[k] = (uint8_t)(lo >> (8 * k)); d[4 + k] = (uint8_t)(hi >> (8 * k)); }
+        }
+    } else {
+        for (int k = 0; q + k < cols; ++k) { const int x = s[k]; bad |= (x < 0 || x > 255); d[k] = (uint8_t)x; }
+    }
+    if (bad) atomicOr(flag, 1);
+}
+
 // Integer-ALU issue-rate probe: a dependent-free stream of VABSDIFF4.U8.ACC (the kernel's dominant ALU
 // instruction); lanes/clk/SM from clock64, SM MHz from clock64 vs the event time.
 __global__ void __launch_bounds__(1024) me_alu_probe_kernel(uint32_t* out, unsigned long long* cyc, int iters, uint32_t seed) {

@@ -431,24 +431,29 @@ __global__ void __launch_bounds__(kFastThreads, 1) me_u8_tile_kernel(const FastP
     // reference's row-wrap behaviour is kept) land in a dense buffer that aliases the not-yet-used record ring; the CTU rows
     // go the same way when they are 16-byte aligned.  All threads then expand the dense rows into sliding words.
     {
-        const int rows = nRG * YB + 63, nPos = twA + 60;      // entries 0 .. (twA-1) + 4*15
+        // rows the unrolled loop addresses (nRG * YB + 63) vs rows that exist in the job's window: when thA is not a multiple of YB
+        // the last one or two belong to masked candidates only and may lie past the plane's last row, so they are not fetched
+        const int rows = nRG * YB + 63, rowsReal = thA + 63, nPos = twA + 60;      // entries 0 .. (twA-1) + 4*15
         const uint8_t* wbase = p.ref + (long long)(jb.y + jb.w + y0) * p.refPitch + (jb.x + jb.z + x0);
         const uint8_t* cbase = p.cur + (long long)jb.y * p.curPitch + jb.x;
         const bool curTma = (((uintptr_t)cbase | (uintptr_t)p.curPitch) & 15) == 0;
         uint8_t* dense = reinterpret_cast<uint8_t*>(sUp);
         if (tid == 0) {
-            mbar_init(&winBar, (uint32_t)(rows + (curTma ? 64 : 0)));
+            mbar_init(&winBar, (uint32_t)(rowsReal + (curTma ? 64 : 0)));
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncthreads();
-        if (tid < rows) {
+        if (tid < rowsReal) {
             const uintptr_t g = (uintptr_t)(wbase + (long long)tid * p.refPitch);
             const uintptr_t g0 = g & ~(uintptr_t)15;
             uint32_t bytes = (uint32_t)(((g - g0) + (uintptr_t)(nPos + 3) + 15) & ~(uintptr_t)15);
-            const uintptr_t room = ((uintptr_t)p.refHi - g0) & ~(uintptr_t)15;          // never read past the allocation (+slack)
+            const uintptr_t room = g0 < (uintptr_t)p.refHi ? ((uintptr_t)p.refHi - g0) & ~(uintptr_t)15 : 0;   // never read past the allocation (+slack)
             bytes = (uint32_t)min((uintptr_t)bytes, room);
-            mbar_arrive_expect_tx(&winBar, bytes);
-            tma_bulk_g2s(dense + tid * kDensePitch, reinterpret_cast<const void*>(g0), bytes, &winBar);
+            if (bytes) {
+                mbar_arrive_expect_tx(&winBar, bytes);
+                tma_bulk_g2s(dense + tid * kDensePitch, reinterpret_cast<const void*>(g0), bytes, &winBar);
+            } else
+                mbar_arrive(&winBar);
         } else if (curTma && tid >= kFastThreads - 64) {
             const int r = tid - (kFastThreads - 64);
             mbar_arrive_expect_tx(&winBar, 64);

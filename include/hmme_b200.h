@@ -36,7 +36,8 @@ typedef enum {
     HMME_ERR_CUDA = -3,       /* a CUDA runtime call failed */
     HMME_ERR_RANGE = -4,      /* search range / CTU size beyond what the context was created for */
     HMME_ERR_CONTENT = -5,    /* plane declared 8-bit holds samples outside [0,255] */
-    HMME_ERR_BOUNDS = -6      /* a job's window leaves the plane allocation (reference: undefined behaviour, App. B4) */
+    HMME_ERR_BOUNDS = -6,     /* a job's window leaves the plane allocation (reference: undefined behaviour, App. B4) */
+    HMME_ERR_NCCL = -7        /* NCCL could not be loaded or a collective failed (only HMME_REF_BROADCAST needs NCCL) */
 } hmme_status;
 
 typedef struct hmme_ctx hmme_ctx;
@@ -87,8 +88,14 @@ int hmme_plane_free(hmme_ctx* ctx, hmme_plane* plane);
  * and fails with HMME_ERR_CONTENT if a sample does not fit.  hostOrigin points at picture sample (0,0);
  * the margins are copied too (they must exist on the host side, as in TComPicYuv, TComPicYuv.cpp:93-94). */
 int hmme_plane_upload_s16(hmme_ctx* ctx, const hmme_plane* plane, const int16_t* hostOrigin, int hostStride);
-/* Host 8-bit plane -> device 8-bit plane (same geometry rules). */
+/* Host 8-bit plane -> device 8-bit plane (same geometry rules): half the bytes of the int16 form for callers that hold 8-bit video. */
 int hmme_plane_upload_u8(hmme_ctx* ctx, const hmme_plane* plane, const uint8_t* hostOrigin, int hostStride);
+int hmme_plane_upload_u8_async(hmme_ctx* ctx, const hmme_plane* plane, const uint8_t* hostOrigin, int hostStride);
+/* The general form: only the rectangle [x0, x1) x [y0, y1) (picture coordinates; negative / beyond the picture = margin samples) of
+ * a host plane whose samples are hostElemBytes wide (1: uint8, 2: int16).  This is how a GPU that owns a band of CTU rows receives
+ * just the rows it reads (band + search-window halo).  Asynchronous, same rules as hmme_plane_upload_s16_async. */
+int hmme_plane_upload_rect_async(hmme_ctx* ctx, const hmme_plane* plane, const void* hostOrigin, int hostStride, int hostElemBytes,
+                                 int x0, int y0, int x1, int y1);
 
 /* ---- whole-frame batch: njobs independent calcMotionVectors calls in one launch sequence.
  * jobs, X, Y, sad, cost are HOST arrays ([njobs] and [njobs][593]); cost may be NULL.
@@ -106,6 +113,61 @@ int hmme_fetch_results(hmme_ctx* ctx, int njobs, int32_t* X, int32_t* Y, uint32_
 int hmme_plane_upload_s16_async(hmme_ctx* ctx, const hmme_plane* plane, const int16_t* hostOrigin, int hostStride);
 int hmme_fetch_results_async(hmme_ctx* ctx, int njobs, int32_t* X, int32_t* Y, uint32_t* sad, uint32_t* cost);
 int hmme_sync(hmme_ctx* ctx);
+
+/* ---- device-resident result tables.  The reference keeps TComMv allMotionVectors[2][33][593] and
+ * Distortion allRuiCost[2][33][593] (TEncSearch.h:114-115) for the CTU being coded, on the host.  A table keeps the same 593-entry
+ * records for EVERY CTU job of a picture in HBM, one slot per (reference list, reference index) -- or per window hypothesis of the
+ * speculative whole-frame search -- so that a B picture's two lists do not overwrite each other.
+ * hmme_search_frame_table_async leaves its results in table[slot] (nothing is copied to the host); hmme_table_fetch_async copies a
+ * job range of a slot to host arrays; hmme_table_device_ptr gives the device address of one of the four [jobsPerSlot][593] arrays
+ * (0: X, 1: Y, 2: sad, 3: cost) for consumers on the GPU. */
+typedef struct hmme_table hmme_table;
+int hmme_table_create(hmme_ctx* ctx, hmme_table** out, int slots, int jobsPerSlot);
+void hmme_table_destroy(hmme_table* table);
+int hmme_search_frame_table_async(hmme_ctx* ctx, const hmme_plane* cur, const hmme_plane* ref, const hmme_job* jobs, int njobs,
+                                  int range, hmme_table* table, int slot);
+int hmme_table_fetch_async(hmme_ctx* ctx, hmme_table* table, int slot, int firstJob, int njobs, int32_t* X, int32_t* Y,
+                           uint32_t* sad, uint32_t* cost);
+const void* hmme_table_device_ptr(hmme_table* table, int slot, int array);
+
+/* ---- multi-GPU (the reference drives one device, TEncOpenCL.cpp:129,185 -- this is north_star's addition).
+ * A group searches ONE frame on several B200s: the job list is cut into contiguous bands (CTU rows, cut at CTU granularity, sizes
+ * differ by at most one job), every GPU searches its band and writes its rows of the caller's [njobs][593] host tables.
+ * Reference-picture distribution:
+ *   HMME_REF_BAND_HALO  every GPU copies, over its own PCIe link, only the rectangle its band reads (band + window halo); no collective
+ *   HMME_REF_BROADCAST  global rank 0 uploads the whole padded plane, ncclBroadcast carries it over NVLink / NVSwitch
+ * Process models: hmme_group_create = one process, ndev GPUs (one enqueue thread per GPU; ncclCommInitAll);
+ * hmme_group_create_rank = this process is rank `rank` of `nranks` one-GPU processes (torchrun); uniqueId (128 bytes, made by rank 0
+ * with hmme_group_unique_id and distributed by the launcher) may be NULL when only HMME_REF_BAND_HALO is used.  With create_rank every
+ * process passes the same whole-frame arguments and fills only its own band's rows of the tables.
+ * Host planes: hostElemBytes 2 = HM's Pel (int16, narrowed on the device), 1 = uint8.  Origins point at picture sample (0,0); the
+ * reference plane's margins must exist (TComPicYuv).  Windows must stay inside the padded picture (HMME_ERR_BOUNDS otherwise).
+ * slot (0 or 1) selects one of two frames in flight; host buffers stay valid (ideally page-locked) until hmme_group_sync(slot). */
+typedef struct hmme_group hmme_group;
+enum { HMME_REF_BAND_HALO = 0, HMME_REF_BROADCAST = 1 };
+int hmme_group_create(hmme_group** out, const int* devices, int ndev, int maxSearchRange);
+int hmme_group_unique_id(void* id, size_t bytes);
+int hmme_group_create_rank(hmme_group** out, int device, int rank, int nranks, const void* uniqueId, int maxSearchRange);
+void hmme_group_destroy(hmme_group* group);
+const char* hmme_group_last_error(hmme_group* group);            /* group may be NULL: error of the last failed create */
+int hmme_group_size(hmme_group* group, int* world, int* nlocal);
+int hmme_group_set_lambda_q16(hmme_group* group, uint32_t lambdaQ16);
+int hmme_group_configure(hmme_group* group, int width, int height, int marginX, int marginY, int refDist);
+int hmme_group_search_frame_async(hmme_group* group, int slot, const void* curHostOrigin, int curHostStride,
+                                  const void* refHostOrigin, int refHostStride, int hostElemBytes, const hmme_job* jobs, int njobs,
+                                  int range, int32_t* X, int32_t* Y, uint32_t* sad, uint32_t* cost);
+int hmme_group_sync(hmme_group* group, int slot);                /* slot -1: both */
+int hmme_group_search_frame(hmme_group* group, const void* curHostOrigin, int curHostStride, const void* refHostOrigin,
+                            int refHostStride, int hostElemBytes, const hmme_job* jobs, int njobs, int range, int32_t* X, int32_t* Y,
+                            uint32_t* sad, uint32_t* cost);
+int hmme_group_band(hmme_group* group, int njobs, int localIndex, int* first, int* count);
+hmme_ctx* hmme_group_context(hmme_group* group, int localIndex, int slot);   /* the per-GPU context behind a slot (refinement, timing) */
+int hmme_group_last_kernel_ms(hmme_group* group, int slot, float* searchKernelMsMaxOverLocalGpus);
+uint64_t hmme_group_kernel_launches(hmme_group* group);
+/* The band arithmetic itself, pure host code: jobs [first, first + count) of njobs belong to `rank` of `world`; and the picture
+ * rectangles {x0, y0, x1, y1} a job range reads from the current frame (its CTUs) and from the reference picture (band + halo). */
+int hmme_band_split(int njobs, int world, int rank, int* first, int* count);
+int hmme_band_extent(const hmme_job* jobs, int njobs, int range, int* curRect, int* refRect);
 
 /* ---- CUDA graphs for launch-bound steps (many GPUs, narrow bands: tens of runtime calls for a fraction of a millisecond of
  * kernels).  hmme_graph_begin .. hmme_graph_end records the asynchronous calls made on this context in between

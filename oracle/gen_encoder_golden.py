@@ -32,6 +32,8 @@ CASES = {
     "ra_416x240_9f_sr8": (416, 240, 9, "encoder_randomaccess_main.cfg", ["--SearchRange=8"]),
     "ldp_1920x1080_2f_sr8": (1920, 1080, 2, "encoder_lowdelay_P_main.cfg", ["--SearchRange=8"]),
     "ra_416x240_9f_sr64": (416, 240, 9, "encoder_randomaccess_main.cfg", ["--SearchRange=64"]),
+    # BASELINE.json configs[1] at its full size: 480 calcMotionVectors calls of 16 641 candidates each (~35 min of lock-step emulation)
+    "ldp_1920x1080_2f_sr64": (1920, 1080, 2, "encoder_lowdelay_P_main.cfg", ["--SearchRange=64"]),
 }
 
 
