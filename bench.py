@@ -1,21 +1,24 @@
 #!/usr/bin/env python
 """bench.py -- whole-CTU integer-pel motion estimation throughput on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload 1080p64|4k128|...] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload 1080p64|4k128|1080p64_ra|...] [--impl reference] [--no-verify]
 
 A step = the integer ME of ONE frame against ONE reference picture: every full 64x64 CTU of the frame,
 (2R+1)^2 candidates each, 593 partitions per candidate (config[1] of BASELINE.json at N=1: 1920x1080,
-+-64 -> 480 jobs x 16641 candidates).  With N > 1 (torchrun, one rank per GPU) the frame is split into
-contiguous CTU-row bands (strong scaling); the reference picture is uploaded by rank 0
-and NCCL-broadcast, each rank uploads and searches only its band.
++-64 -> 480 jobs x 16641 candidates).  With N > 1 (torchrun, one rank per GPU) the frame's jobs are cut into
+contiguous CTU-row bands by the LIBRARY (hmme_group_*, include/hmme_b200.h): every rank passes the same whole-frame
+arguments to hmme_group_search_frame_async and gets its band's rows of the result tables back; the reference picture
+reaches the GPUs either as band + halo rectangles over each GPU's own PCIe link (default) or by NCCL broadcast over
+NVLink from rank 0 (`e2e.broadcast`, also measured).  Python only loops over steps.
 
-Output: ONE JSON line on rank 0 (contract in the task statement): `value` = block-SAD evaluations/s with
-inputs resident in HBM (K frames alternating over two library contexts/streams, CUDA events around the whole region,
-inputs cycled through more plane copies than fit in L2), `e2e` = the same
-metric through the public C-ABI calls with pinned HOST buffers (H2D of both int16 planes + jobs, D2H of the
-four result arrays inside the timed region), `roofline` = algorithmic integer lane-ops/s of the dominant
-kernel against the ALU issue rate measured live, `cpu_baseline` = the reference's own CPU full-search ME
-(oracle/_ref/TAppEncoder_cpume, one single-threaded process per core), `cpu_port` = the CPU oracle port.
+Output: ONE JSON line on rank 0 (contract in the task statement): `value` = block-SAD evaluations/s with inputs
+resident in HBM (K frames alternating over the group's two frame slots = two streams, CUDA events around the whole
+region, inputs cycled through more plane copies than fit in L2), `e2e` = the same metric through the group call with
+pinned HOST planes (HM's int16 Pel; H2D of both planes' band rectangles + jobs, D2H of the four result arrays inside
+the timed region), `roofline` = algorithmic integer lane-ops/s of the dominant kernel against the ALU issue rate
+measured live (`frac`, the survey's definition) and against both integer pipes (`frac_issue`), `verified` = every
+CTU of every rank's band compared bit for bit with the CPU oracle after the timed regions, `per_ctu` = the
+synchronous per-CTU call the encoder makes, `cpu_baseline` = the reference's own CPU full-search ME.
 """
 import argparse
 import json
@@ -33,6 +36,7 @@ from synth import frame_jobs, luma_frames, pad_plane  # noqa: E402
 
 WORKLOADS = {                      # name: (W, H, R)   -- BASELINE.json configs
     "1080p64": (1920, 1080, 64),   # config[1] (and the metric's "1080p frames/s (+-64)")
+    "1080p64_ra": (1920, 1080, 64),  # config[2]: random access, two reference lists + bi-prediction refinement (+-4, 16-bit block)
     "4k128": (3840, 2160, 128),    # config[3]
     "1080p32": (1920, 1080, 32),
     "1080p16": (1920, 1080, 16),
@@ -40,14 +44,29 @@ WORKLOADS = {                      # name: (W, H, R)   -- BASELINE.json configs
 }
 NPARTS = 593
 INT_OPS_PER_CAND = 2803            # 1024 packed SADs + 593 adds + 593 cost adds + 593 min
+INT_OPS_PER_CAND_16 = 3827         # same with 2048 packed 2x16-bit absolute differences (bi-prediction block)
 PX_PER_CAND = 4096
 LAMBDA_Q16 = 460000                # QP ~32 (SURVEY.md section 8d synthetic inputs)
+BI_RANGE = 4                       # bipredSearchRange of the reference's configurations (cfg/encoder_randomaccess_main.cfg)
+REF_ARM_CLIP = (416, 240)          # the reference arm's bounded sample: this crop of the workload's own frame pair (18 full CTUs, ~10 s on 16 cores)
 
 
 def workload_geometry(name):
     W, H, R = WORKLOADS[name]
     margin = max(80, R + 16)       # HM pads by 80 (TComPicYuv.cpp:93-94); larger ranges need more for in-bounds windows
     return W, H, R, margin
+
+
+def shared_config(name):
+    """`config` of the JSON line: identical in the b200 arm and the reference arm (the driver compares them)."""
+    W, H, R = WORKLOADS[name]
+    ncx, ncy = W // 64, H // 64
+    return {"workload": "%s: %dx%d luma, 64x64 CTU, integer-pel full search +-%d, 1 reference picture, %d CTU jobs x %d candidates x 593 partitions"
+                        % (name, W, H, R, ncx * ncy, (2 * R + 1) ** 2),
+            "lambda_q16": LAMBDA_Q16,
+            "reference_arm_sample": "the reference arm (--impl reference) times the reference's CPU full search (+-%d) on the top-left %dx%d crop of this "
+                                    "workload's frame pair per step, one single-threaded encoder process per host core; rates are per block-SAD evaluation"
+                                    % (R, REF_ARM_CLIP[0], REF_ARM_CLIP[1])}
 
 
 class ClockSampler:
@@ -115,21 +134,26 @@ CPUME_BIN = os.path.join(ROOT, "oracle", "_ref", "TAppEncoder_cpume")
 CPUME_CFG = os.path.join(ROOT, "oracle", "_ref", "cfg", "encoder_lowdelay_P_main.cfg")
 
 
-def reference_cpu_me(R, clip, procs, fast_search=0):
+def write_clip(path, frames):
+    with open(path, "wb") as fh:
+        for y in frames:
+            h, w = y.shape
+            fh.write(np.ascontiguousarray(y).tobytes())
+            fh.write(np.full((h // 2) * (w // 2) * 2, 128, np.uint8).tobytes())
+
+
+def reference_cpu_me(R, frames, procs, fast_search=0):
     """The reference's OWN CPU integer ME (--OpenCL=0 --FastSearch=0: TEncSearch::xPatternSearch + TComRdCost::xGetSAD*,
     TEncSearch.cpp:3774-3791,3835-3897) timed inside the reference encoder built from source with the counters of
     BASELINE.md section 3 (oracle/patch_cpume.py): `procs` independent single-threaded encoder processes (HM has no threads)
-    encode the same 2-frame synthetic clip (I + P, one reference picture).  Returns block-SAD evaluations/s summed over
-    processes, ME seconds (max over processes), DistFunc calls."""
+    encode the same 2-frame clip `frames` (I + P, one reference picture).  Returns block-SAD evaluations/s summed over
+    processes, ME seconds (max over processes), DistFunc calls, wall seconds."""
     import re
     import tempfile
-    W, H = clip
+    H, W = frames[0].shape
     with tempfile.TemporaryDirectory() as d:
         yuv = os.path.join(d, "clip.yuv")
-        with open(yuv, "wb") as fh:
-            for y in luma_frames(W, H, 2):
-                fh.write(y.tobytes())
-                fh.write(np.full((H // 2) * (W // 2) * 2, 128, np.uint8).tobytes())
+        write_clip(yuv, frames)
         cmds = [[CPUME_BIN, "-c", CPUME_CFG, "-i", yuv, "-wdt", str(W), "-hgt", str(H), "-fr", "30", "-f", "2", "-q", "32",
                  "-b", os.path.join(d, "o%d.hevc" % i), "-o", "", "--OpenCL=0", "--FastSearch=%d" % fast_search, "--SearchRange=%d" % R] for i in range(procs)]
         t0 = time.perf_counter()
@@ -154,10 +178,7 @@ def reference_cpu_frac():
     W, H = 416, 240
     with tempfile.TemporaryDirectory() as d:
         yuv = os.path.join(d, "clip.yuv")
-        with open(yuv, "wb") as fh:
-            for y in luma_frames(W, H, 2):
-                fh.write(y.tobytes())
-                fh.write(np.full((H // 2) * (W // 2) * 2, 128, np.uint8).tobytes())
+        write_clip(yuv, luma_frames(W, H, 2))
         r = subprocess.run([CPUME_BIN, "-c", CPUME_CFG, "-i", yuv, "-wdt", str(W), "-hgt", str(H), "-fr", "30", "-f", "2", "-q", "32",
                             "-b", os.path.join(d, "o.hevc"), "-o", "", "--OpenCL=0", "--FastSearch=1", "--SearchRange=64"],
                            stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
@@ -169,32 +190,40 @@ def reference_cpu_frac():
             "sample": "%d xPatternSearchFracDIF calls (%d PU pixels) in %.3f s inside the reference encoder, 416x240 I+P, one core" % (calls, px, secs)}
 
 
-def cpu_baseline_entry(R, budget_s, all_cores=True):
-    """cpu_baseline object: the reference's CPU ME when oracle/_ref holds its build, else the oracle port."""
+def workload_crop(name, clip):
+    """The top-left clip[0] x clip[1] crop of the workload's own synthetic frame pair (frame 0 = reference, frame 1 = current)."""
+    W, H, _ = WORKLOADS[name]
+    cw, ch = min(clip[0], W // 64 * 64), min(clip[1], H // 64 * 64)
+    f = luma_frames(W, H, 2)
+    return [np.ascontiguousarray(y[:ch, :cw]) for y in f], (cw, ch)
+
+
+def cpu_baseline_entry(name, clip, all_cores=True):
+    """cpu_baseline object: the reference's CPU ME on a fixed crop of the workload when oracle/_ref holds its build, else the oracle port."""
+    W, H, R = WORKLOADS[name]
     threads = os.cpu_count() or 1
     if os.path.exists(CPUME_BIN) and os.path.exists(CPUME_CFG):
-        clip = (416, 240) if budget_s >= 30 else (192, 128) if budget_s >= 10 else (128, 64) if budget_s >= 4 else (64, 64)
+        frames, (cw, ch) = workload_crop(name, clip)
         procs = threads if all_cores else 1
-        v, me_s, calls, wall = reference_cpu_me(R, clip, procs)
+        v, me_s, calls, wall = reference_cpu_me(R, frames, procs)
         return {"value": v, "unit": "block-SAD evaluations/s", "cores": procs, "kind": "reference",
-                "sample": "reference encoder built from source (oracle/_ref/TAppEncoder_cpume), --OpenCL=0 --FastSearch=0 --SearchRange=%d, "
-                          "%dx%d synthetic clip, 2 frames (I+P, 1 ref), %d independent single-threaded processes: %d DistFunc calls in %.1f s of "
-                          "xPatternSearch (max over processes), %.1f s wall" % (R, clip[0], clip[1], procs, calls, me_s, wall)}, wall
-    W, H, R_, margin = workload_geometry("1080p64")
+                "sample": "reference encoder built from source (oracle/_ref/TAppEncoder_cpume), --OpenCL=0 --FastSearch=0 --SearchRange=%d, top-left %dx%d crop "
+                          "(%d CTUs) of the workload's frame pair (I+P, 1 ref), %d independent single-threaded processes: %d DistFunc calls in %.1f s of "
+                          "xPatternSearch (max over processes), %.1f s wall" % (R, cw, ch, (cw // 64) * (ch // 64), procs, calls, me_s, wall)}, wall
     v, dt, n = cpu_oracle_throughput(W, H, R, max(80, R + 16), max(8 * threads, 64), threads)
     return {"value": v, "unit": "block-SAD evaluations/s", "cores": threads, "kind": "port",
-            "sample": "%d CTU jobs of the 1080p frame, %.1f s wall on %d threads (oracle/hmme_oracle.c; oracle/_ref absent)" % (n, dt, threads)}, dt
+            "sample": "%d CTU jobs of the frame, %.1f s wall on %d threads (oracle/hmme_oracle.c; oracle/_ref absent)" % (n, dt, threads)}, dt
 
 
 def run_reference(args, rank):
-    """--impl reference: the reference's own CPU implementation of integer ME on the host cores (see reference_cpu_me)."""
+    """--impl reference: the reference's own CPU implementation of integer ME on the host cores.  Every step times the SAME fixed
+    sample (REF_ARM_CLIP crop of the workload's frames), whatever --steps is."""
     if rank != 0:
         return
     W, H, R, margin = workload_geometry(args.workload)
-    budget = 240.0 / max(1, args.steps + args.warmup)
     vals, entry = [], None
     for s in range(args.warmup + args.steps):
-        entry, wall = cpu_baseline_entry(R, budget)
+        entry, wall = cpu_baseline_entry(args.workload, REF_ARM_CLIP)
         if s >= args.warmup:
             vals.append((entry["value"], wall))
     value = float(np.mean([v for v, _ in vals]))
@@ -205,8 +234,7 @@ def run_reference(args, rank):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "s16", "data": "synthetic",
         "frames_per_s_equivalent": value / (NPARTS * (2 * R + 1) ** 2 * (W // 64) * (H // 64)),
-        "config": {"workload": "%s: %dx%d luma, 64x64 CTU, integer-pel full search +-%d, 1 reference picture" % (args.workload, W, H, R),
-                   "sample": entry["sample"]},
+        "config": shared_config(args.workload),
         "cpu_baseline": entry,
         "e2e": {"value": value, "unit": "block-SAD evaluations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -220,12 +248,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="1080p64", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--ref-dist", default="broadcast", choices=["allgather", "broadcast"],
-                    help="N > 1: how the reference plane reaches every GPU: rank 0 uploads all of it and NCCL broadcasts (default), or each "
-                         "rank uploads 1/N of it and NCCL all-gathers (faster when steps are serial, no gain once frames are pipelined)")
-    ap.add_argument("--graphs", action="store_true", help="e2e: replay CUDA graphs of the step (hmme_graph_*) instead of issuing it call by call; measured: "
-                                                          "same at N = 1 (1.269 ms), 0.187 vs 0.191 ms for an 8-GPU-sized band on one GPU, slower at N = 2 "
-                                                          "(0.74 vs 0.66 ms: the split around the NCCL broadcast loses overlap), hence off by default")
+    ap.add_argument("--no-verify", action="store_true", help="skip the bit-exact comparison of every rank's band with the CPU oracle after the timed regions")
+    ap.add_argument("--no-extras", action="store_true", help="skip the fractional-refinement / distortion / per-CTU / random-access legs (profiling runs)")
+    ap.add_argument("--ref-dist", default="band_halo", choices=["band_halo", "broadcast"],
+                    help="how the reference picture reaches the GPUs in the reported e2e leg (the other one is measured as well at N > 1)")
     ap.add_argument("--virtual-world", type=int, default=0, help="experiments: on ONE GPU, run only the band rank 0 would get in a world of this size")
     args = ap.parse_args()
     if args.impl == "reference":          # each step is seconds of single-threaded CPU encoders: keep the default run short
@@ -249,168 +275,40 @@ def main():
         raise SystemExit("bench.py needs a B200: the product has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    uid = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL kernels on a high-priority stream: the reference-plane broadcast of one context slips in between the search CTAs of the
-        # other context instead of queueing behind them (HMME_NCCL_LOW_PRIORITY=1 restores the default for comparison)
-        pg_opts = None
-        if not os.environ.get("HMME_NCCL_LOW_PRIORITY"):
-            try:
-                pg_opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
-            except Exception:
-                pg_opts = None
-        dist.init_process_group("nccl", device_id=dev, pg_options=pg_opts)
+        dist.init_process_group("nccl", device_id=dev)
+        box = [hm.Group.unique_id() if rank == 0 else None]          # the library's own NCCL communicator: id made by rank 0, carried by the launcher's group
+        dist.broadcast_object_list(box, src=0)
+        uid = box[0]
 
     W, H, R, margin = workload_geometry(args.workload)
     ncx, ncy = W // 64, H // 64
-    jobs, (r0, r1) = hm.band_jobs(W, H, R, args.virtual_world or world, rank)
-    njobs = len(jobs)
+    vworld = args.virtual_world or world
+    all_jobs = frame_jobs(W, H, R)
+    lib = hm.HmmeLib.get()
+    if args.virtual_world:                                            # one GPU plays rank 0 of a larger world: only that band exists
+        f0, n0 = lib.band_split(len(all_jobs), vworld, 0)
+        all_jobs = np.ascontiguousarray(all_jobs[f0:f0 + n0])
+    total_jobs = len(all_jobs)
     cands_per_job = (2 * R + 1) ** 2
-    total_jobs = len(jobs) if args.virtual_world else ncx * ncy
 
-    # pinned host frames in HM's sample type (Pel = int16), synthetic content
+    grp = hm.Group(device=local_rank, rank=rank, world=world, unique_id=uid, max_search_range=max(R, 64))
+    grp.set_lambda_q16(LAMBDA_Q16)
+    first, njobs = grp.band(total_jobs)
+    jobs = np.ascontiguousarray(all_jobs[first:first + njobs])
+    mes = [grp.context(0, s) for s in range(2)]                       # the per-GPU contexts behind the group's two frame slots
+    me = mes[0]
+    exts = [torch.cuda.ExternalStream(m.stream_ptr, device=dev) for m in mes]
+
+    # pinned host frames: HM's sample type (Pel = int16) and the same content as uint8; synthetic
     f = luma_frames(W, H, 2)
-    h_cur = torch.from_numpy(pad_plane(f[1], margin, margin)).pin_memory()
-    h_ref = torch.from_numpy(pad_plane(f[0], margin, margin)).pin_memory()
-    n_cur, n_ref = h_cur.numpy(), h_ref.numpy()
-    band_h = 64 * (r1 - r0)
-    n_cur_band = n_cur[margin + 64 * r0: margin + 64 * r1] if band_h else None
-    pitch = (W + 2 * margin + 15) // 16 * 16
-    rows = H + 2 * margin
-    slice_rows = -(-rows // world)                      # reference rows each rank uploads when the plane is all-gathered
-    s0, s1 = min(rank * slice_rows, rows), min((rank + 1) * slice_rows, rows)
-
-    class Pipe:
-        """One library context with its own stream, device planes (torch tensors, so NCCL can broadcast them; the library
-        works on views) and page-locked result arrays."""
-
-        def __init__(self):
-            self.me = hm.MotionEstimator(local_rank, R)
-            self.me.set_lambda_q16(LAMBDA_Q16)
-            self.ext = torch.cuda.ExternalStream(self.me.stream_ptr, device=dev)
-            self.t_cur = torch.zeros(rows * pitch + 64, dtype=torch.uint8, device=dev)
-            self.t_ref = torch.zeros(slice_rows * world * pitch + 64, dtype=torch.uint8, device=dev)
-            self.p_cur = self.me.wrap_plane(self.t_cur.data_ptr(), 1, pitch, W, H, margin, margin)
-            self.p_ref = self.me.wrap_plane(self.t_ref.data_ptr(), 1, pitch, W, H, margin, margin)
-            # this rank's band of the current frame as its own upload target (rows [64*r0, 64*r1), no vertical margin)
-            self.p_cur_band = self.me.wrap_plane(self.t_cur.data_ptr() + (margin + 64 * r0) * pitch, 1, pitch, W, band_h, margin, 0) if band_h else None
-            # this rank's horizontal slice of the (padded) reference plane as its own upload target
-            self.p_ref_slice = self.me.wrap_plane(self.t_ref.data_ptr() + s0 * pitch, 1, pitch, W, s1 - s0, margin, 0) if s1 > s0 else None
-            self.outs = [torch.zeros((max(njobs, 1), NPARTS), dtype=torch.int32).pin_memory().numpy().view(t)
-                         for t in (np.int32, np.int32, np.uint32, np.uint32)]
-
-        def upload_inputs(self, asynchronous=False):
-            """The per-step host->device leg of the public API: reference picture (rank 0, then NCCL broadcast over NVLink),
-            band of the current frame (every rank)."""
-            if world > 1 and args.ref_dist == "allgather":
-                # every rank pushes 1/N of the reference over its own PCIe link, then NCCL all-gathers the 8-bit slices in place
-                if self.p_ref_slice is not None:
-                    self.me.upload(self.p_ref_slice, n_ref[s0:s1], origin_x=margin, origin_y=0, asynchronous=asynchronous)
-                with torch.cuda.stream(self.ext):
-                    full = self.t_ref[:slice_rows * world * pitch]
-                    dist.all_gather_into_tensor(full, full[rank * slice_rows * pitch:(rank + 1) * slice_rows * pitch])
-            else:
-                if rank == 0:
-                    self.me.upload(self.p_ref, n_ref, asynchronous=asynchronous)
-                if world > 1:
-                    with torch.cuda.stream(self.ext):
-                        dist.broadcast(self.t_ref, src=0)
-            if band_h:
-                self.me.upload(self.p_cur_band, n_cur_band, origin_x=margin, origin_y=0, asynchronous=asynchronous)
-
-        def step_e2e(self, asynchronous):
-            self.upload_inputs(asynchronous)
-            if njobs:
-                self.me.search_frame_async(self.p_cur, self.p_ref, jobs, R)
-                self.me.fetch_results(njobs, self.outs, asynchronous=asynchronous)
-
-        def bind(self):
-            """Pre-marshalled calls of the pipelined e2e step (same C entry points as upload / search_frame_async / fetch_results):
-            at N = 8 a step is 0.16 ms of kernels, so the Python argument handling of every call counts."""
-            m = self.me
-            self.b_sync = m.bind_sync()
-            self.b_ref = None
-            if world > 1 and args.ref_dist == "allgather":
-                if self.p_ref_slice is not None:
-                    self.b_ref = m.bind_upload(self.p_ref_slice, n_ref[s0:s1], origin_x=margin, origin_y=0)
-            elif rank == 0:
-                self.b_ref = m.bind_upload(self.p_ref, n_ref)
-            self.b_cur = m.bind_upload(self.p_cur_band, n_cur_band, origin_x=margin, origin_y=0) if band_h else None
-            self.b_search = m.bind_search(self.p_cur, self.p_ref, jobs, R) if njobs else None
-            self.b_fetch = m.bind_fetch(njobs, self.outs) if njobs else None
-
-        def step_e2e_bound(self):
-            if self.b_ref is not None:
-                self.b_ref()
-            if world > 1:
-                with torch.cuda.stream(self.ext):
-                    if args.ref_dist == "allgather":
-                        full = self.t_ref[:slice_rows * world * pitch]
-                        dist.all_gather_into_tensor(full, full[rank * slice_rows * pitch:(rank + 1) * slice_rows * pitch])
-                    else:
-                        dist.broadcast(self.t_ref, src=0)
-            if self.b_cur is not None:
-                self.b_cur()
-            if self.b_search is not None:
-                self.b_search()
-                self.b_fetch()
-
-        def build_graphs(self):
-            """The pipelined e2e step recorded as CUDA graphs (hmme_graph_*): at N = 8 a step is ~25 runtime calls for 0.16 ms of
-            kernels.  One graph when the reference needs no collective, else {upload reference} -> NCCL -> {upload current, search, fetch}."""
-            self.g_ref = self.g_main = None
-            if world == 1:
-                self.me.graph_begin()
-                self.step_e2e(True)
-                self.g_main = self.me.graph_end()
-                return
-            uploads_ref = (self.p_ref_slice is not None) if args.ref_dist == "allgather" else rank == 0
-            if uploads_ref:
-                self.me.graph_begin()
-                if args.ref_dist == "allgather":
-                    self.me.upload(self.p_ref_slice, n_ref[s0:s1], origin_x=margin, origin_y=0, asynchronous=True)
-                else:
-                    self.me.upload(self.p_ref, n_ref, asynchronous=True)
-                self.g_ref = self.me.graph_end()
-            if band_h and njobs:
-                self.me.graph_begin()
-                self.me.upload(self.p_cur_band, n_cur_band, origin_x=margin, origin_y=0, asynchronous=True)
-                self.me.search_frame_async(self.p_cur, self.p_ref, jobs, R)
-                self.me.fetch_results(njobs, self.outs, asynchronous=True)
-                self.g_main = self.me.graph_end()
-
-        def step_e2e_graph(self):
-            if self.g_ref is not None:
-                self.me.graph_launch(self.g_ref)
-            if world > 1:
-                with torch.cuda.stream(self.ext):
-                    if args.ref_dist == "allgather":
-                        full = self.t_ref[:slice_rows * world * pitch]
-                        dist.all_gather_into_tensor(full, full[rank * slice_rows * pitch:(rank + 1) * slice_rows * pitch])
-                    else:
-                        dist.broadcast(self.t_ref, src=0)
-            if self.g_main is not None:
-                self.me.graph_launch(self.g_main)
-
-        def step_e2e_frac(self):
-            """Integer search + fractional refinement of all 593 partitions, host to host."""
-            if not hasattr(self, "frac_out"):
-                self.frac_out = torch.zeros((max(njobs, 1), NPARTS, 4), dtype=torch.int32).pin_memory().numpy()
-            self.upload_inputs(True)
-            if njobs:
-                self.me.search_frame_async(self.p_cur, self.p_ref, jobs, R)
-                self.me.fetch_results(njobs, self.outs, asynchronous=True)
-                self.me.refine_frame(self.p_cur, self.p_ref, njobs, None, True, asynchronous=True, out=self.frac_out)
-
-    pipes = [Pipe(), Pipe()]
-    me, ext, p_cur, p_ref = pipes[0].me, pipes[0].ext, pipes[0].p_cur, pipes[0].p_ref
-    upload_inputs = pipes[0].upload_inputs
-
-    for pp in pipes:
-        pp.upload_inputs()
-        pp.me.sync()
-    torch.cuda.synchronize()
-    peak = me.measure_int_alu_peak()
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()   # noqa: E731
+    n_cur, n_ref = pin(pad_plane(f[1], margin, margin)), pin(pad_plane(f[0], margin, margin))
+    n_cur8, n_ref8 = pin(n_cur.astype(np.uint8)), pin(n_ref.astype(np.uint8))
+    org = (margin, margin)
+    outs = [[pin(np.zeros((total_jobs, NPARTS), t)) for t in (np.int32, np.int32, np.uint32, np.uint32)] for _ in range(2)]
 
     def barrier():
         torch.cuda.synchronize()
@@ -418,125 +316,144 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_resident():
-        if njobs:
-            me.search_frame_async(p_cur, p_ref, jobs, R)
+    def allmax(vals):
+        t = torch.tensor(vals, dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(v) for v in t.tolist()]
+
+    def allsum(vals):
+        t = torch.tensor(vals, dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return [float(v) for v in t.tolist()]
 
     # ------------------------------------------------------------------ value: inputs resident in HBM
-    # Resident inputs: NSETS copies of the (current, reference) plane pair at distinct addresses, together larger than twice
-    # the 126 MB L2, cycled through step by step ("inputs larger than L2"; the kernel is compute bound, but the rule is kept).
-    plane_stride = rows * pitch + 64
-    nsets = max(2, -(-2 * 126 * (1 << 20) // (2 * rows * pitch)))
-    t_sets = torch.zeros(2 * nsets * plane_stride, dtype=torch.uint8, device=dev)
+    # NSETS copies of the (current, reference) plane pair at distinct addresses, together larger than twice the 126 MB L2, cycled
+    # through step by step ("inputs larger than L2"; the kernel is compute bound, but the rule is kept).
+    plane_bytes = (H + 2 * margin) * ((W + 2 * margin + 15) // 16 * 16)
+    nsets = max(2, -(-2 * 126 * (1 << 20) // (2 * plane_bytes)))
     sets = []
-    with torch.cuda.stream(ext):
-        for k in range(nsets):
-            oc, orf = (2 * k) * plane_stride, (2 * k + 1) * plane_stride
-            t_sets[oc:oc + rows * pitch].copy_(pipes[0].t_cur[:rows * pitch])
-            t_sets[orf:orf + rows * pitch].copy_(pipes[0].t_ref[:rows * pitch])
-            sets.append((me.wrap_plane(t_sets.data_ptr() + oc, 1, pitch, W, H, margin, margin),
-                         me.wrap_plane(t_sets.data_ptr() + orf, 1, pitch, W, H, margin, margin)))
+    for k in range(nsets):
+        pc, pr = me.alloc_plane(1, W, H, margin, margin), me.alloc_plane(1, W, H, margin, margin)
+        me.upload(pc, n_cur8, asynchronous=True)
+        me.upload(pr, n_ref8, asynchronous=True)
+        sets.append((pc, pr))
+    me.sync()
     barrier()
+    peak = me.measure_int_alu_peak()
 
     # (a) dominant-kernel duration and single-stream step time: one context, CUDA events per step on its stream
-    for _ in range(args.warmup):
-        step_resident()
+    for s in range(args.warmup):
+        if njobs:
+            me.search_frame_async(sets[s % nsets][0], sets[s % nsets][1], jobs, R)
     barrier()
     n_single = min(args.steps, 40)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_single)]
     kernel_ms = []
-    with torch.cuda.stream(ext):
-        for s in range(n_single):
-            ev[s][0].record(ext)
-            if njobs:
-                me.search_frame_async(sets[s % nsets][0], sets[s % nsets][1], jobs, R)
-            ev[s][1].record(ext)
-            if njobs:
-                kernel_ms.append(me.last_kernel_ms())                  # CUDA events around the dominant kernel, same stream
+    for s in range(n_single):
+        ev[s][0].record(exts[0])
+        if njobs:
+            me.search_frame_async(sets[s % nsets][0], sets[s % nsets][1], jobs, R)
+        ev[s][1].record(exts[0])
+        if njobs:
+            kernel_ms.append(me.last_kernel_ms())                  # CUDA events around the dominant kernel, same stream
     barrier()
     single_ms = sum(a.elapsed_time(b) for a, b in ev) / n_single
 
-    # (b) the reported value: EXACTLY K steps, frames alternating over two contexts (two streams), nothing but the library's
-    # kernels in the timed region; consecutive frames overlap at their wave tails.  CUDA events around the whole region.
+    # (b) the reported value: EXACTLY K steps, frames alternating over the two slots' contexts (two streams), nothing but the
+    # library's kernels in the timed region; consecutive frames overlap at their wave tails.  CUDA events around the whole region.
     for s in range(max(args.warmup, 4)):
         if njobs:
-            pipes[s & 1].me.search_frame_async(sets[s % nsets][0], sets[s % nsets][1], jobs, R)
+            mes[s & 1].search_frame_async(sets[s % nsets][0], sets[s % nsets][1], jobs, R)
     barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
-    launches0 = sum(pp.me.kernel_launches for pp in pipes)
-    ev_start, ev_end = torch.cuda.Event(enable_timing=True), [torch.cuda.Event(enable_timing=True) for _ in pipes]
+    launches0 = grp.kernel_launches
+    ev_start, ev_end = torch.cuda.Event(enable_timing=True), [torch.cuda.Event(enable_timing=True) for _ in mes]
     barrier()
     wall0 = time.perf_counter()
-    ev_start.record(pipes[0].ext)
+    ev_start.record(exts[0])
     for s in range(args.steps):
         if njobs:
-            pipes[s & 1].me.search_frame_async(sets[s % nsets][0], sets[s % nsets][1], jobs, R)
-    for pp, e_ in zip(pipes, ev_end):
-        e_.record(pp.ext)
+            mes[s & 1].search_frame_async(sets[s % nsets][0], sets[s % nsets][1], jobs, R)
+    for x_, e_ in zip(exts, ev_end):
+        e_.record(x_)
     barrier()
     wall1 = time.perf_counter()
-    launches = sum(pp.me.kernel_launches for pp in pipes) - launches0
-    total_ms = torch.tensor([max(ev_start.elapsed_time(e_) for e_ in ev_end), single_ms], dtype=torch.float64, device=dev)
-    kern_ms = torch.tensor([float(np.mean(kernel_ms)) if kernel_ms else 0.0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-        dist.all_reduce(kern_ms, op=dist.ReduceOp.MAX)
-    total_ms, single_ms, kern_ms = float(total_ms[0].item()), float(total_ms[1].item()), float(kern_ms.item())
+    launches = grp.kernel_launches - launches0
+    total_ms, single_ms, kern_ms = allmax([max(ev_start.elapsed_time(e_) for e_ in ev_end), single_ms, float(np.mean(kernel_ms)) if kernel_ms else 0.0])
     clocks = sampler.summary() if sampler else None
+    resident = None
+    if njobs and not args.no_verify:
+        resident = me.fetch_results(njobs)                         # the last resident search of context 0: verified below with the e2e results
 
-    # ------------------------------------------------------------------ e2e: host buffers through the public API
+    # ------------------------------------------------------------------ e2e: host planes through the group call (C++ does the band split,
+    # the rectangle uploads / NCCL broadcast, the search and the result copies; Python issues one call per frame)
     # (a) serial: every step waits for its own results before the next upload starts (a low-delay encoder's dependency);
-    # (b) pipelined (the reported e2e): frames alternate between two contexts, so the H2D/D2H copies of one frame overlap
-    #     the kernels of the other -- every step still uploads both int16 planes and downloads its four result arrays.
-    for _ in range(2):
-        pipes[0].step_e2e(False)
-        pipes[1].step_e2e(False)
-    barrier()
-    e0 = time.perf_counter()
-    for s in range(args.steps):
-        pipes[0].step_e2e(False)
-    barrier()
-    serial_ms = (time.perf_counter() - e0) * 1e3
-    use_graphs = args.graphs
-    if use_graphs:
-        for pp in pipes:
-            pp.me.sync()
-            pp.build_graphs()
-        for pp in pipes:                               # one replay each before the clock starts
-            pp.step_e2e_graph()
-            pp.me.sync()
+    # (b) pipelined (the reported e2e): frames alternate between the two slots, so the copies of one frame overlap the kernels of
+    #     the other -- every step still uploads both planes' rectangles and downloads its four result arrays.
+    def e2e_leg(ref_dist, cur_h, ref_h, steps):
+        grp.configure(W, H, margin, margin, grp.BROADCAST if ref_dist == "broadcast" else grp.BAND_HALO)
+        calls = [grp.bind_frame(s, cur_h, org, ref_h, org, all_jobs, R, outs[s]) for s in range(2)]
+        syncs = [grp.bind_sync(s) for s in range(2)]
+        for s in range(4):
+            calls[s & 1]()
+            syncs[s & 1]()
         barrier()
-    for pp in pipes:
-        pp.bind()
-    barrier()
-    e0 = time.perf_counter()
-    for s in range(args.steps):
-        pp = pipes[s & 1]
-        pp.b_sync()                                    # this context's previous frame (two steps ago) is complete
-        if use_graphs:
-            pp.step_e2e_graph()
-        else:
-            pp.step_e2e_bound()
-    for pp in pipes:
-        pp.me.sync()
-    barrier()
-    e1 = time.perf_counter()
-    e2e_ms = torch.tensor([(e1 - e0) * 1e3, serial_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-    e2e_ms, serial_ms = float(e2e_ms[0].item()), float(e2e_ms[1].item())
-    ref_bytes = n_ref[s0:s1].nbytes if (world > 1 and args.ref_dist == "allgather") else (n_ref.nbytes if rank == 0 else 0)
-    h2d = ref_bytes + (n_cur_band.nbytes if band_h else 0) + jobs.nbytes
-    d2h = 4 * njobs * NPARTS * 4
-    io = torch.tensor([h2d, d2h], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(io, op=dist.ReduceOp.SUM)
+        t0 = time.perf_counter()
+        for s in range(steps):
+            calls[0]()
+            syncs[0]()
+        barrier()
+        serial = (time.perf_counter() - t0) * 1e3 / steps
+        t0 = time.perf_counter()
+        for s in range(steps):
+            syncs[s & 1]()                                          # this slot's previous frame (two steps ago) is complete
+            calls[s & 1]()
+        syncs[0]()
+        syncs[1]()
+        barrier()
+        piped = (time.perf_counter() - t0) * 1e3 / steps
+        piped, serial = allmax([piped, serial])
+        return piped, serial
+
+    e2e = {}
+    legs = [(args.ref_dist, "s16")]
+    if not args.no_extras:
+        legs.append((args.ref_dist, "u8"))
+        if world > 1:
+            legs.append(("broadcast" if args.ref_dist == "band_halo" else "band_halo", "s16"))
+    for ref_dist, ty in legs[::-1]:                                 # the reported leg last: its results stay in `outs` for the verification
+        e2e[(ref_dist, ty)] = e2e_leg(ref_dist, n_cur if ty == "s16" else n_cur8, n_ref if ty == "s16" else n_ref8, args.steps)
+    e2e_ms, serial_ms = e2e[legs[0]]
+    if njobs:
+        cr, rr = lib.band_extent(jobs, R)
+    else:
+        cr = rr = (0, 0, 0, 0)
+    rect_px = lambda r: (r[2] - r[0]) * (r[3] - r[1])              # noqa: E731
+    ref_px = ((W + 2 * margin) * (H + 2 * margin) if rank == 0 else 0) if args.ref_dist == "broadcast" and world > 1 else rect_px(rr)
+    h2d, d2h = allsum([2 * (ref_px + rect_px(cr)) + jobs.nbytes, 4 * njobs * NPARTS * 4])
+
+    # ------------------------------------------------------------------ verification: EVERY CTU of this rank's band, bit for bit, against the CPU oracle
+    verified = None
+    if not args.no_verify:
+        from oracle.pyoracle import Oracle                          # the checker, after the timed regions; never the thing measured
+        mism, checked = 0, 0
+        if njobs:
+            want = Oracle().search_frame(n_cur, org, n_ref, org, jobs, R, LAMBDA_Q16, nthreads=max(1, (os.cpu_count() or 1) // max(1, world)))
+            for got in ([o[first:first + njobs] for o in outs[0]], [o[first:first + njobs] for o in outs[1]], resident):
+                mism += int(sum(int((np.asarray(g) != np.asarray(w_)).any(axis=1).sum()) for g, w_ in zip(got, want)))
+                checked += njobs
+        mism, checked, band = allsum([mism, checked, njobs])
+        verified = {"ctus": int(band), "ctu_result_sets_compared": int(checked), "mismatches": int(mism),
+                    "what": "X, Y, sad and cost of all 593 partitions of every CTU job of every rank's band (results of both e2e frame slots and of the last "
+                            "resident search) against oracle.search_frame on the same inputs"}
 
     # ------------------------------------------------------------------ next row: fractional-pel refinement
     frac = None
-    if not args.virtual_world:
+    if not args.virtual_world and not args.no_extras:
         nfr = min(args.steps, 60)
         fk, fk_sad = [], []
         for s in range(nfr + 2 if njobs else 0):           # kernel time: CUDA events inside the library, resident inputs
@@ -556,53 +473,40 @@ def main():
             fk, fk_sad = [0.0], [0.0]
         barrier()
         ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev_a.record(ext)
+        ev_a.record(exts[0])
         for s in range(nfr):                                # search + refinement per frame, one context: the two kernels of a frame
             pc_, pr_ = sets[s % nsets]                      # depend on each other and both fill the GPU, so there is nothing to overlap
-            if njobs:                                       # (two contexts with deep queues showed erratic CTA interleaving: 2.5-5 ms)
+            if njobs:
                 me.search_frame_async(pc_, pr_, jobs, R)
                 me.refine_frame(pc_, pr_, njobs, None, True, asynchronous=True)
-        ev_b.record(ext)
+        ev_b.record(exts[0])
         barrier()
         both_ms = ev_a.elapsed_time(ev_b) / nfr
-        for pp in pipes:
-            pp.step_e2e_frac(); pp.me.sync()
-        e0 = time.perf_counter()
-        for s in range(nfr):
-            pp = pipes[s & 1]
-            pp.me.sync()
-            pp.step_e2e_frac()
-        for pp in pipes:
-            pp.me.sync()
-        barrier()
-        e2e_frac_ms = (time.perf_counter() - e0) * 1e3 / nfr
-        ft = torch.tensor([float(np.mean(fk)), float(np.mean(fk_sad)), both_ms, e2e_frac_ms], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(ft, op=dist.ReduceOp.MAX)
-        fk, fk_sad, both_ms, e2e_frac_ms = [float(ft[0].item())], [float(ft[1].item())], float(ft[2].item()), float(ft[3].item())
+        fkm, fksm, both_ms = allmax([float(np.mean(fk)), float(np.mean(fk_sad)), both_ms])
         pu_px = total_jobs * 24 * 4096                      # sum of the 593 partition areas = 24 CTU areas
         # algorithmic operations of the reference's own scheme per CTU (all 593 partitions, half-pel winner at the centre): filter MACs over
         # the plane sizes of xExtDIFUpSamplingH/Q + 8 (8x8 Hadamard) or 6 (4x4) operations per pixel and candidate; formula in DESIGN.md 3.4
         frac_ops = FRAC_OPS_PER_CTU * njobs
-        frac_peak = 2.0 * peak["lane_ops_per_s"]            # both integer pipes (ALU + FMA-heavy/IMAD), each at the measured 64 lanes/clk/SM
+        ach = frac_ops / (fkm * 1e-3) if fkm > 0 else 0.0
         frac = {"scope": "fractional-pel refinement (xPatternSearchFracDIF: 9 half-pel + 9 quarter-pel candidates, 8-tap interpolation, Hadamard cost) "
                          "of all 593 partitions of every CTU, from the integer winners left on the device",
-                "kernel": "me_frac_kernel", "pus_per_frame": total_jobs * NPARTS, "kernel_ms": float(np.mean(fk)), "kernel_ms_sad": float(np.mean(fk_sad)),
-                "pu_refinements_per_s": total_jobs * NPARTS / (np.mean(fk) * 1e-3), "pu_pixels_per_s": pu_px / (np.mean(fk) * 1e-3),
-                "search_plus_refine_ms_per_frame": both_ms, "search_plus_refine_frames_per_s": 1e3 / both_ms,
-                "e2e_ms_per_frame": e2e_frac_ms, "e2e_frames_per_s": 1e3 / e2e_frac_ms,
-                "e2e_d2h_bytes_per_step": 4 * total_jobs * NPARTS * 4 + total_jobs * NPARTS * 16, "steps": nfr,
-                "roofline": {"bound": "int_issue", "achieved": frac_ops / (np.mean(fk) * 1e-3) / 1e12 if np.mean(fk) > 0 else 0.0, "peak": frac_peak / 1e12,
-                             "unit": "T int-op/s", "frac": (frac_ops / (np.mean(fk) * 1e-3)) / frac_peak if np.mean(fk) > 0 and frac_peak else None,
-                             "ops_per_ctu": FRAC_OPS_PER_CTU, "peak_source": "2 x the live-measured integer-ALU issue rate (ALU and FMA-heavy pipes issue concurrently)"},
+                "kernel": "me_frac_kernel", "pus_per_frame": total_jobs * NPARTS, "kernel_ms": fkm, "kernel_ms_sad": fksm,
+                "pu_refinements_per_s": total_jobs * NPARTS / (fkm * 1e-3) if fkm else None, "pu_pixels_per_s": pu_px / (fkm * 1e-3) if fkm else None,
+                "search_plus_refine_ms_per_frame": both_ms, "search_plus_refine_frames_per_s": 1e3 / both_ms if both_ms else None, "steps": nfr,
+                "roofline": {"bound": "int_issue", "achieved": ach / 1e12, "peak": 2.0 * peak["lane_ops_per_s"] / 1e12, "unit": "T int-op/s",
+                             "frac": ach / peak["lane_ops_per_s"] if peak["lane_ops_per_s"] else None,
+                             "frac_issue": ach / (2.0 * peak["lane_ops_per_s"]) if peak["lane_ops_per_s"] else None,
+                             "ops_per_ctu": FRAC_OPS_PER_CTU,
+                             "peak_source": "frac: against ONE integer pipe (the ALU issue rate measured live, same denominator as the search kernel); "
+                                            "frac_issue: against both integer pipes (ALU + FMA-heavy/IMAD, 2 x 64 lanes/clk/SM = every issue slot)"},
                 "timer": "kernel_ms: CUDA events around me_frac_kernel on its stream; search_plus_refine: CUDA events around K frames on one context/stream, "
-                         "resident inputs; e2e: host wall clock, uploads + search + refine + all result arrays fetched, two contexts"}
+                         "resident inputs"}
 
     # ------------------------------------------------------------------ row f3: motion-compensated distortion at quarter-pel MVs
     mc = None
-    if world == 1 and njobs and not args.virtual_world:
+    if world == 1 and njobs and not args.virtual_world and not args.no_extras:
         rng = np.random.default_rng(7)
-        rects = me.lib.partition_table()
+        rects = lib.partition_table()
         mpus = np.zeros((njobs, NPARTS, 6), np.int32)
         mpus[:, :, 0] = jobs[:, None, 0] + rects[None, :, 0]
         mpus[:, :, 1] = jobs[:, None, 1] + rects[None, :, 1]
@@ -626,62 +530,90 @@ def main():
               "kernel": "me_mc_cost_kernel", "pus": njobs * NPARTS, "kernel_ms_sad": km["sad"], "kernel_ms_hadamard": km["hadamard"], "kernel_ms_bi_hadamard": km["bi_hadamard"],
               "pu_pixels_per_s_sad": njobs * 24 * 4096 / (km["sad"] * 1e-3), "timer": "CUDA events around the kernel on its stream, resident planes"}
 
+    # ------------------------------------------------------------------ the call the encoder makes: synchronous per-CTU search with HOST pointers
+    per_ctu = None
+    if world == 1 and njobs and not args.virtual_world and not args.no_extras:
+        per_ctu = per_ctu_leg(hm, me, n_cur, n_ref, margin, all_jobs, R, W, H)
+
+    # ------------------------------------------------------------------ BASELINE config[2]: random access, two lists + bi-prediction refinement
+    ra = None
+    if args.workload == "1080p64_ra" and world == 1 and not args.no_extras:
+        ra = random_access_leg(hm, me, exts[0], torch, sets, nsets, n_cur, n_ref, f, margin, all_jobs, R, W, H, peak, args)
+
+    rc = 0
     if rank == 0:
         total_cands = total_jobs * cands_per_job
         ms_per_step = total_ms / args.steps
         value = total_cands * NPARTS / (ms_per_step * 1e-3)
-        e2e_value = total_cands * NPARTS / (e2e_ms / args.steps * 1e-3)
+        e2e_value = total_cands * NPARTS / (e2e_ms * 1e-3)
         # dominant kernel roofline: algorithmic integer lane-ops of THIS rank's launch / its CUDA-event duration
         cands_rank = njobs * cands_per_job
         achieved = cands_rank * INT_OPS_PER_CAND / (kern_ms * 1e-3) if kern_ms > 0 else 0.0
         alg_bytes = (W + 2 * margin) * (H + 2 * margin) + W * H + total_jobs * NPARTS * 16
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        cfg = shared_config(args.workload)
         out = {
             "metric": "me_block_sad_evaluations_per_s", "value": value, "unit": "block-SAD evaluations/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "frames_per_s": 1e3 / ms_per_step,
             "ctu_candidates_per_s": total_cands / (ms_per_step * 1e-3),
-            "config": {"workload": "%s: %dx%d luma, 64x64 CTU, integer-pel full search +-%d, 1 reference picture, %d CTU jobs x %d candidates x 593 partitions"
-                                   % (args.workload, W, H, R, total_jobs, cands_per_job),
-                       "sharding": "CTU-row bands (cut at CTU granularity) over %d GPU(s); reference plane: %s" % (world, "single GPU" if world == 1 else ("each rank uploads 1/N, NCCL all-gather over NVLink" if args.ref_dist == "allgather" else "rank 0 uploads, NCCL broadcast over NVLink")),
-                       "lambda_q16": LAMBDA_Q16,
-                       "l2": "inputs larger than L2: %d resident (current, reference) plane pairs at distinct addresses (%.0f MiB), cycled step by step" % (nsets, 2 * nsets * plane_stride / 2**20),
-                       "timer": "CUDA events around the whole K-step region, frames alternating over two library contexts/streams, max over ranks; "
+            "config": cfg,
+            "detail": {"sharding": "CTU-row bands cut at CTU granularity by the library (hmme_band_split) over %d GPU(s), one process per GPU; reference picture: %s"
+                                   % (world, "single GPU" if world == 1 else ("band + halo rectangle per GPU over its own PCIe link, no collective" if args.ref_dist == "band_halo"
+                                                                              else "rank 0 uploads, ncclBroadcast over NVLink inside the library")),
+                       "l2": "inputs larger than L2: %d resident (current, reference) plane pairs at distinct addresses (%.0f MiB), cycled step by step" % (nsets, 2 * nsets * plane_bytes / 2**20),
+                       "timer": "CUDA events around the whole K-step region, frames alternating over the group's two frame slots (two contexts/streams), max over ranks; "
                                 "single_stream_ms_per_step = one context, events per step"},
             "single_stream_ms_per_step": single_ms,
             "clocks": clocks,
             "gpu_launches": int(launches),
             "wall_ms_timed_region": (wall1 - wall0) * 1e3,
-            "e2e": {"value": e2e_value, "unit": "block-SAD evaluations/s", "h2d_bytes_per_step": int(io[0].item()),
-                    "d2h_bytes_per_step": int(io[1].item()), "frames_per_s": 1e3 / (e2e_ms / args.steps),
-                    "ms_per_step": e2e_ms / args.steps,
-                    "serial_ms_per_step": serial_ms / args.steps, "serial_frames_per_s": 1e3 / (serial_ms / args.steps),
-                    "timer": "host wall clock around K x {upload both int16 planes from pinned memory (+ NCCL broadcast), search, fetch four result arrays}, "
-                             "frames alternating over two contexts/streams so copies overlap kernels" + ("; each context's step is recorded once as CUDA graph(s) and replayed (hmme_graph_*)" if use_graphs else "") +
-                             "; serial_* = one context, call by call, each step waits for its results; max over ranks"},
+            "e2e": {"value": e2e_value, "unit": "block-SAD evaluations/s", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "frames_per_s": 1e3 / e2e_ms, "ms_per_step": e2e_ms,
+                    "serial_ms_per_step": serial_ms, "serial_frames_per_s": 1e3 / serial_ms,
+                    "host_samples": "int16 (HM's Pel), page-locked; narrowed to 8 bit on the device", "ref_dist": args.ref_dist,
+                    "timer": "host wall clock around K x hmme_group_search_frame_async (+ hmme_group_sync of the slot two steps back): per rank, rectangle uploads of the band's rows of "
+                             "the current frame and of band + halo of the reference picture from pinned memory, jobs, search, four result arrays back; frames alternate over two slots "
+                             "so copies overlap kernels; serial_* = one slot, each step waits for its results; max over ranks"},
             "roofline": {"bound": "int_alu", "kernel": "me_u8_tile_kernel", "achieved": achieved / 1e12, "peak": peak["lane_ops_per_s"] / 1e12,
                          "unit": "T int-lane-op/s", "frac": achieved / peak["lane_ops_per_s"] if peak["lane_ops_per_s"] else None,
+                         "frac_issue": achieved / (2.0 * peak["lane_ops_per_s"]) if peak["lane_ops_per_s"] else None,
                          "traffic": _ncu_traffic(args.workload) if world == 1 else None,
                          "ops_per_ctu_candidate": INT_OPS_PER_CAND, "kernel_ms": kern_ms,
                          "frac_at_step_rate": (cands_rank * INT_OPS_PER_CAND / (ms_per_step * 1e-3)) / peak["lane_ops_per_s"] if peak["lane_ops_per_s"] else None,
                          "pixel_abs_diffs_per_s": cands_rank * PX_PER_CAND / (kern_ms * 1e-3) if kern_ms > 0 else 0.0,
-                         "peak_source": "measured live: VABSDIFF4.U8.ACC issue rate, %.1f lanes/clk/SM x %d SMs at %.0f MHz"
-                                        % (peak["lanes_per_clk_sm"], torch.cuda.get_device_properties(dev).multi_processor_count, peak["sm_mhz"]),
+                         "peak_source": "measured live: VABSDIFF4.U8.ACC issue rate, %.1f lanes/clk/SM x %d SMs at %.0f MHz = ONE integer pipe (the survey's denominator, `frac`); "
+                                        "`frac_issue` divides by both integer pipes (ALU + FMA-heavy/IMAD = 128 lanes/clk/SM, i.e. every issue slot), the same ceiling for every kernel of this line"
+                                        % (peak["lanes_per_clk_sm"], sms, peak["sm_mhz"]),
                          "hbm": {"algorithmic_bytes_per_step": alg_bytes, "achieved_gbs": alg_bytes / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else 0.0,
                                  "peak_gbs": _measured_hbm()}},
         }
+        for (rd, ty), (p_ms, s_ms) in e2e.items():
+            if (rd, ty) != legs[0]:
+                out["e2e"]["%s_%s" % (rd, ty)] = {"ms_per_step": p_ms, "serial_ms_per_step": s_ms, "value": total_cands * NPARTS / (p_ms * 1e-3)}
+        if verified is not None:
+            out["verified"] = verified
+            if verified["mismatches"] or verified["ctus"] != total_jobs:
+                rc = 1
         if frac:
             out["frac_refine"] = frac
         if mc:
             out["mc_cost"] = mc
+        if per_ctu:
+            out["per_ctu"] = per_ctu
+        if ra:
+            out["random_access"] = ra
+            if ra.get("verified", {}).get("mismatches"):
+                rc = 1
         if world == 1 and not args.no_cpu_baseline:
-            out["cpu_baseline"], _ = cpu_baseline_entry(R, 30.0)
+            out["cpu_baseline"], _ = cpu_baseline_entry(args.workload, (416, 240))
             if frac and os.path.exists(CPUME_BIN):
                 fr = reference_cpu_frac()
                 frac["cpu_reference"] = fr
                 frac["gpu_over_one_core"] = frac["pu_pixels_per_s"] / fr["pu_pixels_per_s"]
             if os.path.exists(CPUME_BIN):       # the reference's default (fast) integer search, for context: TZ evaluates ~600x fewer candidates
-                v, me_s, calls, wall = reference_cpu_me(R, (416, 240), 1, fast_search=1)
+                v, me_s, calls, wall = reference_cpu_me(R, luma_frames(416, 240, 2), 1, fast_search=1)
                 out["cpu_tz"] = {"value": v, "unit": "block-SAD evaluations/s", "cores": 1, "kind": "reference",
                                  "sample": "same encoder, --FastSearch=1 (xTZSearch): %d DistFunc calls in %.3f s of integer ME for the P frame of a "
                                            "416x240 clip (18 full CTUs) on one core" % (calls, me_s)}
@@ -690,19 +622,124 @@ def main():
             out["cpu_port"] = {"value": v, "unit": "block-SAD evaluations/s", "cores": threads, "kind": "port",
                                "sample": "GPU-ME semantics on the CPU (oracle/hmme_oracle.c): %d of %d CTU jobs of the same frame, %.1f s wall on %d threads" % (n, total_jobs, dt, threads)}
         print(json.dumps(out))
-    for pp in pipes:
-        pp.me.close()
+    for pc, pr in sets:
+        pc.free()
+        pr.free()
+    grp.close()
     if world > 1:
         dist.destroy_process_group()
+    if rc:
+        sys.exit("bench.py: verification against the oracle FAILED (see the `verified` object of the JSON line)")
+
+
+def per_ctu_leg(hm, me, n_cur, n_ref, margin, all_jobs, R, W, H):
+    """hmme_search_ctu as TEncSearch::xMotionEstimation calls it (TEncSearch.cpp:3749): one CTU, host pointers into the int16 planes,
+    synchronous.  Latency per call over every CTU of the frame, and the frame rate 480 sequential calls give."""
+    import ctypes as C
+    L = me.lib.L
+    stride = n_ref.shape[1]
+    X, Y = np.zeros(NPARTS, np.int32), np.zeros(NPARTS, np.int32)
+    S, Cs = np.zeros(NPARTS, np.uint32), np.zeros(NPARTS, np.uint32)
+    blocks = [np.ascontiguousarray(n_cur[margin + j[1]:margin + j[1] + 64, margin + j[0]:margin + j[0] + 64]) for j in all_jobs]
+
+    def call(k):
+        j = all_jobs[k]
+        off = int(((margin + j[1]) * stride + margin + j[0]) * 2)
+        rc = L.hmme_search_ctu(me.h, blocks[k].ctypes.data, 64, n_ref.ctypes.data + off, stride, int(R), int(j[2]), int(j[3]),
+                               X.ctypes.data, Y.ctypes.data, S.ctypes.data, Cs.ctypes.data)
+        if rc:
+            raise hm.HmmeError(rc, L.hmme_last_error(me.h).decode())
+
+    for k in range(min(8, len(all_jobs))):
+        call(k)
+    t0 = time.perf_counter()
+    for k in range(len(all_jobs)):
+        call(k)
+    dt = time.perf_counter() - t0
+    kms = me.last_kernel_ms()
+    return {"call": "hmme_search_ctu (TEncOpenCL::calcMotionVectors): one CTU, +-%d, host pointers into int16 planes, synchronous" % R,
+            "calls": len(all_jobs), "latency_ms": dt * 1e3 / len(all_jobs), "frame_ms": dt * 1e3, "frames_per_s": 1.0 / dt,
+            "search_kernel_ms_last_call": kms,
+            "timer": "host wall clock around %d sequential calls (every CTU of the frame), after 8 warm-up calls" % len(all_jobs)}
+
+
+def random_access_leg(hm, me, ext, torch, sets, nsets, n_cur, n_ref, frames, margin, all_jobs, R, W, H, peak, args):
+    """BASELINE config[2]: one B frame = two reference lists (one +-R search each, 8-bit) + the bi-prediction refinement
+    (TEncSearch.cpp:3168-3221: the block becomes 2*org - pred of the other list, 16 bit, searched +-4 around the list's winner,
+    :3702-3712), all three result sets kept in a device-resident table (slots 0/1/2)."""
+    from oracle.pyoracle import Oracle
+    njobs = len(all_jobs)
+    # list 1 reference: the frame after the current one (the synthetic pan continues); bi-prediction block: 2*org - list-0 reference
+    f3 = luma_frames(W, H, 3)
+    n_ref1 = pad_plane(f3[2], margin, margin)
+    n_bi = (2 * n_cur.astype(np.int32) - n_ref.astype(np.int32)).astype(np.int16)
+    p_ref1, p_bi = me.alloc_plane(1, W, H, margin, margin), me.alloc_plane(2, W, H, margin, margin)
+    me.upload(p_ref1, n_ref1)
+    me.upload(p_bi, n_bi)
+    table = me.create_table(3, njobs)
+    pc, pr = sets[0]
+    me.search_frame_table(pc, p_ref1, all_jobs, R, table, 1)
+    x1, y1, _, _ = me.table_fetch(table, 1, 0, njobs)
+    bi_jobs = all_jobs.copy()
+    bi_jobs[:, 2] = x1[:, 592] - BI_RANGE                            # window centred on the 64x64 winner of list 1
+    bi_jobs[:, 3] = y1[:, 592] - BI_RANGE
+
+    def frame():
+        me.search_frame_table(pc, pr, all_jobs, R, table, 0)
+        me.search_frame_table(pc, p_ref1, all_jobs, R, table, 1)
+        me.search_frame_table(p_bi, p_ref1, bi_jobs, BI_RANGE, table, 2)
+
+    for _ in range(3):
+        frame()
+    me.sync()
+    bi_ms = []
+    for _ in range(5):
+        me.search_frame_table(p_bi, p_ref1, bi_jobs, BI_RANGE, table, 2)
+        me.sync()
+        bi_ms.append(me.last_kernel_ms())
+    n = min(args.steps, 50)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(ext)
+    for _ in range(n):
+        frame()
+    b.record(ext)
+    me.sync()
+    ms = a.elapsed_time(b) / n
+    res = [me.table_fetch(table, s, 0, njobs) for s in range(3)]
+    ver = None
+    if not args.no_verify:
+        o = Oracle()
+        th = os.cpu_count() or 1
+        want = [o.search_frame(n_cur, (margin, margin), n_ref, (margin, margin), all_jobs, R, LAMBDA_Q16, nthreads=th),
+                o.search_frame(n_cur, (margin, margin), n_ref1, (margin, margin), all_jobs, R, LAMBDA_Q16, nthreads=th),
+                o.search_frame(n_bi, (margin, margin), n_ref1, (margin, margin), bi_jobs, BI_RANGE, LAMBDA_Q16, nthreads=th)]
+        mism = sum(int((np.asarray(g) != np.asarray(w_)).any(axis=1).sum()) for got, wnt in zip(res, want) for g, w_ in zip(got, wnt))
+        ver = {"ctus": 3 * njobs, "mismatches": int(mism), "what": "list 0, list 1 and bi-prediction result tables of every CTU against the oracle"}
+    bi = float(np.mean(bi_ms[1:]))
+    cands = njobs * (2 * BI_RANGE + 1) ** 2
+    ach = cands * INT_OPS_PER_CAND_16 / (bi * 1e-3)
+    me.destroy_table(table)
+    p_ref1.free()
+    p_bi.free()
+    return {"scope": "one B frame of 1080p random access: list 0 and list 1 (480 jobs x 16641 candidates each, 8 bit) + bi-prediction refinement "
+                     "(480 jobs x 81 candidates, int16 block 2*org-pred against the 8-bit list-1 picture), results in a device-resident [3][480][593] table",
+            "ms_per_b_frame": ms, "b_frames_per_s": 1e3 / ms, "bipred_kernel": "me_s16_tile_kernel", "bipred_kernel_ms": bi,
+            "bipred_roofline": {"bound": "int_alu", "achieved": ach / 1e12, "peak": peak["lane_ops_per_s"] / 1e12, "unit": "T int-lane-op/s",
+                                "frac": ach / peak["lane_ops_per_s"], "frac_issue": ach / (2 * peak["lane_ops_per_s"]), "ops_per_ctu_candidate": INT_OPS_PER_CAND_16},
+            "block_sad_evaluations_per_s": (2 * njobs * (2 * R + 1) ** 2 + cands) * NPARTS / (ms * 1e-3),
+            "timer": "CUDA events around %d B frames on one context/stream, resident planes" % n, "verified": ver}
 
 
 def _ncu_traffic(workload):
     """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the committed ncu capture."""
-    try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-        return t["traffic_bytes_per_launch"] if t["workload"].startswith(workload) else None
-    except Exception:
-        return None
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        try:
+            t = json.load(open(os.path.join(ROOT, "profiles", name)))
+            if t["workload"].startswith(workload.split("_")[0]):
+                return t["traffic_bytes_per_launch"]
+        except Exception:
+            pass
+    return None
 
 
 def _measured_hbm():

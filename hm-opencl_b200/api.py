@@ -208,10 +208,17 @@ class MotionEstimator:
         self.h = h
         self.max_search_range = max_search_range
 
+    @classmethod
+    def borrowed(cls, handle, owner):
+        """Wrapper of a context somebody else owns (hmme_group_context): close() leaves it alone."""
+        me = cls.__new__(cls)
+        me.lib, me.h, me.max_search_range, me._owner = HmmeLib.get(), C.c_void_p(handle), 0, owner
+        return me
+
     def close(self):
-        if getattr(self, "h", None):
+        if getattr(self, "h", None) and getattr(self, "_owner", None) is None:
             self.lib.L.hmme_destroy(self.h)
-            self.h = None
+        self.h = None
 
     def __del__(self):
         try:
@@ -594,11 +601,7 @@ class Group:
         h = self.lib.L.hmme_group_context(self.g, int(local_index), int(slot))
         if not h:
             raise HmmeError(-1, "no such context")
-        me = MotionEstimator.__new__(MotionEstimator)
-        me.lib, me.h, me.max_search_range = self.lib, None, 0
-        me.__dict__["h"] = C.c_void_p(h)
-        me.close = lambda: None
-        return me
+        return MotionEstimator.borrowed(h, self)
 
     def last_kernel_ms(self, slot=0):
         ms = C.c_float()

@@ -265,12 +265,31 @@ int enqueue_search(hmme_ctx* c, const SearchIO& io, const void* curOrigin, int c
                    long long refPitch, const void* refLo, const void* refHi, int njobs, int R) {
     const int W = 2 * R + 1;
     const size_t nres = (size_t)njobs * HMME_NPARTS;
+    // A 16-bit block against an 8-bit picture (the bi-prediction refinement): clamped block + per-partition constants, then the
+    // packed 8-bit kernel (me_bipred_prep_kernel explains why that is exact)
+    const bool bipred = curElem == 2 && refElem == 1;
+    if (bipred) {
+        if ((size_t)njobs > c->biCap) {
+            if (c->capturing) return fail(c, HMME_ERR_ARG, "bi-prediction buffers would grow while capturing (run the step once first)");
+            const size_t cap = std::max<size_t>((size_t)njobs, std::max<size_t>(64, c->biCap * 2));
+            for (cudaStream_t s : {c->ioStream[0], c->ioStream[1], c->stream}) CU_TRY(c, cudaStreamSynchronize(s));
+            cudaFree(c->dBiBlocks); cudaFree(c->dBiOffsets);
+            c->dBiBlocks = nullptr; c->dBiOffsets = nullptr; c->biCap = 0;
+            CU_TRY(c, cudaMalloc(&c->dBiBlocks, cap * 4096 + 64));
+            CU_TRY(c, cudaMalloc(&c->dBiOffsets, cap * HMME_NPARTS * sizeof(uint32_t)));
+            c->biCap = cap;
+            ++c->bufGen;
+        }
+        me_bipred_prep_kernel<<<njobs, 256, 0, c->stream>>>(static_cast<const int16_t*>(curOrigin), curPitch, io.jobs, c->dBiBlocks, c->dBiOffsets);
+        c->launches += 1;
+    }
     if (!c->capturing) CU_TRY(c, cudaEventRecord(c->ev0, c->stream));   // timing events stay out of captured graphs
-    if (curElem == 1 && refElem == 1) {
+    if ((curElem == 1 || bipred) && refElem == 1) {
         constexpr int yb = HMME_FAST_YB;             // candidate rows per thread (3: measured best; 2 is 17 % slower, 4 does not fit)
         const FastGeom g = fast_geometry(W, yb, njobs, c->prop.multiProcessorCount, c->forceRG);
         FastParams fp{};
         fp.cur = static_cast<const uint8_t*>(curOrigin);
+        fp.curBlocks = bipred ? c->dBiBlocks : nullptr;
         fp.ref = static_cast<const uint8_t*>(refOrigin);
         fp.refLo = static_cast<const uint8_t*>(refLo);
         fp.refHi = static_cast<const uint8_t*>(refHi);
@@ -292,15 +311,14 @@ int enqueue_search(hmme_ctx* c, const SearchIO& io, const void* curOrigin, int c
         gp.chunk = (nCand + nChunks - 1) / nChunks;
         gp.chunk = (gp.chunk + kGenBatch - 1) / kGenBatch * kGenBatch;
         gp.nChunks = (nCand + gp.chunk - 1) / gp.chunk;
-        if (curElem == 1 && refElem == 2) launch_generic<uint8_t, int16_t>(c, gp, njobs);
-        else if (curElem == 2 && refElem == 1) launch_generic<int16_t, uint8_t>(c, gp, njobs);
-        else launch_generic<int16_t, int16_t>(c, gp, njobs);
+        if (curElem == 1) launch_generic<uint8_t, int16_t>(c, gp, njobs);     // non-8-bit reference planes: outside the reference's defined
+        else launch_generic<int16_t, int16_t>(c, gp, njobs);                  // domain (App. A.2), kept exact and slow
     }
     CU_TRY(c, cudaEventRecord(c->ev1, c->stream));
     c->evValid = !c->capturing;
     c->launches += 2;
     if (io.finalizeInline) {
-        me_finalize_kernel<<<(unsigned)((nres + 255) / 256), 256, 0, c->stream>>>(c->dBest, io.jobs, njobs, W, c->lambda, io.X, io.Y, io.S, io.Cst);
+        me_finalize_kernel<<<(unsigned)((nres + 255) / 256), 256, 0, c->stream>>>(c->dBest, io.jobs, njobs, W, c->lambda, io.X, io.Y, io.S, io.Cst, bipred ? c->dBiOffsets : nullptr);
         CU_TRY(c, cudaGetLastError());
         return mark_compute(c);
     }
@@ -308,7 +326,7 @@ int enqueue_search(hmme_ctx* c, const SearchIO& io, const void* curOrigin, int c
     // kernel on the compute stream would queue behind every pending CTA of another context's search, delaying the result
     // copy -- and with it the host -- by a whole search.
     CU_TRY(c, cudaStreamWaitEvent(c->ioStream[0], c->ev1, 0));
-    me_finalize_kernel<<<(unsigned)((nres + 255) / 256), 256, 0, c->ioStream[0]>>>(c->dBest, io.jobs, njobs, W, c->lambda, io.X, io.Y, io.S, io.Cst);
+    me_finalize_kernel<<<(unsigned)((nres + 255) / 256), 256, 0, c->ioStream[0]>>>(c->dBest, io.jobs, njobs, W, c->lambda, io.X, io.Y, io.S, io.Cst, bipred ? c->dBiOffsets : nullptr);
     CU_TRY(c, cudaEventRecord(c->evFinal, c->ioStream[0]));
     CU_TRY(c, cudaStreamWaitEvent(c->stream, c->evFinal, 0));
     CU_TRY(c, cudaGetLastError());
@@ -414,6 +432,7 @@ void hmme_destroy(hmme_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->dJobs); cudaFree(c->dBest); cudaFree(c->dRes); cudaFreeHost(c->hJobs);
     cudaFreeHost(c->hWin); cudaFree(c->dWin); cudaFreeHost(c->hCurBlk); cudaFree(c->dCurBlk); cudaFreeHost(c->hCtuRes); cudaFree(c->dCtuRes);
+    cudaFree(c->dBiBlocks); cudaFree(c->dBiOffsets);
     cudaFree(c->dStage[0]); cudaFree(c->dStage[1]); cudaFree(c->dFlag); cudaFreeHost(c->hFlag);
     cudaFree(c->dPus); cudaFree(c->dSlots); cudaFree(c->dFrac); cudaFree(c->dCand); cudaFree(c->dOrder); cudaFree(c->dPreds);
     if (c->evFork) cudaEventDestroy(c->evFork);
@@ -472,21 +491,20 @@ int hmme_search_ctu(hmme_ctx* c, const int16_t* cur, int curStride, const int16_
     char* hs = static_cast<char*>(c->hWin);
     char* ds = static_cast<char*>(c->dWin);
     constexpr size_t kCurOff = 64, kWinOff = 64 + 8192;
-    uint32_t orAll = 0;
+    const int16_t* w0 = refAtCtu + (ptrdiff_t)refStride * lty + ltx;
+    uint32_t orCur = 0, orWin = 0;
     {
         uint8_t* hc8 = reinterpret_cast<uint8_t*>(hs + kCurOff);
-        for (int r = 0; r < 64; ++r) orAll |= narrow_row(cur + (size_t)r * curStride, hc8 + r * 64, 64);
-        const int16_t* w0 = refAtCtu + (ptrdiff_t)refStride * lty + ltx;
+        for (int r = 0; r < 64; ++r) orCur |= narrow_row(cur + (size_t)r * curStride, hc8 + r * 64, 64);
         uint8_t* hw8 = reinterpret_cast<uint8_t*>(hs + kWinOff);
-        if (!(orAll & 0xFF00u))
-            for (int r = 0; r < side; ++r) orAll |= narrow_row(w0 + (ptrdiff_t)r * refStride, hw8 + (size_t)r * wp, side);
+        for (int r = 0; r < side; ++r) orWin |= narrow_row(w0 + (ptrdiff_t)r * refStride, hw8 + (size_t)r * wp, side);
     }
-    const bool eight = (orAll & 0xFF00u) == 0;
-    const int elem = eight ? 1 : 2;
-    if (!eight) {
+    const int curElem = (orCur & 0xFF00u) ? 2 : 1, elem = (orWin & 0xFF00u) ? 2 : 1;
+    if (curElem == 2) {                                   // e.g. the bi-prediction block 2*org - pred
         int16_t* hc = reinterpret_cast<int16_t*>(hs + kCurOff);
         for (int r = 0; r < 64; ++r) std::memcpy(hc + r * 64, cur + (size_t)r * curStride, 128);
-        const int16_t* w0 = refAtCtu + (ptrdiff_t)refStride * lty + ltx;
+    }
+    if (elem == 2) {                                      // not 8-bit video: outside the reference's defined domain, kept exact
         int16_t* hw = reinterpret_cast<int16_t*>(hs + kWinOff);
         for (int r = 0; r < side; ++r) std::memcpy(hw + (size_t)r * wp, w0 + (ptrdiff_t)r * refStride, (size_t)side * 2);
     }
@@ -501,7 +519,7 @@ int hmme_search_ctu(hmme_ctx* c, const int16_t* cur, int curStride, const int16_
     io.X = c->dCtuRes; io.Y = io.X + HMME_NPARTS;
     io.S = reinterpret_cast<uint32_t*>(io.Y + HMME_NPARTS); io.Cst = io.S + HMME_NPARTS;
     io.finalizeInline = true;
-    int rc = enqueue_search(c, io, ds + kCurOff, elem, 64, refOrigin, elem, wp, dWin, dWin + winBytes + 64, 1, range);
+    int rc = enqueue_search(c, io, ds + kCurOff, curElem, 64, refOrigin, elem, wp, dWin, dWin + winBytes + 64, 1, range);
     if (rc != HMME_OK) return rc;
     CU_TRY(c, cudaMemcpyAsync(c->hCtuRes, c->dCtuRes, 4 * HMME_NPARTS * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
     CU_TRY(c, cudaStreamSynchronize(c->stream));

@@ -43,6 +43,8 @@ struct hmme_ctx {
     size_t fastSmemSet = 0;       // dynamic shared memory the packed kernel has been opted in for
     void* hCurBlk = nullptr;      // pinned 64x64 int16
     void* dCurBlk = nullptr;
+    // bi-prediction blocks (16-bit current samples against an 8-bit picture): clamped 64x64 records + per-partition SAD constants
+    uint8_t* dBiBlocks = nullptr; uint32_t* dBiOffsets = nullptr; size_t biCap = 0;
     // upload staging
     int16_t* dStage[2] = {nullptr, nullptr}; size_t stageElems[2] = {0, 0}; int stageNext = 0;   // two staging buffers: a frame's reference
                                                                                                   // and current plane copy back to back

@@ -140,16 +140,63 @@ __device__ __forceinline__ void decode_key(unsigned long long key, int ltx, int 
     X[i] = mvx; Y[i] = mvy; cost[i] = c; sad[i] = c - mv_cost(lambda, mvx, mvy);
 }
 
+// ---- bi-prediction blocks on the packed 8-bit kernel.  The refinement's block is cur = 2*org - pred, a signed 16-bit value
+// (TEncSearch.cpp:3702-3712), searched against an 8-bit picture.  For r in [0, 255] and any integer c:
+//     |c - r| = |clamp(c, 0, 255) - r| + |c - clamp(c, 0, 255)|
+// (c < 0: r - c = (r - 0) + (0 - c);  c > 255: c - r = (c - 255) + (255 - r)).  The second term does not depend on the candidate, so
+// the SAD of a partition is the 8-bit SAD of the clamped block plus a per-partition constant; the arg-min and its tie-break are
+// unchanged, and sad / cost get the constant added at finalisation.  This kernel prepares both: per job the clamped 64x64 block
+// (dense 4 KiB record) and the 593 constants (4x4 sums -> integral image -> rectangle sums).  One CTA per job, 256 threads.
+__global__ void __launch_bounds__(256) me_bipred_prep_kernel(const int16_t* __restrict__ cur, long long curPitch, const int4* __restrict__ jobs,
+                                                             uint8_t* __restrict__ blocks, uint32_t* __restrict__ offsets) {
+    __shared__ uint32_t sA[16][16], sB[16][16], sII[17][17];
+    const int tid = threadIdx.x, job = blockIdx.x, bi = tid & 15, bj = tid >> 4;
+    const int4 jb = jobs[job];
+    const int16_t* c0 = cur + (long long)(jb.y + 4 * bj) * curPitch + jb.x + 4 * bi;
+    uint8_t* out = blocks + (size_t)job * 4096 + (4 * bj) * 64 + 4 * bi;
+    uint32_t ex = 0;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        uint32_t w = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int v = c0[r * curPitch + q];
+            const int cl = min(max(v, 0), 255);
+            ex += (uint32_t)abs(v - cl);
+            w |= (uint32_t)cl << (8 * q);
+        }
+        *reinterpret_cast<uint32_t*>(out + r * 64) = w;
+    }
+    sA[bj][bi] = ex;
+    if (tid < 17) { sII[0][tid] = 0; sII[tid][0] = 0; }
+    __syncthreads();
+    uint32_t s = 0;
+    for (int i = 0; i <= bi; ++i) s += sA[bj][i];
+    sB[bj][bi] = s;
+    __syncthreads();
+    s = 0;
+    for (int j = 0; j <= bj; ++j) s += sB[j][bi];
+    sII[bj + 1][bi + 1] = s;
+    __syncthreads();
+    for (int part = tid; part < HMME_NPARTS; part += 256) {
+        const PartRect r = part_rect(part);
+        const int x0 = r.x >> 2, y0 = r.y >> 2, x1 = (r.x + r.w) >> 2, y1 = (r.y + r.h) >> 2;
+        offsets[(size_t)job * HMME_NPARTS + part] = sII[y1][x1] - sII[y0][x1] - sII[y1][x0] + sII[y0][x0];
+    }
+}
+
 // Finalisation pass of the generic path; outputs are four planes of [njobs][593].  Every key is handed back as "no winner"
 // (the state me_init_kernel set up once), so the arg-min scratch is always ready for the next search.
+// `offsets` (NULL, or [njobs][593]): the candidate-independent part of a bi-prediction block's SADs (me_bipred_prep_kernel).
 __global__ void me_finalize_kernel(unsigned long long* best, const int4* jobs, int njobs, int W, uint32_t lambda,
-                                   int32_t* X, int32_t* Y, uint32_t* sad, uint32_t* cost) {
+                                   int32_t* X, int32_t* Y, uint32_t* sad, uint32_t* cost, const uint32_t* __restrict__ offsets) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= njobs * HMME_NPARTS) return;
     const unsigned long long key = best[i];
     best[i] = kNoWinner;
     const int4 jb = jobs[i / HMME_NPARTS];
     decode_key(key, jb.z, jb.w, W, lambda, i, X, Y, sad, cost);
+    if (offsets && key != kNoWinner) { const uint32_t o = offsets[i]; sad[i] += o; cost[i] += o; }
 }
 
 // int16 -> uint8 narrowing of a whole padded plane with a content check (the reference path is only

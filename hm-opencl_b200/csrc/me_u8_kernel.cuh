@@ -51,6 +51,7 @@ constexpr int kRing = 2 * kLag + 2;           // record buffers: a slot may be r
 
 struct FastParams {
     const uint8_t* cur;        // picture sample (0,0) of the current plane
+    const uint8_t* curBlocks;  // non-NULL: job j's 64x64 block is the dense 4 KiB record curBlocks + 4096*j instead (bi-prediction path)
     const uint8_t* ref;        // picture sample (0,0) of the reference plane
     const uint8_t* refLo;      // first addressable byte of the reference allocation (16B aligned)
     const uint8_t* refHi;      // one past the last addressable byte
@@ -435,8 +436,9 @@ __global__ void __launch_bounds__(kFastThreads, 1) me_u8_tile_kernel(const FastP
         // the last one or two belong to masked candidates only and may lie past the plane's last row, so they are not fetched
         const int rows = nRG * YB + 63, rowsReal = thA + 63, nPos = twA + 60;      // entries 0 .. (twA-1) + 4*15
         const uint8_t* wbase = p.ref + (long long)(jb.y + jb.w + y0) * p.refPitch + (jb.x + jb.z + x0);
-        const uint8_t* cbase = p.cur + (long long)jb.y * p.curPitch + jb.x;
-        const bool curTma = (((uintptr_t)cbase | (uintptr_t)p.curPitch) & 15) == 0;
+        const long long curPitch = p.curBlocks ? 64 : p.curPitch;
+        const uint8_t* cbase = p.curBlocks ? p.curBlocks + (size_t)job * 4096 : p.cur + (long long)jb.y * p.curPitch + jb.x;
+        const bool curTma = (((uintptr_t)cbase | (uintptr_t)curPitch) & 15) == 0;
         uint8_t* dense = reinterpret_cast<uint8_t*>(sUp);
         if (tid == 0) {
             mbar_init(&winBar, (uint32_t)(rowsReal + (curTma ? 64 : 0)));
@@ -457,11 +459,11 @@ __global__ void __launch_bounds__(kFastThreads, 1) me_u8_tile_kernel(const FastP
         } else if (curTma && tid >= kFastThreads - 64) {
             const int r = tid - (kFastThreads - 64);
             mbar_arrive_expect_tx(&winBar, 64);
-            tma_bulk_g2s(sCur + r * 16, cbase + (long long)r * p.curPitch, 64, &winBar);
+            tma_bulk_g2s(sCur + r * 16, cbase + (long long)r * curPitch, 64, &winBar);
         }
         if (!curTma) {
             for (int idx = tid; idx < 1024; idx += kFastThreads) {
-                const uint8_t* c = cbase + (long long)(idx >> 4) * p.curPitch + 4 * (idx & 15);
+                const uint8_t* c = cbase + (long long)(idx >> 4) * curPitch + 4 * (idx & 15);
                 sCur[idx] = (uint32_t)c[0] | ((uint32_t)c[1] << 8) | ((uint32_t)c[2] << 16) | ((uint32_t)c[3] << 24);
             }
         }

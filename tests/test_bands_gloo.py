@@ -28,8 +28,17 @@ def _worker(rank, world, port, out_dir):
     jobs, (r0, r1) = hm.band_jobs(W, H, R, world, rank)
     c0, c1 = hm.band_ctus((W // 64) * (H // 64), world, rank)
     assert len(jobs) == c1 - c0 and (r0, r1) == (c0 // (W // 64), (c1 - 1) // (W // 64) + 1)
+    lib = hm.HmmeLib.get()                              # the library's own band arithmetic (what hmme_group_* uses) agrees with the helpers
+    assert lib.band_split((W // 64) * (H // 64), world, rank) == (c0, c1 - c0)
     y0, y1 = hm.band_reference_rows(r0, r1, R, -R, -R)
+    cr, rr = lib.band_extent(jobs, R)
+    assert (rr[1], rr[3]) == (y0, y1) and (cr[1], cr[3]) == (64 * r0, 64 * r1)
     assert y0 >= -M and y1 <= H + M                     # the halo stays inside the padded plane
+    ref_np = ref.numpy().copy()                         # band + halo distribution: everything outside the rectangle may be garbage
+    keep = np.zeros_like(ref_np, dtype=bool)
+    keep[M + rr[1]:M + rr[3], M + rr[0]:M + rr[2]] = True
+    ref_np[~keep] = -9999
+    ref = torch.from_numpy(ref_np)
     res = Oracle().search_frame(cur, (M, M), ref.numpy(), (M, M), jobs, R, lam)
     np.savez(os.path.join(out_dir, "rank%d.npz" % rank), X=res[0], Y=res[1], S=res[2], C=res[3], r=np.array([r0, r1]))
     dist.barrier()
@@ -83,3 +92,31 @@ def test_band_rows_cover_exactly():
             assert all(a[1] == b[0] for a, b in zip(bands, bands[1:]))
             sizes = [b - a for a, b in bands]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_library_band_split_and_extent_on_the_baseline_shapes():
+    """hmme_band_split / hmme_band_extent (pure host code of the C ABI, used by hmme_group_*): exact cover, balance, and the band + halo
+    rectangles of BASELINE configs 2 and 4 at 8 GPUs."""
+    import sys
+    sys.path.insert(0, ROOT)
+    from _pkg import hm
+    from synth import frame_jobs
+    lib = hm.HmmeLib.get()
+    for n in (1, 5, 18, 480, 1980):
+        for world in (1, 2, 4, 8):
+            bands = [lib.band_split(n, world, r) for r in range(world)]
+            assert [b for b in bands] == [(hm.band_ctus(n, world, r)[0], hm.band_ctus(n, world, r)[1] - hm.band_ctus(n, world, r)[0]) for r in range(world)]
+            assert sum(c for _, c in bands) == n
+    jobs = frame_jobs(1920, 1080, 64)
+    f, c = lib.band_split(len(jobs), 8, 7)
+    cr, rr = lib.band_extent(jobs[f:f + c], 64)
+    assert (f, c) == (420, 60) and cr == (0, 896, 1920, 1024) and rr == (-64, 832, 1984, 1088)
+    rows = rr[3] - rr[1]
+    assert rows / (1080 + 160) < 0.27                    # each of 8 GPUs receives about a quarter of the padded plane
+    jobs = frame_jobs(3840, 2160, 128)
+    f, c = lib.band_split(len(jobs), 8, 0)
+    cr, rr = lib.band_extent(jobs[f:f + c], 128)
+    assert c == 248 and cr == (0, 0, 3840, 320) and rr == (-128, -128, 3968, 448)
+    import pytest
+    with pytest.raises(hm.HmmeError):
+        lib.band_split(10, 4, 4)

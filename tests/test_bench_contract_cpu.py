@@ -22,6 +22,10 @@ def test_reference_arm_json_line():
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     assert "workload" in d["config"] and "model" not in d["config"]
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"] == bench.shared_config("1080p16")          # the same `config` object the b200 arm prints
+    assert "416x240" in cb["sample"] or cb["kind"] == "port"        # a fixed crop of the workload's own frames, whatever --steps is
 
 
 def test_b200_arm_has_no_cpu_fallback():

@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_bench_line_on_gpu():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "12", "--warmup", "3", "--no-cpu-baseline"],
-                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900)
     assert r.returncode == 0, r.stderr[-3000:]
     d = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
     assert d["metric"] == "me_block_sad_evaluations_per_s" and d["unit"] == "block-SAD evaluations/s" and d["n_gpus"] == 1
@@ -21,10 +21,17 @@ def test_bench_line_on_gpu():
     assert abs(d["value"] - 480 * 16641 * 593 / (d["ms_per_step"] * 1e-3)) / d["value"] < 1e-6
     assert d["gpu_launches"] == 2 * 12                              # search + finalize per step, all of them this library's kernels
     e = d["e2e"]
-    assert e["value"] > 0 and e["h2d_bytes_per_step"] > 9_000_000 and e["d2h_bytes_per_step"] == 480 * 593 * 16
+    # int16 host planes: the band's CTU rows of the current frame (1920 x 1024) + band and halo of the reference (2048 x 1152), jobs
+    assert e["value"] > 0 and e["h2d_bytes_per_step"] == 2 * (1920 * 1024 + 2048 * 1152) + 480 * 16 and e["d2h_bytes_per_step"] == 480 * 593 * 16
+    assert e["band_halo_u8"]["value"] > 0
+    v = d["verified"]
+    assert v["ctus"] == 480 and v["mismatches"] == 0 and v["ctu_result_sets_compared"] == 3 * 480
     rf = d["roofline"]
     assert rf["bound"] == "int_alu" and 0.3 < rf["frac"] < 1.5 and rf["peak"] > 10 and rf["achieved"] > 5 and rf["traffic"]
-    assert abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9
+    assert abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9 and abs(rf["frac_issue"] - rf["frac"] / 2) < 1e-9
+    assert d["frac_refine"]["roofline"]["frac_issue"] > 0
+    pc = d["per_ctu"]
+    assert pc["calls"] == 480 and 0 < pc["latency_ms"] < 5
     c = d["clocks"]
     assert c["sm_mhz"] and c["sm_max_mhz"] and not set(c["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
     assert 0.5 < d["ms_per_step"] < 5.0                             # 1080p +-64 on one B200: ~1.3 ms

@@ -171,7 +171,7 @@ def test_refine_pu_host_pointers(me, oracle):
 
 def test_full_size_1080p_refine(me, oracle):
     """BASELINE configuration: 1080p +-64 search, then all 284 640 PUs refined; every result obeys the size-independent
-    properties (offset within +-3 quarter samples, cost >= distortion), 24 sampled CTUs (14 232 PUs) equal the oracle."""
+    properties (offset within +-3 quarter samples, cost >= distortion) and EVERY PU of every CTU equals the oracle."""
     W, H, R, M = 1920, 1080, 64, 80
     f = luma_frames(W, H, 2)
     cur, ref = pad_plane(f[1], M, M), pad_plane(f[0], M, M)
@@ -184,15 +184,14 @@ def test_full_size_1080p_refine(me, oracle):
     assert res.shape == (len(jobs), 593)
     assert np.abs(res["mvx"] - 4 * X).max() <= 3 and np.abs(res["mvy"] - 4 * Y).max() <= 3
     assert (res["cost"] >= res["dist"]).all()
-    pick = np.linspace(0, len(jobs) - 1, 24).astype(int)
     rects = me.lib.partition_table()
-    pus = np.zeros((len(pick), 593, 8), np.int32)
-    pus[:, :, 0] = jobs[pick, None, 0] + rects[None, :, 0]
-    pus[:, :, 1] = jobs[pick, None, 1] + rects[None, :, 1]
+    pus = np.zeros((len(jobs), 593, 8), np.int32)
+    pus[:, :, 0] = jobs[:, None, 0] + rects[None, :, 0]
+    pus[:, :, 1] = jobs[:, None, 1] + rects[None, :, 1]
     pus[:, :, 2], pus[:, :, 3] = rects[None, :, 2], rects[None, :, 3]
-    pus[:, :, 4], pus[:, :, 5] = X[pick], Y[pick]
+    pus[:, :, 4], pus[:, :, 5] = X, Y
     want = oracle.refine_frac(cur, (M, M), ref, (M, M), pus.reshape(-1, 8), lam, True)
-    check(res[pick].reshape(-1), None, want, "1080p sample")
+    check(res.reshape(-1), None, want, "1080p, all 284 640 PUs")
     pc.free(); pr.free()
 
 
