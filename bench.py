@@ -657,7 +657,24 @@ def per_ctu_leg(hm, me, n_cur, n_ref, margin, all_jobs, R, W, H):
         call(k)
     dt = time.perf_counter() - t0
     kms = me.last_kernel_ms()
-    return {"call": "hmme_search_ctu (TEncOpenCL::calcMotionVectors): one CTU, +-%d, host pointers into int16 planes, synchronous" % R,
+    spec = None
+    probe = os.path.join(ROOT, "tools", "spec_probe")
+    if os.path.exists(probe):                                       # the C++ class over a whole picture: synchronous calls vs the speculative whole-frame search
+        r = subprocess.run([probe, str(W), str(H), str(R)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+        line = [l for l in r.stdout.splitlines() if l.startswith("{")]
+        if r.returncode == 0 and line:
+            p = json.loads(line[-1])
+            spec = {"what": "TEncOpenCL (C++ drop-in class) over one picture, one calcMotionVectors call per CTU in coding order: `sync` = every call searches synchronously; "
+                            "`spec_hit` = beginPicture/addReferencePicture/speculate first, zero predictors, every call answered from the device-resident tables; "
+                            "`spec_drift` = the predictor changes every 40 CTUs (miss -> synchronous search + re-speculation of the CTUs still to come, then hits)",
+                    "sync_frame_ms": p["sync_frame_ms"], "sync_frames_per_s": 1e3 / p["sync_frame_ms"],
+                    "spec_hit_frame_ms": p["spec_hit_frame_ms"], "spec_hit_frames_per_s": 1e3 / p["spec_hit_frame_ms"],
+                    "spec_drift_frame_ms": p["spec_drift_frame_ms"], "spec_drift_frames_per_s": 1e3 / p["spec_drift_frame_ms"],
+                    "spec_hit_rate": p["spec_hit_hits"] / max(1, p["spec_hit_calls"]), "spec_drift_hit_rate": p["spec_drift_hits"] / max(1, p["spec_drift_calls"]),
+                    "tables_equal_sync": p["tables_equal_sync"], "timer": "host wall clock inside tools/spec_probe (includes the picture uploads from pageable memory)"}
+        else:
+            spec = {"error": (r.stderr or r.stdout)[-300:]}
+    return {"speculative": spec, "call": "hmme_search_ctu (TEncOpenCL::calcMotionVectors): one CTU, +-%d, host pointers into int16 planes, synchronous" % R,
             "calls": len(all_jobs), "latency_ms": dt * 1e3 / len(all_jobs), "frame_ms": dt * 1e3, "frames_per_s": 1.0 / dt,
             "search_kernel_ms_last_call": kms,
             "timer": "host wall clock around %d sequential calls (every CTU of the frame), after 8 warm-up calls" % len(all_jobs)}

@@ -23,7 +23,7 @@ EXPORTS = [
     "hmme_plane_upload_s16_async", "hmme_fetch_results_async",
     "hmme_refine_pu", "hmme_refine_frac", "hmme_refine_frame", "hmme_refine_frame_async", "hmme_fetch_frac_async", "hmme_last_frac_ms", "hmme_mc_cost", "hmme_mc_cost_pu", "hmme_mc_cost_bi", "hmme_mc_cost_bi_pu",
     "hmme_graph_begin", "hmme_graph_end", "hmme_graph_launch", "hmme_graph_destroy",
-    "hmme_plane_upload_u8_async", "hmme_plane_upload_rect_async",
+    "hmme_plane_upload_u8_async", "hmme_plane_upload_rect_async", "hmme_host_alloc", "hmme_host_free",
     "hmme_table_create", "hmme_table_destroy", "hmme_search_frame_table_async", "hmme_table_fetch_async", "hmme_table_device_ptr",
     "hmme_group_create", "hmme_group_unique_id", "hmme_group_create_rank", "hmme_group_destroy", "hmme_group_last_error", "hmme_group_size",
     "hmme_group_set_lambda_q16", "hmme_group_configure", "hmme_group_search_frame_async", "hmme_group_sync", "hmme_group_search_frame",
@@ -101,6 +101,8 @@ class HmmeLib:
             "hmme_mc_cost_bi": (i32, [vp, P(PlaneDesc), P(PlaneDesc), P(PlaneDesc), vp, i32, i32, vp]),
             "hmme_mc_cost_bi_pu": (i32, [vp, vp, i32, vp, i32, i32, i32, vp, i32, i32, i32, i32, i32, i32, P(u32)]),
             "hmme_mc_cost": (i32, [vp, P(PlaneDesc), P(PlaneDesc), vp, i32, i32, vp]),
+            "hmme_host_alloc": (vp, [C.c_size_t]),
+            "hmme_host_free": (None, [vp]),
             "hmme_plane_upload_u8_async": (i32, [vp, P(PlaneDesc), vp, i32]),
             "hmme_plane_upload_rect_async": (i32, [vp, P(PlaneDesc), vp, i32, i32, i32, i32, i32, i32]),
             "hmme_table_create": (i32, [vp, P(vp), i32, i32]),

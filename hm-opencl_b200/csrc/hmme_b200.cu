@@ -451,6 +451,14 @@ void hmme_destroy(hmme_ctx* c) {
     delete c;
 }
 
+// page-locked host memory for callers that do not link the CUDA runtime themselves (asynchronous copies need it to be truly asynchronous)
+void* hmme_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void hmme_host_free(void* p) { if (p) cudaFreeHost(p); }
+
 const char* hmme_device_name(hmme_ctx* c) { return c ? c->prop.name : ""; }
 const char* hmme_last_error(hmme_ctx* c) {
     if (c) return c->err.c_str();
@@ -538,7 +546,10 @@ int hmme_plane_alloc(hmme_ctx* c, hmme_plane* out, int elemBytes, int width, int
     p.elemBytes = elemBytes; p.width = width; p.height = height; p.marginX = marginX; p.marginY = marginY;
     p.pitch = (width + 2 * marginX + 15) & ~15;       // 16-element pitch keeps every row 16-byte aligned (TMA-ready)
     CU_TRY(c, cudaMalloc(&p.base, plane_elems(&p) * elemBytes + 64));
-    CU_TRY(c, cudaMemset(p.base, 0, plane_elems(&p) * elemBytes + 64));   // pitch padding and slack read as defined samples
+    // pitch padding and slack read as defined samples.  On the context's own stream and waited for: a plain cudaMemset runs on the
+    // legacy stream, which the (non-blocking) upload streams do not order against -- it could land after the first upload
+    CU_TRY(c, cudaMemsetAsync(p.base, 0, plane_elems(&p) * elemBytes + 64, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
     *out = p;
     return HMME_OK;
 }

@@ -46,6 +46,7 @@ public:
 #include <string>
 
 struct hmme_ctx;
+struct TEncOpenCLSpec;                          // state of the speculative whole-frame search (TEncOpenCL.cpp)
 
 class TEncOpenCL {
 protected:
@@ -63,6 +64,7 @@ protected:
     Int          Yarray[NUM_CTU_PARTS];
     Distortion   minSad[NUM_CTU_PARTS];         ///< SAD + MV-bit cost of the winner
     Distortion   ruiCosts[NUM_CTU_PARTS];       ///< pure SAD of the winner
+    TEncOpenCLSpec* m_spec;                     ///< NULL until beginPicture is used
 
 public:
     TEncOpenCL();
@@ -89,6 +91,23 @@ public:
     /// uni-directional PU (piRefY1 == NULL) or a bi-directional one (xPredInterBi + addAvg); MVs already clipped, plane pointers at the PU origin.
     Distortion      interPredictionError(Pel* pelOrg, Int iOrgStride, Int iWidth, Int iHeight, Pel* piRefY0, Int iRefStride0, const TComMv& rcMv0,
                                          Pel* piRefY1, Int iRefStride1, const TComMv& rcMv1, Bool bUseHadamard);
+
+    /// Additions: speculative whole-frame search.  The reference searches one CTU per calcMotionVectors call
+    /// because the window position (pcMvSrchRngLT) depends on the AMVP predictor of the CTU being coded.  Here the slice encoder announces the
+    /// picture before its CTU loop (TEncSlice::compressSlice, TEncSlice.cpp:730; the reference pictures are final and border-extended since
+    /// TComSlice::setRefPicList, TComSlice.cpp:351-377): beginPicture(original luma) + addReferencePicture(reconstructed luma) per reference +
+    /// speculate(range).  Every full CTU of the picture is then searched against every reference in ONE launch per reference, with the window a
+    /// zero predictor gives, into device-resident [hypothesis][ctu][593] tables (hmme_table).  calcMotionVectors keeps its signature: it recognises
+    /// the CTU and the reference picture from its pointers, and when block content, window position, range and lambda equal a table entry it
+    /// answers from the table; otherwise it runs the synchronous search as before AND re-speculates the CTUs still to come with the window
+    /// centre it just saw (motion is coherent, so the next CTUs usually hit).  Results are those of the same kernels on the same inputs: the
+    /// bitstream cannot change.  HMME_SPEC_VERIFY=1 makes every hit also run the synchronous search and abort on any difference.
+    Void            beginPicture(const Pel* orgLuma, Int orgStride, Int width, Int height);
+    Void            addReferencePicture(const Pel* recLuma, Int recStride, Int marginX, Int marginY);
+    Void            speculate(Int searchRange);
+    Void            endPicture();
+    struct SpecStats { unsigned long long calls, hits, missBlock, missWindow, missOther, speculations, jobsSpeculated; };
+    SpecStats       getSpecStats() const;
 
     //======== getters and setters ================
     Int             getDeviceId         ()              { return deviceId; }

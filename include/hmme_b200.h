@@ -64,6 +64,8 @@ void hmme_destroy(hmme_ctx* ctx);
 const char* hmme_device_name(hmme_ctx* ctx);          /* TEncOpenCL::getDeviceInfo */
 const char* hmme_last_error(hmme_ctx* ctx);           /* ctx may be NULL: error of the last failed hmme_create */
 void* hmme_stream(hmme_ctx* ctx);                     /* the cudaStream_t all work of this context runs on */
+void* hmme_host_alloc(size_t bytes);                  /* page-locked host memory (asynchronous copies are only asynchronous from / to it) */
+void hmme_host_free(void* p);
 
 /* ---- lambda: TEncOpenCL::setLambda (TEncOpenCL.h:121), m_lambda = (UInt)floor(65536*sqrt(lambda)) */
 int hmme_set_lambda(hmme_ctx* ctx, double lambda);

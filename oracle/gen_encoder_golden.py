@@ -68,17 +68,19 @@ def decode_check(bitstream, recon, workdir):
     return r.stdout.count("(OK)")
 
 
-def run_case(binary, name, kernel_path, workdir):
+def run_case(binary, name, kernel_path, workdir, env=None):
     W, H, F, cfg, extra = CASES[name]
     yuv, bit, rec = (os.path.join(workdir, name + e) for e in (".yuv", ".hevc", "_rec.yuv"))
     write_yuv(yuv, W, H, F)
     t0 = time.time()
-    r = subprocess.run([binary] + encoder_args(W, H, F, cfg, extra, yuv, bit, rec, kernel_path), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    r = subprocess.run([binary] + encoder_args(W, H, F, cfg, extra, yuv, bit, rec, kernel_path), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
+                       env=dict(os.environ, **env) if env else None)
     if r.returncode != 0:
         raise RuntimeError("encoder failed:\n" + r.stdout[-3000:])
     return {"bitstream_md5": md5(bit), "bitstream_bytes": os.path.getsize(bit), "recon_md5": md5(rec), "yuv_md5": md5(yuv),
             "decoded_ok": decode_check(bit, rec, workdir), "frames": F,
-            "seconds": round(time.time() - t0, 1), "poc_lines": [l.strip()[:120] for l in r.stdout.splitlines() if l.startswith("POC")]}
+            "seconds": round(time.time() - t0, 1), "poc_lines": [l.strip()[:120] for l in r.stdout.splitlines() if l.startswith("POC")],
+            "spec_line": next((l.strip() for l in r.stdout.splitlines() if l.startswith("HMME_SPEC")), None)}
 
 
 def main():

@@ -16,6 +16,32 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BIN = os.path.join(REFDIR, "TAppEncoder_b200")
 BIN_FRAC = os.path.join(REFDIR, "TAppEncoder_b200frac")
+BIN_SPEC = os.path.join(REFDIR, "TAppEncoder_b200spec")
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_bitstream_identical_with_speculative_whole_frame_search(name):
+    """Row f2 inside the encoder: TEncSlice::compressSlice announces each inter picture, every CTU x reference is searched ahead of the
+    CTU loop, and calcMotionVectors (unchanged signature, unchanged caller) answers from the device-resident tables whenever block,
+    window, range and lambda match -- else it searches synchronously and re-speculates.  HMME_SPEC_VERIFY=1 (small cases) makes every
+    table hit also run the synchronous search and abort on a difference.  Bitstream and reconstruction must equal the goldens."""
+    import re
+    if not os.path.exists(BIN_SPEC):
+        pytest.skip("oracle/_ref/TAppEncoder_b200spec was not built (needs /root/reference at build time)")
+    gold = json.load(open(os.path.join(ROOT, "tests/golden/encoder_bitstreams.json")))["cases"][name]
+    verify = {"HMME_SPEC_VERIFY": "1"} if CASES[name][0] < 1000 else None
+    with tempfile.TemporaryDirectory() as d:
+        got = run_case(BIN_SPEC, name, os.path.join(REFDIR, "cfg", "encoder_lowdelay_P_main.cfg"), d, env=verify)
+    assert got["bitstream_bytes"] == gold["bitstream_bytes"]
+    assert got["bitstream_md5"] == gold["bitstream_md5"]
+    assert got["recon_md5"] == gold["recon_md5"]
+    if got["decoded_ok"] is not None:
+        assert got["decoded_ok"] == got["frames"]
+    assert got["spec_line"], "the encoder did not report its speculation statistics"
+    st = {k: int(v) for k, v in re.findall(r"(\w+)=(\d+)", got["spec_line"])}
+    assert st["calls"] > 0 and st["hits"] > 0 and st["hits"] + st["miss_block"] + st["miss_window"] + st["miss_other"] == st["calls"]
+    uni = st["calls"] - st["miss_block"]                  # calls with the original block (the bi-prediction refinement never matches)
+    print(name, got["spec_line"], "hit rate of uni-directional calls %.3f" % (st["hits"] / max(1, uni)), "encode %.1f s" % got["seconds"])
 
 
 @pytest.mark.parametrize("name", sorted(CASES))

@@ -1,0 +1,76 @@
+// spec_probe.cpp -- drives the drop-in C++ class (hm-opencl_b200/host/TEncOpenCL) over ONE whole picture the way the patched slice
+// encoder does: beginPicture / addReferencePicture / speculate, then one calcMotionVectors call per CTU in
+// coding order with the window a given predictor field produces.  Prints one JSON line: time per picture and per call for
+//   sync        : no speculation, every call is the synchronous search (what round 1 shipped)
+//   spec_hit    : zero predictors, every call is answered from the device-resident tables
+//   spec_drift  : the predictor changes every `run` CTUs (a miss + re-speculation, then hits): the adaptive path
+// and checks the 64x64 winners of the three passes against each other.  Built by __graft_entry__.build(), run by bench.py (per_ctu leg).
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "TEncOpenCL.h"
+#include "hmme_b200.h"
+
+static unsigned lcg(unsigned& s) { s = s * 1664525u + 1013904223u; return s >> 8; }
+static double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+int main(int argc, char** argv) {
+    const int W = argc > 1 ? atoi(argv[1]) : 1920, H = argc > 2 ? atoi(argv[2]) : 1080, R = argc > 3 ? atoi(argv[3]) : 64, run = argc > 4 ? atoi(argv[4]) : 40;
+    const int M = 80, S = W + 2 * M, rows = H + 2 * M;
+    TEncOpenCL me;
+    if (!me.findDevice(0) || !me.compileKernelSource("cl/sad.cl", "calcSAD_AMP") || !me.createBuffers(64, 64, R)) { printf("{\"error\": \"init\"}\n"); return 1; }
+    me.setEnabled(true);
+    me.setLambda(49.3);
+    std::vector<Pel> ref((size_t)S * rows), cur((size_t)S * rows);
+    unsigned seed = 4242;
+    for (int y = 0; y < rows; ++y)
+        for (int x = 0; x < S; ++x) ref[(size_t)y * S + x] = (Pel)(((x * 7 + y * 13) ^ (lcg(seed) & 63)) & 255);
+    for (int y = 0; y < rows; ++y)
+        for (int x = 0; x < S; ++x) {
+            const int sy = y + 2 < rows ? y + 2 : y, sx = x + 3 < S ? x + 3 : x;
+            cur[(size_t)y * S + x] = ref[(size_t)sy * S + sx];
+        }
+    Pel* curO = &cur[(size_t)M * S + M];
+    Pel* refO = &ref[(size_t)M * S + M];
+    const int ncx = W / 64, ncy = H / 64, nctu = ncx * ncy;
+    std::vector<int> check[3];
+    double secs[3] = {0, 0, 0};
+    TEncOpenCL::SpecStats st[3];
+    for (int pass = 0; pass < 3; ++pass) {
+        for (int rep = 0; rep < 2; ++rep) {                       // rep 0 warms up (allocations), rep 1 is timed
+            check[pass].clear();
+            const double t0 = now();
+            if (pass > 0) {
+                me.beginPicture(curO, S, W, H);
+                me.addReferencePicture(refO, S, M, M);
+                me.speculate(R);
+            }
+            for (int c = 0; c < nctu; ++c) {
+                const int cx = (c % ncx) * 64, cy = (c / ncx) * 64;
+                int px = 0, py = 0;
+                if (pass == 2) { px = 4 * ((c / run) % 5) * 3; py = -4 * ((c / run) % 3) * 2; }       // quarter-pel predictor, piecewise constant
+                int ltx, lty;
+                hmme_search_window(px, py, R, cx, cy, W, H, &ltx, &lty, NULL, NULL);
+                TComMv lt((Short)ltx, (Short)lty);
+                Pel blk[64 * 64];
+                for (int r = 0; r < 64; ++r) memcpy(blk + 64 * r, curO + (size_t)(cy + r) * S + cx, 64 * sizeof(Pel));
+                me.calcMotionVectors(blk, refO + (size_t)cy * S + cx, S, 64, R, &lt);
+                check[pass].push_back(me.getX()[592] * 1000 + me.getY()[592]);
+                check[pass].push_back((int)me.getRuiCost()[592]);
+            }
+            if (pass > 0) me.endPicture();
+            secs[pass] = now() - t0;
+        }
+        st[pass] = me.getSpecStats();
+    }
+    const bool same = check[0] == check[1];                       // pass 2 uses other windows: compared through its own hit/miss verification only
+    printf("{\"width\": %d, \"height\": %d, \"range\": %d, \"ctus\": %d, \"sync_frame_ms\": %.3f, \"spec_hit_frame_ms\": %.3f, \"spec_drift_frame_ms\": %.3f, "
+           "\"spec_hit_calls\": %llu, \"spec_hit_hits\": %llu, \"spec_drift_calls\": %llu, \"spec_drift_hits\": %llu, \"spec_drift_speculations\": %llu, "
+           "\"tables_equal_sync\": %s}\n",
+           W, H, R, nctu, secs[0] * 1e3, secs[1] * 1e3, secs[2] * 1e3, st[1].calls - st[0].calls, st[1].hits - st[0].hits, st[2].calls - st[1].calls,
+           st[2].hits - st[1].hits, st[2].speculations - st[1].speculations, same ? "true" : "false");
+    return same ? 0 : 2;
+}
