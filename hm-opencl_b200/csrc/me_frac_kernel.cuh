@@ -454,34 +454,51 @@ __device__ __forceinline__ uint32_t mc_cost_pu(const McParams& p, const int n, M
     const int rcp = (65536 + ntxT - 1) / ntxT;
     const int rowL = lane >> 1, halfL = lane & 1, curR = lane >> 2, curC = (lane & 3) * 2;
     uint32_t acc = 0;
+    // Patches and current tiles of a group of up to four tiles travel global -> registers -> shared memory; the registers of group
+    // g + 4 are loaded right after group g has been handed to shared memory, so their latency hides behind the filtering of group g.
+    // A lane's 8 patch bytes (any alignment) come from three aligned 32-bit words and two funnel shifts (the planes carry slack bytes
+    // behind the last row, see hmme_plane); its two current samples from one 16- or 32-bit load (PU x, tile x and column are even).
+    uint32_t pw0[NL][4], pw1[NL][4], pcur[4];
+    auto fetch = [&](const int g0) {
+#pragma unroll
+        for (int s4 = 0; s4 < 4; ++s4) {
+            const int t = g0 + s4;
+#pragma unroll
+            for (int l = 0; l < NL; ++l) { pw0[l][s4] = 0; pw1[l][s4] = 0; }
+            pcur[s4] = 0;
+            if (t >= nT) continue;                             // warp-uniform: tiles past the last one are masked in the V step
+            const int ty = ((t * rcp) >> 16) * 8, tx = t * 8 - ty * ntxT;
+            const int tw = min(8, Pw - tx), th = min(8, Ph - ty);
+#pragma unroll
+            for (int l = 0; l < NL; ++l) {
+                const uint8_t* q = refPu[l] + (long long)(ty + rowL) * pitchL[l] + tx + halfL * 8;
+                const uint32_t sh = 8u * (uint32_t)((uintptr_t)q & 3);
+                const uint32_t* qa = reinterpret_cast<const uint32_t*>((uintptr_t)q & ~(uintptr_t)3);
+                const uint32_t a0 = __ldg(qa), a1 = __ldg(qa + 1), a2 = __ldg(qa + 2);
+                pw0[l][s4] = __funnelshift_r(a0, a1, sh);
+                pw1[l][s4] = __funnelshift_r(a1, a2, sh);
+            }
+            if (curR < th && curC < tw) {
+                const long long o = (long long)(Py + ty + curR) * p.curPitch + Px + tx + curC;
+                if (p.curBytes == 1) {
+                    const uint32_t v = __ldg(reinterpret_cast<const uint16_t*>(static_cast<const uint8_t*>(p.cur) + o));
+                    pcur[s4] = (v & 0xFFu) | ((v >> 8) << 16);
+                } else
+                    pcur[s4] = __ldg(reinterpret_cast<const uint32_t*>(static_cast<const int16_t*>(p.cur) + o));
+            }
+        }
+    };
+    fetch(0);
     for (int g = 0; g < nT; g += 4) {
 #pragma unroll
-        for (int s4 = 0; s4 < 4; ++s4) {                      // patches and current tiles of up to four tiles
-            const int t = g + s4;
-            if (t >= nT) break;                                // warp-uniform: tiles past the last one are masked in the V step, their
-            uint32_t w0[NL], w1[NL]; int c0 = 0, c1 = 0;       // shared memory may hold anything
+        for (int s4 = 0; s4 < 4; ++s4) {
+            if (g + s4 >= nT) break;
 #pragma unroll
-            for (int l = 0; l < NL; ++l) { w0[l] = 0; w1[l] = 0; }
-            {
-                const int ty = ((t * rcp) >> 16) * 8, tx = t * 8 - ty * ntxT;
-                const int tw = min(8, Pw - tx), th = min(8, Ph - ty);
-#pragma unroll
-                for (int l = 0; l < NL; ++l) {
-                    const uint8_t* q = refPu[l] + (long long)(ty + rowL) * pitchL[l] + tx + halfL * 8;
-                    w0[l] = q[0] | (q[1] << 8) | (q[2] << 16) | ((uint32_t)q[3] << 24);
-                    w1[l] = q[4] | (q[5] << 8) | (q[6] << 16) | ((uint32_t)q[7] << 24);
-                }
-                if (curR < th) {
-                    const long long o = (long long)(Py + ty + curR) * p.curPitch + Px + tx + curC;
-                    if (curC < tw) c0 = p.curBytes == 1 ? (int)static_cast<const uint8_t*>(p.cur)[o] : (int)static_cast<const int16_t*>(p.cur)[o];
-                    if (curC + 1 < tw) c1 = p.curBytes == 1 ? (int)static_cast<const uint8_t*>(p.cur)[o + 1] : (int)static_cast<const int16_t*>(p.cur)[o + 1];
-                }
-            }
-#pragma unroll
-            for (int l = 0; l < NL; ++l) *reinterpret_cast<uint2*>(&S.ref[l][s4][rowL][halfL * 2]) = make_uint2(w0[l], w1[l]);
-            S.cur[s4][curC][curR] = (int16_t)c0;
-            S.cur[s4][curC + 1][curR] = (int16_t)c1;
+            for (int l = 0; l < NL; ++l) *reinterpret_cast<uint2*>(&S.ref[l][s4][rowL][halfL * 2]) = make_uint2(pw0[l][s4], pw1[l][s4]);
+            S.cur[s4][curC][curR] = (int16_t)(pcur[s4] & 0xFFFFu);
+            S.cur[s4][curC + 1][curR] = (int16_t)(pcur[s4] >> 16);
         }
+        if (g + 4 < nT) fetch(g + 4);
         __syncwarp();
 #pragma unroll
         for (int l = 0; l < NL; ++l)
