@@ -95,16 +95,22 @@ class ClockSampler:
                 self.t.append(time.perf_counter())
 
     def start(self):
-        time.sleep(0.15)                       # let the first samples arrive before the region starts
+        t_end = time.perf_counter() + 3.0      # let the first samples arrive before the region starts (nvidia-smi takes a while to come up)
+        while self.proc and not self.rows and time.perf_counter() < t_end:
+            time.sleep(0.02)
         self.t0 = time.perf_counter()
 
     def summary(self):
         t1 = time.perf_counter()
         time.sleep(0.05)
+        n0 = len(self.rows)
+        t_end = time.perf_counter() + 1.0      # a region shorter than the sampling period: take the sample that follows it
+        while self.proc and len(self.rows) == n0 and not any(self.t0 <= t for t in self.t) and time.perf_counter() < t_end:
+            time.sleep(0.02)
         if self.proc:
             self.proc.terminate()
         self.thread.join(timeout=3)
-        rows = [r for r, t in zip(self.rows, self.t) if self.t0 <= t <= t1 + 0.03] or self.rows[-3:]
+        rows = [r for r, t in zip(self.rows, self.t) if self.t0 <= t <= t1 + 0.03] or self.rows[-3:]   # none inside: the nearest ones
         if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         sm = sorted(float(r[0]) for r in rows)

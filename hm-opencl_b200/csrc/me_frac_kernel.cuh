@@ -457,7 +457,9 @@ __device__ __forceinline__ uint32_t mc_cost_pu(const McParams& p, const int n, M
     // Patches and current tiles of a group of up to four tiles travel global -> registers -> shared memory; the registers of group
     // g + 4 are loaded right after group g has been handed to shared memory, so their latency hides behind the filtering of group g.
     // A lane's 8 patch bytes (any alignment) come from three aligned 32-bit words and two funnel shifts (the planes carry slack bytes
-    // behind the last row, see hmme_plane); its two current samples from one 16- or 32-bit load (PU x, tile x and column are even).
+    // behind the last row, see hmme_plane); its two current samples the same way from two aligned words.  (Measured and dropped: carrying
+    // the pipeline across PUs -- next PU's record and first group fetched under the current PU -- costs 80 registers instead of 64
+    // and is slower, 0.27 vs 0.23 ms for the frame's 284 640 PUs: occupancy hides the inter-PU latency better.)
     uint32_t pw0[NL][4], pw1[NL][4], pcur[4];
     auto fetch = [&](const int g0) {
 #pragma unroll
@@ -478,13 +480,12 @@ __device__ __forceinline__ uint32_t mc_cost_pu(const McParams& p, const int n, M
                 pw0[l][s4] = __funnelshift_r(a0, a1, sh);
                 pw1[l][s4] = __funnelshift_r(a1, a2, sh);
             }
-            if (curR < th && curC < tw) {
+            if (curR < th && curC < tw) {                      // two neighbouring samples, any alignment (PU x is arbitrary here)
                 const long long o = (long long)(Py + ty + curR) * p.curPitch + Px + tx + curC;
-                if (p.curBytes == 1) {
-                    const uint32_t v = __ldg(reinterpret_cast<const uint16_t*>(static_cast<const uint8_t*>(p.cur) + o));
-                    pcur[s4] = (v & 0xFFu) | ((v >> 8) << 16);
-                } else
-                    pcur[s4] = __ldg(reinterpret_cast<const uint32_t*>(static_cast<const int16_t*>(p.cur) + o));
+                const uintptr_t b = (uintptr_t)p.cur + (uintptr_t)(o * p.curBytes);
+                const uint32_t* qa = reinterpret_cast<const uint32_t*>(b & ~(uintptr_t)3);
+                const uint32_t v = __funnelshift_r(__ldg(qa), __ldg(qa + 1), 8u * (uint32_t)(b & 3));
+                pcur[s4] = p.curBytes == 1 ? (v & 0xFFu) | ((v & 0xFF00u) << 8) : v;
             }
         }
     };

@@ -199,7 +199,8 @@ typedef struct { int32_t mvx, mvy; uint32_t cost, dist; } hmme_frac_result;
 int hmme_refine_frac(hmme_ctx* ctx, const hmme_plane* cur, const hmme_plane* ref, const hmme_pu* pus, int npus, int useHad,
                      hmme_frac_result* results, uint32_t* candCosts);
 /* One PU with HOST pointers, synchronous -- what the body of xPatternSearchFracDIF needs: cur = the pattern key block (w x h,
- * int16, stride curStride; 16-bit values allowed), refAtPu = piRefY, i.e. a pointer INTO the padded int16 reference plane at
+ * int16, stride curStride; original samples or the bi-prediction target 2*org - pred of 8-bit video, i.e. values in [-255, 510] --
+ * the Hadamard intermediates are packed into 16 bits, exact for |cur - prediction| <= 4095), refAtPu = piRefY, i.e. a pointer INTO the padded int16 reference plane at
  * the PU origin (samples [mv-4, mv+w+3] x [mv-4, mv+h+3] around it are read), integer MV, quarter-pel predictor.  Returns the
  * final quarter-pel MV (4*mv + 2*half + quarter), ruiCost, and optionally cost minus the MV cost. */
 int hmme_refine_pu(hmme_ctx* ctx, const int16_t* cur, int curStride, const int16_t* refAtPu, int refStride, int w, int h,

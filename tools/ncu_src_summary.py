@@ -5,6 +5,10 @@ import csv
 import sys
 
 rows = list(csv.reader(open(sys.argv[1])))
+ends = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
+if len(ends) > 1:                      # several launches in one report: summarise the first
+    rows = rows[:ends[1]]
+print("kernel:", rows[0][1] if len(rows[0]) > 1 else "?")
 hdr = rows[1]
 col = {h: i for i, h in enumerate(hdr)}
 ops = collections.Counter(); stalls = collections.Counter(); tot = 0
