@@ -39,7 +39,7 @@ std::string g_createErr;
 
 struct FastGeom { int tw, th, nTx, nTy; size_t smemBytes; };
 
-constexpr size_t kSmemBudget = 200 * 1024;
+constexpr size_t kSmemBudget = 220 * 1024;   // of the 227 KB a CTA may opt in to (1 CTA per SM anyway: 128 registers x 512 threads)
 
 size_t fast_smem_bytes(int tw, int th, int yb) {
     const size_t words = (((size_t)fast_win_rows(th, yb) * kWinPitch + 3) & ~(size_t)3) + 1024 + kRing * (size_t)(32 * yb) * kRecWords + ((tw + 3) & ~3) +

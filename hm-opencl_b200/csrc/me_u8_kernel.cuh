@@ -23,9 +23,9 @@
 // and one atomicMin per (warp, partition) into best[job][593]; a tiny finalize kernel decodes MVs.
 //
 // Reference window staging: rows arrive by TMA bulk copies (cp.async.bulk + mbarrier) and are expanded in shared memory
-// into SLIDING WORDS -- entry x of a row is the
-// 32-bit word made of bytes x..x+3 -- so lane l (candidate column x0+l) reads entry x+4i with a plain LDS.32 and 32
-// lanes with consecutive candidate x always hit 32 distinct banks, whatever the alignment of x.  The row pitch is a
+// into SLIDING ENTRIES -- entry x of a row holds bytes x..x+7 (64 bit; round 1: x..x+3) -- so lane l (candidate column x0+l) gets the 16
+// reference bytes of a row with two LDS.64 (entries x and x+8) and lanes with consecutive candidate x never conflict, whatever the
+// alignment of x.  The row pitch is a
 // compile-time constant, which turns every address in the unrolled inner loop into an immediate offset.
 // Addressing of the source plane is linear (row*pitch + col), which is exactly the reference's
 // pelSearchArray[j + i*iRefStride] including its row-wrap quirk.
@@ -37,9 +37,20 @@ namespace hmme {
 constexpr int kFastThreads = 512;
 constexpr int kIdxBits = 11;                  // candidates per tile <= 2048
 constexpr int kMaxTileCands = 1 << kIdxBits;
+#ifndef HMME_WIN32
+#define HMME_WIN64 1                          // default since round 2 (measured: 1.270 -> 1.253 ms per 1080p +-64 frame); -DHMME_WIN32 builds the 32-bit layout
+#endif
+#ifdef HMME_WIN64
+// Sliding 64-bit entries: entry x of a row = bytes x..x+7, so the 16 reference bytes a lane needs per row are TWO LDS.64 (entries x and
+// x + 8) instead of four LDS.32 -- half the shared-memory load instructions for twice the window footprint (117 KB instead of 63 KB).
+constexpr int kWinPitch64 = 187;              // entries per row: (tw-1) + 48 + 8 + 1 <= 185 for tw <= 129, padded so that YB * pitch == 1 (mod 16):
+                                              // a half-warp straddling two row groups of a 129-wide tile still covers 16 distinct 8-byte bank pairs
+constexpr int kWinPitch = 2 * kWinPitch64;    // words per window row
+#else
 constexpr int kWinPitch = 203;                // sliding-word entries per window row: (tw-1) + 4*15 + 1 <= 189 for tw <= 129, padded so that
                                               // YB * pitch == 129 (mod 32): a warp whose 32 units straddle two row groups of a 129-wide
                                               // tile (+-64) still reads 32 distinct banks
+#endif
 constexpr int kMaxTileW = 129;
 constexpr int kDensePitch = 224;              // bytes per row of the TMA landing buffer: 15 (alignment) + 129 + 63 + 3, rounded up to 16
 constexpr int kRecWords = 49;                 // upper-phase words per candidate slot: 32 (8x8 pairs, u16) + 16 (16x16<<11) + 1 (key base),
@@ -339,7 +350,11 @@ __device__ __forceinline__ void round_body(const uint32_t* sWin, const uint32_t*
     constexpr int SLOTS = 32 * YB;
     const bool uvalid = !CHECKED || rg < nRG;
     const int rgc = (CHECKED && !uvalid) ? 0 : rg, uxc = (CHECKED && !uvalid) ? 0 : ux;
+#ifdef HMME_WIN64
+    const uint2* wp = reinterpret_cast<const uint2*>(sWin) + (rgc * YB + by) * kWinPitch64 + uxc + bx;
+#else
     const uint32_t* wp = sWin + (rgc * YB + by) * kWinPitch + uxc + bx;
+#endif
     uint32_t kb[YB], kbRec[YB];
     const uint32_t bitsX = sBitsX[uxc];
 #pragma unroll
@@ -365,7 +380,12 @@ __device__ __forceinline__ void round_body(const uint32_t* sWin, const uint32_t*
     uint4 cw[YB];
 #pragma unroll
     for (int rho = 0; rho < 16 + YB - 1; ++rho) {
+#ifdef HMME_WIN64
+        const uint2 ra = wp[rho * kWinPitch64], rb = wp[rho * kWinPitch64 + 8];
+        const uint32_t r0 = ra.x, r1 = ra.y, r2 = rb.x, r3 = rb.y;
+#else
         const uint32_t r0 = wp[rho * kWinPitch + 0], r1 = wp[rho * kWinPitch + 4], r2 = wp[rho * kWinPitch + 8], r3 = wp[rho * kWinPitch + 12];
+#endif
         if (rho < 16) cw[rho % YB] = *reinterpret_cast<const uint4*>(cp + rho * 16);
 #pragma unroll
         for (int j = 0; j < YB; ++j) {
@@ -473,11 +493,20 @@ __global__ void __launch_bounds__(kFastThreads, 1) me_u8_tile_kernel(const FastP
         for (int row = warp; row < rows; row += kFastThreads / 32) {
             const uint32_t off = (uint32_t)((uintptr_t)(wbase + (long long)row * p.refPitch) & 15);
             const uint32_t* d = reinterpret_cast<const uint32_t*>(dense + row * kDensePitch);
+#ifdef HMME_WIN64
+            uint2* dst = reinterpret_cast<uint2*>(sWin) + row * kWinPitch64;
+            for (int x = lane; x < nPos - 4; x += 32) {       // entries 0 .. (twA-1) + 48 + 8
+                const uint32_t q = off + (uint32_t)x, sh = 8 * (q & 3);
+                const uint32_t w0 = d[q >> 2], w1 = d[(q >> 2) + 1], w2 = d[(q >> 2) + 2];
+                dst[x] = make_uint2(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh));
+            }
+#else
             uint32_t* dst = sWin + row * kWinPitch;
             for (int x = lane; x < nPos; x += 32) {           // lane-contiguous stores, 4-lane broadcast loads: conflict-free
                 const uint32_t q = off + (uint32_t)x;
                 dst[x] = __funnelshift_r(d[q >> 2], d[(q >> 2) + 1], 8 * (q & 3));
             }
+#endif
         }
     }
     __syncthreads();

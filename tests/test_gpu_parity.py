@@ -501,3 +501,49 @@ def test_device_resident_tables_keep_both_lists(me, oracle):
     me.destroy_table(t)
     for p in (pc, p0, p1, pb):
         p.free()
+
+
+def test_graphs_survive_plain_calls_and_refuse_stale_buffers(oracle):
+    """Advisor findings on hmme_graph_*: (a) after hmme_graph_end, plain asynchronous calls and the timing getters must work although
+    events were recorded while capturing; (b) a graph replays its OWN page-locked copy of the job list, so a later per-CTU call or
+    another search cannot change what it runs; (c) once a device buffer the graph references has been reallocated, launching it
+    is an error instead of a use-after-free."""
+    import torch
+    W, H, R, M, lam = 256, 128, 8, 24, 460000
+    m = hm.MotionEstimator(0, 16)
+    m.set_lambda_q16(lam)
+    f = luma_frames(W, H, 2, seed=5)
+    cur, ref = pad_plane(f[1], M, M), pad_plane(f[0], M, M)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()   # noqa: E731
+    h_cur, h_ref = pin(cur), pin(ref)
+    jobs = frame_jobs(W, H, R)
+    outs = [pin(np.zeros((len(jobs), 593), t)) for t in (np.int32, np.int32, np.uint32, np.uint32)]
+    pc, pr = m.alloc_plane(1, W, H, M, M), m.alloc_plane(1, W, H, M, M)
+
+    def step(j):
+        m.upload(pr, h_ref, asynchronous=True)
+        m.upload(pc, h_cur, asynchronous=True)
+        m.search_frame_async(pc, pr, j, R)
+        m.fetch_results(len(j), outs, asynchronous=True)
+
+    step(jobs); m.sync()
+    m.graph_begin(); step(jobs); g = m.graph_end()
+    m.upload(pc, h_cur, asynchronous=True)                      # (a) waits on an event that must not belong to the capture
+    m.sync()
+    with pytest.raises(hm.HmmeError):
+        m.last_kernel_ms()                                       # timing events of the capture are not readable: a clean error, not a CUDA fault
+    want = oracle.search_frame(cur, (M, M), ref, (M, M), jobs, R, lam, nthreads=4)
+    other = jobs.copy(); other[:, 2] += 3                        # (b) different jobs through the ordinary calls and the per-CTU call in between
+    m.search_frame(pc, pr, other, R)
+    m.search_ctu(cur[M:M + 64, M:M + 64], ref, 0, 0, M, M, R, -R + 1, -R)
+    for o in outs:
+        o[:] = 0
+    m.graph_launch(g); m.sync()
+    assert_same(outs, want, "graph after foreign jobs")
+    many = np.tile(jobs, (12, 1))                                # (c) 96 jobs > the context's initial capacity of 64: buffers are reallocated
+    m.search_frame(pc, pr, many, R)
+    with pytest.raises(hm.HmmeError) as e:
+        m.graph_launch(g)
+    assert e.value.code == -1 and "reallocated" in str(e.value)
+    m.graph_destroy(g)
+    pc.free(); pr.free(); m.close()
