@@ -746,7 +746,7 @@ def random_access_leg(hm, me, ext, torch, sets, nsets, n_cur, n_ref, frames, mar
     p_bi.free()
     return {"scope": "one B frame of 1080p random access: list 0 and list 1 (480 jobs x 16641 candidates each, 8 bit) + bi-prediction refinement "
                      "(480 jobs x 81 candidates, int16 block 2*org-pred against the 8-bit list-1 picture), results in a device-resident [3][480][593] table",
-            "ms_per_b_frame": ms, "b_frames_per_s": 1e3 / ms, "bipred_kernel": "me_s16_tile_kernel", "bipred_kernel_ms": bi,
+            "ms_per_b_frame": ms, "b_frames_per_s": 1e3 / ms, "bipred_kernel": "me_bipred_prep_kernel + me_u8_tile_kernel (clamped block + per-partition constants, DESIGN.md 3.2)", "bipred_kernel_ms": bi,
             "bipred_roofline": {"bound": "int_alu", "achieved": ach / 1e12, "peak": peak["lane_ops_per_s"] / 1e12, "unit": "T int-lane-op/s",
                                 "frac": ach / peak["lane_ops_per_s"], "frac_issue": ach / (2 * peak["lane_ops_per_s"]), "ops_per_ctu_candidate": INT_OPS_PER_CAND_16},
             "block_sad_evaluations_per_s": (2 * njobs * (2 * R + 1) ** 2 + cands) * NPARTS / (ms * 1e-3),

@@ -268,6 +268,7 @@ int enqueue_search(hmme_ctx* c, const SearchIO& io, const void* curOrigin, int c
     // A 16-bit block against an 8-bit picture (the bi-prediction refinement): clamped block + per-partition constants, then the
     // packed 8-bit kernel (me_bipred_prep_kernel explains why that is exact)
     const bool bipred = curElem == 2 && refElem == 1;
+    if (!c->capturing) CU_TRY(c, cudaEventRecord(c->ev0, c->stream));   // timing events stay out of captured graphs
     if (bipred) {
         if ((size_t)njobs > c->biCap) {
             if (c->capturing) return fail(c, HMME_ERR_ARG, "bi-prediction buffers would grow while capturing (run the step once first)");
@@ -283,7 +284,6 @@ int enqueue_search(hmme_ctx* c, const SearchIO& io, const void* curOrigin, int c
         me_bipred_prep_kernel<<<njobs, 256, 0, c->stream>>>(static_cast<const int16_t*>(curOrigin), curPitch, io.jobs, c->dBiBlocks, c->dBiOffsets);
         c->launches += 1;
     }
-    if (!c->capturing) CU_TRY(c, cudaEventRecord(c->ev0, c->stream));   // timing events stay out of captured graphs
     if ((curElem == 1 || bipred) && refElem == 1) {
         constexpr int yb = HMME_FAST_YB;             // candidate rows per thread (3: measured best; 2 is 17 % slower, 4 does not fit)
         const FastGeom g = fast_geometry(W, yb, njobs, c->prop.multiProcessorCount, c->forceRG);

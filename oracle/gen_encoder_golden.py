@@ -34,6 +34,8 @@ CASES = {
     "ra_416x240_9f_sr64": (416, 240, 9, "encoder_randomaccess_main.cfg", ["--SearchRange=64"]),
     # BASELINE.json configs[1] at its full size: 480 calcMotionVectors calls of 16 641 candidates each (~35 min of lock-step emulation)
     "ldp_1920x1080_2f_sr64": (1920, 1080, 2, "encoder_lowdelay_P_main.cfg", ["--SearchRange=64"]),
+    # BASELINE.json configs[2] at its full picture size: random access (two lists + bi-prediction refinement), 3 pictures (~100 min of emulation)
+    "ra_1920x1080_3f_sr64": (1920, 1080, 3, "encoder_randomaccess_main.cfg", ["--SearchRange=64"]),
 }
 
 

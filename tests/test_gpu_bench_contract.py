@@ -35,3 +35,15 @@ def test_bench_line_on_gpu():
     c = d["clocks"]
     assert c["sm_mhz"] and c["sm_max_mhz"] and not set(c["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
     assert 0.5 < d["ms_per_step"] < 5.0                             # 1080p +-64 on one B200: ~1.3 ms
+
+
+def test_random_access_workload_verifies_every_table():
+    """BASELINE config[2] at full size: two reference lists + the bi-prediction refinement of every CTU of a 1080p B frame, results in a
+    device-resident table, all 3 x 480 result sets compared with the oracle inside bench.py."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--workload", "1080p64_ra", "--steps", "6", "--warmup", "3", "--no-cpu-baseline"],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-3000:]
+    d = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    ra = d["random_access"]
+    assert ra["verified"] == {"ctus": 1440, "mismatches": 0, "what": ra["verified"]["what"]}
+    assert 1.0 < ra["ms_per_b_frame"] < 10.0 and 0 < ra["bipred_kernel_ms"] < 1.0 and ra["bipred_roofline"]["frac"] > 0
