@@ -136,11 +136,18 @@ __device__ __forceinline__ void frac_eval(const FracParams& p, const FracPu& P, 
     const int curR = lane >> 2, curC = (lane & 3) * 2;       // current-tile loader role
 
     // next tile's samples travel in registers while the current tile is being worked on
-    uint32_t nb[8]; int ncur[2];
+    // (a lane's 8 patch bytes, any alignment: three aligned 32-bit words + two funnel shifts instead of eight byte loads and their
+    // packing; the planes carry slack bytes behind the last row, see hmme_plane)
+    uint32_t nw0, nw1; int ncur[2];
     auto fetch = [&](const int tx, const int ty) {
         const uint8_t* g = refPu + (long long)(ty + rowL) * p.refPitch + tx + halfL * 8;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) nb[q] = g[q];
+        {
+            const uint32_t sh = 8u * (uint32_t)((uintptr_t)g & 3);
+            const uint32_t* qa = reinterpret_cast<const uint32_t*>((uintptr_t)g & ~(uintptr_t)3);
+            const uint32_t a0 = __ldg(qa), a1 = __ldg(qa + 1), a2 = __ldg(qa + 2);
+            nw0 = __funnelshift_r(a0, a1, sh);
+            nw1 = __funnelshift_r(a1, a2, sh);
+        }
         const int tw = min(8, P.w - tx), th = min(8, P.h - ty);
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
@@ -159,8 +166,7 @@ __device__ __forceinline__ void frac_eval(const FracParams& p, const FracPu& P, 
     while (true) {
         const int tw = min(8, P.w - tx), th = min(8, P.h - ty);
         {
-            const uint32_t w0 = nb[0] | (nb[1] << 8) | (nb[2] << 16) | (nb[3] << 24), w1 = nb[4] | (nb[5] << 8) | (nb[6] << 16) | (nb[7] << 24);
-            *reinterpret_cast<uint2*>(&S.ref[rowL][halfL * 2]) = make_uint2(w0, w1);
+            *reinterpret_cast<uint2*>(&S.ref[rowL][halfL * 2]) = make_uint2(nw0, nw1);
             S.cur[curC][curR] = (int16_t)ncur[0];
             S.cur[curC + 1][curR] = (int16_t)ncur[1];
         }
