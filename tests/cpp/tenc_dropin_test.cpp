@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "TEncOpenCL.h"
+#include "hmme_b200.h"
 #include "hmme_oracle.h"
 
 static unsigned lcg(unsigned& s) { s = s * 1664525u + 1013904223u; return s >> 8; }
@@ -118,6 +119,53 @@ int main() {
         ++icalls;
         if (d != od && bad++ < 10) printf("MISMATCH interPredictionError %dx%d bi=%d: got %u want %u\n", w, h, (int)bi, d, od);
     }
+    // the speculative whole-frame search as the patched TEncSlice::compressSlice drives it: announce the picture,
+    // then one calcMotionVectors call per CTU in coding order.  Pass 0: windows of a zero predictor -> every call must be a table hit.
+    // Pass 1: the predictor changes at CTU 5 -> one miss (synchronous search + re-speculation), hits again afterwards.  Pass 2: a
+    // bi-prediction style block (not the original picture's) -> never served from the table.  Every answer is checked against the oracle.
+    int scalls = 0;
+    {
+        const int R = 16;
+        me.setLambda(49.3);
+        const TEncOpenCL::SpecStats s0 = me.getSpecStats();
+        for (int pass = 0; pass < 3; ++pass) {
+            me.beginPicture(&cur[(size_t)M * S + M], S, W, H);
+            me.addReferencePicture(&ref[(size_t)M * S + M], S, M, M);
+            me.addReferencePicture(&ref[(size_t)M * S + M], S, M, M);   // the same picture in the other list: announced once
+            me.speculate(R);
+            int c = 0;
+            for (int cy = 0; cy + 64 <= H; cy += 64)
+                for (int cx = 0; cx + 64 <= W; cx += 64, ++c) {
+                    const int px = (pass == 1 && c >= 5) ? 24 : 0, py = (pass == 1 && c >= 5) ? -12 : 0;
+                    int ltx, lty;
+                    hmme_search_window(px, py, R, cx, cy, W, H, &ltx, &lty, NULL, NULL);
+                    TComMv lt((Short)ltx, (Short)lty);
+                    Pel blk[64 * 64];
+                    for (int r = 0; r < 64; ++r) memcpy(blk + 64 * r, &cur[(size_t)(M + cy + r) * S + M + cx], 64 * sizeof(Pel));
+                    if (pass == 2) blk[100] = (Pel)(blk[100] + 300);
+                    Pel* refAtCtu = &ref[(size_t)(M + cy) * S + M + cx];
+                    me.calcMotionVectors(blk, refAtCtu, S, 64, R, &lt);
+                    int32_t X[593], Y[593]; uint32_t sad[593], cost[593];
+                    hmme_oracle_search_ctu(blk, 64, refAtCtu, S, R, ltx, lty, hmme_oracle_lambda_q16(49.3), X, Y, sad, cost);
+                    ++scalls;
+                    for (int p = 0; p < 593; ++p)
+                        if (me.getX()[p] != X[p] || me.getY()[p] != Y[p] || me.getRuiCost()[p] != sad[p]) {
+                            if (bad++ < 5) printf("MISMATCH speculative pass %d ctu %d part %d\n", pass, c, p);
+                        }
+                }
+            me.endPicture();
+            const TEncOpenCL::SpecStats st = me.getSpecStats();
+            const int n = c;
+            const unsigned long long calls = st.calls - s0.calls, hits = st.hits - s0.hits;
+            const unsigned long long wantHits = pass == 0 ? n : pass == 1 ? 2 * n - 1 : 2 * n - 1;
+            if (calls != (unsigned long long)(pass + 1) * n || hits != wantHits) {
+                printf("FAIL speculative pass %d: calls %llu hits %llu (want %llu), miss_block %llu miss_window %llu\n", pass, calls, hits, wantHits,
+                       st.missBlock - s0.missBlock, st.missWindow - s0.missWindow);
+                ++bad;
+            }
+        }
+    }
+    printf("%d speculative calls; ", scalls);
     printf("%s: %d calcMotionVectors calls, %d refineFractional, %d templateDistortion, %d interPredictionError calls, %d mismatches\n",
            bad ? "FAIL" : "PASS", calls, fcalls, tcalls, icalls, bad);
     return bad ? 1 : 0;
