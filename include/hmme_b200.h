@@ -119,7 +119,7 @@ int hmme_sync(hmme_ctx* ctx);
 /* ---- device-resident result tables.  The reference keeps TComMv allMotionVectors[2][33][593] and
  * Distortion allRuiCost[2][33][593] (TEncSearch.h:114-115) for the CTU being coded, on the host.  A table keeps the same 593-entry
  * records for EVERY CTU job of a picture in HBM, one slot per (reference list, reference index) -- or per window hypothesis of the
- * speculative whole-frame search (INTEGRATION.md section 6) -- so that a B picture's two lists do not overwrite each other.
+ * speculative whole-frame search (INTEGRATION.md section 4.2) -- so that a B picture's two lists do not overwrite each other.
  * hmme_search_frame_table_async leaves its results in table[slot] (nothing is copied to the host); hmme_table_fetch_async copies a
  * job range of a slot to host arrays; hmme_table_device_ptr gives the device address of one of the four [jobsPerSlot][593] arrays
  * (0: X, 1: Y, 2: sad, 3: cost) for consumers on the GPU. */

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Patches a SCRATCH COPY of the reference's TEncSlice.cpp for the `TAppEncoder_b200spec` parity build (SURVEY.md section 8 row f2,
-INTEGRATION.md section 6): before the CTU loop of TEncSlice::compressSlice (/root/reference/source/Lib/TLibEncoder/TEncSlice.cpp:730)
+INTEGRATION.md section 4.2): before the CTU loop of TEncSlice::compressSlice (/root/reference/source/Lib/TLibEncoder/TEncSlice.cpp:730)
 the slice encoder announces the original picture and the slice's reference pictures to the drop-in TEncOpenCL, which searches every
 CTU of the picture speculatively.  TEncSearch::xMotionEstimation and its calcMotionVectors call are left untouched.
 
@@ -10,7 +10,7 @@ TEST / INTEGRATION INFRASTRUCTURE: writes only to the path given (never under /r
 import sys
 
 ANCHOR = "  // for every CTU in the slice segment (may terminate sooner if there is a byte limit on the slice-segment)\n"
-HOOK = """  // hm-opencl_b200: announce the picture to the GPU motion estimator (speculative whole-frame search, INTEGRATION.md section 6)
+HOOK = """  // hm-opencl_b200: announce the picture to the GPU motion estimator (speculative whole-frame search, INTEGRATION.md section 4.2)
   if ( pcSlice->getSliceType() != I_SLICE && m_pcOpenCLME->isEnabled() )
   {
     TComPicYuv* pcOrgYuv = pcPic->getPicYuvOrg();

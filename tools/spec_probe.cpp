@@ -1,5 +1,5 @@
 // spec_probe.cpp -- drives the drop-in C++ class (hm-opencl_b200/host/TEncOpenCL) over ONE whole picture the way the patched slice
-// encoder does (INTEGRATION.md section 6): beginPicture / addReferencePicture / speculate, then one calcMotionVectors call per CTU in
+// encoder does (INTEGRATION.md section 4.2): beginPicture / addReferencePicture / speculate, then one calcMotionVectors call per CTU in
 // coding order with the window a given predictor field produces.  Prints one JSON line: time per picture and per call for
 //   sync        : no speculation, every call is the synchronous search (what round 1 shipped)
 //   spec_hit    : zero predictors, every call is answered from the device-resident tables
