@@ -26,7 +26,7 @@ struct hmme_ctx {
     uint32_t lambda = 0;
     int maxRange = 0;
     uint64_t launches = 0;
-    int stagger = 1300;          // cycles of start skew between the two warp groups of the packed kernel (HMME_STAGGER env overrides)
+    int stagger = 1050;          // cycles of start skew between the two warp groups of the packed kernel (HMME_STAGGER env overrides)
     int forceRG = 0;             // HMME_FAST_RG env: force the number of row groups per tile (experiments)
     // job / result buffers (grown on demand)
     size_t jobCap = 0;
