@@ -138,6 +138,7 @@ def cpu_oracle_throughput(W, H, R, margin, njobs_sample, threads):
 FRAC_OPS_PER_CTU = 24020326        # see DESIGN.md 3.4 (sum over the 593 partitions)
 CPUME_BIN = os.path.join(ROOT, "oracle", "_ref", "TAppEncoder_cpume")
 CPUME_CFG = os.path.join(ROOT, "oracle", "_ref", "cfg", "encoder_lowdelay_P_main.cfg")
+CPUME_CFG_RA = os.path.join(ROOT, "oracle", "_ref", "cfg", "encoder_randomaccess_main.cfg")
 
 
 def write_clip(path, frames):
@@ -148,7 +149,7 @@ def write_clip(path, frames):
             fh.write(np.full((h // 2) * (w // 2) * 2, 128, np.uint8).tobytes())
 
 
-def reference_cpu_me(R, frames, procs, fast_search=0):
+def reference_cpu_me(R, frames, procs, fast_search=0, cfg=None):
     """The reference's OWN CPU integer ME (--OpenCL=0 --FastSearch=0: TEncSearch::xPatternSearch + TComRdCost::xGetSAD*,
     TEncSearch.cpp:3774-3791,3835-3897) timed inside the reference encoder built from source with the counters of
     BASELINE.md section 3 (oracle/patch_cpume.py): `procs` independent single-threaded encoder processes (HM has no threads)
@@ -160,7 +161,7 @@ def reference_cpu_me(R, frames, procs, fast_search=0):
     with tempfile.TemporaryDirectory() as d:
         yuv = os.path.join(d, "clip.yuv")
         write_clip(yuv, frames)
-        cmds = [[CPUME_BIN, "-c", CPUME_CFG, "-i", yuv, "-wdt", str(W), "-hgt", str(H), "-fr", "30", "-f", "2", "-q", "32",
+        cmds = [[CPUME_BIN, "-c", cfg or CPUME_CFG, "-i", yuv, "-wdt", str(W), "-hgt", str(H), "-fr", "30", "-f", str(len(frames)), "-q", "32",
                  "-b", os.path.join(d, "o%d.hevc" % i), "-o", "", "--OpenCL=0", "--FastSearch=%d" % fast_search, "--SearchRange=%d" % R] for i in range(procs)]
         t0 = time.perf_counter()
         ps = [subprocess.Popen(c, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for c in cmds]
@@ -196,11 +197,11 @@ def reference_cpu_frac():
             "sample": "%d xPatternSearchFracDIF calls (%d PU pixels) in %.3f s inside the reference encoder, 416x240 I+P, one core" % (calls, px, secs)}
 
 
-def workload_crop(name, clip):
-    """The top-left clip[0] x clip[1] crop of the workload's own synthetic frame pair (frame 0 = reference, frame 1 = current)."""
+def workload_crop(name, clip, nframes=2):
+    """The top-left clip[0] x clip[1] crop of the workload's own synthetic frames (frame 0 = reference, frame 1 = current, ...)."""
     W, H, _ = WORKLOADS[name]
     cw, ch = min(clip[0], W // 64 * 64), min(clip[1], H // 64 * 64)
-    f = luma_frames(W, H, 2)
+    f = luma_frames(W, H, nframes)
     return [np.ascontiguousarray(y[:ch, :cw]) for y in f], (cw, ch)
 
 
@@ -209,13 +210,16 @@ def cpu_baseline_entry(name, clip, all_cores=True):
     W, H, R = WORKLOADS[name]
     threads = os.cpu_count() or 1
     if os.path.exists(CPUME_BIN) and os.path.exists(CPUME_CFG):
-        frames, (cw, ch) = workload_crop(name, clip)
+        ra = name.endswith("_ra")                                   # config[2]: the random-access configuration (two lists, bi-prediction refinement), 3 pictures
+        frames, (cw, ch) = workload_crop(name, clip, 3 if ra else 2)
         procs = threads if all_cores else 1
-        v, me_s, calls, wall = reference_cpu_me(R, frames, procs)
+        v, me_s, calls, wall = reference_cpu_me(R, frames, procs, cfg=CPUME_CFG_RA if ra else None)
         return {"value": v, "unit": "block-SAD evaluations/s", "cores": procs, "kind": "reference",
-                "sample": "reference encoder built from source (oracle/_ref/TAppEncoder_cpume), --OpenCL=0 --FastSearch=0 --SearchRange=%d, top-left %dx%d crop "
-                          "(%d CTUs) of the workload's frame pair (I+P, 1 ref), %d independent single-threaded processes: %d DistFunc calls in %.1f s of "
-                          "xPatternSearch (max over processes), %.1f s wall" % (R, cw, ch, (cw // 64) * (ch // 64), procs, calls, me_s, wall)}, wall
+                "sample": "reference encoder built from source (oracle/_ref/TAppEncoder_cpume), %s, --OpenCL=0 --FastSearch=0 --SearchRange=%d, top-left %dx%d crop "
+                          "(%d CTUs) of the workload's frames (%s), %d independent single-threaded processes: %d DistFunc calls in %.1f s of "
+                          "xPatternSearch (max over processes), %.1f s wall"
+                          % ("encoder_randomaccess_main.cfg" if ra else "encoder_lowdelay_P_main.cfg", R, cw, ch, (cw // 64) * (ch // 64),
+                             "3 pictures, two lists + bi-prediction refinement" if ra else "I+P, 1 ref", procs, calls, me_s, wall)}, wall
     v, dt, n = cpu_oracle_throughput(W, H, R, max(80, R + 16), max(8 * threads, 64), threads)
     return {"value": v, "unit": "block-SAD evaluations/s", "cores": threads, "kind": "port",
             "sample": "%d CTU jobs of the frame, %.1f s wall on %d threads (oracle/hmme_oracle.c; oracle/_ref absent)" % (n, dt, threads)}, dt
