@@ -37,36 +37,55 @@ namespace {
 std::mutex g_errMu;
 std::string g_createErr;
 
-struct FastGeom { int tw, th, nTx, nTy; size_t smemBytes; };
+struct FastGeom { int tw, upt, tileRows, nTx, nTy; size_t smemBytes; };
 
-constexpr size_t kSmemBudget = 220 * 1024;   // of the 227 KB a CTA may opt in to (1 CTA per SM anyway: 128 registers x 512 threads)
+constexpr size_t kSmemBudget = 224 * 1024;   // of the 227 KB a CTA may opt in to (1 CTA per SM anyway: 128 registers x 512 threads)
 
-size_t fast_smem_bytes(int tw, int th, int yb) {
-    const size_t words = (((size_t)fast_win_rows(th, yb) * kWinPitch + 3) & ~(size_t)3) + 1024 + kRing * (size_t)(32 * yb) * kRecWords + ((tw + 3) & ~3) +
-                         (size_t)(((th + yb - 1) / yb) * yb) + 4;
+size_t fast_smem_bytes(int tileRows, int yb) {
+    const size_t words = (((size_t)fast_win_rows(tileRows) * kWinPitch + 3) & ~(size_t)3) + 1024 + kRing * (size_t)(32 * yb) * kRecWords +
+                         (size_t)tileRows * (kKbPitch + 1) + kMaxTileW + 4;
     return words * 4;
 }
 
+// row groups a tile of `upt` consecutive units can touch in a stripe `w` columns wide (worst case over the tile's start column)
+int span_rgs(int upt, int w) { return upt % w == 0 ? upt / w : (upt + 2 * w - 2) / w; }
+
 // Tile geometry of the packed kernel for a (2R+1)^2 window and njobs jobs on `sms` SMs (1 CTA per SM).
-// x: tiles of at most 129 columns.  y: k row groups (YB rows each) per tile, k <= what the 11-bit in-tile index and the
-// shared-memory budget allow.  The largest k has the least per-tile overhead and is used whenever it still yields at
-// least one full wave of CTAs (partially filled last waves are covered by the next frame's CTAs when frames are
-// pipelined over two streams).  For smaller launches -- the per-CTU call of the encoder is ONE job -- the k with the
-// smallest predicted makespan wins, which spreads a single job over up to 43 SMs:
-//   waves(k) * (rounds(k) + c),  waves = ceil(CTAs / sms),  rounds = ceil(tw * k / 32),  c ~ 4 rounds of per-tile overhead
+// x: column stripes of at most 129 candidates.  Within a stripe the units (column x row group of YB candidate rows) are numbered row
+// group by row group and cut into tiles of `upt` consecutive units, upt * YB <= 2048 (11-bit rank in the key) and the window of the
+// row groups a tile touches within the shared-memory budget.
+//  * Frame-sized launches (at least one CTA per SM with the largest tiles): upt is a multiple of 32 -- every round of every tile but the
+//    stripe's last is full -- chosen so that the tiles of a stripe are as equal as possible (+-64: 5547 units = 8 x 640 + 427, 174 rounds
+//    per job and warp instead of the 181 that 129 x 15 rectangles need).
+//  * Small launches -- the per-CTU call of the encoder is ONE job -- use rectangular tiles (upt = columns x k row groups) and also split
+//    the columns, with the k of the smallest predicted makespan, which spreads a single job over up to 129 SMs:
+//      waves(k) * (rounds(k) + c),  waves = ceil(CTAs / sms),  rounds = ceil(tw * k / 32),  c ~ 4 rounds of per-tile overhead
 FastGeom fast_geometry(int W, int yb, int njobs, int sms, int forceRG) {
     FastGeom g{};
     const int nTxMin = (W + kMaxTileW - 1) / kMaxTileW;
     const int nRGjob = (W + yb - 1) / yb;
-    auto max_rg = [&](int tw) {
+    auto tile_rows = [&](int upt, int nx, int tw) {
+        const int twLast = W - (nx - 1) * tw;
+        return yb * std::min(nRGjob, std::max(span_rgs(upt, tw), span_rgs(upt, twLast)));
+    };
+    auto fits = [&](int upt, int nx, int tw) { return upt * yb <= kMaxTileCands && fast_smem_bytes(tile_rows(upt, nx, tw), yb) <= kSmemBudget; };
+    auto max_rg = [&](int nx, int tw) {
         int m = std::max(1, std::min(kMaxTileCands / (tw * yb), nRGjob));
-        while (m > 1 && fast_smem_bytes(tw, m * yb, yb) > kSmemBudget) --m;
+        while (m > 1 && !fits(m * tw, nx, tw)) --m;
         return m;
     };
     int bestNx = nTxMin, bestTw = (W + nTxMin - 1) / nTxMin;
-    int bestK = max_rg(bestTw);
+    int bestK = max_rg(bestNx, bestTw), upt = 0;
     const bool fullWave = (long long)njobs * nTxMin * ((nRGjob + bestK - 1) / bestK) >= sms;
-    if (!fullWave) {
+    if (forceRG >= 1 && forceRG <= bestK) upt = forceRG * bestTw;
+    else if (fullWave) {
+        const int total = nRGjob * bestTw;
+        int uMax = (kMaxTileCands / yb) & ~31;
+        while (uMax > 32 && !fits(uMax, bestNx, bestTw)) uMax -= 32;
+        const int nT = (total + uMax - 1) / uMax;
+        upt = std::min(uMax, (((total + nT - 1) / nT) + 31) & ~31);
+        if (total <= 32 || !fits(upt, bestNx, bestTw)) upt = bestK * bestTw;     // tiny windows: one rectangular tile
+    } else {
         // Small launch (the encoder's per-CTU call is ONE job): split columns as well as rows so that the job reaches every SM.
         // cost = waves * (rounds + c): rounds = ceil(units / 32) with units = tw * k (lane = candidate column x row group),
         // c ~ 4 rounds of per-tile staging.  +-64, one job: 129 x 3 tiles (43 CTAs, 5 rounds) -> 43 x 3 tiles (129 CTAs, 2 rounds).
@@ -74,19 +93,19 @@ FastGeom fast_geometry(int W, int yb, int njobs, int sms, int forceRG) {
         for (int nx = nTxMin; nx <= 4 * nTxMin && nx <= W; ++nx) {
             const int tw = (W + nx - 1) / nx;
             if ((W + tw - 1) / tw != nx) continue;                        // this column count does not change the tile width
-            const int maxRG = max_rg(tw);
+            const int maxRG = max_rg(nx, tw);
             for (int k = maxRG; k >= 1; --k) {
                 const long long ctas = (long long)njobs * nx * ((nRGjob + k - 1) / k);
                 const double cost = (double)((ctas + sms - 1) / sms) * ((tw * k + 31) / 32 + 4.0);
                 if (cost < bestCost * 0.995) { bestCost = cost; bestK = k; bestNx = nx; bestTw = tw; }   // prefer the larger tile unless clearly worse
             }
         }
+        upt = bestK * bestTw;
     }
-    if (forceRG >= 1 && forceRG <= max_rg(bestTw)) bestK = forceRG;
-    g.nTx = bestNx; g.tw = bestTw;
-    g.th = bestK * yb;
-    g.nTy = (nRGjob + bestK - 1) / bestK;
-    g.smemBytes = fast_smem_bytes(g.tw, g.th, yb);
+    g.nTx = bestNx; g.tw = bestTw; g.upt = upt;
+    g.tileRows = tile_rows(upt, bestNx, bestTw);
+    g.nTy = (nRGjob * bestTw + upt - 1) / upt;
+    g.smemBytes = fast_smem_bytes(g.tileRows, yb);
     return g;
 }
 
@@ -295,7 +314,7 @@ int enqueue_search(hmme_ctx* c, const SearchIO& io, const void* curOrigin, int c
         fp.refHi = static_cast<const uint8_t*>(refHi);
         fp.curPitch = curPitch; fp.refPitch = refPitch;
         fp.jobs = io.jobs; fp.best = c->dBest; fp.lambda = c->lambda; fp.W = W;
-        fp.tw = g.tw; fp.th = g.th; fp.nTx = g.nTx; fp.nTy = g.nTy; fp.stagger = c->stagger;
+        fp.tw = g.tw; fp.upt = g.upt; fp.tileRows = g.tileRows; fp.nTx = g.nTx; fp.nTy = g.nTy; fp.stagger = c->stagger;
         const unsigned grid = (unsigned)(njobs * g.nTx * g.nTy);
         if (g.smemBytes > c->fastSmemSet) {           // the opt-in only ever has to grow
             CU_TRY(c, cudaFuncSetAttribute(me_u8_tile_kernel<HMME_FAST_YB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));

@@ -52,6 +52,7 @@ constexpr int kWinPitch = 203;                // sliding-word entries per window
                                               // tile (+-64) still reads 32 distinct banks
 #endif
 constexpr int kMaxTileW = 129;
+constexpr int kKbPitch = kMaxTileW;           // words per row of the per-tile key-base table (constant: LDS offsets of a unit's YB rows are immediates)
 constexpr int kDensePitch = 224;              // bytes per row of the TMA landing buffer: 15 (alignment) + 129 + 63 + 3, rounded up to 16
 constexpr int kRecWords = 49;                 // upper-phase words per candidate slot: 32 (8x8 pairs, u16) + 16 (16x16<<11) + 1 (key base),
                                               // stored slot-minor ([word][slot]) so that every access is lane-contiguous
@@ -59,6 +60,7 @@ constexpr uint32_t kInvalidBlockKeyBase = 0xF0000000u;   // block sums << 11 sta
 constexpr uint32_t kInvalidSlot = 0xFFFFFFFFu;
 constexpr int kLag = 1;                       // the upper phase of round k runs after the block phase of round k + kLag
 constexpr int kRing = 2 * kLag + 2;           // record buffers: a slot may be rewritten only after every warp consumed it (ring >= 2*lag + 2)
+static_assert((kRing & (kRing - 1)) == 0, "ring slots wrap with a mask");
 
 struct FastParams {
     const uint8_t* cur;        // picture sample (0,0) of the current plane
@@ -71,12 +73,32 @@ struct FastParams {
     unsigned long long* best;  // [njobs][593] arg-min keys, all "no winner" between searches
     uint32_t lambda;
     int W;                     // 2R+1 candidates per axis
-    int tw, th;                // nominal tile size in candidates
-    int nTx, nTy;
+    int tw;                    // nominal width of a column stripe in candidates (<= kMaxTileW)
+    int upt;                   // units per tile: a tile is `upt` consecutive units of its stripe's unit sequence (row group major)
+    int tileRows;              // candidate rows (a multiple of YB) the row groups of any tile span at most: sizes the window
+    int nTx, nTy;              // stripes per job, tiles per stripe
     int stagger;               // SM cycles by which warps 8..15 start their first round late (0 = off), see the kernel
 };
 
-__host__ __device__ inline int fast_win_rows(int th, int yb) { return ((th + yb - 1) / yb) * yb + 63; }
+__host__ __device__ inline int fast_win_rows(int tileRows) { return tileRows + 63; }
+
+// A tile = `upt` consecutive units of one column stripe (unit = candidate column x one row group of YB candidate rows; units are
+// numbered row group by row group).  With upt a multiple of 32 every round of every tile but a stripe's last has 32 busy lanes
+// -- rectangular tiles of 129 columns waste most of one round per tile (129 = 4 * 32 + 1).  The first and the last row group of a tile
+// are therefore partial in x: columns [xs, twA) of row group 0, [0, xe) of row group nRG - 1 ([xs, xe) if the tile has one row group).
+struct TileGeo {
+    int twA;                   // columns of the stripe
+    int xs, xe, nRG;           // see above
+    int w0;                    // columns of the first row group that belong to the tile
+    int x0, y0;                // candidate (column, row) of the stripe's column 0 / the tile's row 0 in the job's window
+};
+// rank of candidate (row y of the tile, column x) in the tile's scan order (row major over the tile's candidates): the low key bits
+__device__ __forceinline__ uint32_t tile_rank(const TileGeo& t, int y, int x, int yb) {
+    const int rg = y / yb;
+    if (rg == 0) return (uint32_t)(y * t.w0 + (x - t.xs));
+    if (rg < t.nRG - 1) return (uint32_t)(yb * t.w0 + (y - yb) * t.twA + x);
+    return (uint32_t)(yb * t.w0 + (t.nRG - 2) * yb * t.twA + (y - (t.nRG - 1) * yb) * t.xe + x);
+}
 
 // one VABSDIFF4.U8.ACC: acc += sum of |a.b[k] - b.b[k]| over the four bytes.  Written as PTX so that the accumulate operand
 // stays chained (the compiler otherwise splits it into VABSDIFF4(...,RZ) + an extra add per packed SAD).
@@ -150,116 +172,149 @@ __device__ __forceinline__ uint32_t fshladd(uint32_t a, uint32_t b) {
     asm("mad.lo.u32 %0, %1, 2048, %2;" : "=r"(d) : "r"(a), "r"(b));
     return d;
 }
-// Per-candidate state carried across the row loop: sums are folded strip by strip (4 rows at a time) as soon as a strip
-// of 4x4 SADs completes, so that the add/key work (FMA pipe) and the min updates interleave with the packed SADs (ALU
-// pipe) of the candidates that are still being accumulated, instead of forming a separate FMA-bound phase.
-// All sums are plain (unshifted) SADs; a key is formed by one IMAD: key = sum * 2^11 + ((mvcost << 11) | idxInTile).
+// Per-candidate state carried across the row loop.  The packed-SAD chains run over EIGHT rows (they restart at rows 0 and 8), so
+// after strip 0 / 2 an accumulator holds a 4x4 sum and after strip 1 / 3 the 4x8 column sum -- the 4x8 level costs no addition.
+// Sums are folded strip by strip as soon as they complete, so that the add/key work (FMA pipe) and the min updates interleave with
+// the packed SADs (ALU pipe) of the candidates that are still being accumulated.  All sums are plain (unshifted) SADs; a key is
+// formed by one IMAD: key = sum * 2^11 + ((mvcost << 11) | idxInTile), and a key of a difference or a sum of a keyed and an
+// unkeyed part by one IMAD on the existing key (exact mod 2^32): 17 additions + 33 key IMADs per candidate for the 33 partitions.
+// -DHMME_CHAIN8: eight-row SAD chains (the 4x8 column sums then cost no addition: 17 instead of 25 additions per candidate).  Measured
+// SLOWER (1.22 vs 1.19 ms per 1080p +-64 frame): the compiler then sinks all folding behind the SADs and the FMA-heavy tail of a round grows.
 struct BlockState {
+#ifndef HMME_CHAIN8
     uint32_t sp[4];     // 4x4 sums of the previous even strip
-    uint32_t hp[2];     // its two 8x4 sums
-    uint32_t q0, q1, q2;  // 16x4 strip sums
-    uint32_t v0[4];     // 4x8 sums of strips 0+1
+#endif
+    uint32_t ha[2];     // 8x4 sums of strip 0 (later: of strip 2)
+    uint32_t q0, q2;    // 16x4 sums of strips 0 and 2
+    uint32_t vl, vr;    // 4x8 sums of the top half, leftmost and rightmost column
     uint32_t e0[2];     // 8x8 sums of the top half
-    uint32_t top;       // 16x8 top
+    uint32_t top, kTop; // 16x8 top and its key
 };
 
-// best = min(best, key(sum[c], kb[c]) for the NC candidates handled together).  Two candidates cost ONE ALU instruction
-// (VIMNMX3) plus two IMADs on the FMA pipe, instead of two ALU add-mins: the ALU pipe is the kernel's bottleneck.
-template <int NC>
-__device__ __forceinline__ void upd(uint32_t& best, const uint32_t (&sum)[NC], const uint32_t (&kb)[NC]) {
-    if constexpr (NC == 1) best = min(best, fshladd(sum[0], kb[0]));
-    else best = min(min(best, fshladd(sum[0], kb[0])), fshladd(sum[1], kb[1]));
+// key of (whole - part) from the key of the whole: one IMAD, no subtraction of sums (keys are exact mod 2^32)
+__device__ __forceinline__ uint32_t fsubkey(uint32_t part, uint32_t keyWhole) {
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, 0xFFFFF800, %2;" : "=r"(d) : "r"(part), "r"(keyWhole));
+    return d;
 }
 
-// Strip T (rows 4T..4T+3 of the 16x16 block) of NC candidates is complete: a[c][i] = the four 4x4 SADs of candidate c.
+// best = min(best, key[c] for the NC candidates handled together).  Two candidates cost ONE ALU instruction (VIMNMX3) instead of two
+// ALU add-mins: the ALU pipe is the kernel's bottleneck, key formation lives on the FMA pipe.
+template <int NC>
+__device__ __forceinline__ void updk(uint32_t& best, const uint32_t (&key)[NC]) {
+    if constexpr (NC == 1) best = min(best, key[0]);
+    else best = min(min(best, key[0]), key[1]);
+}
+template <int NC>
+__device__ __forceinline__ void upd(uint32_t& best, const uint32_t (&sum)[NC], const uint32_t (&kb)[NC]) {
+    uint32_t k[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) k[c] = fshladd(sum[c], kb[c]);
+    updk<NC>(best, k);
+}
+
+// Strip T (rows 4T..4T+3 of the 16x16 block) of NC candidates is complete: a[c][i] = the four accumulators of candidate c -- the 4x4
+// sums of the strip for T = 0, 2, the 4x8 column sums of the half for T = 1, 3.
 // rec[c] points at candidate c's slot of the upper-level record (word w lives at rec[c][w * slots]).
 template <int T, int NC>
-__device__ __forceinline__ void emit_strip(const uint32_t (&a)[NC][4], BlockState (&st)[NC], const uint32_t (&kb)[NC], uint32_t (&best)[33],
+__device__ __forceinline__ void emit_strip(const uint32_t (&ain)[NC][4], BlockState (&st)[NC], const uint32_t (&kb)[NC], uint32_t (&best)[33],
                                            uint32_t* const (&rec)[NC], int b, bool writeBase, const uint32_t (&recBase)[NC], int slots) {
-    uint32_t h0[NC], h1[NC], q[NC];
+    uint32_t k[NC];
+#ifdef HMME_CHAIN8
+    const uint32_t (&a)[NC][4] = ain;
+#else
+    uint32_t a[NC][4];                                             // four-row chains: the 4x8 column sums are formed here
 #pragma unroll
-    for (int c = 0; c < NC; ++c) { h0[c] = fadd(a[c][0], a[c][1]); h1[c] = fadd(a[c][2], a[c][3]); q[c] = fadd(h0[c], h1[c]); }
-    upd<NC>(best[2 * T], h0, kb);                                  // 8x4
-    upd<NC>(best[2 * T + 1], h1, kb);
-    if constexpr (T == 0) {
-        upd<NC>(best[20], q, kb);                                  // 16x4  (2NxnU part 0)
+    for (int c = 0; c < NC; ++c)
 #pragma unroll
-        for (int c = 0; c < NC; ++c) st[c].q0 = q[c];
-    }
+        for (int i = 0; i < 4; ++i) {
+            if (T == 0 || T == 2) { a[c][i] = ain[c][i]; st[c].sp[i] = ain[c][i]; }
+            else a[c][i] = fadd(st[c].sp[i], ain[c][i]);
+        }
+#endif
     if constexpr (T == 0 || T == 2) {
+        uint32_t h0[NC], h1[NC], q[NC];
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) st[c].sp[i] = a[c][i];
-            st[c].hp[0] = h0[c]; st[c].hp[1] = h1[c];
+            h0[c] = st[c].ha[0] = fadd(a[c][0], a[c][1]);
+            h1[c] = st[c].ha[1] = fadd(a[c][2], a[c][3]);
+            q[c] = fadd(h0[c], h1[c]);
+            if (T == 0) st[c].q0 = q[c]; else st[c].q2 = q[c];
         }
-    }
-    if constexpr (T == 1) {
+        upd<NC>(best[2 * T], h0, kb);                              // 8x4
+        upd<NC>(best[2 * T + 1], h1, kb);
+        if constexpr (T == 0) upd<NC>(best[20], q, kb);            // 16x4  (2NxnU part 0)
+    } else {
+        uint32_t e0[NC], e1[NC], hf[NC], kE0[NC], kE1[NC], kH[NC];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             uint32_t v[NC];
 #pragma unroll
-            for (int c = 0; c < NC; ++c) v[c] = st[c].v0[i] = fadd(st[c].sp[i], a[c][i]);
-            upd<NC>(best[8 + i], v, kb);                           // 4x8
+            for (int c = 0; c < NC; ++c) v[c] = a[c][i];
+            upd<NC>(best[(T == 1 ? 8 : 12) + i], v, kb);           // 4x8: the chain itself
         }
-        uint32_t e0[NC], e1[NC], top[NC];
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
-            e0[c] = st[c].e0[0] = fadd(st[c].hp[0], h0[c]);
-            e1[c] = st[c].e0[1] = fadd(st[c].hp[1], h1[c]);
-            st[c].q1 = q[c];
-            top[c] = st[c].top = fadd(st[c].q0, q[c]);
+            e0[c] = fadd(a[c][0], a[c][1]); e1[c] = fadd(a[c][2], a[c][3]);   // 8x8
+            hf[c] = fadd(e0[c], e1[c]);                                        // 16x8
+            kE0[c] = fshladd(e0[c], kb[c]); kE1[c] = fshladd(e1[c], kb[c]); kH[c] = fshladd(hf[c], kb[c]);
         }
-        upd<NC>(best[16], e0, kb);                                 // 8x8
-        upd<NC>(best[17], e1, kb);
-        upd<NC>(best[28], top, kb);                                // 16x8 top
-    }
-    if constexpr (T == 2) {
-        uint32_t t12[NC];
+        updk<NC>(best[T == 1 ? 16 : 18], kE0);                     // 8x8
+        updk<NC>(best[T == 1 ? 17 : 19], kE1);
+        updk<NC>(best[T == 1 ? 28 : 29], kH);                      // 16x8
 #pragma unroll
-        for (int c = 0; c < NC; ++c) { st[c].q2 = q[c]; t12[c] = fadd(st[c].top, q[c]); }
-        upd<NC>(best[22], t12, kb);                                // 16x12 rows 0..11
-    }
-    if constexpr (T == 3) {
-        uint32_t cs[4][NC];
+        for (int c = 0; c < NC; ++c) k[c] = fsubkey(st[c].ha[0], kE0[c]);
+        updk<NC>(best[2 * T], k);                                  // 8x4 of this strip = 8x8 - 8x4 of the strip above
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            uint32_t v[NC];
+        for (int c = 0; c < NC; ++c) k[c] = fsubkey(st[c].ha[1], kE1[c]);
+        updk<NC>(best[2 * T + 1], k);
+        if constexpr (T == 1) {
 #pragma unroll
-            for (int c = 0; c < NC; ++c) { v[c] = fadd(st[c].sp[i], a[c][i]); cs[i][c] = fadd(st[c].v0[i], v[c]); }
-            upd<NC>(best[12 + i], v, kb);                          // 4x8
-        }
-        uint32_t e10[NC], e11[NC], bot[NC], b12[NC], left[NC], right[NC], l12[NC], r12[NC], all[NC];
+            for (int c = 0; c < NC; ++c) {
+                st[c].vl = a[c][0]; st[c].vr = a[c][3];
+                st[c].e0[0] = e0[c]; st[c].e0[1] = e1[c];
+                st[c].top = hf[c]; st[c].kTop = kH[c];
+            }
+        } else {
+            uint32_t cl[NC], cr[NC], left[NC], right[NC], all[NC], kAll[NC];
 #pragma unroll
-        for (int c = 0; c < NC; ++c) {
-            e10[c] = fadd(st[c].hp[0], h0[c]); e11[c] = fadd(st[c].hp[1], h1[c]);
-            bot[c] = fadd(st[c].q2, q[c]); b12[c] = fadd(st[c].q1, bot[c]);
-            left[c] = fadd(cs[0][c], cs[1][c]); right[c] = fadd(cs[2][c], cs[3][c]);
-            l12[c] = fadd(left[c], cs[2][c]); r12[c] = fadd(cs[1][c], right[c]);
-            all[c] = fadd(st[c].top, bot[c]);
-        }
-        upd<NC>(best[18], e10, kb);                                // 8x8
-        upd<NC>(best[19], e11, kb);
-        upd<NC>(best[21], q, kb);                                  // 16x4  (2NxnD part 1)
-        upd<NC>(best[29], bot, kb);                                // 16x8 bottom
-        upd<NC>(best[23], b12, kb);                                // 16x12 rows 4..15
-        upd<NC>(best[24], cs[0], kb);                              // 4x16  (nLx2N part 0)
-        upd<NC>(best[25], cs[3], kb);                              // 4x16  (nRx2N part 1)
-        upd<NC>(best[26], l12, kb);                                // 12x16 cols 0..11
-        upd<NC>(best[27], r12, kb);                                // 12x16 cols 4..15
-        upd<NC>(best[30], left, kb);                               // 8x16
-        upd<NC>(best[31], right, kb);
-        upd<NC>(best[32], all, kb);                                // 16x16
-        // upper-level hand-over: 8x8 sums as u16 pairs (<= 16320 each), 16x16 sum (<= 65280)
+            for (int c = 0; c < NC; ++c) {
+                cl[c] = fadd(st[c].vl, a[c][0]); cr[c] = fadd(st[c].vr, a[c][3]);
+                left[c] = fadd(st[c].e0[0], e0[c]); right[c] = fadd(st[c].e0[1], e1[c]);
+                all[c] = fadd(st[c].top, hf[c]);
+                kAll[c] = fshladd(all[c], kb[c]);
+            }
 #pragma unroll
-        for (int c = 0; c < NC; ++c) {
-            uint32_t pk0, pk1;
-            asm("mad.lo.u32 %0, %1, 65536, %2;" : "=r"(pk0) : "r"(st[c].e0[1]), "r"(st[c].e0[0]));
-            asm("mad.lo.u32 %0, %1, 65536, %2;" : "=r"(pk1) : "r"(e11[c]), "r"(e10[c]));
-            rec[c][(2 * b) * slots] = pk0;
-            rec[c][(2 * b + 1) * slots] = pk1;
-            rec[c][(32 + b) * slots] = all[c];
-            if (writeBase) rec[c][48 * slots] = recBase[c];
+            for (int c = 0; c < NC; ++c) k[c] = fsubkey(st[c].q2, kH[c]);
+            updk<NC>(best[21], k);                                 // 16x4  (2NxnD part 1) = bottom half - strip 2
+            upd<NC>(best[24], cl, kb);                             // 4x16  (nLx2N part 0)
+            upd<NC>(best[25], cr, kb);                             // 4x16  (nRx2N part 1)
+            upd<NC>(best[30], left, kb);                           // 8x16
+            upd<NC>(best[31], right, kb);
+            updk<NC>(best[32], kAll);                              // 16x16
+#pragma unroll
+            for (int c = 0; c < NC; ++c) k[c] = fshladd(st[c].q2, st[c].kTop);
+            updk<NC>(best[22], k);                                 // 16x12 rows 0..11 = top half + strip 2
+#pragma unroll
+            for (int c = 0; c < NC; ++c) k[c] = fsubkey(st[c].q0, kAll[c]);
+            updk<NC>(best[23], k);                                 // 16x12 rows 4..15 = all - strip 0
+#pragma unroll
+            for (int c = 0; c < NC; ++c) k[c] = fsubkey(cr[c], kAll[c]);
+            updk<NC>(best[26], k);                                 // 12x16 cols 0..11 = all - right column
+#pragma unroll
+            for (int c = 0; c < NC; ++c) k[c] = fsubkey(cl[c], kAll[c]);
+            updk<NC>(best[27], k);                                 // 12x16 cols 4..15 = all - left column
+            // upper-level hand-over: 8x8 sums as u16 pairs (<= 16320 each), 16x16 sum (<= 65280)
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                uint32_t pk0, pk1;
+                asm("mad.lo.u32 %0, %1, 65536, %2;" : "=r"(pk0) : "r"(st[c].e0[1]), "r"(st[c].e0[0]));
+                asm("mad.lo.u32 %0, %1, 65536, %2;" : "=r"(pk1) : "r"(e1[c]), "r"(e0[c]));
+                rec[c][(2 * b) * slots] = pk0;
+                rec[c][(2 * b + 1) * slots] = pk1;
+                rec[c][(32 + b) * slots] = all[c];
+                if (writeBase) rec[c][48 * slots] = recBase[c];
+            }
         }
     }
 }
@@ -285,19 +340,20 @@ __device__ __forceinline__ void emit_quadrant(const uint32_t* rec, int q, uint32
     const uint32_t cl = fadd(fadd(T.x, T.y), fadd(B.x, B.y)), cr = fadd(fadd(T.z, T.w), fadd(B.z, B.w));
     const uint32_t C0 = cl & 0xFFFFu, C1 = cl >> 16, C2 = cr & 0xFFFFu, C3 = cr >> 16;
     const uint32_t top = fadd(R0, R1), bot = fadd(R2, R3), left = fadd(C0, C1), right = fadd(C2, C3);
+    const uint32_t kAll = fshladd(fadd(top, bot), kb);
     upd1(ub[0], R0, kb);                           // 32x8  (2NxnU part 0)
     upd1(ub[1], R3, kb);                           // 32x8  (2NxnD part 1)
-    upd1(ub[2], fadd(top, R2), kb);                // 32x24 rows 0..23
-    upd1(ub[3], fadd(R1, bot), kb);                // 32x24 rows 8..31
+    ub[2] = min(ub[2], fsubkey(R3, kAll));         // 32x24 rows 0..23 = all - last strip
+    ub[3] = min(ub[3], fsubkey(R0, kAll));         // 32x24 rows 8..31 = all - first strip
     upd1(ub[4], C0, kb);                           // 8x32
     upd1(ub[5], C3, kb);
-    upd1(ub[6], fadd(left, C2), kb);               // 24x32 cols 0..23
-    upd1(ub[7], fadd(C1, right), kb);              // 24x32 cols 8..31
+    ub[6] = min(ub[6], fsubkey(C3, kAll));         // 24x32 cols 0..23
+    ub[7] = min(ub[7], fsubkey(C0, kAll));         // 24x32 cols 8..31
     upd1(ub[8], top, kb);                          // 32x16
     upd1(ub[9], bot, kb);
     upd1(ub[10], left, kb);                        // 16x32
     upd1(ub[11], right, kb);
-    upd1(ub[12], fadd(top, bot), kb);              // 32x32
+    ub[12] = min(ub[12], kAll);                    // 32x32
 }
 
 __device__ __forceinline__ void emit_ctu(const uint32_t* rec, uint32_t (&ub)[13], int slots) {
@@ -317,38 +373,44 @@ __device__ __forceinline__ void emit_ctu(const uint32_t* rec, uint32_t (&ub)[13]
     C[2] = fadd(fadd(m[0].z, m[1].z), fadd(m[2].z, m[3].z));
     C[3] = fadd(fadd(m[0].w, m[1].w), fadd(m[2].w, m[3].w));
     const uint32_t top = fadd(R[0], R[1]), bot = fadd(R[2], R[3]), left = fadd(C[0], C[1]), right = fadd(C[2], C[3]);
+    const uint32_t kAll = fshladd(fadd(top, bot), kb);
     upd1(ub[0], R[0], kb);                         // 64x16 (2NxnU part 0)
     upd1(ub[1], R[3], kb);                         // 64x16 (2NxnD part 1)
-    upd1(ub[2], fadd(top, R[2]), kb);              // 64x48 rows 0..47
-    upd1(ub[3], fadd(R[1], bot), kb);              // 64x48 rows 16..63
+    ub[2] = min(ub[2], fsubkey(R[3], kAll));       // 64x48 rows 0..47 = all - last strip
+    ub[3] = min(ub[3], fsubkey(R[0], kAll));       // 64x48 rows 16..63
     upd1(ub[4], C[0], kb);                         // 16x64
     upd1(ub[5], C[3], kb);
-    upd1(ub[6], fadd(left, C[2]), kb);             // 48x64 cols 0..47
-    upd1(ub[7], fadd(C[1], right), kb);            // 48x64 cols 16..63
+    ub[6] = min(ub[6], fsubkey(C[3], kAll));       // 48x64 cols 0..47
+    ub[7] = min(ub[7], fsubkey(C[0], kAll));       // 48x64 cols 16..63
     upd1(ub[8], top, kb);                          // 64x32
     upd1(ub[9], bot, kb);
     upd1(ub[10], left, kb);                        // 32x64
     upd1(ub[11], right, kb);
-    upd1(ub[12], fadd(top, bot), kb);              // 64x64
+    ub[12] = min(ub[12], kAll);                    // 64x64
 }
 
 // tile key -> global key, one atomicMin into best[job][part]
-__device__ __forceinline__ void publish(unsigned long long* bestJob, int part, uint32_t key, int twA, int x0, int y0, int W) {
+template <int YB>
+__device__ __forceinline__ void publish(unsigned long long* bestJob, int part, uint32_t key, const TileGeo& t, int W) {
     if (key == 0xFFFFFFFFu) return;
-    const uint32_t cost = key >> kIdxBits, tidx = key & (kMaxTileCands - 1);
-    const uint32_t ty = tidx / (uint32_t)twA, tx = tidx - ty * (uint32_t)twA;
-    const uint32_t gidx = (uint32_t)(y0 + (int)ty) * (uint32_t)W + (uint32_t)(x0 + (int)tx);
+    const uint32_t cost = key >> kIdxBits;
+    int r = (int)(key & (kMaxTileCands - 1)), ty, tx;
+    const int nFirst = YB * t.w0, nMid = (t.nRG - 2) * YB * t.twA;
+    if (r < nFirst) { ty = r / t.w0; tx = t.xs + r - ty * t.w0; }
+    else if (r - nFirst < nMid) { r -= nFirst; ty = r / t.twA; tx = r - ty * t.twA; ty += YB; }
+    else { r -= nFirst + nMid; ty = r / t.xe; tx = r - ty * t.xe; ty += (t.nRG - 1) * YB; }
+    const uint32_t gidx = (uint32_t)(t.y0 + ty) * (uint32_t)W + (uint32_t)(t.x0 + tx);
     atomicMin(bestJob + part, ((unsigned long long)cost << 32) | gidx);
 }
 
 // One round of one warp: lane = unit (candidate column ux, rows rg*YB .. rg*YB+YB-1), block (bx, by).
 // CHECKED = false is the steady state (all lanes and rows valid); CHECKED = true handles the ragged last rounds.
 template <int YB, bool CHECKED>
-__device__ __forceinline__ void round_body(const uint32_t* sWin, const uint32_t* cp, const uint32_t* sBitsX, const uint32_t* sBitsY,
+__device__ __forceinline__ void round_body(const uint32_t* sWin, const uint32_t* cp, const uint32_t* sKb,
                                            uint32_t* recBuf, uint32_t (&best)[33], int rg, int ux, int by, int bx, int b, int lane,
-                                           int twA, int thA, int nRG, uint32_t lambda) {
+                                           bool unitValid) {
     constexpr int SLOTS = 32 * YB;
-    const bool uvalid = !CHECKED || rg < nRG;
+    const bool uvalid = !CHECKED || unitValid;
     const int rgc = (CHECKED && !uvalid) ? 0 : rg, uxc = (CHECKED && !uvalid) ? 0 : ux;
 #ifdef HMME_WIN64
     const uint2* wp = reinterpret_cast<const uint2*>(sWin) + (rgc * YB + by) * kWinPitch64 + uxc + bx;
@@ -356,13 +418,11 @@ __device__ __forceinline__ void round_body(const uint32_t* sWin, const uint32_t*
     const uint32_t* wp = sWin + (rgc * YB + by) * kWinPitch + uxc + bx;
 #endif
     uint32_t kb[YB], kbRec[YB];
-    const uint32_t bitsX = sBitsX[uxc];
+    const uint32_t* kp = sKb + rgc * (YB * kKbPitch) + uxc;
 #pragma unroll
     for (int j = 0; j < YB; ++j) {
-        const int y = rgc * YB + j;
-        const uint32_t mvc = (uint32_t)(lambda * (bitsX + sBitsY[y])) >> 16;
-        const uint32_t k = (mvc << kIdxBits) | (uint32_t)(y * twA + uxc);
-        const bool valid = !CHECKED || (uvalid && y < thA);
+        const uint32_t k = kp[j * kKbPitch];             // (mvcost << 11) | rank in tile, tabulated while the window was in flight
+        const bool valid = !CHECKED || (uvalid && k != kInvalidBlockKeyBase);   // rows past the window's last one are marked in the table
         kb[j] = valid ? k : kInvalidBlockKeyBase;
         kbRec[j] = valid ? k : kInvalidSlot;
     }
@@ -413,8 +473,13 @@ __device__ __forceinline__ void round_body(const uint32_t* sWin, const uint32_t*
                         if (r == 11) emit_strip<2, 1>(a1, stS, kbS, best, recS, b, b == 0, kbRecS, SLOTS);
                         if (r == 15) emit_strip<3, 1>(a1, stS, kbS, best, recS, b, b == 0, kbRecS, SLOTS);
                     }
+#ifdef HMME_CHAIN8
+                    if ((r & 7) == 7)                            // the chains restart at rows 0 and 8
+#endif
+                    {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) acc[j][i] = 0;
+                        for (int i = 0; i < 4; ++i) acc[j][i] = 0;
+                    }
                 }
             }
         }
@@ -425,20 +490,38 @@ template <int YB>
 __global__ void __launch_bounds__(kFastThreads, 1) me_u8_tile_kernel(const FastParams p) {
     extern __shared__ __align__(16) uint32_t smem[];
     constexpr int SLOTS = 32 * YB;
-    const int winRows = fast_win_rows(p.th, YB);
+    const int winRows = fast_win_rows(p.tileRows);
     uint32_t* sWin = smem;                                  // winRows x kWinPitch sliding words
     uint32_t* sCur = sWin + ((winRows * kWinPitch + 3) & ~3); // 64 rows x 16 words, 16-byte aligned (LDS.128, TMA destination)
     uint32_t* sUp = sCur + 1024;                            // kRing x kRecWords x SLOTS
-    uint32_t* sBitsX = sUp + kRing * SLOTS * kRecWords;     // tw
-    uint32_t* sBitsY = sBitsX + ((p.tw + 3) & ~3);          // roundup(th, YB)
+    uint32_t* sKb = sUp + kRing * SLOTS * kRecWords;        // tileRows x kKbPitch key bases
+    uint32_t* sBitsX = sKb + p.tileRows * kKbPitch;         // kMaxTileW MV-bit counts of the tile's columns, then tileRows of its rows
+    uint32_t* sBitsY = sBitsX + kMaxTileW;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#ifdef HMME_DIAG_TIMES
+    long long dt[6];
+    dt[0] = clock64();
+#define HMME_DIAG_T(i) dt[i] = clock64()
+#else
+#define HMME_DIAG_T(i)
+#endif
     const int tilesPerJob = p.nTx * p.nTy;
     const int job = blockIdx.x / tilesPerJob, tile = blockIdx.x - job * tilesPerJob;
     const int tiy = tile / p.nTx, tix = tile - tiy * p.nTx;
-    const int x0 = tix * p.tw, y0 = tiy * p.th;
-    const int twA = min(p.tw, p.W - x0), thA = min(p.th, p.W - y0);
-    const int nRG = (thA + YB - 1) / YB, nUnits = twA * nRG;
+    const int x0 = tix * p.tw;
+    const int twA = min(p.tw, p.W - x0);
+    const int u0 = tiy * p.upt;                              // first unit of the tile in its stripe's unit sequence
+    const int nUnits = min(p.upt, ((p.W + YB - 1) / YB) * twA - u0);
+    if (nUnits <= 0) return;                                 // a narrower last stripe has fewer units than the nominal one
+    const int rg0 = u0 / twA, rgLast = (u0 + nUnits - 1) / twA;
+    TileGeo tg;
+    tg.twA = twA; tg.nRG = rgLast - rg0 + 1;
+    tg.xs = u0 - rg0 * twA; tg.xe = u0 + nUnits - rgLast * twA;
+    tg.w0 = (tg.nRG == 1 ? tg.xe : twA) - tg.xs;
+    tg.x0 = x0; tg.y0 = rg0 * YB;
+    const int nRG = tg.nRG, y0 = tg.y0;
+    const int thA = min(nRG * YB, p.W - y0);                 // candidate rows of the tile's row groups that exist in the window
     const int4 jb = p.jobs[job];
     __shared__ uint64_t fullBar[kRing];
     __shared__ uint64_t winBar;
@@ -464,7 +547,12 @@ __global__ void __launch_bounds__(kFastThreads, 1) me_u8_tile_kernel(const FastP
             mbar_init(&winBar, (uint32_t)(rowsReal + (curTma ? 64 : 0)));
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
+        if (tid >= 256) {                                     // MV-bit counts per column and per row of the tile (the warps that issue no copies)
+            for (int x = tid - 256; x < twA; x += 256) sBitsX[x] = mv_bits(4 * (jb.z + x0 + x));
+            for (int y = tid - 256; y < nRG * YB; y += 256) sBitsY[y] = mv_bits(4 * (jb.w + y0 + y));
+        }
         __syncthreads();
+        HMME_DIAG_T(1);
         if (tid < rowsReal) {
             const uintptr_t g = (uintptr_t)(wbase + (long long)tid * p.refPitch);
             const uintptr_t g0 = g & ~(uintptr_t)15;
@@ -487,9 +575,16 @@ __global__ void __launch_bounds__(kFastThreads, 1) me_u8_tile_kernel(const FastP
                 sCur[idx] = (uint32_t)c[0] | ((uint32_t)c[1] << 8) | ((uint32_t)c[2] << 16) | ((uint32_t)c[3] << 24);
             }
         }
-        for (int x = tid; x < twA; x += kFastThreads) sBitsX[x] = mv_bits(4 * (jb.z + x0 + x));
-        for (int y = tid; y < nRG * YB; y += kFastThreads) sBitsY[y] = mv_bits(4 * (jb.w + y0 + y));
+        // key base of every candidate of the tile: (lambda * (bits(mvx) + bits(mvy)) >> 16) << 11 | scan-order index in the tile
+        for (int y = warp; y < nRG * YB; y += kFastThreads / 32) {
+            const uint32_t bitsY = sBitsY[y];
+            for (int x = lane; x < twA; x += 32)
+                sKb[y * kKbPitch + x] = y < thA ? ((((uint32_t)(p.lambda * (sBitsX[x] + bitsY)) >> 16) << kIdxBits) | (tile_rank(tg, y, x, YB) & (kMaxTileCands - 1)))
+                                                : kInvalidBlockKeyBase;
+        }
+        HMME_DIAG_T(2);
         mbar_wait(&winBar, 0);
+        HMME_DIAG_T(3);
         for (int row = warp; row < rows; row += kFastThreads / 32) {
             const uint32_t off = (uint32_t)((uintptr_t)(wbase + (long long)row * p.refPitch) & 15);
             const uint32_t* d = reinterpret_cast<const uint32_t*>(dense + row * kDensePitch);
@@ -511,6 +606,7 @@ __global__ void __launch_bounds__(kFastThreads, 1) me_u8_tile_kernel(const FastP
     }
     __syncthreads();
 
+    HMME_DIAG_T(4);
     const int b = warp, bx = (b & 3) * 16, by = (b >> 2) * 16;
     uint32_t best[33], ub[13];
 #pragma unroll
@@ -520,9 +616,15 @@ __global__ void __launch_bounds__(kFastThreads, 1) me_u8_tile_kernel(const FastP
     const int role = tid / SLOTS, slot = tid - role * SLOTS;   // upper phase: role 0..3 quadrant, 4 CTU level, >=5 idle
     const uint32_t* cp = sCur + by * 16 + (bx >> 2);
 
+#ifdef HMME_DIAG_NOROUNDS
+    const int nRounds = 0;                                  // diagnostic build: staging and tile end only
+#else
     const int nRounds = (nUnits + 31) >> 5;
-    const int nFull = (twA * (thA / YB)) >> 5;              // rounds in which every lane and every candidate row is valid
-    int rg = lane / twA, ux = lane - rg * twA;              // this lane's unit of round 0, advanced incrementally
+#endif
+    // rounds in which every lane has a unit and every candidate row exists (rows are missing only in a window's last, partial row group)
+    const int nFull = min(nUnits, thA < nRG * YB ? max(0, (nRG - 1) * twA - tg.xs) : nUnits) >> 5;
+    int rg = (tg.xs + lane) / twA, ux = tg.xs + lane - rg * twA;   // this lane's unit of round 0 (row group within the tile, column), advanced incrementally
+    int unit = lane;
     // Warps are NOT barrier-locked per round: records travel through a ring of kRing buffers guarded by mbarriers, and the
     // upper phase of round k runs after the block phase of round k+kLag, by which time every producer has long arrived.  That
     // lets the two warps of each scheduler that start `stagger` cycles late stay half a round out of phase, so the
@@ -537,9 +639,10 @@ __global__ void __launch_bounds__(kFastThreads, 1) me_u8_tile_kernel(const FastP
         if (round < nRounds) {
             uint32_t* recBuf = sUp + wSlot * (SLOTS * kRecWords);
             if (round < nFull)
-                round_body<YB, false>(sWin, cp, sBitsX, sBitsY, recBuf, best, rg, ux, by, bx, b, lane, twA, thA, nRG, p.lambda);
+                round_body<YB, false>(sWin, cp, sKb, recBuf, best, rg, ux, by, bx, b, lane, true);
             else
-                round_body<YB, true>(sWin, cp, sBitsX, sBitsY, recBuf, best, rg, ux, by, bx, b, lane, twA, thA, nRG, p.lambda);
+                round_body<YB, true>(sWin, cp, sKb, recBuf, best, rg, ux, by, bx, b, lane, unit < nUnits);
+            unit += 32;
             ux += 32;
             while (ux >= twA) { ux -= twA; ++rg; }
             __syncwarp();
@@ -555,6 +658,12 @@ __global__ void __launch_bounds__(kFastThreads, 1) me_u8_tile_kernel(const FastP
         }
     }
 
+    HMME_DIAG_T(5);
+#ifdef HMME_DIAG_TIMES
+    if (tid == 0 && (blockIdx.x % 997) == 5)
+        printf("cta %d: init %lld, issue+tables %lld, tma wait %lld, expand %lld, rounds %lld cycles\n", (int)blockIdx.x, dt[1] - dt[0], dt[2] - dt[1], dt[3] - dt[2],
+               dt[4] - dt[3], dt[5] - dt[4]);
+#endif
     // ---- tile end: warp arg-min per key (CREDUX.MIN), lane k keeps key k, then all lanes publish in parallel
     unsigned long long* bestJob = p.best + (size_t)job * HMME_NPARTS;
     uint32_t mine = 0xFFFFFFFFu, last = 0xFFFFFFFFu;
@@ -564,8 +673,8 @@ __global__ void __launch_bounds__(kFastThreads, 1) me_u8_tile_kernel(const FastP
         if (k < 32) mine = (lane == k) ? m : mine;
         else last = m;
     }
-    publish(bestJob, block_part_index(b, lane), mine, twA, x0, y0, p.W);
-    if (lane == 0) publish(bestJob, block_part_index(b, 32), last, twA, x0, y0, p.W);
+    publish<YB>(bestJob, block_part_index(b, lane), mine, tg, p.W);
+    if (lane == 0) publish<YB>(bestJob, block_part_index(b, 32), last, tg, p.W);
     if (role <= 4) {                                          // warp-uniform: SLOTS is a multiple of 32
         mine = 0xFFFFFFFFu;
 #pragma unroll
@@ -573,7 +682,7 @@ __global__ void __launch_bounds__(kFastThreads, 1) me_u8_tile_kernel(const FastP
             const uint32_t m = __reduce_min_sync(0xFFFFFFFFu, ub[k]);
             mine = (lane == k) ? m : mine;
         }
-        if (lane < 13) publish(bestJob, role < 4 ? quad_part_index(role, lane) : ctu_part_index(lane), mine, twA, x0, y0, p.W);
+        if (lane < 13) publish<YB>(bestJob, role < 4 ? quad_part_index(role, lane) : ctu_part_index(lane), mine, tg, p.W);
     }
 }
 
