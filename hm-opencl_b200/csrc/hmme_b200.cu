@@ -39,10 +39,33 @@ std::string g_createErr;
 
 struct FastGeom { int tw, upt, tileRows, nTx, nTy; size_t smemBytes; };
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point query: no link-time dependency on libcuda
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+    static const EncodeTiledFn fn = [] {
+        if (std::getenv("HMME_NO_TMA2D")) return (EncodeTiledFn) nullptr;      // experiments: per-row copies only
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return (EncodeTiledFn) nullptr;
+        return (EncodeTiledFn)f;
+    }();
+    return fn;
+}
+// u8 rows of `pitch` bytes from `base`, box = boxW x boxH bytes; false when the layout does not meet the copy engine's alignment rules
+bool make_u8_map(CUtensorMap* m, const void* base, long long pitch, long long rows, int boxW, int boxH) {
+    const EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn || ((uintptr_t)base & 15) || (pitch & 15) || pitch < boxW || rows < 1 || boxW > 256 || boxH > 256) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)pitch, (cuuint64_t)rows}, strides[1] = {(cuuint64_t)pitch};
+    const cuuint32_t box[2] = {(cuuint32_t)boxW, (cuuint32_t)boxH}, es[2] = {1, 1};
+    return fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 constexpr size_t kSmemBudget = 224 * 1024;   // of the 227 KB a CTA may opt in to (1 CTA per SM anyway: 128 registers x 512 threads)
 
 size_t fast_smem_bytes(int tileRows, int yb) {
-    const size_t words = (((size_t)fast_win_rows(tileRows) * kWinPitch + 3) & ~(size_t)3) + 1024 + kRing * (size_t)(32 * yb) * kRecWords +
+    const size_t words = (((size_t)fast_win_rows(tileRows) * kWinPitch + 31) & ~(size_t)31) + 1024 + kRing * (size_t)(32 * yb) * kRecWords +
                          (size_t)tileRows * (kKbPitch + 1) + kMaxTileW + 4;
     return words * 4;
 }
@@ -315,6 +338,15 @@ int enqueue_search(hmme_ctx* c, const SearchIO& io, const void* curOrigin, int c
         fp.curPitch = curPitch; fp.refPitch = refPitch;
         fp.jobs = io.jobs; fp.best = c->dBest; fp.lambda = c->lambda; fp.W = W;
         fp.tw = g.tw; fp.upt = g.upt; fp.tileRows = g.tileRows; fp.nTx = g.nTx; fp.nTy = g.nTy; fp.stagger = c->stagger;
+        // one 2-D copy per window / block where the planes allow it (the kernel decides per tile, see FastParams)
+        const long long refOff = fp.ref - fp.refLo;
+        if (refOff >= 0 && refPitch > 0 &&
+            make_u8_map(&fp.refMap, fp.refLo, refPitch, (fp.refHi - fp.refLo) / refPitch, kDensePitch, fast_win_rows(g.tileRows))) {
+            fp.refMapOk = 1;
+            fp.refRow0 = (int)(refOff / refPitch); fp.refCol0 = (int)(refOff % refPitch);
+            fp.refMapRows = (int)std::min<long long>((fp.refHi - fp.refLo) / refPitch, 1 << 30);
+        }
+        if (!bipred && curPitch > 0 && make_u8_map(&fp.curMap, fp.cur, curPitch, 1 << 20, 64, 64)) fp.curMapOk = 1;
         const unsigned grid = (unsigned)(njobs * g.nTx * g.nTy);
         if (g.smemBytes > c->fastSmemSet) {           // the opt-in only ever has to grow
             CU_TRY(c, cudaFuncSetAttribute(me_u8_tile_kernel<HMME_FAST_YB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));

@@ -30,6 +30,8 @@
 // Addressing of the source plane is linear (row*pitch + col), which is exactly the reference's
 // pelSearchArray[j + i*iRefStride] including its row-wrap quirk.
 #pragma once
+#include <cuda.h>   // CUtensorMap (type only: the encode function is fetched through cudaGetDriverEntryPoint, no link against libcuda)
+
 #include "me_common.cuh"
 
 namespace hmme {
@@ -58,11 +60,24 @@ constexpr int kRecWords = 49;                 // upper-phase words per candidate
                                               // stored slot-minor ([word][slot]) so that every access is lane-contiguous
 constexpr uint32_t kInvalidBlockKeyBase = 0xF0000000u;   // block sums << 11 stay below 2^27: no wrap, never wins
 constexpr uint32_t kInvalidSlot = 0xFFFFFFFFu;
+#ifndef HMME_SCHED_FENCE
+#define HMME_SCHED_FENCE 0x22220
+#endif
+constexpr unsigned kSchedFence = HMME_SCHED_FENCE;
 constexpr int kLag = 1;                       // the upper phase of round k runs after the block phase of round k + kLag
 constexpr int kRing = 2 * kLag + 2;           // record buffers: a slot may be rewritten only after every warp consumed it (ring >= 2*lag + 2)
 static_assert((kRing & (kRing - 1)) == 0, "ring slots wrap with a mask");
 
-struct FastParams {
+struct alignas(64) FastParams {
+    // Tensor maps (2-D tiled TMA): the whole reference window of a tile arrives with ONE cp.async.bulk.tensor instead of one bulk copy
+    // per row (the copy engine takes about 20 cycles per request: 81 + 64 requests were 3000 cycles per tile), the 64x64 block with another.
+    // Used per CTA when the window lies inside one plane row (no row wrap) and inside the rows the map covers; otherwise that CTA falls
+    // back to the per-row copies, whose linear addressing keeps the reference's row-wrap behaviour.
+    CUtensorMap refMap;        // u8 [refMapRows][refPitch] from refLo, box = kDensePitch x (tileRows + 63)
+    CUtensorMap curMap;        // u8 rows of curPitch bytes from `cur`, box = 64 x 64
+    int refMapOk, curMapOk;
+    int refCol0, refRow0;      // (column, row) of picture sample (0,0) in refMap
+    int refMapRows;
     const uint8_t* cur;        // picture sample (0,0) of the current plane
     const uint8_t* curBlocks;  // non-NULL: job j's 64x64 block is the dense 4 KiB record curBlocks + 4096*j instead (bi-prediction path)
     const uint8_t* ref;        // picture sample (0,0) of the reference plane
@@ -132,6 +147,15 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                      (uint32_t)__cvta_generic_to_shared(dst)),
                  "l"(src), "r"(bytes), "r"((uint32_t)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
+
+// 2-D tiled TMA (cp.async.bulk.tensor, SASS UTMALDG): box of the tensor map at element coordinates (x, y); x * element size must be a
+// multiple of 16 bytes, out-of-range elements arrive as zeros, the destination must be 128-byte aligned.
+__device__ __forceinline__ void tma_tile_2d(void* dst, const CUtensorMap* map, int x, int y, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                     (uint32_t)__cvta_generic_to_shared(dst)),
+                 "l"(map), "r"(x), "r"(y), "r"((uint32_t)__cvta_generic_to_shared(bar))
                  : "memory");
 }
 
@@ -408,7 +432,7 @@ __device__ __forceinline__ void publish(unsigned long long* bestJob, int part, u
 template <int YB, bool CHECKED>
 __device__ __forceinline__ void round_body(const uint32_t* sWin, const uint32_t* cp, const uint32_t* sKb,
                                            uint32_t* recBuf, uint32_t (&best)[33], int rg, int ux, int by, int bx, int b, int lane,
-                                           bool unitValid) {
+                                           bool unitValid, bool never) {
     constexpr int SLOTS = 32 * YB;
     const bool uvalid = !CHECKED || unitValid;
     const int rgc = (CHECKED && !uvalid) ? 0 : rg, uxc = (CHECKED && !uvalid) ? 0 : ux;
@@ -483,16 +507,21 @@ __device__ __forceinline__ void round_body(const uint32_t* sWin, const uint32_t*
                 }
             }
         }
+        // A never-executed, predicated `trap` that ptxas does not move code across: without such fences it hoists all packed SADs of the
+        // round to the front and sinks the folding work (FMA pipe) behind them, so a warp alternates between long single-pipe stretches.
+        // kSchedFence = bit mask of the rows fenced; rows 5, 9, 13, 17 measured best of 15 masks (1.179 ms; none: 1.210, every row: 1.188).
+        if ((kSchedFence >> rho) & 1)
+            if (never) asm volatile("trap;");
     }
 }
 
 template <int YB>
-__global__ void __launch_bounds__(kFastThreads, 1) me_u8_tile_kernel(const FastParams p) {
-    extern __shared__ __align__(16) uint32_t smem[];
+__global__ void __launch_bounds__(kFastThreads, 1) me_u8_tile_kernel(const __grid_constant__ FastParams p) {
+    extern __shared__ __align__(128) uint32_t smem[];
     constexpr int SLOTS = 32 * YB;
     const int winRows = fast_win_rows(p.tileRows);
     uint32_t* sWin = smem;                                  // winRows x kWinPitch sliding words
-    uint32_t* sCur = sWin + ((winRows * kWinPitch + 3) & ~3); // 64 rows x 16 words, 16-byte aligned (LDS.128, TMA destination)
+    uint32_t* sCur = sWin + ((winRows * kWinPitch + 31) & ~31); // 64 rows x 16 words, 128-byte aligned (LDS.128, TMA destination)
     uint32_t* sUp = sCur + 1024;                            // kRing x kRecWords x SLOTS
     uint32_t* sKb = sUp + kRing * SLOTS * kRecWords;        // tileRows x kKbPitch key bases
     uint32_t* sBitsX = sKb + p.tileRows * kKbPitch;         // kMaxTileW MV-bit counts of the tile's columns, then tileRows of its rows
@@ -542,9 +571,15 @@ __global__ void __launch_bounds__(kFastThreads, 1) me_u8_tile_kernel(const FastP
         const long long curPitch = p.curBlocks ? 64 : p.curPitch;
         const uint8_t* cbase = p.curBlocks ? p.curBlocks + (size_t)job * 4096 : p.cur + (long long)jb.y * p.curPitch + jb.x;
         const bool curTma = (((uintptr_t)cbase | (uintptr_t)curPitch) & 15) == 0;
+        // how the 64x64 block arrives: 0 = thread loads, 1 = 64 row copies, 2 = one 4 KiB copy (dense record), 3 = one 2-D tile
+        const int curMode = p.curBlocks ? 2 : (p.curMapOk ? 3 : (curTma ? 1 : 0));
+        // the window as one 2-D tile: its columns must lie inside one plane row (the per-row path keeps the reference's row wrap) and its rows
+        // inside the map; rows past the map arrive as zeros and belong to masked candidates only
+        const int wc = p.refCol0 + jb.x + jb.z + x0, wr = p.refRow0 + jb.y + jb.w + y0;
+        const bool ref2d = p.refMapOk && wc >= 0 && (long long)wc + nPos + 3 <= p.refPitch && wr >= 0 && wr + rowsReal <= p.refMapRows;
         uint8_t* dense = reinterpret_cast<uint8_t*>(sUp);
         if (tid == 0) {
-            mbar_init(&winBar, (uint32_t)(rowsReal + (curTma ? 64 : 0)));
+            mbar_init(&winBar, (uint32_t)((ref2d ? 1 : rowsReal) + (curMode == 1 ? 64 : (curMode ? 1 : 0))));
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         if (tid >= 256) {                                     // MV-bit counts per column and per row of the tile (the warps that issue no copies)
@@ -553,7 +588,12 @@ __global__ void __launch_bounds__(kFastThreads, 1) me_u8_tile_kernel(const FastP
         }
         __syncthreads();
         HMME_DIAG_T(1);
-        if (tid < rowsReal) {
+        if (ref2d) {
+            if (tid == 0) {
+                mbar_arrive_expect_tx(&winBar, (uint32_t)(winRows * kDensePitch));
+                tma_tile_2d(dense, &p.refMap, wc & ~15, wr, &winBar);
+            }
+        } else if (tid < rowsReal) {
             const uintptr_t g = (uintptr_t)(wbase + (long long)tid * p.refPitch);
             const uintptr_t g0 = g & ~(uintptr_t)15;
             uint32_t bytes = (uint32_t)(((g - g0) + (uintptr_t)(nPos + 3) + 15) & ~(uintptr_t)15);
@@ -564,12 +604,17 @@ __global__ void __launch_bounds__(kFastThreads, 1) me_u8_tile_kernel(const FastP
                 tma_bulk_g2s(dense + tid * kDensePitch, reinterpret_cast<const void*>(g0), bytes, &winBar);
             } else
                 mbar_arrive(&winBar);
-        } else if (curTma && tid >= kFastThreads - 64) {
+        }
+        if (curMode == 1 && tid >= kFastThreads - 64) {
             const int r = tid - (kFastThreads - 64);
             mbar_arrive_expect_tx(&winBar, 64);
             tma_bulk_g2s(sCur + r * 16, cbase + (long long)r * curPitch, 64, &winBar);
+        } else if (curMode >= 2 && tid == kFastThreads - 32) {
+            mbar_arrive_expect_tx(&winBar, 4096);
+            if (curMode == 2) tma_bulk_g2s(sCur, cbase, 4096, &winBar);
+            else tma_tile_2d(sCur, &p.curMap, jb.x, jb.y, &winBar);
         }
-        if (!curTma) {
+        if (curMode == 0) {
             for (int idx = tid; idx < 1024; idx += kFastThreads) {
                 const uint8_t* c = cbase + (long long)(idx >> 4) * curPitch + 4 * (idx & 15);
                 sCur[idx] = (uint32_t)c[0] | ((uint32_t)c[1] << 8) | ((uint32_t)c[2] << 16) | ((uint32_t)c[3] << 24);
@@ -625,6 +670,7 @@ __global__ void __launch_bounds__(kFastThreads, 1) me_u8_tile_kernel(const FastP
     const int nFull = min(nUnits, thA < nRG * YB ? max(0, (nRG - 1) * twA - tg.xs) : nUnits) >> 5;
     int rg = (tg.xs + lane) / twA, ux = tg.xs + lane - rg * twA;   // this lane's unit of round 0 (row group within the tile, column), advanced incrementally
     int unit = lane;
+    const bool never = p.W < 0;                             // false, but not to the compiler (see HMME_SCHED_FENCE)
     // Warps are NOT barrier-locked per round: records travel through a ring of kRing buffers guarded by mbarriers, and the
     // upper phase of round k runs after the block phase of round k+kLag, by which time every producer has long arrived.  That
     // lets the two warps of each scheduler that start `stagger` cycles late stay half a round out of phase, so the
@@ -639,9 +685,9 @@ __global__ void __launch_bounds__(kFastThreads, 1) me_u8_tile_kernel(const FastP
         if (round < nRounds) {
             uint32_t* recBuf = sUp + wSlot * (SLOTS * kRecWords);
             if (round < nFull)
-                round_body<YB, false>(sWin, cp, sKb, recBuf, best, rg, ux, by, bx, b, lane, true);
+                round_body<YB, false>(sWin, cp, sKb, recBuf, best, rg, ux, by, bx, b, lane, true, never);
             else
-                round_body<YB, true>(sWin, cp, sKb, recBuf, best, rg, ux, by, bx, b, lane, unit < nUnits);
+                round_body<YB, true>(sWin, cp, sKb, recBuf, best, rg, ux, by, bx, b, lane, unit < nUnits, never);
             unit += 32;
             ux += 32;
             while (ux >= twA) { ux -= twA; ++rg; }
