@@ -27,8 +27,8 @@ def test_bench_line_on_gpu():
     v = d["verified"]
     assert v["ctus"] == 480 and v["mismatches"] == 0 and v["ctu_result_sets_compared"] == 3 * 480
     rf = d["roofline"]
-    assert rf["bound"] == "int_alu" and 0.3 < rf["frac"] < 1.5 and rf["peak"] > 10 and rf["achieved"] > 5 and rf["traffic"]
-    assert abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9 and abs(rf["frac_issue"] - rf["frac"] / 2) < 1e-9
+    assert rf["bound"] == "int_issue" and 0.3 < rf["frac"] < 1.0 and rf["peak"] > 20 and rf["achieved"] > 5 and rf["traffic"]
+    assert abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9 and abs(rf["frac_issue"] - rf["frac"]) < 1e-9 and abs(rf["frac_one_pipe"] - 2 * rf["frac"]) < 1e-9
     assert d["frac_refine"]["roofline"]["frac_issue"] > 0
     pc = d["per_ctu"]
     assert pc["calls"] == 480 and 0 < pc["latency_ms"] < 5
