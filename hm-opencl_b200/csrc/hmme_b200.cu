@@ -338,6 +338,8 @@ int enqueue_search(hmme_ctx* c, const SearchIO& io, const void* curOrigin, int c
         fp.curPitch = curPitch; fp.refPitch = refPitch;
         fp.jobs = io.jobs; fp.best = c->dBest; fp.lambda = c->lambda; fp.W = W;
         fp.tw = g.tw; fp.upt = g.upt; fp.tileRows = g.tileRows; fp.nTx = g.nTx; fp.nTy = g.nTy; fp.stagger = c->stagger;
+        auto magic = [](int d) { return d <= 1 ? 0u : (uint32_t)(0x100000000ull / (unsigned)d) + 1u; };   // see fast_div
+        fp.magicTiles = magic(g.nTx * g.nTy); fp.magicNTx = magic(g.nTx); fp.magicTw = magic(g.tw); fp.magicTwLast = magic(W - (g.nTx - 1) * g.tw);
         // one 2-D copy per window / block where the planes allow it (the kernel decides per tile, see FastParams)
         const long long refOff = fp.ref - fp.refLo;
         if (refOff >= 0 && refPitch > 0 &&

@@ -61,7 +61,7 @@ constexpr int kRecWords = 49;                 // upper-phase words per candidate
 constexpr uint32_t kInvalidBlockKeyBase = 0xF0000000u;   // block sums << 11 stay below 2^27: no wrap, never wins
 constexpr uint32_t kInvalidSlot = 0xFFFFFFFFu;
 #ifndef HMME_SCHED_FENCE
-#define HMME_SCHED_FENCE 0x22220
+#define HMME_SCHED_FENCE 0x3CF3C
 #endif
 constexpr unsigned kSchedFence = HMME_SCHED_FENCE;
 constexpr int kLag = 1;                       // the upper phase of round k runs after the block phase of round k + kLag
@@ -92,10 +92,13 @@ struct alignas(64) FastParams {
     int upt;                   // units per tile: a tile is `upt` consecutive units of its stripe's unit sequence (row group major)
     int tileRows;              // candidate rows (a multiple of YB) the row groups of any tile span at most: sizes the window
     int nTx, nTy;              // stripes per job, tiles per stripe
+    uint32_t magicTiles, magicNTx, magicTw, magicTwLast;   // floor(2^32 / d) + 1 for d = nTx * nTy, nTx, tw, width of the last stripe: n / d = umulhi(n, magic)
     int stagger;               // SM cycles by which warps 8..15 start their first round late (0 = off), see the kernel
 };
 
 __host__ __device__ inline int fast_win_rows(int tileRows) { return tileRows + 63; }
+// n / d with magic = floor(2^32 / d) + 1 (d >= 2; exact while n * d < 2^32) or 0 for d = 1
+__device__ __forceinline__ int fast_div(uint32_t n, uint32_t magic) { return magic ? (int)__umulhi(n, magic) : (int)n; }
 
 // A tile = `upt` consecutive units of one column stripe (unit = candidate column x one row group of YB candidate rows; units are
 // numbered row group by row group).  With upt a multiple of 32 every round of every tile but a stripe's last has 32 busy lanes
@@ -202,8 +205,12 @@ __device__ __forceinline__ uint32_t fshladd(uint32_t a, uint32_t b) {
 // the packed SADs (ALU pipe) of the candidates that are still being accumulated.  All sums are plain (unshifted) SADs; a key is
 // formed by one IMAD: key = sum * 2^11 + ((mvcost << 11) | idxInTile), and a key of a difference or a sum of a keyed and an
 // unkeyed part by one IMAD on the existing key (exact mod 2^32): 17 additions + 33 key IMADs per candidate for the 33 partitions.
-// -DHMME_CHAIN8: eight-row SAD chains (the 4x8 column sums then cost no addition: 17 instead of 25 additions per candidate).  Measured
-// SLOWER (1.22 vs 1.19 ms per 1080p +-64 frame): the compiler then sinks all folding behind the SADs and the FMA-heavy tail of a round grows.
+// Eight-row SAD chains (the 4x8 column sums then cost no addition: 17 instead of 25 additions per candidate) are the default; -DHMME_CHAIN4
+// builds the four-row form.  Without the scheduling fences of round_body the eight-row form was the slower one (1.22 vs 1.19 ms per 1080p +-64
+// frame: ptxas sank all folding behind the SADs); with them it is the faster (1.140 vs 1.179 ms).
+#ifndef HMME_CHAIN4
+#define HMME_CHAIN8 1
+#endif
 struct BlockState {
 #ifndef HMME_CHAIN8
     uint32_t sp[4];     // 4x4 sums of the previous even strip
@@ -509,7 +516,7 @@ __device__ __forceinline__ void round_body(const uint32_t* sWin, const uint32_t*
         }
         // A never-executed, predicated `trap` that ptxas does not move code across: without such fences it hoists all packed SADs of the
         // round to the front and sinks the folding work (FMA pipe) behind them, so a warp alternates between long single-pipe stretches.
-        // kSchedFence = bit mask of the rows fenced; rows 5, 9, 13, 17 measured best of 15 masks (1.179 ms; none: 1.210, every row: 1.188).
+        // kSchedFence = bit mask of the rows fenced (default 0x3CF3C); the masks tried span 1.13 .. 1.16 ms, no fences 1.159, every row 1.151.
         if ((kSchedFence >> rho) & 1)
             if (never) asm volatile("trap;");
     }
@@ -535,15 +542,18 @@ __global__ void __launch_bounds__(kFastThreads, 1) me_u8_tile_kernel(const __gri
 #else
 #define HMME_DIAG_T(i)
 #endif
+    // divisions by launch constants as multiplications (exact for these magnitudes: n * d < 2^32): the tile geometry is on the critical path
+    // to the job record and the copies
     const int tilesPerJob = p.nTx * p.nTy;
-    const int job = blockIdx.x / tilesPerJob, tile = blockIdx.x - job * tilesPerJob;
-    const int tiy = tile / p.nTx, tix = tile - tiy * p.nTx;
+    const int job = fast_div(blockIdx.x, p.magicTiles), tile = blockIdx.x - job * tilesPerJob;
+    const int tiy = fast_div((uint32_t)tile, p.magicNTx), tix = tile - tiy * p.nTx;
     const int x0 = tix * p.tw;
     const int twA = min(p.tw, p.W - x0);
     const int u0 = tiy * p.upt;                              // first unit of the tile in its stripe's unit sequence
     const int nUnits = min(p.upt, ((p.W + YB - 1) / YB) * twA - u0);
     if (nUnits <= 0) return;                                 // a narrower last stripe has fewer units than the nominal one
-    const int rg0 = u0 / twA, rgLast = (u0 + nUnits - 1) / twA;
+    const uint32_t magicW = twA == p.tw ? p.magicTw : p.magicTwLast;
+    const int rg0 = fast_div((uint32_t)u0, magicW), rgLast = fast_div((uint32_t)(u0 + nUnits - 1), magicW);
     TileGeo tg;
     tg.twA = twA; tg.nRG = rgLast - rg0 + 1;
     tg.xs = u0 - rg0 * twA; tg.xe = u0 + nUnits - rgLast * twA;
@@ -634,11 +644,22 @@ __global__ void __launch_bounds__(kFastThreads, 1) me_u8_tile_kernel(const __gri
             const uint32_t off = (uint32_t)((uintptr_t)(wbase + (long long)row * p.refPitch) & 15);
             const uint32_t* d = reinterpret_cast<const uint32_t*>(dense + row * kDensePitch);
 #ifdef HMME_WIN64
+            // entries 0 .. (twA-1) + 48 + 8, two per lane and step: the pair shares its three source words and leaves with one 128-bit store
+            // when the row starts on a 16-byte boundary of the window (even rows: the pitch is an odd number of entries)
             uint2* dst = reinterpret_cast<uint2*>(sWin) + row * kWinPitch64;
-            for (int x = lane; x < nPos - 4; x += 32) {       // entries 0 .. (twA-1) + 48 + 8
+            const int odd = row & 1;                          // entry index of the first 16-byte aligned entry of this row
+            if (odd && lane == 0) {
+                const uint32_t sh = 8 * (off & 3);
+                const uint32_t w0 = d[off >> 2], w1 = d[(off >> 2) + 1], w2 = d[(off >> 2) + 2];
+                dst[0] = make_uint2(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh));
+            }
+            for (int x = odd + 2 * lane; x < nPos - 4; x += 64) {
                 const uint32_t q = off + (uint32_t)x, sh = 8 * (q & 3);
                 const uint32_t w0 = d[q >> 2], w1 = d[(q >> 2) + 1], w2 = d[(q >> 2) + 2];
-                dst[x] = make_uint2(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh));
+                const bool cross = (q & 3) == 3;               // the second entry starts on the next word
+                const uint4 e = make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), cross ? w1 : __funnelshift_r(w0, w1, sh + 8),
+                                           cross ? w2 : __funnelshift_r(w1, w2, sh + 8));
+                *reinterpret_cast<uint4*>(dst + x) = e;         // x + 1 <= twA + 56 < kWinPitch64: the spare entry stays inside the row
             }
 #else
             uint32_t* dst = sWin + row * kWinPitch;
@@ -668,7 +689,7 @@ __global__ void __launch_bounds__(kFastThreads, 1) me_u8_tile_kernel(const __gri
 #endif
     // rounds in which every lane has a unit and every candidate row exists (rows are missing only in a window's last, partial row group)
     const int nFull = min(nUnits, thA < nRG * YB ? max(0, (nRG - 1) * twA - tg.xs) : nUnits) >> 5;
-    int rg = (tg.xs + lane) / twA, ux = tg.xs + lane - rg * twA;   // this lane's unit of round 0 (row group within the tile, column), advanced incrementally
+    int rg = fast_div((uint32_t)(tg.xs + lane), magicW), ux = tg.xs + lane - rg * twA;   // this lane's unit of round 0 (row group within the tile, column), advanced incrementally
     int unit = lane;
     const bool never = p.W < 0;                             // false, but not to the compiler (see HMME_SCHED_FENCE)
     // Warps are NOT barrier-locked per round: records travel through a ring of kRing buffers guarded by mbarriers, and the
@@ -679,6 +700,40 @@ __global__ void __launch_bounds__(kFastThreads, 1) me_u8_tile_kernel(const __gri
         const long long t0 = clock64();
         while (clock64() - t0 < p.stagger) {}
     }
+#ifndef HMME_LOOP_PLAIN
+    // loop control in down-counters (loop-carried, so the compiler cannot re-derive the round counts from the tile geometry in every
+    // iteration); a round advances every lane by 32 units = stepRg row groups + stepUx columns (one predicated wrap, no loop)
+    const int stepRg = fast_div(32u, magicW), stepUx = 32 - stepRg * twA;
+    int blockLeft = nRounds, fullLeft = nFull, upperLeft = nRounds, lagLeft = kLag;
+    int wSlot = 0, rSlot = 0;
+    uint32_t rPhase = 0;
+    while (upperLeft > 0) {
+        if (blockLeft > 0) {
+            uint32_t* recBuf = sUp + wSlot * (SLOTS * kRecWords);
+            if (fullLeft > 0)
+                round_body<YB, false>(sWin, cp, sKb, recBuf, best, rg, ux, by, bx, b, lane, true, never);
+            else
+                round_body<YB, true>(sWin, cp, sKb, recBuf, best, rg, ux, by, bx, b, lane, unit < nUnits, never);
+            --blockLeft; --fullLeft;
+            unit += 32;
+            ux += stepUx; rg += stepRg;
+            if (ux >= twA) { ux -= twA; ++rg; }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&fullBar[wSlot]);
+            wSlot = (wSlot + 1) & (kRing - 1);
+        }
+        if (lagLeft > 0) --lagLeft;
+        else {
+            mbar_wait(&fullBar[rSlot], rPhase);
+            const uint32_t* recBuf = sUp + rSlot * (SLOTS * kRecWords);
+            if (role < 4) emit_quadrant(recBuf + slot, role, ub, SLOTS);
+            else if (role == 4) emit_ctu(recBuf + slot, ub, SLOTS);
+            rSlot = (rSlot + 1) & (kRing - 1);
+            if (rSlot == 0) rPhase ^= 1u;
+            --upperLeft;
+        }
+    }
+#else
     int wSlot = 0, rSlot = 0;
     uint32_t rPhase = 0;
     for (int round = 0; round < nRounds + kLag; ++round) {
@@ -704,6 +759,7 @@ __global__ void __launch_bounds__(kFastThreads, 1) me_u8_tile_kernel(const __gri
         }
     }
 
+#endif
     HMME_DIAG_T(5);
 #ifdef HMME_DIAG_TIMES
     if (tid == 0 && (blockIdx.x % 997) == 5)
