@@ -202,9 +202,12 @@ int ensure_pus(hmme_ctx* c, size_t npus) {
         std::vector<int> order(HMME_NPARTS);
         for (int i = 0; i < HMME_NPARTS; ++i) order[i] = i;
         auto tiles = [](int q) { const PartRect r = part_rect(q); return ((r.w + 7) / 8) * ((r.h + 7) / 8); };
-        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return tiles(a) > tiles(b); });
+        auto seg = [](int q) { const PartRect r = part_rect(q); return frac_segment(r.w, r.h); };
+        // by segment of the group kernel (which starts with the PUs of four tiles or more), inside a segment by tile count
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return seg(a) != seg(b) ? seg(a) < seg(b) : tiles(a) > tiles(b); });
         c->bigParts = 0; c->tilesPerCtu = 0;
-        for (int q : order) { c->bigParts += tiles(q) >= kFracCoopTiles; c->tilesPerCtu += tiles(q); }
+        for (int q = 0; q < 5; ++q) c->segParts[q] = 0;
+        for (int q : order) { c->bigParts += tiles(q) >= kFracCoopTiles; c->tilesPerCtu += tiles(q); c->segParts[seg(q)] += 1; }
         CU_TRY(c, cudaMalloc(&c->dOrder, HMME_NPARTS * sizeof(int)));
         CU_TRY(c, cudaMemcpy(c->dOrder, order.data(), HMME_NPARTS * sizeof(int), cudaMemcpyHostToDevice));
     }
@@ -244,9 +247,19 @@ int mark_compute(hmme_ctx* c) {
     return HMME_OK;
 }
 
-int enqueue_frac(hmme_ctx* c, const hmme_plane* cur, const hmme_plane* ref, int npus, int nBig, long long totalTiles, bool slots, int useHad, bool wantCand) {
+// segment boundaries of the group kernel from the number of PUs in each segment (the list is ordered by segment)
+void frac_segments(const long long (&cnt)[5], FracGroupParams& fp) {
+    fp.segPu[0] = 0; fp.segGrp[0] = 0;
+    for (int q = 0; q < 5; ++q) {
+        fp.segPu[q + 1] = fp.segPu[q] + (int)cnt[q];
+        fp.segGrp[q + 1] = fp.segGrp[q] + (int)((cnt[q] + kFracSegPus[q] - 1) / kFracSegPus[q]);
+    }
+}
+
+int enqueue_frac(hmme_ctx* c, const hmme_plane* cur, const hmme_plane* ref, int npus, int nBig, long long totalTiles, bool slots, int useHad, bool wantCand,
+                 const long long (&segCount)[5]) {
     if (wantCand && !c->dCand) CU_TRY(c, cudaMalloc(&c->dCand, c->puCap * 18 * sizeof(uint32_t)));
-    FracParams fp{};
+    FracGroupParams fp{};
     fp.cur = origin_ptr(cur); fp.ref = reinterpret_cast<const uint8_t*>(origin_ptr(ref));
     fp.curPitch = cur->pitch; fp.refPitch = ref->pitch; fp.curBytes = cur->elemBytes;
     // Large PUs get a CTA each only when the batch is too small for longest-first scheduling to hide a 64-tile PU running on one
@@ -260,9 +273,14 @@ int enqueue_frac(hmme_ctx* c, const hmme_plane* cur, const hmme_plane* ref, int 
     // about one PU per warp: CTAs start in index order, so with the list ordered large to small the hardware's CTA scheduler does
     // longest-first load balancing (measured 1080p: 16 CTAs per SM 1.25 ms, 32: 1.20, 128 and more: 1.14; one resident wave: 1.30)
     static const int perSm = std::getenv("HMME_FRAC_CTAS_PER_SM") ? std::max(1, std::atoi(std::getenv("HMME_FRAC_CTAS_PER_SM"))) : 256;
-    const int ctas = std::max(1, nBig + std::min((npus - nBig + kFracWarps - 1) / kFracWarps, c->prop.multiProcessorCount * perSm));
+    frac_segments(segCount, fp);
+    static const int formEnv = std::getenv("HMME_FRAC_FORM") ? std::atoi(std::getenv("HMME_FRAC_FORM")) : 2;   // experiments: 1 = one PU per warp (round 1's kernel)
+    const bool group = !coop && formEnv != 1;
+    const int units = group ? fp.segGrp[5] : npus - nBig;   // one group / one PU per warp
+    const int ctas = std::max(1, nBig + std::min((units + kFracWarps - 1) / kFracWarps, c->prop.multiProcessorCount * perSm));
     if (!c->capturing) CU_TRY(c, cudaEventRecord(c->evF0, c->stream));
     if (coop) me_frac_coop_kernel<<<ctas, kFracThreads, 0, c->stream>>>(fp);
+    else if (group) me_frac_group_kernel<<<ctas, kFracThreads, 0, c->stream>>>(fp);
     else me_frac_kernel<<<ctas, kFracThreads, 0, c->stream>>>(fp);
     if (!c->capturing) CU_TRY(c, cudaEventRecord(c->evF1, c->stream));
     c->evFracValid = !c->capturing;
@@ -847,17 +865,18 @@ int hmme_refine_frac(hmme_ctx* c, const hmme_plane* cur, const hmme_plane* ref, 
     static_assert(sizeof(hmme_pu) == sizeof(FracPu) && sizeof(hmme_frac_result) == sizeof(int4), "ABI structs mirror the kernel's");
     // PUs by 8x8-tile count, large to small (longest-first scheduling; the large ones get a CTA each); results go back to list order
     auto tiles = [&](int i) { return ((pus[i].w + 7) / 8) * ((pus[i].h + 7) / 8); };
+    auto seg = [&](int i) { return frac_segment(pus[i].w, pus[i].h); };
     std::vector<int> idx(npus);
     for (int i = 0; i < npus; ++i) idx[i] = i;
-    std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return tiles(a) > tiles(b); });
+    std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return seg(a) != seg(b) ? seg(a) < seg(b) : tiles(a) > tiles(b); });
     std::vector<hmme_pu> sorted(npus);
     int nBig = 0;
-    long long totalTiles = 0;
-    for (int i = 0; i < npus; ++i) { sorted[i] = pus[idx[i]]; nBig += tiles(idx[i]) >= kFracCoopTiles; totalTiles += tiles(idx[i]); }
+    long long totalTiles = 0, segCount[5] = {0, 0, 0, 0, 0};
+    for (int i = 0; i < npus; ++i) { sorted[i] = pus[idx[i]]; nBig += tiles(idx[i]) >= kFracCoopTiles; totalTiles += tiles(idx[i]); segCount[seg(idx[i])] += 1; }
     CU_TRY(c, cudaMemcpyAsync(c->dPus, sorted.data(), (size_t)npus * sizeof(hmme_pu), cudaMemcpyHostToDevice, c->stream));
     CU_TRY(c, cudaMemcpyAsync(c->dSlots, idx.data(), (size_t)npus * sizeof(int), cudaMemcpyHostToDevice, c->stream));
     CU_TRY(c, cudaStreamSynchronize(c->stream));           // the two vectors are pageable and go out of scope
-    rc = enqueue_frac(c, cur, ref, npus, nBig, totalTiles, true, useHad, candCosts != nullptr);
+    rc = enqueue_frac(c, cur, ref, npus, nBig, totalTiles, true, useHad, candCosts != nullptr, segCount);
     if (rc != HMME_OK) return rc;
     CU_TRY(c, cudaMemcpyAsync(results, c->dFrac, (size_t)npus * sizeof(int4), cudaMemcpyDeviceToHost, c->stream));
     if (candCosts) CU_TRY(c, cudaMemcpyAsync(candCosts, c->dCand, (size_t)npus * 18 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
@@ -1059,7 +1078,9 @@ int hmme_refine_frame_async(hmme_ctx* c, const hmme_plane* cur, const hmme_plane
     me_frac_build_kernel<<<(unsigned)((npus + 255) / 256), 256, 0, c->stream>>>(c->dJobs, X, Y, predsQpel ? c->dPreds : nullptr, c->dOrder, njobs,
                                                                                 c->dPus, c->dSlots);
     c->launches += 1;
-    return enqueue_frac(c, cur, ref, (int)npus, njobs * c->bigParts, (long long)njobs * c->tilesPerCtu, true, useHad, false);
+    long long segCount[5];
+    for (int q = 0; q < 5; ++q) segCount[q] = (long long)c->segParts[q] * njobs;
+    return enqueue_frac(c, cur, ref, (int)npus, njobs * c->bigParts, (long long)njobs * c->tilesPerCtu, true, useHad, false, segCount);
 }
 
 int hmme_fetch_frac_async(hmme_ctx* c, int njobs, hmme_frac_result* results) {

@@ -56,6 +56,7 @@ struct hmme_ctx {
     int* dOrder = nullptr;        // 593 partition indices, by 8x8-tile count, large to small
     int bigParts = 0;             // how many of them get a whole CTA in the small-batch form (kFracCoopTiles tiles or more)
     int tilesPerCtu = 0;          // 8x8 tiles of all 593 partitions (1792)
+    int segParts[5] = {0, 0, 0, 0, 0};   // partitions per segment of the group kernel (hmme::frac_segment)
     int2* dPreds = nullptr; size_t predCap = 0;
     cudaEvent_t evF0 = nullptr, evF1 = nullptr; bool evFracValid = false;
     uint64_t bufGen = 0;          // bumped whenever a device buffer a graph may reference is reallocated

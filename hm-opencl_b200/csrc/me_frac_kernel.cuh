@@ -44,6 +44,19 @@ struct FracParams {
     int4* out;                  // {mv x, mv y (quarter pel), cost, distortion}
     uint32_t* cand;             // optional [npus][18]: cost of every candidate in the reference's table order
 };
+// group form (me_frac_group_kernel): the list is cut into five segments -- PUs of >= 4 tiles (one PU per warp), 2..3 tiles with the
+// 8x8 / the 4x4 Hadamard (two PUs per warp), one tile with the 8x8 / the 4x4 Hadamard (four PUs per warp)
+struct FracGroupParams : FracParams {
+    int segPu[6];               // first PU of segment q (segPu[5] = npus)
+    int segGrp[6];              // first group of segment q (segGrp[5] = number of groups)
+};
+constexpr int kFracSegPus[5] = {1, 2, 2, 4, 4};    // PUs per group (= per warp at a time) in each segment
+// segment of a PU: 0 = four tiles or more; 1 / 2 = two or three tiles, 8x8 / 4x4 Hadamard; 3 / 4 = one tile, 8x8 / 4x4 Hadamard
+__host__ __device__ inline int frac_segment(int w, int h) {
+    const int nT = ((w + 7) >> 3) * ((h + 7) >> 3);
+    if (nT >= 4) return 0;
+    return (nT >= 2 ? 1 : 3) + (((w | h) & 7) ? 1 : 0);
+}
 
 // HEVC luma taps (TComInterpolationFilter.cpp:57-63), as ints and as packed signed bytes {k0..k3}, {k4..k7}
 __constant__ int kLumaTap[4][8] = {
@@ -408,6 +421,355 @@ __global__ void me_frac_build_kernel(const int4* jobs, const int32_t* X, const i
     const int2 pr = preds ? preds[job] : make_int2(0, 0);
     pus[n] = FracPu{jb.x + r.x, jb.y + r.y, r.w, r.h, X[slot], Y[slot], pr.x, pr.y};
     slots[n] = slot;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// Group form of the refinement (the throughput kernel): a warp is four independent TILE PROCESSORS of eight lanes ("octets").
+// An octet works on one 8x8 tile at a time, all roles inside the octet:
+//   fetch / H step : lane r holds patch rows 2r, 2r+1 (16 bytes each, in registers -- the patch never goes through shared memory)
+//                    and filters them into the three horizontal planes, stored as packed row pairs
+//   V step         : lane c = column c, one plane per pass (3 passes), all 32 lanes busy
+//   Hadamard pass  : lane i = coefficient row i, one candidate per pass (9 or 8 passes), all 32 lanes busy
+// What the four octets work on depends on the PU size: a PU of four tiles or more has all four (tiles t = octet, octet + 4, ...),
+// PUs of two or three tiles two octets each (two PUs per warp), one-tile PUs one octet each (four PUs per warp): small PUs no longer
+// leave lanes idle, and their set-up and their decision logic run four at a time.  Everything a lane needs about "its" PU is lane
+// state, so the three cases are one code path; the PUs of a group share the distortion mode (the host orders the list that way).
+// With one tile per warp and iteration (frac_eval) the V step has 24 busy lanes, the half-pel Hadamard pass 72 tasks on 96 lanes.
+struct __align__(16) FracScratch4 {
+    int16_t cur[4][72];         // [octet][row * 8 + column], zero outside the PU (+8: octets 36 words apart)
+    uint32_t h[3][4][104];      // [dx index][octet][column * 12 + row pair]: rows 2q | 2q+1 << 16 (12: conflict-free 128-bit column loads, +8 per octet)
+    int16_t t[9][4][72];        // [candidate][octet][column * 8 + coefficient row] (+8)
+};
+// ceil(65536 / n): t / n == (t * rcp) >> 16 for t < 128, n <= 8
+__constant__ int kTileRcp[9] = {0, 65536, 32768, 21846, 16384, 13108, 10923, 9363, 8192};
+
+struct FracOct {                // lane state of the group form: the PU this lane's octet works on
+    const uint8_t* refPu;       // patch origin: PU position + integer MV - (4, 4)
+    long long curOff;           // element offset of the PU's sample (0, 0) in the current plane
+    int w, h, ntxT, nT, rcp;
+    int t0, tstep;              // this octet's tiles: t0, t0 + tstep, ...
+    bool valid;                 // the octet has a PU at all (ragged last group of a segment)
+};
+
+template <int MODE, bool HALF>
+__device__ __forceinline__ void frac_eval_oct(const FracParams& p, const FracOct& O, FracScratch4& S, const int lane, const int iters,
+                                              const int cx, const int cy, uint32_t (&acc)[9]) {
+    constexpr int step = HALF ? 2 : 1;
+    const int s = lane >> 3, r = lane & 7;
+    int hOff[3], vOff[3];
+    uint32_t cLo[3], cHi[3], vLo[3], vHi[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const int dx = cx + (i - 1) * step, dy = cy + (i - 1) * step;
+        hOff[i] = 1 + (dx >> 2); vOff[i] = 1 + (dy >> 2);
+        cLo[i] = kLumaPack[dx & 3][0]; cHi[i] = kLumaPack[dx & 3][1];
+        vLo[i] = kLumaPack[dy & 3][0]; vHi[i] = kLumaPack[dy & 3][1];
+    }
+#pragma unroll
+    for (int g = 0; g < 9; ++g) acc[g] = 0;
+    const bool allInt = __all_sync(0xFFFFFFFFu, cy == 0);    // every octet's middle candidate row is a rounding copy (always in the half-pel stage)
+
+    // the next tile's samples travel in registers while the current one is worked on; an octet without a tile gets zeros, which
+    // flow through as zero planes, zero differences and zero sums: no masks further down
+    uint32_t nW[2][4], nC[4];
+    int ntw = 8, nth = 8;
+    auto fetch = [&](const int t) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) nW[k][q] = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) nC[q] = 0;
+        if (O.valid && t < O.nT) {
+            const int ty = ((t * O.rcp) >> 16) * 8, tx = t * 8 - ty * O.ntxT;
+            ntw = min(8, O.w - tx); nth = min(8, O.h - ty);
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {                    // 16 patch bytes of a row, any alignment: five aligned words, four funnel shifts
+                const uint8_t* g = O.refPu + (long long)(ty + 2 * r + k) * p.refPitch + tx;
+                const uint32_t sh = 8u * (uint32_t)((uintptr_t)g & 3);
+                const uint32_t* qa = reinterpret_cast<const uint32_t*>((uintptr_t)g & ~(uintptr_t)3);
+                const uint32_t a0 = __ldg(qa), a1 = __ldg(qa + 1), a2 = __ldg(qa + 2), a3 = __ldg(qa + 3), a4 = __ldg(qa + 4);
+                nW[k][0] = __funnelshift_r(a0, a1, sh); nW[k][1] = __funnelshift_r(a1, a2, sh);
+                nW[k][2] = __funnelshift_r(a2, a3, sh); nW[k][3] = __funnelshift_r(a3, a4, sh);
+            }
+            if (r < nth) {                                   // row r of the current tile as four pairs of 16-bit samples
+                const long long o = O.curOff + (long long)(ty + r) * p.curPitch + tx;
+                if (p.curBytes == 1) {
+                    const uint8_t* g = static_cast<const uint8_t*>(p.cur) + o;
+                    const uint32_t sh = 8u * (uint32_t)((uintptr_t)g & 3);
+                    const uint32_t* qa = reinterpret_cast<const uint32_t*>((uintptr_t)g & ~(uintptr_t)3);
+                    const uint32_t a0 = __ldg(qa), a1 = __ldg(qa + 1), a2 = __ldg(qa + 2);
+                    const uint32_t b0 = __funnelshift_r(a0, a1, sh), b1 = __funnelshift_r(a1, a2, sh);
+                    nC[0] = __byte_perm(b0, 0, 0x4140); nC[1] = __byte_perm(b0, 0, 0x4342);
+                    nC[2] = __byte_perm(b1, 0, 0x4140); nC[3] = __byte_perm(b1, 0, 0x4342);
+                } else {
+                    const int16_t* g = static_cast<const int16_t*>(p.cur) + o;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) nC[q] = ((uint32_t)(uint16_t)g[2 * q]) | ((uint32_t)(uint16_t)g[2 * q + 1] << 16);
+                }
+                if (ntw < 8) { nC[2] = 0; nC[3] = 0; }       // tile widths are 4 or 8
+            }
+        }
+    };
+    int t = O.t0;
+    fetch(t);
+#pragma unroll 1
+    for (int it = 0; it < iters; ++it) {
+        uint32_t W[2][4];
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) W[k][q] = nW[k][q];
+        *reinterpret_cast<uint4*>(&S.cur[s][r * 8]) = make_uint4(nC[0], nC[1], nC[2], nC[3]);
+        const int tw = ntw, th = nth;
+        t += O.tstep;
+        if (it + 1 < iters) fetch(t);
+        {   // H step: rows 2r and 2r+1, eight columns, three planes; a row pair leaves as one 32-bit word per column and plane
+            if (HALF) {
+                // dx = -2 and dx = +2 are the same half-sample row one column apart (nine windows serve both); dx = 0 is 64 * sample
+                int f[2][9];
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    uint32_t L[13];                          // L[o] = bytes o .. o+3 of the row
+#pragma unroll
+                    for (int o = 0; o < 13; ++o) L[o] = (o & 3) ? __funnelshift_r(W[k][o >> 2], W[k][(o >> 2) + 1], 8 * (o & 3)) : W[k][o >> 2];
+#pragma unroll
+                    for (int o = 0; o < 9; ++o) f[k][o] = dp4a_us(L[o + 4], cHi[0], dp4a_us(L[o], cLo[0], 0));
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    S.h[0][s][j * 12 + r] = __byte_perm(f[0][j], f[1][j], 0x5410);
+                    S.h[2][s][j * 12 + r] = __byte_perm(f[0][j + 1], f[1][j + 1], 0x5410);
+                    // sample j + 4 of both rows, times 64: bytes {row 2r, 0, row 2r+1, 0} << 6
+                    const uint32_t lo = __byte_perm(W[0][1 + (j >> 2)], 0, 0x4440 | (j & 3)), hi = __byte_perm(W[1][1 + (j >> 2)], 0, 0x4044 | ((j & 3) << 8));
+                    S.h[1][s][j * 12 + r] = (lo | hi) << 6;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    int out[2][8];
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        // the row moved left by hOff bytes (0 or 1; the patch has 16 bytes, windows reach byte 7 + 1 + 7), then fixed windows
+                        const uint32_t sh = 8u * (uint32_t)hOff[i];
+                        uint32_t V[4];
+                        V[0] = __funnelshift_r(W[k][0], W[k][1], sh); V[1] = __funnelshift_r(W[k][1], W[k][2], sh);
+                        V[2] = __funnelshift_r(W[k][2], W[k][3], sh); V[3] = W[k][3] >> sh;
+                        uint32_t L[12];
+#pragma unroll
+                        for (int o = 0; o < 12; ++o) L[o] = (o & 3) ? __funnelshift_r(V[o >> 2], V[min((o >> 2) + 1, 3)], 8 * (o & 3)) : V[o >> 2];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) out[k][j] = dp4a_us(L[j + 4], cHi[i], dp4a_us(L[j], cLo[i], 0));
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) S.h[i][s][j * 12 + r] = __byte_perm(out[0][j], out[1][j], 0x5410);
+                }
+            }
+        }
+        __syncwarp();
+        {   // V step: lane = column r of the octet's tile, one plane per pass
+            int cu[8];
+#pragma unroll
+            for (int rr = 0; rr < 8; ++rr) cu[rr] = (int)S.cur[s][rr * 8 + r];
+            const bool colDead = MODE != kFracHad8 && r >= tw;                // columns right of a 4-wide tile: zero plane -> zero prediction
+#pragma unroll 1
+            for (int di = 0; di < 3; ++di) {
+                const uint4 ha = *reinterpret_cast<const uint4*>(&S.h[di][s][r * 12]), hb = *reinterpret_cast<const uint4*>(&S.h[di][s][r * 12 + 4]);
+                uint32_t wv[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
+                if (MODE != kFracHad8) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) wv[q] = colDead ? 0u : wv[q];
+                }
+                auto emit = [&](const int j, int (&d)[8]) {
+#pragma unroll
+                    for (int rr = 0; rr < 8; ++rr) d[rr] = cu[rr] - d[rr];
+                    if (MODE != kFracHad8 && th < 8) { d[4] = 0; d[5] = 0; d[6] = 0; d[7] = 0; }
+                    if (MODE == kFracSad) {
+                        uint32_t sm = 0;
+#pragma unroll
+                        for (int rr = 0; rr < 8; ++rr) sm = __sad(d[rr], 0, sm);
+                        acc[j * 3] += sm;                     // the three sums of a candidate row rotate with di (below); lanes are added at the end
+                    } else {
+                        if (MODE == kFracHad8) hadamard_inplace<8>(d);
+                        else { hadamard_inplace<4>(d); hadamard_inplace<4>(d + 4); }
+                        uint4 pk;
+                        pk.x = __byte_perm(d[0], d[1], 0x5410); pk.y = __byte_perm(d[2], d[3], 0x5410);
+                        pk.z = __byte_perm(d[4], d[5], 0x5410); pk.w = __byte_perm(d[6], d[7], 0x5410);
+                        *reinterpret_cast<uint4*>(&S.t[j * 3 + di][s][r * 8]) = pk;
+                    }
+                };
+                int d[8];
+                auto copy_rows = [&]() {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        d[2 * q] = __vimin_s32_relu(((int)(int16_t)(wv[q + 2] & 0xFFFFu) + 32) >> 6, 255);
+                        d[2 * q + 1] = __vimin_s32_relu((((int)wv[q + 2] >> 16) + 32) >> 6, 255);
+                    }
+                };
+                if (HALF) {
+                    int o9[9];                               // half-sample rows -1..7: dy = -2 reads 0..7 of them, dy = +2 reads 1..8
+                    frac_vfilter<0, 9>(wv, vLo[0], vHi[0], o9);
+#pragma unroll
+                    for (int rr = 0; rr < 8; ++rr) d[rr] = o9[rr];
+                    emit(0, d);
+#pragma unroll
+                    for (int rr = 0; rr < 8; ++rr) d[rr] = o9[rr + 1];
+                    emit(2, d);
+                    copy_rows();
+                    emit(1, d);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        if (MODE != kFracSad && di == 1 && j == 1) continue;   // the half-pel winner: its distortion is known
+                        if (j == 1 && allInt) copy_rows();   // dy = 0 in every octet (else the general filter does the same with the taps of phase 0)
+                        else {
+                            uint32_t ws[8];                  // column moved up by vOff rows, so that output r starts at row r
+#pragma unroll
+                            for (int q = 0; q < 7; ++q) ws[q] = __funnelshift_r(wv[q], wv[q + 1], 16 * vOff[j]);
+                            ws[7] = wv[7] >> (16 * vOff[j]);
+                            frac_vfilter<0, 8>(ws, vLo[j], vHi[j], d);
+                        }
+                        emit(j, d);
+                    }
+                }
+                if (MODE == kFracSad) {                       // acc[3j + i] <- acc[3j + i + 1]: after the three planes every sum is back in place
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) { const uint32_t a0 = acc[3 * j]; acc[3 * j] = acc[3 * j + 1]; acc[3 * j + 1] = acc[3 * j + 2]; acc[3 * j + 2] = a0; }
+                }
+            }
+        }
+        if (MODE != kFracSad) {
+            __syncwarp();
+            // Hadamard pass: lane = coefficient row r, one candidate per pass.  (This loop, the plane loop above and the iteration loop
+            // stay rolled: unrolled, the bodies of the two stages exceed the 32 KB instruction cache next to the SM -- measured on the
+            // first version of this form: 28 % of the stall samples "no instruction".)
+#pragma unroll 1
+            for (int j = 0; j < 3; ++j) {
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    if (!HALF && i == 1 && j == 1) continue;
+                    int e[8];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) e[c] = (int)S.t[j * 3 + i][s][c * 8 + r];
+                    uint32_t tot;
+                    if (MODE == kFracHad8) {
+                        hadamard_inplace<8>(e);
+                        uint32_t sm = 0;
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) sm = __sad(e[c], 0, sm);
+                        sm += __shfl_xor_sync(0xFFFFFFFFu, sm, 1); sm += __shfl_xor_sync(0xFFFFFFFFu, sm, 2); sm += __shfl_xor_sync(0xFFFFFFFFu, sm, 4);
+                        tot = (sm + 2) >> 2;                                    // xCalcHADs8x8 rounding
+                    } else {
+                        hadamard_inplace<4>(e); hadamard_inplace<4>(e + 4);
+                        uint32_t sa = 0, sb = 0;
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) { sa = __sad(e[c], 0, sa); sb = __sad(e[c + 4], 0, sb); }
+                        sa += __shfl_xor_sync(0xFFFFFFFFu, sa, 1); sa += __shfl_xor_sync(0xFFFFFFFFu, sa, 2);
+                        sb += __shfl_xor_sync(0xFFFFFFFFu, sb, 1); sb += __shfl_xor_sync(0xFFFFFFFFu, sb, 2);
+                        uint32_t bl = ((sa + 1) >> 1) + ((sb + 1) >> 1);       // xCalcHADs4x4 rounding, per 4x4 block
+                        bl += __shfl_xor_sync(0xFFFFFFFFu, bl, 4);
+                        tot = bl;
+                    }
+                    acc[i] += tot;                            // identical on the eight lanes of the octet
+                }
+                // acc[g] <- acc[g + 3]: the sums of candidate row j sit in acc[0..2] during its pass; after three passes all are back in place
+                const uint32_t a0 = acc[0], a1 = acc[1], a2 = acc[2];
+#pragma unroll
+                for (int g = 0; g < 6; ++g) acc[g] = acc[g + 3];
+                acc[6] = a0; acc[7] = a1; acc[8] = a2;
+            }
+        }
+        __syncwarp();
+    }
+    if (MODE == kFracSad) {                                   // column sums -> tile sums
+#pragma unroll
+        for (int g = 0; g < 9; ++g) {
+            acc[g] += __shfl_xor_sync(0xFFFFFFFFu, acc[g], 1); acc[g] += __shfl_xor_sync(0xFFFFFFFFu, acc[g], 2); acc[g] += __shfl_xor_sync(0xFFFFFFFFu, acc[g], 4);
+        }
+    }
+}
+
+// One group: `nIn` PUs (first PU `first`), each on `m` = 4, 2 or 1 octets.
+template <int MODE>
+__device__ __forceinline__ void frac_group(const FracParams& p, FracScratch4& S, const int lane, const int first, const int nIn, const int m) {
+    const int s = lane >> 3, k = lane & 7;
+    const int puLocal = m == 4 ? 0 : (m == 2 ? s >> 1 : s);
+    FracOct O;
+    O.valid = puLocal < nIn;
+    const int n = first + (O.valid ? puLocal : 0);
+    const FracPu P = p.pus[n];
+    const int slot = p.slots ? p.slots[n] : n;
+    O.refPu = p.ref + (long long)(P.y + P.mvy - 4) * p.refPitch + (P.x + P.mvx - 4);
+    O.curOff = (long long)P.y * p.curPitch + P.x;
+    O.w = P.w; O.h = P.h;
+    O.ntxT = (P.w + 7) >> 3; O.nT = O.ntxT * ((P.h + 7) >> 3); O.rcp = kTileRcp[O.ntxT];
+    O.t0 = s & (m - 1); O.tstep = m;
+    const int iters = __reduce_max_sync(0xFFFFFFFFu, O.valid ? (O.nT + m - 1) >> (m >> 1) : 0);   // ceil(nT / m), m = 1, 2, 4
+    const bool writer = O.valid && O.t0 == 0;               // the PU's first octet reports
+    // grid position g = 3 * (dy index) + (dx index) -> index in the reference's candidate tables (TEncSearch.cpp:51-75), 4 bits each
+    const unsigned long long lutHalf = 0x827403615ull, lutQter = 0x827605413ull;
+    int cx = 0, cy = 0;                                      // stage centre, quarter-pel offset from the integer MV
+    uint32_t bestCost = 0, bestMvc = 0;
+#pragma unroll 1
+    for (int stage = 0; stage < 2; ++stage) {
+        const int step = stage == 0 ? 2 : 1;
+        uint32_t acc[9];
+        if (stage == 0) frac_eval_oct<MODE, true>(p, O, S, lane, iters, 0, 0, acc);
+        else frac_eval_oct<MODE, false>(p, O, S, lane, iters, cx, cy, acc);
+        if (m >= 2) {                                        // warp-uniform: add up the octets of a PU
+#pragma unroll
+            for (int g = 0; g < 9; ++g) acc[g] += __shfl_xor_sync(0xFFFFFFFFu, acc[g], 8);
+        }
+        if (m == 4) {
+#pragma unroll
+            for (int g = 0; g < 9; ++g) acc[g] += __shfl_xor_sync(0xFFFFFFFFu, acc[g], 16);
+        }
+        // decision per PU: lane k of an octet costs candidate k, every lane candidate 8; key = cost | table index | grid position
+        const unsigned long long lut = stage == 0 ? lutHalf : lutQter;
+        uint32_t distK = acc[0];
+#pragma unroll
+        for (int g = 1; g < 8; ++g) distK = k == g ? acc[g] : distK;
+        if (MODE != kFracSad && stage == 1 && k == 4) distK = bestCost - bestMvc;      // the half-pel winner, evaluated in stage 0
+        const int gi = k % 3, gj = k / 3;
+        const int bx = 4 * P.mvx + cx, by = 4 * P.mvy + cy;
+        const uint32_t costK = distK + frac_mv_cost(p.lambda, bx + (gi - 1) * step, by + (gj - 1) * step, P.predx, P.predy);
+        const uint32_t cost8 = acc[8] + frac_mv_cost(p.lambda, bx + step, by + step, P.predx, P.predy);
+        const uint32_t tK = (uint32_t)(lut >> (4 * k)) & 15u, t8 = (uint32_t)(lut >> 32) & 15u;
+        if (p.cand && writer) {
+            p.cand[(size_t)slot * 18 + stage * 9 + tK] = costK;
+            if (k == 0) p.cand[(size_t)slot * 18 + stage * 9 + t8] = cost8;
+        }
+        unsigned long long key = ((unsigned long long)costK << 8) | (tK << 4) | (uint32_t)k;
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) { const unsigned long long q = __shfl_xor_sync(0xFFFFFFFFu, key, o); key = q < key ? q : key; }
+        const unsigned long long key8 = ((unsigned long long)cost8 << 8) | (t8 << 4) | 8u;
+        key = key8 < key ? key8 : key;
+        const int win = (int)(key & 15u);
+        cx += ((win % 3) - 1) * step; cy += ((win / 3) - 1) * step;
+        bestCost = (uint32_t)(key >> 8);
+        bestMvc = frac_mv_cost(p.lambda, 4 * P.mvx + cx, 4 * P.mvy + cy, P.predx, P.predy);
+    }
+    if (writer && k == 0) p.out[slot] = make_int4(4 * P.mvx + cx, 4 * P.mvy + cy, (int)bestCost, (int)(bestCost - bestMvc));
+}
+
+// Throughput form: every warp takes groups of the list (see FracParams::segPu), large PUs first.
+__global__ void __launch_bounds__(kFracThreads) me_frac_group_kernel(const FracGroupParams p) {
+    __shared__ FracScratch4 scratch[kFracWarps];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int stride = (int)gridDim.x * kFracWarps, nGroups = p.segGrp[5];
+    for (int G = (int)blockIdx.x * kFracWarps + warp; G < nGroups; G += stride) {
+        int seg = 0;
+#pragma unroll
+        for (int q = 1; q < 5; ++q) seg += G >= p.segGrp[q];
+        const int per = seg == 0 ? 1 : (seg <= 2 ? 2 : 4);
+        const int first = p.segPu[seg] + (G - p.segGrp[seg]) * per;
+        const int nIn = min(per, p.segPu[seg + 1] - first);
+        bool had8 = seg == 1 || seg == 3;
+        if (seg == 0) had8 = ((p.pus[first].w | p.pus[first].h) & 7) == 0;
+        if (!p.useHad) frac_group<kFracSad>(p, scratch[warp], lane, first, nIn, 4 / per);
+        else if (had8) frac_group<kFracHad8>(p, scratch[warp], lane, first, nIn, 4 / per);
+        else frac_group<kFracHad4>(p, scratch[warp], lane, first, nIn, 4 / per);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------

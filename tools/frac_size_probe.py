@@ -14,7 +14,8 @@ from _pkg import hm  # noqa: E402
 from synth import luma_frames, pad_plane  # noqa: E402
 
 W, H, R, M = 1920, 1080, 64, 80
-use_had = not (len(sys.argv) > 1 and sys.argv[1] == "sad")
+use_had = "sad" not in sys.argv[1:]
+only = [a for a in sys.argv[1:] if "x" in a]          # e.g. 64x64: that size only (profiling runs)
 f = luma_frames(W, H, 2)
 cur, ref = pad_plane(f[1], M, M, np.uint8), pad_plane(f[0], M, M, np.uint8)
 me = hm.MotionEstimator(0, R)
@@ -24,6 +25,8 @@ me.upload(pc, cur); me.upload(pr, ref)
 rng = np.random.default_rng(7)
 out = {}
 for (w, h) in [(8, 8), (8, 4), (4, 8), (16, 8), (8, 16), (16, 4), (16, 12), (12, 16), (16, 16), (32, 8), (32, 32), (64, 16), (64, 64)]:
+    if only and "%dx%d" % (w, h) not in only:
+        continue
     xs, ys = np.meshgrid(np.arange(0, W - w + 1, w), np.arange(0, H - h + 1, h))
     n = xs.size
     reps = max(1, 150000 // n)                 # small grids are repeated so that every launch fills the GPU
