@@ -952,17 +952,54 @@ int mc_cost_planes(hmme_ctx* c, const hmme_plane* cur, const hmme_plane* ref, co
     rc = ensure_pus(c, (size_t)npus);                       // dPus (32 B per entry) holds the 24- or 32-byte records, dFrac the results
     if (rc != HMME_OK) return rc;
     static_assert(sizeof(hmme_mc_pu) == 24 && sizeof(hmme_mc_bi_pu) == 32 && sizeof(FracPu) == 32, "record sizes");
-    CU_TRY(c, cudaMemcpyAsync(c->dPus, pus, (size_t)npus * stride * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
-    McParams mp{};
+    // The list goes to the device ordered by segment of the group kernel (counting sort; the PUs of four tiles or more by tile count, large
+    // to small), results come back in list order through the slot table.
+    static const int formEnv = std::getenv("HMME_MC_FORM") ? std::atoi(std::getenv("HMME_MC_FORM")) : 2;   // experiments: 1 = one PU per warp, list order
+    const bool group = formEnv != 1 && npus >= 64;
+    McGroupParams mp{};
+    if (group) {
+        auto key = [&](int n) {
+            const int32_t* u = pus + (size_t)n * stride;
+            const int sg = frac_segment(u[2], u[3]);
+            return sg == 0 ? 64 - ((u[2] + 7) / 8) * ((u[3] + 7) / 8) : 60 + sg;       // 0..60 for 64..4 tiles, 61..64 for segments 1..4
+        };
+        std::vector<int> start(66, 0), idx(npus);
+        for (int n = 0; n < npus; ++n) start[key(n) + 1] += 1;
+        long long segCount[5] = {0, 0, 0, 0, 0};
+        for (int k = 0; k < 65; ++k) segCount[k <= 60 ? 0 : k - 60] += start[k + 1];
+        for (int k = 0; k < 65; ++k) start[k + 1] += start[k];
+        std::vector<int32_t> sorted((size_t)npus * stride);
+        for (int n = 0; n < npus; ++n) {
+            const int at = start[key(n)]++;
+            idx[at] = n;
+            std::memcpy(&sorted[(size_t)at * stride], pus + (size_t)n * stride, stride * sizeof(int32_t));
+        }
+        CU_TRY(c, cudaMemcpyAsync(c->dPus, sorted.data(), (size_t)npus * stride * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+        CU_TRY(c, cudaMemcpyAsync(c->dSlots, idx.data(), (size_t)npus * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        CU_TRY(c, cudaStreamSynchronize(c->stream));       // the two vectors are pageable and go out of scope
+        mp.slots = c->dSlots;
+        mp.segPu[0] = 0; mp.segGrp[0] = 0;
+        for (int q = 0; q < 5; ++q) {
+            mp.segPu[q + 1] = mp.segPu[q] + (int)segCount[q];
+            mp.segGrp[q + 1] = mp.segGrp[q] + (int)((segCount[q] + kFracSegPus[q] - 1) / kFracSegPus[q]);
+        }
+    } else
+        CU_TRY(c, cudaMemcpyAsync(c->dPus, pus, (size_t)npus * stride * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
     mp.cur = origin_ptr(cur); mp.ref = reinterpret_cast<const uint8_t*>(origin_ptr(ref));
     mp.ref1 = bi ? reinterpret_cast<const uint8_t*>(origin_ptr(ref1)) : nullptr;
     mp.curPitch = cur->pitch; mp.refPitch = ref->pitch; mp.ref1Pitch = bi ? ref1->pitch : 0; mp.curBytes = cur->elemBytes;
     mp.pus = reinterpret_cast<const int*>(c->dPus); mp.npus = npus; mp.useHad = useHad ? 1 : 0;
     mp.out = reinterpret_cast<uint32_t*>(c->dFrac);
-    const int ctas = std::max(1, std::min((npus + kFracWarps - 1) / kFracWarps, c->prop.multiProcessorCount * 512));   // one PU per warp (the list is not ordered here)
+    const int units = group ? mp.segGrp[5] : npus;         // one group / one PU per warp
+    const int ctas = std::max(1, std::min((units + kFracWarps - 1) / kFracWarps, c->prop.multiProcessorCount * 512));
     CU_TRY(c, cudaEventRecord(c->evF0, c->stream));
-    if (bi) me_mc_cost_kernel<true><<<ctas, kFracThreads, 0, c->stream>>>(mp);
-    else me_mc_cost_kernel<false><<<ctas, kFracThreads, 0, c->stream>>>(mp);
+    if (group) {
+        if (bi) me_mc_group_kernel<true><<<ctas, kFracThreads, 0, c->stream>>>(mp);
+        else me_mc_group_kernel<false><<<ctas, kFracThreads, 0, c->stream>>>(mp);
+    } else {
+        if (bi) me_mc_cost_kernel<true><<<ctas, kFracThreads, 0, c->stream>>>(mp);
+        else me_mc_cost_kernel<false><<<ctas, kFracThreads, 0, c->stream>>>(mp);
+    }
     CU_TRY(c, cudaEventRecord(c->evF1, c->stream));
     c->evFracValid = true;
     c->launches += 1;

@@ -988,4 +988,235 @@ __global__ void __launch_bounds__(kFracThreads) me_mc_cost_kernel(const McParams
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// Group form of the distortion kernel: the same four tile processors per warp as me_frac_group_kernel, one candidate per PU.  With one PU
+// per warp (me_mc_cost_kernel) the 320 one-tile and 128 two-tile partitions of a CTU leave three quarters / half of the warp idle in the
+// V step and the Hadamard pass; here they run four / two at a time.  Filter phases are lane state (every octet has its own PU), so the
+// integer phases go through the general filter with the taps {0,0,0,64,0,0,0,0} unless the whole warp has them.
+struct McGroupParams : McParams {
+    const int* slots;           // result index of PU n of the (segment-ordered) list
+    int segPu[6], segGrp[6];    // as FracGroupParams
+};
+
+template <bool BI>
+struct __align__(16) McScratch4 {
+    int16_t cur[4][72];                  // [octet][row * 8 + column]
+    uint32_t h[BI ? 2 : 1][4][104];      // [list][octet][column * 12 + row pair]
+    int16_t t[4][72];                    // [octet][column * 8 + coefficient row]
+};
+
+template <int MODE, bool BI>
+__device__ __forceinline__ void mc_group(const McGroupParams& p, McScratch4<BI>& S, const int lane, const int first, const int nIn, const int m) {
+    constexpr int NL = BI ? 2 : 1;
+    const int s = lane >> 3, r = lane & 7;
+    const int puLocal = m == 4 ? 0 : (m == 2 ? s >> 1 : s);
+    const bool valid = puLocal < nIn;
+    const int n = first + (valid ? puLocal : 0);
+    const int* pu = p.pus + (size_t)n * (BI ? 8 : 6);
+    const int Px = pu[0], Py = pu[1], Pw = pu[2], Ph = pu[3];
+    const int slot = p.slots ? p.slots[n] : n;
+    uint32_t cLo[NL], cHi[NL], vLo[NL], vHi[NL];
+    bool allInt[NL];
+    const uint8_t* refPu[NL];
+    long long pitchL[NL];
+#pragma unroll
+    for (int l = 0; l < NL; ++l) {
+        const int mx = pu[4 + 2 * l], my = pu[5 + 2 * l];
+        cLo[l] = kLumaPack[mx & 3][0]; cHi[l] = kLumaPack[mx & 3][1];
+        vLo[l] = kLumaPack[my & 3][0]; vHi[l] = kLumaPack[my & 3][1];
+        allInt[l] = __all_sync(0xFFFFFFFFu, (my & 3) == 0);
+        pitchL[l] = l ? p.ref1Pitch : p.refPitch;
+        // patch origin: the integer part of the MV is folded in, so the taps of output 0 always start at patch index 1
+        refPu[l] = (l ? p.ref1 : p.ref) + (long long)(Py + (my >> 2) - 4) * pitchL[l] + (Px + (mx >> 2) - 4);
+    }
+    const long long curOff = (long long)Py * p.curPitch + Px;
+    const int ntxT = (Pw + 7) >> 3, nT = ntxT * ((Ph + 7) >> 3), rcp = kTileRcp[ntxT];
+    const int t0 = s & (m - 1);
+    const int iters = __reduce_max_sync(0xFFFFFFFFu, valid ? (nT + m - 1) >> (m >> 1) : 0);
+    uint32_t acc = 0;
+
+    uint32_t nW[NL][2][4], nC[4];
+    int ntw = 8, nth = 8;
+    auto fetch = [&](const int t) {
+#pragma unroll
+        for (int l = 0; l < NL; ++l)
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) nW[l][k][q] = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) nC[q] = 0;
+        if (valid && t < nT) {
+            const int ty = ((t * rcp) >> 16) * 8, tx = t * 8 - ty * ntxT;
+            ntw = min(8, Pw - tx); nth = min(8, Ph - ty);
+#pragma unroll
+            for (int l = 0; l < NL; ++l)
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const uint8_t* g = refPu[l] + (long long)(ty + 2 * r + k) * pitchL[l] + tx;
+                    const uint32_t sh = 8u * (uint32_t)((uintptr_t)g & 3);
+                    const uint32_t* qa = reinterpret_cast<const uint32_t*>((uintptr_t)g & ~(uintptr_t)3);
+                    const uint32_t a0 = __ldg(qa), a1 = __ldg(qa + 1), a2 = __ldg(qa + 2), a3 = __ldg(qa + 3), a4 = __ldg(qa + 4);
+                    nW[l][k][0] = __funnelshift_r(a0, a1, sh); nW[l][k][1] = __funnelshift_r(a1, a2, sh);
+                    nW[l][k][2] = __funnelshift_r(a2, a3, sh); nW[l][k][3] = __funnelshift_r(a3, a4, sh);
+                }
+            if (r < nth) {
+                const long long o = curOff + (long long)(ty + r) * p.curPitch + tx;
+                if (p.curBytes == 1) {
+                    const uint8_t* g = static_cast<const uint8_t*>(p.cur) + o;
+                    const uint32_t sh = 8u * (uint32_t)((uintptr_t)g & 3);
+                    const uint32_t* qa = reinterpret_cast<const uint32_t*>((uintptr_t)g & ~(uintptr_t)3);
+                    const uint32_t a0 = __ldg(qa), a1 = __ldg(qa + 1), a2 = __ldg(qa + 2);
+                    const uint32_t b0 = __funnelshift_r(a0, a1, sh), b1 = __funnelshift_r(a1, a2, sh);
+                    nC[0] = __byte_perm(b0, 0, 0x4140); nC[1] = __byte_perm(b0, 0, 0x4342);
+                    nC[2] = __byte_perm(b1, 0, 0x4140); nC[3] = __byte_perm(b1, 0, 0x4342);
+                } else {
+                    const int16_t* g = static_cast<const int16_t*>(p.cur) + o;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) nC[q] = ((uint32_t)(uint16_t)g[2 * q]) | ((uint32_t)(uint16_t)g[2 * q + 1] << 16);
+                }
+                if (ntw < 8) { nC[2] = 0; nC[3] = 0; }
+            }
+        }
+    };
+    int t = t0;
+    fetch(t);
+#pragma unroll 1
+    for (int it = 0; it < iters; ++it) {
+        uint32_t W[NL][2][4];
+#pragma unroll
+        for (int l = 0; l < NL; ++l)
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) W[l][k][q] = nW[l][k][q];
+        *reinterpret_cast<uint4*>(&S.cur[s][r * 8]) = make_uint4(nC[0], nC[1], nC[2], nC[3]);
+        const int tw = ntw, th = nth;
+        t += m;
+        if (it + 1 < iters) fetch(t);
+#pragma unroll
+        for (int l = 0; l < NL; ++l) {                       // H step: rows 2r, 2r+1 of the list's patch, output j from bytes j+1 .. j+8
+            int out[2][8];
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                uint32_t L[13];
+#pragma unroll
+                for (int o = 1; o < 13; ++o) L[o] = (o & 3) ? __funnelshift_r(W[l][k][o >> 2], W[l][k][(o >> 2) + 1], 8 * (o & 3)) : W[l][k][o >> 2];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) out[k][j] = dp4a_us(L[j + 5], cHi[l], dp4a_us(L[j + 1], cLo[l], 0));
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) S.h[l][s][j * 12 + r] = __byte_perm(out[0][j], out[1][j], 0x5410);
+        }
+        __syncwarp();
+        {   // V step: lane = column r of the octet's tile
+            int d[8];
+            const bool colDead = MODE != kFracHad8 && r >= tw;
+            if (!BI) {
+                const uint4 ha = *reinterpret_cast<const uint4*>(&S.h[0][s][r * 12]), hb = *reinterpret_cast<const uint4*>(&S.h[0][s][r * 12 + 4]);
+                uint32_t wv[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
+                if (MODE != kFracHad8) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) wv[q] = colDead ? 0u : wv[q];
+                }
+                if (allInt[0]) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        d[2 * q] = __vimin_s32_relu(((int)(int16_t)(wv[q + 2] & 0xFFFFu) + 32) >> 6, 255);
+                        d[2 * q + 1] = __vimin_s32_relu((((int)wv[q + 2] >> 16) + 32) >> 6, 255);
+                    }
+                } else frac_vfilter<1, 8>(wv, vLo[0], vHi[0], d);
+            } else {
+                int qs[8];
+#pragma unroll
+                for (int rr = 0; rr < 8; ++rr) qs[rr] = 64;                 // addAvg rounding
+#pragma unroll
+                for (int l = 0; l < NL; ++l) {
+                    const uint4 ha = *reinterpret_cast<const uint4*>(&S.h[l][s][r * 12]), hb = *reinterpret_cast<const uint4*>(&S.h[l][s][r * 12 + 4]);
+                    uint32_t wv[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
+                    if (MODE != kFracHad8) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) wv[q] = colDead ? 0u : wv[q];
+                    }
+                    int q8[8];
+                    if (allInt[l]) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) { q8[2 * q] = (int)(int16_t)(wv[q + 2] & 0xFFFFu); q8[2 * q + 1] = (int)wv[q + 2] >> 16; }
+                    } else frac_vfilter<1, 8, true>(wv, vLo[l], vHi[l], q8);
+#pragma unroll
+                    for (int rr = 0; rr < 8; ++rr) qs[rr] += q8[rr];
+                }
+#pragma unroll
+                for (int rr = 0; rr < 8; ++rr) d[rr] = __vimin_s32_relu(qs[rr] >> 7, 255);
+            }
+#pragma unroll
+            for (int rr = 0; rr < 8; ++rr) d[rr] = (int)S.cur[s][rr * 8 + r] - d[rr];
+            if (MODE != kFracHad8 && th < 8) { d[4] = 0; d[5] = 0; d[6] = 0; d[7] = 0; }
+            if (MODE == kFracSad) {
+                uint32_t sm = 0;
+#pragma unroll
+                for (int rr = 0; rr < 8; ++rr) sm = __sad(d[rr], 0, sm);
+                acc += sm;                                       // column sums: added over the octet at the end
+            } else {
+                if (MODE == kFracHad8) hadamard_inplace<8>(d);
+                else { hadamard_inplace<4>(d); hadamard_inplace<4>(d + 4); }
+                uint4 pk;
+                pk.x = __byte_perm(d[0], d[1], 0x5410); pk.y = __byte_perm(d[2], d[3], 0x5410);
+                pk.z = __byte_perm(d[4], d[5], 0x5410); pk.w = __byte_perm(d[6], d[7], 0x5410);
+                *reinterpret_cast<uint4*>(&S.t[s][r * 8]) = pk;
+            }
+        }
+        if (MODE != kFracSad) {
+            __syncwarp();
+            int e[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) e[c] = (int)S.t[s][c * 8 + r];
+            if (MODE == kFracHad8) {
+                hadamard_inplace<8>(e);
+                uint32_t sm = 0;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) sm = __sad(e[c], 0, sm);
+                sm += __shfl_xor_sync(0xFFFFFFFFu, sm, 1); sm += __shfl_xor_sync(0xFFFFFFFFu, sm, 2); sm += __shfl_xor_sync(0xFFFFFFFFu, sm, 4);
+                acc += (sm + 2) >> 2;                            // identical on the eight lanes of the octet
+            } else {
+                hadamard_inplace<4>(e); hadamard_inplace<4>(e + 4);
+                uint32_t sa = 0, sb = 0;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) { sa = __sad(e[c], 0, sa); sb = __sad(e[c + 4], 0, sb); }
+                sa += __shfl_xor_sync(0xFFFFFFFFu, sa, 1); sa += __shfl_xor_sync(0xFFFFFFFFu, sa, 2);
+                sb += __shfl_xor_sync(0xFFFFFFFFu, sb, 1); sb += __shfl_xor_sync(0xFFFFFFFFu, sb, 2);
+                uint32_t bl = ((sa + 1) >> 1) + ((sb + 1) >> 1);
+                bl += __shfl_xor_sync(0xFFFFFFFFu, bl, 4);
+                acc += bl;
+            }
+        }
+        __syncwarp();
+    }
+    if (MODE == kFracSad) { acc += __shfl_xor_sync(0xFFFFFFFFu, acc, 1); acc += __shfl_xor_sync(0xFFFFFFFFu, acc, 2); acc += __shfl_xor_sync(0xFFFFFFFFu, acc, 4); }
+    if (m >= 2) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, 8);
+    if (m == 4) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, 16);
+    if (valid && t0 == 0 && r == 0) p.out[slot] = acc;
+}
+
+template <bool BI>
+__global__ void __launch_bounds__(kFracThreads) me_mc_group_kernel(const McGroupParams p) {
+    __shared__ McScratch4<BI> scratch[kFracWarps];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int stride = (int)gridDim.x * kFracWarps, nGroups = p.segGrp[5];
+    for (int G = (int)blockIdx.x * kFracWarps + warp; G < nGroups; G += stride) {
+        int seg = 0;
+#pragma unroll
+        for (int q = 1; q < 5; ++q) seg += G >= p.segGrp[q];
+        const int per = seg == 0 ? 1 : (seg <= 2 ? 2 : 4);
+        const int first = p.segPu[seg] + (G - p.segGrp[seg]) * per;
+        const int nIn = min(per, p.segPu[seg + 1] - first);
+        bool had8 = seg == 1 || seg == 3;
+        if (seg == 0) { const int* pu = p.pus + (size_t)first * (BI ? 8 : 6); had8 = ((pu[2] | pu[3]) & 7) == 0; }
+        if (!p.useHad) mc_group<kFracSad, BI>(p, scratch[warp], lane, first, nIn, 4 / per);
+        else if (had8) mc_group<kFracHad8, BI>(p, scratch[warp], lane, first, nIn, 4 / per);
+        else mc_group<kFracHad4, BI>(p, scratch[warp], lane, first, nIn, 4 / per);
+    }
+}
+
 }  // namespace hmme
