@@ -510,7 +510,7 @@ def main():
         ach = frac_ops / (fkm * 1e-3) if fkm > 0 else 0.0
         frac = {"scope": "fractional-pel refinement (xPatternSearchFracDIF: 9 half-pel + 9 quarter-pel candidates, 8-tap interpolation, Hadamard cost) "
                          "of all 593 partitions of every CTU, from the integer winners left on the device",
-                "kernel": "me_frac_kernel", "pus_per_frame": total_jobs * NPARTS, "kernel_ms": fkm, "kernel_ms_sad": fksm,
+                "kernel": "me_frac_group_kernel", "pus_per_frame": total_jobs * NPARTS, "kernel_ms": fkm, "kernel_ms_sad": fksm,
                 "pu_refinements_per_s": total_jobs * NPARTS / (fkm * 1e-3) if fkm else None, "pu_pixels_per_s": pu_px / (fkm * 1e-3) if fkm else None,
                 "search_plus_refine_ms_per_frame": both_ms, "search_plus_refine_frames_per_s": 1e3 / both_ms if both_ms else None, "steps": nfr,
                 "roofline": {"bound": "int_issue", "achieved": ach / 1e12, "peak": 2.0 * peak["lane_ops_per_s"] / 1e12, "unit": "T int-op/s",
@@ -520,7 +520,7 @@ def main():
                              "ops_per_ctu": FRAC_OPS_PER_CTU,
                              "peak_source": "peak = both integer pipes (ALU + FMA-heavy/IMAD, 2 x the live-measured 64 lanes/clk/SM = every issue slot), the same ceiling as the "
                                             "search kernel's; frac = frac_issue = achieved / peak; frac_one_pipe = against one pipe (round 1's denominator)"},
-                "timer": "kernel_ms: CUDA events around me_frac_kernel on its stream; search_plus_refine: CUDA events around K frames on one context/stream, "
+                "timer": "kernel_ms: CUDA events around me_frac_group_kernel on its stream; search_plus_refine: CUDA events around K frames on one context/stream, "
                          "resident inputs"}
 
     # ------------------------------------------------------------------ row f3: motion-compensated distortion at quarter-pel MVs
@@ -548,7 +548,7 @@ def main():
         km["bi_hadamard"] = float(np.mean(tb[1:]))
         mc = {"scope": "distortion of the motion-compensated uni-prediction (8-tap interpolation at a quarter-pel MV) of all 593 partitions of every CTU: "
                        "the arithmetic of xGetTemplateCost (SAD) / uni-directional merge candidates (Hadamard)",
-              "kernel": "me_mc_cost_kernel", "pus": njobs * NPARTS, "kernel_ms_sad": km["sad"], "kernel_ms_hadamard": km["hadamard"], "kernel_ms_bi_hadamard": km["bi_hadamard"],
+              "kernel": "me_mc_group_kernel", "pus": njobs * NPARTS, "kernel_ms_sad": km["sad"], "kernel_ms_hadamard": km["hadamard"], "kernel_ms_bi_hadamard": km["bi_hadamard"],
               "pu_pixels_per_s_sad": njobs * 24 * 4096 / (km["sad"] * 1e-3), "timer": "CUDA events around the kernel on its stream, resident planes"}
 
     # ------------------------------------------------------------------ the call the encoder makes: synchronous per-CTU search with HOST pointers

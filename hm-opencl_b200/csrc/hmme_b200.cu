@@ -247,6 +247,27 @@ int mark_compute(hmme_ctx* c) {
     return HMME_OK;
 }
 
+// Order of a PU list for the group kernels: by segment (hmme::frac_segment), the PUs of four tiles or more by tile count, large to small;
+// stable inside equal keys.  Counting sort: the lists have a few hundred thousand entries.  wh(n, w, h) reports PU n's size.
+template <typename WH>
+void segment_order(int npus, WH wh, std::vector<int>& idx, long long (&segCount)[5], int& nBig, long long& totalTiles) {
+    auto key = [&](int n, int& tiles) {
+        int w, h;
+        wh(n, w, h);
+        tiles = ((w + 7) / 8) * ((h + 7) / 8);
+        const int sg = frac_segment(w, h);
+        return sg == 0 ? 64 - std::min(tiles, 64) : 60 + sg;   // 0..60 for 64..4 tiles, 61..64 for segments 1..4
+    };
+    std::vector<int> start(66, 0);
+    nBig = 0; totalTiles = 0;
+    for (int n = 0, t; n < npus; ++n) { start[key(n, t) + 1] += 1; nBig += t >= kFracCoopTiles; totalTiles += t; }
+    for (int q = 0; q < 5; ++q) segCount[q] = 0;
+    for (int k = 0; k < 65; ++k) segCount[k <= 60 ? 0 : k - 60] += start[k + 1];
+    for (int k = 0; k < 65; ++k) start[k + 1] += start[k];
+    idx.resize(npus);
+    for (int n = 0, t; n < npus; ++n) idx[start[key(n, t)]++] = n;
+}
+
 // segment boundaries of the group kernel from the number of PUs in each segment (the list is ordered by segment)
 void frac_segments(const long long (&cnt)[5], FracGroupParams& fp) {
     fp.segPu[0] = 0; fp.segGrp[0] = 0;
@@ -864,15 +885,12 @@ int hmme_refine_frac(hmme_ctx* c, const hmme_plane* cur, const hmme_plane* ref, 
     if (rc != HMME_OK) return rc;
     static_assert(sizeof(hmme_pu) == sizeof(FracPu) && sizeof(hmme_frac_result) == sizeof(int4), "ABI structs mirror the kernel's");
     // PUs by 8x8-tile count, large to small (longest-first scheduling; the large ones get a CTA each); results go back to list order
-    auto tiles = [&](int i) { return ((pus[i].w + 7) / 8) * ((pus[i].h + 7) / 8); };
-    auto seg = [&](int i) { return frac_segment(pus[i].w, pus[i].h); };
-    std::vector<int> idx(npus);
-    for (int i = 0; i < npus; ++i) idx[i] = i;
-    std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return seg(a) != seg(b) ? seg(a) < seg(b) : tiles(a) > tiles(b); });
-    std::vector<hmme_pu> sorted(npus);
+    std::vector<int> idx;
     int nBig = 0;
-    long long totalTiles = 0, segCount[5] = {0, 0, 0, 0, 0};
-    for (int i = 0; i < npus; ++i) { sorted[i] = pus[idx[i]]; nBig += tiles(idx[i]) >= kFracCoopTiles; totalTiles += tiles(idx[i]); segCount[seg(idx[i])] += 1; }
+    long long totalTiles = 0, segCount[5];
+    segment_order(npus, [&](int n, int& w, int& h) { w = pus[n].w; h = pus[n].h; }, idx, segCount, nBig, totalTiles);
+    std::vector<hmme_pu> sorted(npus);
+    for (int i = 0; i < npus; ++i) sorted[i] = pus[idx[i]];
     CU_TRY(c, cudaMemcpyAsync(c->dPus, sorted.data(), (size_t)npus * sizeof(hmme_pu), cudaMemcpyHostToDevice, c->stream));
     CU_TRY(c, cudaMemcpyAsync(c->dSlots, idx.data(), (size_t)npus * sizeof(int), cudaMemcpyHostToDevice, c->stream));
     CU_TRY(c, cudaStreamSynchronize(c->stream));           // the two vectors are pageable and go out of scope
@@ -958,22 +976,12 @@ int mc_cost_planes(hmme_ctx* c, const hmme_plane* cur, const hmme_plane* ref, co
     const bool group = formEnv != 1 && npus >= 64;
     McGroupParams mp{};
     if (group) {
-        auto key = [&](int n) {
-            const int32_t* u = pus + (size_t)n * stride;
-            const int sg = frac_segment(u[2], u[3]);
-            return sg == 0 ? 64 - ((u[2] + 7) / 8) * ((u[3] + 7) / 8) : 60 + sg;       // 0..60 for 64..4 tiles, 61..64 for segments 1..4
-        };
-        std::vector<int> start(66, 0), idx(npus);
-        for (int n = 0; n < npus; ++n) start[key(n) + 1] += 1;
-        long long segCount[5] = {0, 0, 0, 0, 0};
-        for (int k = 0; k < 65; ++k) segCount[k <= 60 ? 0 : k - 60] += start[k + 1];
-        for (int k = 0; k < 65; ++k) start[k + 1] += start[k];
+        std::vector<int> idx;
+        int nBig = 0;
+        long long totalTiles = 0, segCount[5];
+        segment_order(npus, [&](int n, int& w, int& h) { w = pus[(size_t)n * stride + 2]; h = pus[(size_t)n * stride + 3]; }, idx, segCount, nBig, totalTiles);
         std::vector<int32_t> sorted((size_t)npus * stride);
-        for (int n = 0; n < npus; ++n) {
-            const int at = start[key(n)]++;
-            idx[at] = n;
-            std::memcpy(&sorted[(size_t)at * stride], pus + (size_t)n * stride, stride * sizeof(int32_t));
-        }
+        for (int i = 0; i < npus; ++i) std::memcpy(&sorted[(size_t)i * stride], pus + (size_t)idx[i] * stride, stride * sizeof(int32_t));
         CU_TRY(c, cudaMemcpyAsync(c->dPus, sorted.data(), (size_t)npus * stride * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
         CU_TRY(c, cudaMemcpyAsync(c->dSlots, idx.data(), (size_t)npus * sizeof(int), cudaMemcpyHostToDevice, c->stream));
         CU_TRY(c, cudaStreamSynchronize(c->stream));       // the two vectors are pageable and go out of scope
