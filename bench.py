@@ -696,7 +696,8 @@ def per_ctu_leg(hm, me, n_cur, n_ref, margin, all_jobs, R, W, H):
                     "spec_hit_frame_ms": p["spec_hit_frame_ms"], "spec_hit_frames_per_s": 1e3 / p["spec_hit_frame_ms"],
                     "spec_drift_frame_ms": p["spec_drift_frame_ms"], "spec_drift_frames_per_s": 1e3 / p["spec_drift_frame_ms"],
                     "spec_hit_rate": p["spec_hit_hits"] / max(1, p["spec_hit_calls"]), "spec_drift_hit_rate": p["spec_drift_hits"] / max(1, p["spec_drift_calls"]),
-                    "tables_equal_sync": p["tables_equal_sync"], "timer": "host wall clock inside tools/spec_probe (includes the picture uploads from pageable memory)"}
+                    "tables_equal_sync": p["tables_equal_sync"], "slowest_of_4_ms": p.get("slowest_ms"),
+                    "timer": "host wall clock inside tools/spec_probe (includes the picture uploads from pageable memory); fastest of 4 timed pictures per mode"}
         else:
             spec = {"error": (r.stderr or r.stdout)[-300:]}
     return {"speculative": spec, "call": "hmme_search_ctu (TEncOpenCL::calcMotionVectors): one CTU, +-%d, host pointers into int16 planes, synchronous" % R,

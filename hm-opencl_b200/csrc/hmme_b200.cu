@@ -285,7 +285,8 @@ int enqueue_frac(hmme_ctx* c, const hmme_plane* cur, const hmme_plane* ref, int 
     fp.curPitch = cur->pitch; fp.refPitch = ref->pitch; fp.curBytes = cur->elemBytes;
     // Large PUs get a CTA each only when the batch is too small for longest-first scheduling to hide a 64-tile PU running on one
     // warp (measured at 1080p: 8 / 30 CTU jobs 0.094 -> 0.035 ms / 0.115 -> 0.086 ms, but 60 jobs 0.156 -> 0.160 and 480 jobs 1.14 -> 1.21)
-    static const int coopEnv = std::getenv("HMME_FRAC_COOP") ? std::atoi(std::getenv("HMME_FRAC_COOP")) : -1;   // experiments: 0 never, 1 always
+    const char* coopStr = std::getenv("HMME_FRAC_COOP");   // experiments and tests: 0 never, 1 always (read per call, so a test can switch forms)
+    const int coopEnv = coopStr ? std::atoi(coopStr) : -1;
     const bool coop = nBig > 0 && (coopEnv >= 0 ? coopEnv != 0 : totalTiles < 32LL * c->prop.multiProcessorCount * 16);
     if (!coop) nBig = 0;
     fp.pus = c->dPus; fp.slots = slots ? c->dSlots : nullptr; fp.npus = npus; fp.nBig = nBig;
@@ -295,7 +296,8 @@ int enqueue_frac(hmme_ctx* c, const hmme_plane* cur, const hmme_plane* ref, int 
     // longest-first load balancing (measured 1080p: 16 CTAs per SM 1.25 ms, 32: 1.20, 128 and more: 1.14; one resident wave: 1.30)
     static const int perSm = std::getenv("HMME_FRAC_CTAS_PER_SM") ? std::max(1, std::atoi(std::getenv("HMME_FRAC_CTAS_PER_SM"))) : 256;
     frac_segments(segCount, fp);
-    static const int formEnv = std::getenv("HMME_FRAC_FORM") ? std::atoi(std::getenv("HMME_FRAC_FORM")) : 2;   // experiments: 1 = one PU per warp (round 1's kernel)
+    const char* formStr = std::getenv("HMME_FRAC_FORM");   // experiments and tests: 1 = one PU per warp (round 1's kernel)
+    const int formEnv = formStr ? std::atoi(formStr) : 2;
     const bool group = !coop && formEnv != 1;
     const int units = group ? fp.segGrp[5] : npus - nBig;   // one group / one PU per warp
     const int ctas = std::max(1, nBig + std::min((units + kFracWarps - 1) / kFracWarps, c->prop.multiProcessorCount * perSm));
@@ -972,8 +974,9 @@ int mc_cost_planes(hmme_ctx* c, const hmme_plane* cur, const hmme_plane* ref, co
     static_assert(sizeof(hmme_mc_pu) == 24 && sizeof(hmme_mc_bi_pu) == 32 && sizeof(FracPu) == 32, "record sizes");
     // The list goes to the device ordered by segment of the group kernel (counting sort; the PUs of four tiles or more by tile count, large
     // to small), results come back in list order through the slot table.
-    static const int formEnv = std::getenv("HMME_MC_FORM") ? std::atoi(std::getenv("HMME_MC_FORM")) : 2;   // experiments: 1 = one PU per warp, list order
-    const bool group = formEnv != 1 && npus >= 64;
+    const char* formStr = std::getenv("HMME_MC_FORM");     // experiments and tests: 1 = one PU per warp in list order, 2 = group form whatever the list length
+    const int formEnv = formStr ? std::atoi(formStr) : 0;
+    const bool group = formEnv == 2 || (formEnv != 1 && npus >= 64);
     McGroupParams mp{};
     if (group) {
         std::vector<int> idx;

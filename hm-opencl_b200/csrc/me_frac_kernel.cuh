@@ -1199,11 +1199,8 @@ __device__ __forceinline__ void mc_group(const McGroupParams& p, McScratch4<BI>&
     if (valid && t0 == 0 && r == 0) p.out[slot] = acc;
 }
 
-#ifndef HMME_MC_MINCTAS
-#define HMME_MC_MINCTAS 1
-#endif
 template <bool BI>
-__global__ void __launch_bounds__(kFracThreads, HMME_MC_MINCTAS) me_mc_group_kernel(const McGroupParams p) {
+__global__ void __launch_bounds__(kFracThreads) me_mc_group_kernel(const McGroupParams p) {
     __shared__ McScratch4<BI> scratch[kFracWarps];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int stride = (int)gridDim.x * kFracWarps, nGroups = p.segGrp[5];

@@ -61,10 +61,27 @@ def test_reference_records_through_c_abi(me):
     assert n == len(recs)
 
 
+@pytest.fixture
+def kernel_form(request, monkeypatch):
+    """Which refinement / distortion kernel a list runs on is the library's choice (list length); the tests pin it, so that every form sees
+    every kind of list: "auto" = the library's choice, "group" = the group kernels (four tile processors per warp), "single" = one PU per
+    warp (round 1's kernels), "coop" = a CTA per large PU.  The library reads these variables per call."""
+    form = request.param
+    env = {"auto": {}, "group": {"HMME_FRAC_COOP": "0", "HMME_FRAC_FORM": "2", "HMME_MC_FORM": "2"},
+           "single": {"HMME_FRAC_COOP": "0", "HMME_FRAC_FORM": "1", "HMME_MC_FORM": "1"}, "coop": {"HMME_FRAC_COOP": "1"}}[form]
+    for k in ("HMME_FRAC_COOP", "HMME_FRAC_FORM", "HMME_MC_FORM"):
+        monkeypatch.delenv(k, raising=False)
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    return form
+
+
+@pytest.mark.parametrize("kernel_form", ["auto", "group", "single"], indirect=True)
 @pytest.mark.parametrize("had,cur16,lam", [(1, 0, 460000), (1, 1, 1000000), (0, 0, 262144), (0, 1, 0), (1, 0, 0), (1, 0, 4500000)])
-def test_random_pus_vs_oracle(me, oracle, had, cur16, lam):
-    """Every PU size of the 593-partition layout plus odd multiples of 4, random integer MVs and predictors, textured content
-    with sub-pel structure; 8-bit and 16-bit (bi-prediction) current planes; Hadamard and SAD."""
+def test_random_pus_vs_oracle(me, oracle, had, cur16, lam, kernel_form):
+    """Every PU size of the 593-partition layout plus odd multiples of 4 (among them two- and three-tile shapes of both Hadamard sizes),
+    random integer MVs and predictors, textured content with sub-pel structure; 8-bit and 16-bit (bi-prediction) current planes;
+    Hadamard and SAD; on every kernel form."""
     rng = np.random.default_rng(1000 + had * 7 + cur16 * 3 + lam % 97)
     W, H, M = 384, 256, 32
     f = luma_frames(W + 2 * M, H + 2 * M, 2, seed=int(rng.integers(1 << 30)))
@@ -72,7 +89,7 @@ def test_random_pus_vs_oracle(me, oracle, had, cur16, lam):
     cur = np.ascontiguousarray(f[1].astype(np.int16))
     if cur16:
         cur = np.ascontiguousarray((2 * cur - rng.integers(0, 256, cur.shape)).astype(np.int16))     # 2*org - pred in [-255, 510]
-    sizes = SIZES + [(20, 28), (4, 4), (60, 4), (4, 60), (28, 36), (64, 12), (40, 40)]
+    sizes = SIZES + [(20, 28), (4, 4), (60, 4), (4, 60), (28, 36), (64, 12), (40, 40), (24, 8), (8, 24), (12, 8), (8, 12), (20, 4), (4, 12), (12, 4)]
     pus = []
     for _ in range(14):
         for (w, h) in sizes:
@@ -231,9 +248,11 @@ def test_mc_cost_reference_records(me):
     pc.free(); pr.free()
 
 
+@pytest.mark.parametrize("kernel_form", ["auto", "single"], indirect=True)
 @pytest.mark.parametrize("had,cur16", [(0, 0), (1, 0), (1, 1), (0, 1)])
-def test_mc_cost_random_vs_oracle(me, oracle, had, cur16):
-    """Every PU size, random quarter-pel MVs (all phases, both signs), SAD and Hadamard, 8-bit and 16-bit current planes."""
+def test_mc_cost_random_vs_oracle(me, oracle, had, cur16, kernel_form):
+    """Every PU size, random quarter-pel MVs (all phases, both signs), SAD and Hadamard, 8-bit and 16-bit current planes; the group
+    kernel (lists of 64 PUs and more: "auto") and the one-PU-per-warp kernel."""
     rng = np.random.default_rng(300 + 2 * had + cur16)
     W, H, M = 384, 256, 32
     f = luma_frames(W + 2 * M, H + 2 * M, 2, seed=int(rng.integers(1 << 30)))
@@ -243,7 +262,7 @@ def test_mc_cost_random_vs_oracle(me, oracle, had, cur16):
         cur = np.ascontiguousarray((2 * cur - rng.integers(0, 256, cur.shape)).astype(np.int16))
     pus = []
     for _ in range(12):
-        for (w, h) in SIZES + [(20, 28), (4, 4), (60, 4), (64, 12), (40, 40)]:
+        for (w, h) in SIZES + [(20, 28), (4, 4), (60, 4), (64, 12), (40, 40), (24, 8), (8, 24), (12, 8), (8, 12), (20, 4), (4, 12)]:
             x, y = int(rng.integers(0, W - w)), int(rng.integers(0, H - h))
             ix = int(rng.integers(max(-M + 4 - x, -20), min(W + M - 12 - ((w + 7) & ~7) - x, 20)))
             iy = int(rng.integers(max(-M + 4 - y, -20), min(H + M - 12 - ((h + 7) & ~7) - y, 20)))
@@ -275,8 +294,9 @@ def test_mc_cost_pu_host_pointers(me, oracle):
             assert got == want, (w, h, mv, had)
 
 
+@pytest.mark.parametrize("kernel_form", ["auto", "single"], indirect=True)
 @pytest.mark.parametrize("had", [0, 1])
-def test_mc_cost_bi_vs_oracle(me, oracle, had):
+def test_mc_cost_bi_vs_oracle(me, oracle, had, kernel_form):
     """Bi-directional PUs (two reference planes, xPredInterBi + addAvg rounding): plane form and host-pointer form."""
     rng = np.random.default_rng(500 + had)
     W, H, M = 320, 192, 32
@@ -284,7 +304,7 @@ def test_mc_cost_bi_vs_oracle(me, oracle, had):
     ref0, ref1, cur = (np.ascontiguousarray(f[k].astype(np.int16)) for k in (0, 2, 1))
     pus = []
     for _ in range(8):
-        for (w, h) in SIZES + [(20, 28), (4, 4), (40, 40)]:
+        for (w, h) in SIZES + [(20, 28), (4, 4), (40, 40), (24, 8), (12, 8), (8, 12)]:
             x, y = int(rng.integers(0, W - w)), int(rng.integers(0, H - h))
             mv = []
             for _l in range(2):
@@ -330,10 +350,11 @@ def test_inter_prediction_error_reference_records(me):
     assert n == len(recs)
 
 
-def test_fuzz_refine_and_mc(me, oracle):
+@pytest.mark.parametrize("kernel_form", ["auto", "group"], indirect=True)
+def test_fuzz_refine_and_mc(me, oracle, kernel_form):
     """Random plane sizes, margins, PU lists (any multiples of 4 up to 64, PUs touching the plane borders so that aprons live in the
-    margins), lambdas, modes and batch sizes -- small batches take the cooperative kernel, large ones the throughput kernel.
-    Soak with HMME_FUZZ_ITERS / HMME_FUZZ_SEED."""
+    margins), lambdas, modes and batch sizes -- "auto": small batches take the cooperative kernel, large ones the group kernel; "group":
+    every list, down to a single PU, on the group kernels (ragged groups, segments with one PU).  Soak with HMME_FUZZ_ITERS / HMME_FUZZ_SEED."""
     import os
     g = np.random.default_rng(int(os.environ.get("HMME_FUZZ_SEED", "2027")))
     for it in range(int(os.environ.get("HMME_FUZZ_ITERS", "40"))):

@@ -37,10 +37,11 @@ int main(int argc, char** argv) {
     Pel* refO = &ref[(size_t)M * S + M];
     const int ncx = W / 64, ncy = H / 64, nctu = ncx * ncy;
     std::vector<int> check[3];
-    double secs[3] = {0, 0, 0};
+    double secs[3] = {0, 0, 0}, slow[3] = {0, 0, 0};
     TEncOpenCL::SpecStats st[3];
     for (int pass = 0; pass < 3; ++pass) {
-        for (int rep = 0; rep < 2; ++rep) {                       // rep 0 warms up (allocations), rep 1 is timed
+        for (int rep = 0; rep < 5; ++rep) {                       // rep 0 warms up (allocations); the fastest of the four timed ones is reported
+                                                                  // (host wall clock with pageable uploads: single samples vary several-fold between boxes)
             check[pass].clear();
             const double t0 = now();
             if (pass > 0) {
@@ -62,15 +63,17 @@ int main(int argc, char** argv) {
                 check[pass].push_back((int)me.getRuiCost()[592]);
             }
             if (pass > 0) me.endPicture();
-            secs[pass] = now() - t0;
+            const double dt = now() - t0;
+            if (rep == 1 || (rep > 1 && dt < secs[pass])) secs[pass] = dt;
+            if (rep >= 1) slow[pass] = dt > slow[pass] ? dt : slow[pass];
         }
         st[pass] = me.getSpecStats();
     }
     const bool same = check[0] == check[1];                       // pass 2 uses other windows: compared through its own hit/miss verification only
     printf("{\"width\": %d, \"height\": %d, \"range\": %d, \"ctus\": %d, \"sync_frame_ms\": %.3f, \"spec_hit_frame_ms\": %.3f, \"spec_drift_frame_ms\": %.3f, "
            "\"spec_hit_calls\": %llu, \"spec_hit_hits\": %llu, \"spec_drift_calls\": %llu, \"spec_drift_hits\": %llu, \"spec_drift_speculations\": %llu, "
-           "\"tables_equal_sync\": %s}\n",
+           "\"slowest_ms\": [%.3f, %.3f, %.3f], \"timed_reps\": 4, \"tables_equal_sync\": %s}\n",
            W, H, R, nctu, secs[0] * 1e3, secs[1] * 1e3, secs[2] * 1e3, st[1].calls - st[0].calls, st[1].hits - st[0].hits, st[2].calls - st[1].calls,
-           st[2].hits - st[1].hits, st[2].speculations - st[1].speculations, same ? "true" : "false");
+           st[2].hits - st[1].hits, st[2].speculations - st[1].speculations, slow[0] * 1e3, slow[1] * 1e3, slow[2] * 1e3, same ? "true" : "false");
     return same ? 0 : 2;
 }
