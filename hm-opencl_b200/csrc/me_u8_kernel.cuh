@@ -135,6 +135,16 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
+#ifdef HMME_POLL_SLEEP
+    asm volatile(
+        "{ .reg .pred p;\n"
+        "W_%=: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra D_%=;\n"
+        "nanosleep.u32 %2;\n"
+        "bra W_%=;\n"
+        "D_%=:\n}" ::"r"(a), "r"(parity), "n"(HMME_POLL_SLEEP) : "memory");
+    return;
+#endif
     asm volatile(
         "{ .reg .pred p;\n"
         "W_%=: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
