@@ -12,7 +12,7 @@ reaches the GPUs either as band + halo rectangles over each GPU's own PCIe link 
 NVLink from rank 0 (`e2e.broadcast`, also measured).  Python only loops over steps.
 
 Output: ONE JSON line on rank 0 (contract in the task statement): `value` = block-SAD evaluations/s with inputs
-resident in HBM (K frames alternating over the group's two frame slots = two streams, CUDA events around the whole
+resident in HBM (K frames alternating over two of the group's frame slots = two streams, CUDA events around the whole
 region, inputs cycled through more plane copies than fit in L2), `e2e` = the same metric through the group call with
 pinned HOST planes (HM's int16 Pel; H2D of both planes' band rectangles + jobs, D2H of the four result arrays inside
 the timed region), `roofline` = algorithmic integer lane-ops/s of the dominant kernel against the issue rate of both
@@ -272,6 +272,7 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip the fractional-refinement / distortion / per-CTU / random-access legs (profiling runs)")
     ap.add_argument("--ref-dist", default="band_halo", choices=["band_halo", "broadcast"],
                     help="how the reference picture reaches the GPUs in the reported e2e leg (the other one is measured as well at N > 1)")
+    ap.add_argument("--slots", type=int, default=0, choices=[0, 2, 3], help="frames in flight in the pipelined e2e leg (0 = hmme_group_pipeline_depth's advice)")
     ap.add_argument("--virtual-world", type=int, default=0, help="experiments: on ONE GPU, run only the band rank 0 would get in a world of this size")
     args = ap.parse_args()
     if args.impl == "reference":          # each step is seconds of single-threaded CPU encoders: keep the default run short
@@ -318,7 +319,7 @@ def main():
     grp.set_lambda_q16(LAMBDA_Q16)
     first, njobs = grp.band(total_jobs)
     jobs = np.ascontiguousarray(all_jobs[first:first + njobs])
-    mes = [grp.context(0, s) for s in range(2)]                       # the per-GPU contexts behind the group's two frame slots
+    mes = [grp.context(0, s) for s in range(2)]                       # the per-GPU contexts behind two of the group's frame slots (resident legs)
     me = mes[0]
     exts = [torch.cuda.ExternalStream(m.stream_ptr, device=dev) for m in mes]
 
@@ -328,7 +329,8 @@ def main():
     n_cur, n_ref = pin(pad_plane(f[1], margin, margin)), pin(pad_plane(f[0], margin, margin))
     n_cur8, n_ref8 = pin(n_cur.astype(np.uint8)), pin(n_ref.astype(np.uint8))
     org = (margin, margin)
-    outs = [[pin(np.zeros((total_jobs, NPARTS), t)) for t in (np.int32, np.int32, np.uint32, np.uint32)] for _ in range(2)]
+    NSLOTS = args.slots or grp.pipeline_depth(total_jobs, R)           # frames in flight in the pipelined e2e leg: the library's advice (2 or 3)
+    outs = [[pin(np.zeros((total_jobs, NPARTS), t)) for t in (np.int32, np.int32, np.uint32, np.uint32)] for _ in range(NSLOTS)]
 
     def barrier():
         torch.cuda.synchronize()
@@ -381,7 +383,7 @@ def main():
     barrier()
     single_ms = sum(a.elapsed_time(b) for a, b in ev) / n_single
 
-    # (b) the reported value: EXACTLY K steps, frames alternating over the two slots' contexts (two streams), nothing but the
+    # (b) the reported value: EXACTLY K steps, frames alternating over two slots' contexts (two streams), nothing but the
     # library's kernels in the timed region; consecutive frames overlap at their wave tails.  CUDA events around the whole region.
     for s in range(max(args.warmup, 4)):
         if njobs:
@@ -412,15 +414,15 @@ def main():
     # ------------------------------------------------------------------ e2e: host planes through the group call (C++ does the band split,
     # the rectangle uploads / NCCL broadcast, the search and the result copies; Python issues one call per frame)
     # (a) serial: every step waits for its own results before the next upload starts (a low-delay encoder's dependency);
-    # (b) pipelined (the reported e2e): frames alternate between the two slots, so the copies of one frame overlap the kernels of
-    #     the other -- every step still uploads both planes' rectangles and downloads its four result arrays.
+    # (b) pipelined (the reported e2e): frames cycle through the group's three slots, so the copies of one frame overlap the kernels of
+    #     the others -- every step still uploads both planes' rectangles and downloads its four result arrays.
     def e2e_leg(ref_dist, cur_h, ref_h, steps):
         grp.configure(W, H, margin, margin, grp.BROADCAST if ref_dist == "broadcast" else grp.BAND_HALO)
-        calls = [grp.bind_frame(s, cur_h, org, ref_h, org, all_jobs, R, outs[s]) for s in range(2)]
-        syncs = [grp.bind_sync(s) for s in range(2)]
-        for s in range(4):
-            calls[s & 1]()
-            syncs[s & 1]()
+        calls = [grp.bind_frame(s, cur_h, org, ref_h, org, all_jobs, R, outs[s]) for s in range(NSLOTS)]
+        syncs = [grp.bind_sync(s) for s in range(NSLOTS)]
+        for s in range(2 * NSLOTS):
+            calls[s % NSLOTS]()
+            syncs[s % NSLOTS]()
         barrier()
         t0 = time.perf_counter()
         for s in range(steps):
@@ -430,10 +432,10 @@ def main():
         serial = (time.perf_counter() - t0) * 1e3 / steps
         t0 = time.perf_counter()
         for s in range(steps):
-            syncs[s & 1]()                                          # this slot's previous frame (two steps ago) is complete
-            calls[s & 1]()
-        syncs[0]()
-        syncs[1]()
+            syncs[s % NSLOTS]()                                     # this slot's previous frame (NSLOTS steps ago) is complete
+            calls[s % NSLOTS]()
+        for sy in syncs:
+            sy()
         barrier()
         piped = (time.perf_counter() - t0) * 1e3 / steps
         piped, serial = allmax([piped, serial])
@@ -463,12 +465,12 @@ def main():
         mism, checked = 0, 0
         if njobs:
             want = Oracle().search_frame(n_cur, org, n_ref, org, jobs, R, LAMBDA_Q16, nthreads=max(1, (os.cpu_count() or 1) // max(1, world)))
-            for got in ([o[first:first + njobs] for o in outs[0]], [o[first:first + njobs] for o in outs[1]], resident):
+            for got in [[o[first:first + njobs] for o in outs[s]] for s in range(NSLOTS)] + [resident]:
                 mism += int(sum(int((np.asarray(g) != np.asarray(w_)).any(axis=1).sum()) for g, w_ in zip(got, want)))
                 checked += njobs
         mism, checked, band = allsum([mism, checked, njobs])
         verified = {"ctus": int(band), "ctu_result_sets_compared": int(checked), "mismatches": int(mism),
-                    "what": "X, Y, sad and cost of all 593 partitions of every CTU job of every rank's band (results of both e2e frame slots and of the last "
+                    "what": "X, Y, sad and cost of all 593 partitions of every CTU job of every rank's band (results of every e2e frame slot and of the last "
                             "resident search) against oracle.search_frame on the same inputs"}
 
     # ------------------------------------------------------------------ next row: fractional-pel refinement
@@ -584,7 +586,7 @@ def main():
                                    % (world, "single GPU" if world == 1 else ("band + halo rectangle per GPU over its own PCIe link, no collective" if args.ref_dist == "band_halo"
                                                                               else "rank 0 uploads, ncclBroadcast over NVLink inside the library")),
                        "l2": "inputs larger than L2: %d resident (current, reference) plane pairs at distinct addresses (%.0f MiB), cycled step by step" % (nsets, 2 * nsets * plane_bytes / 2**20),
-                       "timer": "CUDA events around the whole K-step region, frames alternating over the group's two frame slots (two contexts/streams), max over ranks; "
+                       "timer": "CUDA events around the whole K-step region, frames alternating over two of the group's frame slots (two contexts/streams), max over ranks; "
                                 "single_stream_ms_per_step = one context, events per step"},
             "single_stream_ms_per_step": single_ms,
             "clocks": clocks,
@@ -592,10 +594,10 @@ def main():
             "wall_ms_timed_region": (wall1 - wall0) * 1e3,
             "e2e": {"value": e2e_value, "unit": "block-SAD evaluations/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "frames_per_s": 1e3 / e2e_ms, "ms_per_step": e2e_ms,
-                    "serial_ms_per_step": serial_ms, "serial_frames_per_s": 1e3 / serial_ms,
+                    "serial_ms_per_step": serial_ms, "serial_frames_per_s": 1e3 / serial_ms, "slots": NSLOTS,
                     "host_samples": "int16 (HM's Pel), page-locked; narrowed to 8 bit on the device", "ref_dist": args.ref_dist,
-                    "timer": "host wall clock around K x hmme_group_search_frame_async (+ hmme_group_sync of the slot two steps back): per rank, rectangle uploads of the band's rows of "
-                             "the current frame and of band + halo of the reference picture from pinned memory, jobs, search, four result arrays back; frames alternate over two slots "
+                    "timer": "host wall clock around K x hmme_group_search_frame_async (+ hmme_group_sync of the slot `slots` steps back): per rank, rectangle uploads of the band's rows of "
+                             "the current frame and of band + halo of the reference picture from pinned memory, jobs, search, four result arrays back; frames cycle through 2 or 3 of the group's slots (hmme_group_pipeline_depth; `slots` below) "
                              "so copies overlap kernels; serial_* = one slot, each step waits for its results; max over ranks"},
             "roofline": {"bound": "int_issue", "kernel": "me_u8_tile_kernel", "achieved": achieved / 1e12, "peak": 2.0 * peak["lane_ops_per_s"] / 1e12,
                          "unit": "T int-lane-op/s", "frac": achieved / (2.0 * peak["lane_ops_per_s"]) if peak["lane_ops_per_s"] else None,

@@ -27,7 +27,7 @@ EXPORTS = [
     "hmme_table_create", "hmme_table_destroy", "hmme_search_frame_table_async", "hmme_table_fetch_async", "hmme_table_device_ptr",
     "hmme_group_create", "hmme_group_unique_id", "hmme_group_create_rank", "hmme_group_destroy", "hmme_group_last_error", "hmme_group_size",
     "hmme_group_set_lambda_q16", "hmme_group_configure", "hmme_group_search_frame_async", "hmme_group_sync", "hmme_group_search_frame",
-    "hmme_group_band", "hmme_group_context", "hmme_group_last_kernel_ms", "hmme_group_kernel_launches", "hmme_band_split", "hmme_band_extent",
+    "hmme_group_band", "hmme_group_pipeline_depth", "hmme_search_launch_size", "hmme_group_context", "hmme_group_last_kernel_ms", "hmme_group_kernel_launches", "hmme_band_split", "hmme_band_extent",
     "hmme_last_kernel_ms", "hmme_kernel_launches", "hmme_measure_int_alu_peak", "hmme_partition_rect", "hmme_index_block", "hmme_search_window", "hmme_version",
 ]
 
@@ -122,6 +122,8 @@ class HmmeLib:
             "hmme_group_sync": (i32, [vp, i32]),
             "hmme_group_search_frame": (i32, [vp, vp, i32, vp, i32, i32, vp, i32, i32, vp, vp, vp, vp]),
             "hmme_group_band": (i32, [vp, i32, i32, P(C.c_int), P(C.c_int)]),
+            "hmme_group_pipeline_depth": (i32, [vp, i32, i32]),
+            "hmme_search_launch_size": (i32, [vp, i32, i32, P(C.c_int), P(C.c_int)]),
             "hmme_group_context": (vp, [vp, i32, i32]),
             "hmme_group_last_kernel_ms": (i32, [vp, i32, P(C.c_float)]),
             "hmme_group_kernel_launches": (C.c_uint64, [vp]),
@@ -509,6 +511,7 @@ class Group:
     results into one host table).  devices=[...] drives them from this process; rank/world/unique_id makes this process one rank of
     a one-process-per-GPU job (torchrun)."""
     BAND_HALO, BROADCAST = 0, 1
+    SLOTS = 3                  # HMME_GROUP_SLOTS: frames in flight per group
 
     def __init__(self, devices=None, max_search_range=64, device=None, rank=None, world=None, unique_id=None):
         self.lib = HmmeLib.get()
@@ -592,6 +595,10 @@ class Group:
         self.search_frame_async(0, cur, cur_origin, ref, ref_origin, jobs, rng, outs)
         self.sync(0)
         return tuple(outs)
+
+    def pipeline_depth(self, njobs, rng):
+        """Frames to keep in flight (slots to cycle through) for frames of njobs jobs at +-rng: 2 or 3 (hmme_group_pipeline_depth)."""
+        return int(self.lib.L.hmme_group_pipeline_depth(self.g, int(njobs), int(rng)))
 
     def band(self, njobs, local_index=0):
         f, n = C.c_int(), C.c_int()

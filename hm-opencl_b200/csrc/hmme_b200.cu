@@ -738,6 +738,14 @@ int hmme_plane_upload_u8(hmme_ctx* c, const hmme_plane* p, const uint8_t* hostOr
     return rc != HMME_OK ? rc : sync_ctx(c);
 }
 
+int hmme_search_launch_size(hmme_ctx* c, int njobs, int range, int* ctas, int* ctasPerWave) {
+    if (!c || njobs <= 0 || range < 0 || range > 1024) return fail(c, HMME_ERR_ARG, "hmme_search_launch_size: bad argument");
+    const FastGeom g = fast_geometry(2 * range + 1, HMME_FAST_YB, njobs, c->prop.multiProcessorCount, c->forceRG);
+    if (ctas) *ctas = njobs * g.nTx * g.nTy;
+    if (ctasPerWave) *ctasPerWave = c->prop.multiProcessorCount;          // one 512-thread block per SM
+    return HMME_OK;
+}
+
 int hmme_search_frame_async(hmme_ctx* c, const hmme_plane* cur, const hmme_plane* ref, const hmme_job* jobs, int njobs, int range) {
     if (!c) return HMME_ERR_ARG;
     if (!jobs || njobs <= 0) return fail(c, HMME_ERR_ARG, "hmme_search_frame: no jobs");

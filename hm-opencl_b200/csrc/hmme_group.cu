@@ -24,7 +24,11 @@
 
 namespace {
 
-constexpr int kSlots = 2;          // frames in flight per GPU (the copies of one overlap the kernels of the other)
+constexpr int kDeepPipelineWaves = 10;      // hmme_group_pipeline_depth: bands shorter than this many waves take the third slot
+constexpr int kSlots = HMME_GROUP_SLOTS;   // frames in flight per GPU: the copies of one overlap the kernels of the others.  Three, because with two a
+                                           // narrow band (8 GPUs: 0.14 ms of kernel) leaves the GPU with ONE queued search while the host waits for a
+                                           // slot's results and refills it, so the last, partly filled wave of that search runs alone: measured on a
+                                           // 60-job band 0.156 ms per frame with two slots, 0.138 with three (= the resident rate), 0.176 with four
 
 struct NcclApi {
     void* lib = nullptr;
@@ -104,14 +108,14 @@ private:
 
 struct GroupDev {
     int device = -1, globalRank = 0;
-    hmme_ctx* ctx[kSlots] = {nullptr, nullptr};
+    hmme_ctx* ctx[kSlots] = {};
     hmme_plane cur[kSlots] = {}, ref[kSlots] = {};
     ncclComm_t comm = nullptr;
     cudaStream_t ncclStream = nullptr;             // high priority: the broadcast slips in between the other slot's search CTAs
     cudaEvent_t evPre = nullptr, evPost = nullptr;
     Worker* worker = nullptr;
     int rc = 0; std::string err;                   // outcome of the most recent per-device enqueue
-    int first[kSlots] = {0, 0}, count[kSlots] = {0, 0};   // band of the frame in flight in each slot
+    int first[kSlots] = {}, count[kSlots] = {};    // band of the frame in flight in each slot
 };
 
 }  // namespace
@@ -341,7 +345,7 @@ int hmme_group_search_frame_async(hmme_group* g, int slot, const void* curHostOr
                                   int refHostStride, int hostElemBytes, const hmme_job* jobs, int njobs, int range, int32_t* X, int32_t* Y,
                                   uint32_t* sad, uint32_t* cost) {
     if (!g) return HMME_ERR_ARG;
-    if (slot < 0 || slot >= kSlots) return gfail(g, HMME_ERR_ARG, "hmme_group_search_frame: slot must be 0 or 1");
+    if (slot < 0 || slot >= kSlots) return gfail(g, HMME_ERR_ARG, "hmme_group_search_frame: slot must be in [0, HMME_GROUP_SLOTS)");
     if (!g->width) return gfail(g, HMME_ERR_ARG, "hmme_group_search_frame: call hmme_group_configure first");
     if (!curHostOrigin || !refHostOrigin || !jobs || njobs <= 0 || !X || !Y || !sad) return gfail(g, HMME_ERR_ARG, "hmme_group_search_frame: null pointer / no jobs");
     if (hostElemBytes != 1 && hostElemBytes != 2) return gfail(g, HMME_ERR_ARG, "hmme_group_search_frame: host samples must be uint8 or int16");
@@ -424,7 +428,7 @@ int hmme_group_search_frame_async(hmme_group* g, int slot, const void* curHostOr
 
 int hmme_group_sync(hmme_group* g, int slot) {
     if (!g) return HMME_ERR_ARG;
-    if (slot < -1 || slot >= kSlots) return gfail(g, HMME_ERR_ARG, "hmme_group_sync: slot must be 0, 1 or -1 (both)");
+    if (slot < -1 || slot >= kSlots) return gfail(g, HMME_ERR_ARG, "hmme_group_sync: slot must be in [0, HMME_GROUP_SLOTS) or -1 (all)");
     for (GroupDev& d : g->devs)
         for (int s = 0; s < kSlots; ++s) {
             if (slot >= 0 && s != slot) continue;
@@ -440,6 +444,21 @@ int hmme_group_search_frame(hmme_group* g, const void* curHostOrigin, int curHos
     const int rc = hmme_group_search_frame_async(g, 0, curHostOrigin, curHostStride, refHostOrigin, refHostStride, hostElemBytes, jobs, njobs, range,
                                                  X, Y, sad, cost);
     return rc != HMME_OK ? rc : hmme_group_sync(g, 0);
+}
+
+int hmme_group_pipeline_depth(hmme_group* g, int njobs, int range) {
+    if (!g || njobs <= 0) return 2;
+    // Frames worth keeping in flight: two while a GPU's band is many waves of thread blocks (the copies of one frame hide behind the other's
+    // kernel), three when it is only a few -- then the last, partly filled wave of a search is a sizeable part of it and must overlap the
+    // next search, which with two slots is not queued yet while the host waits for a slot's results and refills it.  Measured, 1080p +-64:
+    // 29 waves (1 GPU) 1.126 / 1.132 ms per frame with 2 / 3 slots, 3.6 waves (8 GPUs) 0.156 / 0.138.
+    int depth = 2;
+    for (GroupDev& d : g->devs) {
+        int first = 0, count = 0, ctas = 0, wave = 1;
+        hmme_band_split(njobs, g->world, d.globalRank, &first, &count);
+        if (count > 0 && hmme_search_launch_size(d.ctx[0], count, range, &ctas, &wave) == HMME_OK && ctas < kDeepPipelineWaves * wave) depth = 3;
+    }
+    return depth;
 }
 
 int hmme_group_band(hmme_group* g, int njobs, int localIndex, int* first, int* count) {

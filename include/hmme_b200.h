@@ -109,6 +109,9 @@ int hmme_search_frame(hmme_ctx* ctx, const hmme_plane* cur, const hmme_plane* re
 int hmme_search_frame_async(hmme_ctx* ctx, const hmme_plane* cur, const hmme_plane* ref, const hmme_job* jobs,
                             int njobs, int range);
 int hmme_fetch_results(hmme_ctx* ctx, int njobs, int32_t* X, int32_t* Y, uint32_t* sad, uint32_t* cost);
+/* Thread blocks the search of njobs jobs at +-range launches, and how many the device runs at once (one per SM): the length of a
+ * frame in waves, which decides how many frames a pipelining caller keeps in flight (hmme_group_pipeline_depth). */
+int hmme_search_launch_size(hmme_ctx* ctx, int njobs, int range, int* ctas, int* ctasPerWave);
 /* Fully asynchronous legs for pipelining frames over two contexts (copies of one context overlap the kernels of the
  * other): enqueue only; host buffers must stay valid (and should be page-locked) until hmme_sync returns.  The 8-bit
  * content check of an asynchronous upload is reported by the next hmme_sync / synchronous call (HMME_ERR_CONTENT). */
@@ -144,9 +147,12 @@ const void* hmme_table_device_ptr(hmme_table* table, int slot, int array);
  * process passes the same whole-frame arguments and fills only its own band's rows of the tables.
  * Host planes: hostElemBytes 2 = HM's Pel (int16, narrowed on the device), 1 = uint8.  Origins point at picture sample (0,0); the
  * reference plane's margins must exist (TComPicYuv).  Windows must stay inside the padded picture (HMME_ERR_BOUNDS otherwise).
- * slot (0 or 1) selects one of two frames in flight; host buffers stay valid (ideally page-locked) until hmme_group_sync(slot). */
+ * slot (0 .. HMME_GROUP_SLOTS - 1) selects one of three frames in flight; host buffers stay valid (ideally page-locked) until
+ * hmme_group_sync(slot).  Callers that pipeline frames cycle through all slots (two are enough while a GPU's band is large; narrow bands
+ * on many GPUs need the third to keep a search queued while a slot is being refilled). */
 typedef struct hmme_group hmme_group;
 enum { HMME_REF_BAND_HALO = 0, HMME_REF_BROADCAST = 1 };
+#define HMME_GROUP_SLOTS 3
 int hmme_group_create(hmme_group** out, const int* devices, int ndev, int maxSearchRange);
 int hmme_group_unique_id(void* id, size_t bytes);
 int hmme_group_create_rank(hmme_group** out, int device, int rank, int nranks, const void* uniqueId, int maxSearchRange);
@@ -158,10 +164,12 @@ int hmme_group_configure(hmme_group* group, int width, int height, int marginX, 
 int hmme_group_search_frame_async(hmme_group* group, int slot, const void* curHostOrigin, int curHostStride,
                                   const void* refHostOrigin, int refHostStride, int hostElemBytes, const hmme_job* jobs, int njobs,
                                   int range, int32_t* X, int32_t* Y, uint32_t* sad, uint32_t* cost);
-int hmme_group_sync(hmme_group* group, int slot);                /* slot -1: both */
+int hmme_group_sync(hmme_group* group, int slot);                /* slot -1: all */
 int hmme_group_search_frame(hmme_group* group, const void* curHostOrigin, int curHostStride, const void* refHostOrigin,
                             int refHostStride, int hostElemBytes, const hmme_job* jobs, int njobs, int range, int32_t* X, int32_t* Y,
                             uint32_t* sad, uint32_t* cost);
+/* How many frames a pipelining caller should keep in flight (slots to cycle through) for frames of njobs jobs at +-range: 2 or 3. */
+int hmme_group_pipeline_depth(hmme_group* group, int njobs, int range);
 int hmme_group_band(hmme_group* group, int njobs, int localIndex, int* first, int* count);
 hmme_ctx* hmme_group_context(hmme_group* group, int localIndex, int slot);   /* the per-GPU context behind a slot (refinement, timing) */
 int hmme_group_last_kernel_ms(hmme_group* group, int slot, float* searchKernelMsMaxOverLocalGpus);

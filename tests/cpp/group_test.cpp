@@ -43,7 +43,7 @@ int main() {
         if (hmme_group_configure(g, W, H, M, M, mode == 0 ? HMME_REF_BAND_HALO : HMME_REF_BROADCAST) != HMME_OK) {
             printf("FAIL hmme_group_configure: %s\n", hmme_group_last_error(g)); return 1;
         }
-        for (int slot = 0; slot < 2; ++slot) {
+        for (int slot = 0; slot < HMME_GROUP_SLOTS; ++slot) {
             std::vector<int32_t> X((size_t)n * 593, -7), Y((size_t)n * 593, -7);
             std::vector<uint32_t> Sd((size_t)n * 593, 7), C((size_t)n * 593, 7);
             if (hmme_group_search_frame_async(g, slot, curO, S, refO, S, 2, jobs.data(), n, R, X.data(), Y.data(), Sd.data(), C.data()) != HMME_OK ||
@@ -60,6 +60,6 @@ int main() {
     for (int i = 0; i < ndev; ++i) { hmme_group_band(g, n, i, &first, &count); if (first != total) ++bad; total += count; }
     if (total != n) ++bad;
     hmme_group_destroy(g);
-    printf("%s: %d GPU(s), %d jobs x 2 modes x 2 slots, %d mismatches\n", bad ? "FAIL" : "PASS", ndev, n, bad);
+    printf("%s: %d GPU(s), %d jobs x 2 modes x %d slots, %d mismatches\n", bad ? "FAIL" : "PASS", ndev, n, HMME_GROUP_SLOTS, bad);
     return bad ? 1 : 0;
 }
