@@ -66,7 +66,7 @@ constexpr size_t kSmemBudget = 224 * 1024;   // of the 227 KB a CTA may opt in t
 
 size_t fast_smem_bytes(int tileRows, int yb) {
     const size_t words = (((size_t)fast_win_rows(tileRows) * kWinPitch + 31) & ~(size_t)31) + 1024 + kRing * (size_t)(32 * yb) * kRecWords +
-                         (size_t)tileRows * (kKbPitch + 1) + kMaxTileW + 4;
+                         (size_t)tileRows * (kKbPitch + 2) + kMaxTileW + 4;
     return words * 4;
 }
 

@@ -543,8 +543,14 @@ __global__ void __launch_bounds__(kFastThreads, 1) me_u8_tile_kernel(const __gri
     uint32_t* sKb = sUp + kRing * SLOTS * kRecWords;        // tileRows x kKbPitch key bases
     uint32_t* sBitsX = sKb + p.tileRows * kKbPitch;         // kMaxTileW MV-bit counts of the tile's columns, then tileRows of its rows
     uint32_t* sBitsY = sBitsX + kMaxTileW;
+    uint32_t* sRowBase = sBitsY + p.tileRows;               // per row of the tile: rank of its column 0 in the tile's scan order (tile_rank(y, 0))
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#ifndef HMME_NO_MAP_PREFETCH
+    // the copy engine reads the 128-byte tensor maps from the parameter space: fetch them while the job record is on its way
+    if (tid == 0 && p.refMapOk) asm volatile("prefetch.tensormap [%0];" ::"l"(&p.refMap) : "memory");
+    if (tid == 32 && p.curMapOk) asm volatile("prefetch.tensormap [%0];" ::"l"(&p.curMap) : "memory");
+#endif
 #ifdef HMME_DIAG_TIMES
     long long dt[6];
     dt[0] = clock64();
@@ -601,19 +607,25 @@ __global__ void __launch_bounds__(kFastThreads, 1) me_u8_tile_kernel(const __gri
         if (tid == 0) {
             mbar_init(&winBar, (uint32_t)((ref2d ? 1 : rowsReal) + (curMode == 1 ? 64 : (curMode ? 1 : 0))));
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
-        if (tid >= 256) {                                     // MV-bit counts per column and per row of the tile (the warps that issue no copies)
-            for (int x = tid - 256; x < twA; x += 256) sBitsX[x] = mv_bits(4 * (jb.z + x0 + x));
-            for (int y = tid - 256; y < nRG * YB; y += 256) sBitsY[y] = mv_bits(4 * (jb.w + y0 + y));
-        }
-        __syncthreads();
-        HMME_DIAG_T(1);
-        if (ref2d) {
-            if (tid == 0) {
+            // the one-copy forms leave from here, before the block-wide barrier: issuing a tile copy holds the thread for ~900 cycles (the copy
+            // engine fetches the tensor map), which now overlaps the MV-bit tables of the other warps and the barrier itself
+            if (ref2d) {
                 mbar_arrive_expect_tx(&winBar, (uint32_t)(winRows * kDensePitch));
                 tma_tile_2d(dense, &p.refMap, wc & ~15, wr, &winBar);
             }
-        } else if (tid < rowsReal) {
+            if (curMode >= 2) {
+                mbar_arrive_expect_tx(&winBar, 4096);
+                if (curMode == 2) tma_bulk_g2s(sCur, cbase, 4096, &winBar);
+                else tma_tile_2d(sCur, &p.curMap, jb.x, jb.y, &winBar);
+            }
+        }
+        if (tid >= 256) {                                     // MV-bit counts per column and per row of the tile (the warps that issue no copies)
+            for (int x = tid - 256; x < twA; x += 256) sBitsX[x] = mv_bits(4 * (jb.z + x0 + x));
+            for (int y = tid - 256; y < nRG * YB; y += 256) { sBitsY[y] = mv_bits(4 * (jb.w + y0 + y)); sRowBase[y] = tile_rank(tg, y, 0, YB); }
+        }
+        __syncthreads();
+        HMME_DIAG_T(1);
+        if (!ref2d && tid < rowsReal) {
             const uintptr_t g = (uintptr_t)(wbase + (long long)tid * p.refPitch);
             const uintptr_t g0 = g & ~(uintptr_t)15;
             uint32_t bytes = (uint32_t)(((g - g0) + (uintptr_t)(nPos + 3) + 15) & ~(uintptr_t)15);
@@ -629,10 +641,6 @@ __global__ void __launch_bounds__(kFastThreads, 1) me_u8_tile_kernel(const __gri
             const int r = tid - (kFastThreads - 64);
             mbar_arrive_expect_tx(&winBar, 64);
             tma_bulk_g2s(sCur + r * 16, cbase + (long long)r * curPitch, 64, &winBar);
-        } else if (curMode >= 2 && tid == kFastThreads - 32) {
-            mbar_arrive_expect_tx(&winBar, 4096);
-            if (curMode == 2) tma_bulk_g2s(sCur, cbase, 4096, &winBar);
-            else tma_tile_2d(sCur, &p.curMap, jb.x, jb.y, &winBar);
         }
         if (curMode == 0) {
             for (int idx = tid; idx < 1024; idx += kFastThreads) {
@@ -641,16 +649,17 @@ __global__ void __launch_bounds__(kFastThreads, 1) me_u8_tile_kernel(const __gri
             }
         }
         // key base of every candidate of the tile: (lambda * (bits(mvx) + bits(mvy)) >> 16) << 11 | scan-order index in the tile
-        for (int y = warp; y < nRG * YB; y += kFastThreads / 32) {
-            const uint32_t bitsY = sBitsY[y];
+        // (warp 0 issues the window copy, which holds it up for about as long as the copy takes: the other fifteen fill the table)
+        for (int y = warp - 1; y >= 0 && y < nRG * YB; y += kFastThreads / 32 - 1) {
+            const uint32_t bitsY = sBitsY[y], rowBase = sRowBase[y];    // the rank is linear in x inside a row
             for (int x = lane; x < twA; x += 32)
-                sKb[y * kKbPitch + x] = y < thA ? ((((uint32_t)(p.lambda * (sBitsX[x] + bitsY)) >> 16) << kIdxBits) | (tile_rank(tg, y, x, YB) & (kMaxTileCands - 1)))
+                sKb[y * kKbPitch + x] = y < thA ? ((((uint32_t)(p.lambda * (sBitsX[x] + bitsY)) >> 16) << kIdxBits) | ((rowBase + (uint32_t)x) & (kMaxTileCands - 1)))
                                                 : kInvalidBlockKeyBase;
         }
         HMME_DIAG_T(2);
         mbar_wait(&winBar, 0);
         HMME_DIAG_T(3);
-        for (int row = warp; row < rows; row += kFastThreads / 32) {
+        for (int row = kFastThreads / 32 - 1 - warp; row < rows; row += kFastThreads / 32) {   // warp 0 issued the copies and starts last: it gets the fewest rows
             const uint32_t off = (uint32_t)((uintptr_t)(wbase + (long long)row * p.refPitch) & 15);
             const uint32_t* d = reinterpret_cast<const uint32_t*>(dense + row * kDensePitch);
 #ifdef HMME_WIN64
@@ -663,7 +672,10 @@ __global__ void __launch_bounds__(kFastThreads, 1) me_u8_tile_kernel(const __gri
                 const uint32_t w0 = d[off >> 2], w1 = d[(off >> 2) + 1], w2 = d[(off >> 2) + 2];
                 dst[0] = make_uint2(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh));
             }
-            for (int x = odd + 2 * lane; x < nPos - 4; x += 64) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {                       // x < nPos - 4 <= 185: three steps of 64 entries, unrolled so that their loads overlap
+                const int x = odd + 2 * lane + 64 * k;
+                if (x >= nPos - 4) break;
                 const uint32_t q = off + (uint32_t)x, sh = 8 * (q & 3);
                 const uint32_t w0 = d[q >> 2], w1 = d[(q >> 2) + 1], w2 = d[(q >> 2) + 2];
                 const bool cross = (q & 3) == 3;               // the second entry starts on the next word
