@@ -778,7 +778,7 @@ def random_access_leg(hm, me, ext, torch, sets, nsets, n_cur, n_ref, frames, mar
 
 def _ncu_traffic(workload):
     """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the committed ncu capture."""
-    for name in ("r02c_traffic.json", "r02b_traffic.json", "r02_traffic.json", "r01_traffic.json"):
+    for name in ("r02d_traffic.json", "r02b_traffic.json", "r02_traffic.json", "r01_traffic.json"):
         try:
             t = json.load(open(os.path.join(ROOT, "profiles", name)))
             if t["workload"].startswith(workload.split("_")[0]):
