@@ -90,6 +90,16 @@ def test_search_window_matches_the_reference_encoder(lib):
     assert {4, 8, 64, 96} <= ranges and clipped > 10
 
 
+def test_python_mirror_constants_match_the_header(lib):
+    """The ctypes mirror repeats a few constants of include/hmme_b200.h: frame slots of a group, partitions per CTU, distribution modes."""
+    from _pkg import hm
+    src = open(os.path.join(ROOT, "include", "hmme_b200.h")).read()
+    assert int(re.search(r"#define\s+HMME_GROUP_SLOTS\s+(\d+)", src).group(1)) == hm.Group.SLOTS
+    assert int(re.search(r"#define\s+HMME_NUM_CTU_PARTS\s+(\d+)", src).group(1)) == 593 == len(lib.partition_table())
+    m = re.search(r"HMME_REF_BAND_HALO\s*=\s*(\d+)\s*,\s*HMME_REF_BROADCAST\s*=\s*(\d+)", src)
+    assert (int(m.group(1)), int(m.group(2))) == (hm.Group.BAND_HALO, hm.Group.BROADCAST)
+
+
 def test_product_and_oracle_layout_agree(lib, oracle):
     assert np.array_equal(lib.partition_table(), oracle.partition_table())
 
