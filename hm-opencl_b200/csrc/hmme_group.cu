@@ -452,13 +452,11 @@ int hmme_group_pipeline_depth(hmme_group* g, int njobs, int range) {
     // kernel), three when it is only a few -- then the last, partly filled wave of a search is a sizeable part of it and must overlap the
     // next search, which with two slots is not queued yet while the host waits for a slot's results and refills it.  Measured, 1080p +-64:
     // 29 waves (1 GPU) 1.126 / 1.132 ms per frame with 2 / 3 slots, 3.6 waves (8 GPUs) 0.156 / 0.138.
-    int depth = 2;
-    for (GroupDev& d : g->devs) {
-        int first = 0, count = 0, ctas = 0, wave = 1;
-        hmme_band_split(njobs, g->world, d.globalRank, &first, &count);
-        if (count > 0 && hmme_search_launch_size(d.ctx[0], count, range, &ctas, &wave) == HMME_OK && ctas < kDeepPipelineWaves * wave) depth = 3;
-    }
-    return depth;
+    // the largest band of the frame (bands differ by at most one job), so that every rank of a one-process-per-GPU job gets the same answer
+    const int count = (njobs + g->world - 1) / g->world;
+    int ctas = 0, wave = 1;
+    if (hmme_search_launch_size(g->devs[0].ctx[0], count, range, &ctas, &wave) == HMME_OK && ctas < kDeepPipelineWaves * wave) return 3;
+    return 2;
 }
 
 int hmme_group_band(hmme_group* g, int njobs, int localIndex, int* first, int* count) {
