@@ -148,8 +148,8 @@ const void* hmme_table_device_ptr(hmme_table* table, int slot, int array);
  * Host planes: hostElemBytes 2 = HM's Pel (int16, narrowed on the device), 1 = uint8.  Origins point at picture sample (0,0); the
  * reference plane's margins must exist (TComPicYuv).  Windows must stay inside the padded picture (HMME_ERR_BOUNDS otherwise).
  * slot (0 .. HMME_GROUP_SLOTS - 1) selects one of three frames in flight; host buffers stay valid (ideally page-locked) until
- * hmme_group_sync(slot).  Callers that pipeline frames cycle through all slots (two are enough while a GPU's band is large; narrow bands
- * on many GPUs need the third to keep a search queued while a slot is being refilled). */
+ * hmme_group_sync(slot).  Callers that pipeline frames cycle through hmme_group_pipeline_depth() slots (two are enough while a GPU's band
+ * is large; narrow bands on many GPUs need the third to keep a search queued while a slot is being refilled). */
 typedef struct hmme_group hmme_group;
 enum { HMME_REF_BAND_HALO = 0, HMME_REF_BROADCAST = 1 };
 #define HMME_GROUP_SLOTS 3
